@@ -1,0 +1,208 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference — TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py            # writes tests/golden/{en_small,enp_small,q_small,relu_small_fwd}.npz
+
+The reference modules `models/{satrans,meta_basemodel,submodules}.py` are imported as they lie
+under /root/reference, with `oracle/ref_shims` supplying the third-party names they import
+(SURVEY.md §8c / Appendix C).  For each case we dump, in fp32 exactly as the reference produced them:
+
+  state/<key>        the reference `state_dict()` at construction (canonical keys; aliased keys dropped)
+  X, y               the (B, n_cols) float32 input matrix (ids stored as floats, as `fit` feeds it) and labels
+  E0                 gathered field embeddings (B, F, d)          — bit-exact target
+  y_pred             eval-mode forward (B, 1)
+  bce, reg           BCE(sum) and L2 regulariser of that batch
+  grad/<key>         every parameter gradient of (bce + reg), eval-mode forward (dropout off)
+  stepK/<key>, stepK_m/<key>, stepK_v/<key>   K in {1,3}: parameters and Adam moments after K dense
+                     torch.optim.Adam steps on batches X[k] (eval-mode forward, dropout off)
+  predict            `model.predict(x_dict, batch_size)` through the reference's own API (N,1) float64
+
+While dumping, the script also asserts that `oracle/satrans_oracle.py` reproduces the reference
+(fp32 vs fp32) — that is the pin.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get('SATRANS_REFERENCE', '/root/reference')
+
+
+def import_reference():
+    sys.path.insert(0, os.path.join(HERE, 'ref_shims'))
+    sys.path.insert(0, REF)
+    from models.satrans import SATrans  # noqa
+    from deepctr_torch.inputs import SparseFeat, DenseFeat  # noqa
+    return SATrans, SparseFeat, DenseFeat
+
+
+CASES = {
+    # name: (schema, vocab_scale, B, ctor overrides)
+    'en_small': ('aliccp', 1e-4, 96, dict(domain_att_layer_num=3, att_head_num=4, meta_mode='QK', flag='sota')),
+    'enp_small': ('alimama', 1e-4, 80, dict(domain_att_layer_num=3, att_head_num=4, meta_mode='QK',
+                                            flag='sota-pos')),
+    'q_small': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=2, meta_mode='Q', flag='sota')),
+    # 'relu' in flag: the reference's own eval-mode backward raises (in-place `result += inputs` on the ReLU
+    # output, satrans.py:91-97, when dropout is the identity), so this case pins the forward only.
+    'relu_small_fwd': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK',
+                                                flag='sota-relu')),
+}
+FORWARD_ONLY = {'relu_small_fwd'}
+
+
+def subsample(key):
+    """The scenario-encoder weight (4096 x 32|64) dominates the fixture size: post-step snapshots keep
+    and gradients keep every 8th row of it (the initial state is stored in full)."""
+    return slice(None, None, 8) if key == 'domain_map_dnn_Q.linears.0.weight' else slice(None)
+
+
+def zero_grad_key(key):
+    """K-side MetaNet LayerNorm bias shifts every key by a constant => softmax-invariant => its true
+    gradient is 0; only present as its own tensor with 'pos'."""
+    return key.endswith('K_meta_mlp.ffn_layer_norm.bias')
+
+
+def build_case(name):
+    sys.path.insert(0, ROOT)
+    from satrans_b200 import synth
+    from oracle import satrans_oracle as O
+    SATrans, SparseFeat, DenseFeat = import_reference()
+    schema_name, scale, B, kw = CASES[name]
+    schema = (synth.aliccp_schema if schema_name == 'aliccp' else synth.alimama_schema)(scale)
+    cols = ([SparseFeat(f, vocabulary_size=schema.data_max[f] + 2, embedding_dim=32) for f in schema.fields]
+            + [DenseFeat(f, 1) for f in schema.dense])
+    torch.set_num_threads(1)
+    model = SATrans(linear_feature_columns=cols, dnn_feature_columns=cols,
+                    domain_column_list=[schema.domain_col], num_domains_list=[schema.num_domains],
+                    att_layer_num=0, use_linear=False, use_dnn=False, seed='1021', device='cpu', **kw)
+    # give the MetaNet LayerNorms and the encoder non-trivial values so that every gradient path is exercised
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            if 'ffn_layer_norm' in k:
+                v.add_(torch.randn(v.shape, generator=g) * 0.1)
+            if k == 'domain_map_dnn_Q.linears.0.weight':
+                v.copy_(torch.randn(v.shape, generator=g) * 0.05)
+            if k.startswith('embedding_dict.'):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.3)
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    names = schema.fields + schema.dense
+    xs, ys = synth.make_inputs(schema, 3 * B, seed=1021, ctr=0.3)
+    Xall = synth.stack_columns(xs, names)
+    yall = ys.astype(np.float32)
+    X = torch.from_numpy(Xall[:B])
+    y = torch.from_numpy(yall[:B])
+
+    cfg = O.OracleConfig(sparse_names=schema.fields, vocab_sizes=schema.vocab_sizes, dense_names=schema.dense,
+                         domain_col=schema.domain_col, num_domains=schema.num_domains, embedding_dim=32,
+                         layers=kw['domain_att_layer_num'], heads=kw['att_head_num'], meta_mode=kw['meta_mode'],
+                         flag=kw['flag'])
+    out = {'config': np.frombuffer(json.dumps(dict(
+        schema=schema_name, vocab_scale=scale, B=B, sparse_names=schema.fields, vocab_sizes=schema.vocab_sizes,
+        dense_names=schema.dense, domain_col=schema.domain_col, num_domains=schema.num_domains, **kw)).encode(),
+        dtype=np.uint8)}
+    for k, v in state0.items():
+        if O.canonical_key(cfg, k) == k:      # aliases (K/V MetaNet LN, encoder _K/_V) are re-created by the tests
+            out['state/' + k] = v.numpy()
+    out['X'] = Xall
+    out['y'] = yall
+
+    # ---- eval-mode forward / gather --------------------------------------------------------------
+    model.eval()
+    emb_list, _ = model.input_from_feature_columns(X, model.dnn_feature_columns, model.embedding_dict)
+    E0 = torch.cat(emb_list, dim=1).detach()
+    out['E0'] = E0.numpy()
+    yp = model(X)
+    out['y_pred'] = yp.detach().numpy()
+    if name in FORWARD_ONLY:
+        st = {k: v.clone() for k, v in state0.items()}
+        with torch.no_grad():
+            assert torch.allclose(O.forward(st, X, cfg), yp.detach(), atol=1e-6, rtol=0)
+        import contextlib
+        import io
+        with contextlib.redirect_stderr(io.StringIO()):
+            out['predict'] = model.predict({k: v[:B] for k, v in xs.items()}, batch_size=37)
+        return out
+    # ---- loss + grads (eval mode ⇒ dropout off), exactly the ops of meta_basemodel.py:314-327 -----
+    model.zero_grad()
+    bce = torch.nn.functional.binary_cross_entropy(yp.squeeze(), y, reduction='sum')
+    reg = model.get_regularization_loss()
+    (bce + reg).backward()
+    out['bce'] = np.float32(bce.item())
+    out['reg'] = np.float32(reg.item())
+    named = dict(model.named_parameters())
+    for k in O.trainable_keys(cfg):
+        gr = named[k].grad
+        out['grad/' + k] = (gr if gr is not None else torch.zeros_like(named[k])).detach().numpy()[subsample(k)].copy()
+
+    # ---- pin the oracle against the reference ---------------------------------------------------
+    st = {k: v.clone() for k, v in state0.items()}
+    o_ids, o_E0 = O.gather_fields(st, X, cfg)
+    assert torch.equal(o_E0, E0), 'oracle gather != reference'
+    o_yp, o_bce, o_reg, o_g = O.loss_and_grads(st, X, y, cfg)
+    assert torch.allclose(o_yp, yp.detach(), atol=1e-6, rtol=0), (o_yp - yp).abs().max()
+    assert abs(o_bce.item() - bce.item()) <= 1e-5 * abs(bce.item())
+    assert abs(o_reg.item() - reg.item()) <= 1e-5 * abs(reg.item())
+    for k in O.trainable_keys(cfg):
+        a, b = o_g[k][subsample(k)], torch.from_numpy(out['grad/' + k])
+        scale_ = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 1e-4 * scale_ + 1e-9, (k, (a - b).abs().max().item(), scale_)
+
+    # ---- dense Adam steps (eval-mode forward) ---------------------------------------------------
+    lr = 0.005 if schema_name == 'aliccp' else 0.001
+    optim = torch.optim.Adam(model.parameters(), lr=lr)
+    o_opt = O.adam_init(st, cfg)
+    for step in range(1, 4):
+        Xk = torch.from_numpy(Xall[(step - 1) * B: step * B])
+        yk = torch.from_numpy(yall[(step - 1) * B: step * B])
+        ypk = model(Xk).squeeze()
+        optim.zero_grad()
+        total = torch.nn.functional.binary_cross_entropy(ypk, yk, reduction='sum') + model.get_regularization_loss()
+        total.backward()
+        optim.step()
+        O.train_step(st, Xk, yk, cfg, o_opt, lr)
+        if step in (1, 3):
+            sd = model.state_dict()
+            for k in O.trainable_keys(cfg):
+                sub = subsample(k)
+                out['step%d/%s' % (step, k)] = sd[k].detach().numpy()[sub].copy()
+                s = optim.state[named[k]]
+                if step == 3:
+                    out['step%d_m/%s' % (step, k)] = s['exp_avg'].numpy()[sub].copy()
+                    out['step%d_v/%s' % (step, k)] = s['exp_avg_sq'].numpy()[sub].copy()
+                # pin: the oracle's Adam restatement tracks the reference within fp32 round-off
+                ref_p = sd[k].detach()
+                err = (st[k] - ref_p).abs().max().item()
+                tol = 2e-5 * max(ref_p.abs().max().item(), 1e-3) + 1e-7
+                if zero_grad_key(k):
+                    tol = 3 * lr * step     # analytically-zero gradient: Adam amplifies round-off noise
+                assert err <= tol, (step, k, err)
+    out['lr'] = np.float32(lr)
+
+    # ---- predict() through the reference API (restore the step-0 weights first) ------------------
+    model.load_state_dict(state0)
+    import contextlib
+    import io
+    with contextlib.redirect_stderr(io.StringIO()):
+        pred = model.predict({k: v[:B] for k, v in xs.items()}, batch_size=37)
+    out['predict'] = pred
+    return out
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
+    for name in CASES:
+        out = build_case(name)
+        path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, '->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+    main()
