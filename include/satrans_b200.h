@@ -1,0 +1,196 @@
+/*
+ * satrans_b200.h — C ABI of the B200-native SATrans hot path (libsatrans_b200.so).
+ *
+ * The reference (qwerfdsaplking/SATrans) is 100 % Python/PyTorch: it has no FFI / plugin layer,
+ * its drop-in boundary is the Python class API.  This header is the native
+ * boundary *underneath* that API: every entry point replaces one group of ATen dispatches of the
+ * reference's eager path, cited as `reference file:line` on each declaration.  The Python host
+ * code in satrans_b200/ binds these symbols with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add) — no torch types cross this boundary: plain device /
+ * host pointers, sizes, and a CUDA stream handle passed as `void*`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SAT_E* code otherwise;
+ *     `sat_last_error()` returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - `stream` is a `cudaStream_t` cast to `void*` (NULL = legacy default stream).
+ *   - no entry point allocates or frees memory, synchronises the device, or throws.
+ *   - fp32 everywhere; embedding dimension d = 32, MetaNet hidden units (64, 32)  [the reference's
+ *     "best performance" configurations, readme.md:17-24]; F <= 32 sparse fields; heads in {1,2,4,8}.
+ */
+#ifndef SATRANS_B200_H
+#define SATRANS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAT_ABI_VERSION 1
+
+#define SAT_OK 0
+#define SAT_EINVAL (-1)      /* bad argument / unsupported shape            */
+#define SAT_ECUDA (-2)       /* a CUDA runtime call or kernel launch failed */
+
+#define SAT_D 32             /* embedding dim                               */
+#define SAT_HID 64           /* MetaNet hidden width                        */
+#define SAT_P 4096           /* generated weights per key: 32*64 + 64*32    */
+#define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
+#define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
+#define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
+#define SAT_WORK_BUFFERS 20  /* pointer members of SatWork */
+#define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
+#define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
+
+/* id_kind: how sample ids reach the kernels */
+#define SAT_IDS_F32 0        /* the reference's (B, n_cols) float32 input matrix; ids = trunc(X[b, col]) */
+#define SAT_IDS_I32 1        /* (B, n_cols) int32 matrix                                                */
+#define SAT_IDS_I64 2        /* (B, n_cols) int64 matrix                                                */
+
+/* flags for SatModel.flags */
+#define SAT_FLAG_POS 1       /* 'pos' in flag: ENP, per-(layer,q/k) generated weights, separate K LayerNorm */
+#define SAT_FLAG_META_Q 2    /* 'Q' in meta_mode                                                          */
+#define SAT_FLAG_META_K 4    /* 'K' in meta_mode                                                          */
+#define SAT_FLAG_RELU 8      /* 'relu' in flag: ReLU on the output projection                             */
+#define SAT_FLAG_RES 16      /* att_res: residual connection                                              */
+
+/*
+ * Model description.  All dense (non-table) parameters live in ONE flat fp32 buffer `dense`
+ * (gradients / Adam moments use the same layout), at these float offsets:
+ *
+ *   off_dom   : domain_embeddings.weight            [n_dom][32]          reference satrans.py:145
+ *   off_lid   : layerid_embeddings.weight           [L][32]   (POS only) reference satrans.py:169
+ *   off_qkv   : qkvid_embeddings.weight             [3][32]   (POS only) reference satrans.py:170
+ *   off_encw  : domain_map_dnn_Q.linears.0.weight   [4096][enc_in]       reference satrans.py:178, submodules.py:31
+ *   off_encb  : domain_map_dnn_Q.linears.0.bias     [4096]
+ *   off_layers: L blocks of SAT_LAYER_FLOATS floats:                     reference satrans.py:31-47
+ *                 +0    W_Query [32][32]  (x @ W)
+ *                 +1024 W_Key   [32][32]
+ *                 +2048 W_Value [32][32]
+ *                 +3072 Out_linear.weight [32 out][32 in]  (x @ W^T)
+ *                 +4096 layer_norm.weight[32]  +4128 layer_norm.bias[32]
+ *                 +4160 Q_meta_mlp.ffn_layer_norm.weight[32]  +4192 .bias[32]
+ *                 +4224 K_meta_mlp.ffn_layer_norm.weight[32]  +4256 .bias[32]   (used only with POS;
+ *                        without POS the K side reads/accumulates the Q block — reference satrans.py:44-46)
+ *   off_headw : dnn_linear.weight [F*32 + n_dense]                        reference satrans.py:183
+ *   off_headb : dnn_linear.bias   [1]
+ */
+typedef struct SatModel {
+    int32_t F;            /* sparse fields = tokens per sample                              */
+    int32_t L;            /* domain_att_layer_num                                           */
+    int32_t H;            /* att_head_num                                                   */
+    int32_t n_dom;        /* rows of domain_embeddings = num_domains + 1                    */
+    int32_t n_dense;      /* DenseFeat columns appended to the head input                   */
+    int32_t n_cols;       /* columns of the input matrix                                    */
+    int32_t flags;        /* SAT_FLAG_*                                                     */
+    int32_t enc_in;       /* 32, or 64 with POS                                             */
+    int32_t dom_col;      /* column of the scenario id in the input matrix                  */
+    int32_t pad0;
+    int64_t n_dense_params; /* floats in the flat dense buffer                              */
+    int64_t off_dom, off_lid, off_qkv, off_encw, off_encb, off_layers, off_headw, off_headb;
+    int64_t total_rows;   /* rows of the concatenated embedding table                       */
+    const int64_t* row_off;   /* [F+1] first row of each field's table in `tables`          */
+    const int32_t* sparse_cols; /* [F] input-matrix column of each sparse field             */
+    const int32_t* dense_cols;  /* [n_dense] input-matrix column of each dense feature      */
+    float* tables;        /* [total_rows][32] all embedding_dict tables back to back        */
+    float* dense;         /* flat dense parameter buffer                                    */
+} SatModel;
+
+/* Per-batch workspace, caller-allocated (sizes from sat_workspace_sizes).  */
+typedef struct SatWork {
+    int32_t B;            /* samples in this batch                                          */
+    int32_t cap_B;        /* capacity the buffers were sized for                            */
+    int32_t* perm;        /* [cap_B] sorted position -> sample index (bucketed by scenario) */
+    int32_t* dom;         /* [cap_B] scenario id per sorted position                        */
+    int32_t* tiles;       /* [max_tiles][4] (key/domain, start, count, pad)                 */
+    int32_t* counters;    /* [64] ints: [0]=n_tiles [1]=error flags [2..] group histogram   */
+    float* theta;         /* [n_keys][4096] generated MetaNet weights per key               */
+    float* dtheta;        /* [n_keys][4096] their gradient                                  */
+    float* enc_du;        /* [n_keys][64] gradient w.r.t. the encoder inputs                */
+    float* acts;          /* training only: [L][5][cap_B*F][32] saved x, zq, zk, v, r + [cap_B*F][32] final x */
+    float* dz;            /* [cap_B] dLoss/dlogit per sorted position                       */
+    float* dx;            /* [2][cap_B*F][32] ping-pong activation gradients                */
+    float* dqkv;          /* [3][cap_B*F][32] dq', dk', dv between the two backward kernels */
+    double* loss_part;    /* [max_tiles] per-tile BCE partial sums                          */
+    float* dgrad;         /* flat dense-parameter gradient buffer (n_dense_params)          */
+    /* touched-row bookkeeping for the embedding update */
+    uint32_t* bitmap;     /* [ceil(total_rows/32)] one bit per table row                    */
+    int32_t* word_rank;   /* [ceil(total_rows/32)] exclusive prefix popcount                */
+    int32_t* block_sums;  /* [ceil(words/1024)+1]                                           */
+    int32_t* uniq_rows;   /* [cap_B*F] sorted unique touched rows                           */
+    float* row_grad;      /* [cap_B*F][32] accumulated dE per unique touched row            */
+    double* reg_part;     /* [SAT_REG_PARTS] partial sums of squares of the tables          */
+    float* scalars;       /* [8] device results: [0]=bce sum [1]=reg loss [2]=n_unique rows [3]=error flags */
+} SatWork;
+
+typedef struct SatAdam {
+    float lr, beta1, beta2, eps;
+    float l2_emb;         /* l2_reg_embedding (reference satrans.py:117, meta_basemodel.py:179) */
+    int32_t step;         /* 1-based step index of THIS update                                  */
+    int32_t dense_mode;   /* 1 = reference semantics (every table row gets L2 + Adam every step,
+                             reference meta_basemodel.py:577-593 + main.py:343);
+                             0 = touched rows only (lazy/sparse Adam)                           */
+    int32_t pad0;
+    float* tab_m; float* tab_v;       /* [total_rows][32] Adam moments of the tables            */
+    float* dense_m; float* dense_v;   /* [n_dense_params]                                       */
+} SatAdam;
+
+/* ---- library info ------------------------------------------------------------------------- */
+int sat_abi_version(void);
+const char* sat_last_error(void);
+/* bytes needed for each SatWork buffer, in the order of the struct's pointer members
+ * (SAT_WORK_BUFFERS entries; 0 = not needed for inference-only use). */
+int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t training, int64_t* sizes_host, int32_t* max_tiles_host);
+
+/* ---- embedding gather: replaces BaseModel.input_from_feature_columns (reference
+ *      meta_basemodel.py:519-545: F slices + F float->long casts + F nn.Embedding calls) and the
+ *      torch.cat at satrans.py:211.  out[b][f][:] = tables[row_off[f] + trunc(ids[b][col_f])][:].
+ *      `x` is the (B, ld) input matrix in the layout given by id_kind.  Out-of-range ids set bit 0
+ *      of *err_flag (device int, may be NULL) and read row 0 of that field. ------------------- */
+int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, int32_t B,
+                   float* out, int32_t* err_flag, void* stream);
+
+/* ---- scenario bucketing: samples grouped by trunc(X[b, dom_col]) (reference satrans.py:203) so that
+ *      every tile of the fused kernels shares one set of generated MetaNet weights. ------------- */
+int sat_bucket_by_domain(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
+                         int32_t samples_per_tile, void* stream);
+
+/* ---- scenario encoder: replaces domain_embeddings + ReLU + DNN_v2 per sample (reference
+ *      satrans.py:203-234, submodules.py:47-61) by one evaluation per distinct key. ------------- */
+int sat_encoder_fwd(const SatModel* m, SatWork* w, void* stream);
+int sat_encoder_bwd(const SatModel* m, SatWork* w, void* stream);
+
+/* ---- fused forward: gather + L x Meta_Transformer_Layer + logit head + sigmoid (+ BCE and dLogit
+ *      when y != NULL).  Replaces SATrans.forward (reference satrans.py:197-256), Meta_Transformer_Layer
+ *      .forward (satrans.py:50-100), MetaNet.forward (submodules.py:77-103) and, with y, the BCE of
+ *      meta_basemodel.py:317.  y_pred is (B,) in ORIGINAL sample order.  training != 0 saves the
+ *      activations the backward needs and applies dropout(p) with a counter-based RNG keyed by
+ *      (seed, sample, field, layer, site).  Requires sat_bucket_by_domain + sat_encoder_fwd first. */
+int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y,
+                SatWork* w, float* y_pred, int32_t training, float dropout_p, uint64_t seed, void* stream);
+
+/* ---- fused backward of the L layers + head; writes the dense-parameter gradient into w->dgrad,
+ *      dtheta, and scatter-adds dLoss/dE0 into w->row_grad (rows ranked through the touched-row
+ *      bitmap).  Replaces autograd over the graph of satrans.py:197-256. ------------------------ */
+int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
+                 float dropout_p, uint64_t seed, void* stream);
+
+/* ---- touched-row bookkeeping: mark + rank the rows this batch reads ------------------------- */
+int sat_rows_mark(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
+
+/* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
+ *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */
+/* touched rows on stream_rows (NULL = skip), untouched rows on stream_sweep (NULL or dense_mode==0 = skip);
+ * the two kernels write disjoint rows and may run concurrently. */
+int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream_rows, void* stream_sweep);
+int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
+/* sum of squares of all table rows into w->reg_part (regulariser without an optimiser step). */
+int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream);
+/* w->scalars[0] = BCE(sum) of the batch, [1] = l2_emb * sum(table^2), [3] = error flags. */
+int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATRANS_B200_H */

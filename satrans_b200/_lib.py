@@ -1,0 +1,107 @@
+"""ctypes binding of libsatrans_b200.so (the C ABI declared in include/satrans_b200.h).
+
+There is no CPU fallback: `lib()` raises if the shared library has not been built
+(`python -c "import __graft_entry__ as g; g.build()"` or `make -C satrans_b200/csrc`).
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libsatrans_b200.so')
+CSRC = os.path.join(HERE, 'csrc')
+
+SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
+SAT_REG_PARTS = 148 * 8 + 148 * 4
+SAT_WORK_BUFFERS = 20
+IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
+FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
+ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class SatModel(C.Structure):
+    _fields_ = [('F', i32), ('L', i32), ('H', i32), ('n_dom', i32), ('n_dense', i32), ('n_cols', i32),
+                ('flags', i32), ('enc_in', i32), ('dom_col', i32), ('pad0', i32),
+                ('n_dense_params', i64),
+                ('off_dom', i64), ('off_lid', i64), ('off_qkv', i64), ('off_encw', i64), ('off_encb', i64),
+                ('off_layers', i64), ('off_headw', i64), ('off_headb', i64),
+                ('total_rows', i64),
+                ('row_off', vp), ('sparse_cols', vp), ('dense_cols', vp), ('tables', vp), ('dense', vp)]
+
+
+WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
+                'loss_part', 'dgrad', 'bitmap', 'word_rank', 'block_sums', 'uniq_rows', 'row_grad', 'reg_part',
+                'scalars']
+assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
+
+
+class SatWork(C.Structure):
+    _fields_ = [('B', i32), ('cap_B', i32)] + [(n, vp) for n in WORK_BUFFERS]
+
+
+class SatAdam(C.Structure):
+    _fields_ = [('lr', f32), ('beta1', f32), ('beta2', f32), ('eps', f32), ('l2_emb', f32),
+                ('step', i32), ('dense_mode', i32), ('pad0', i32),
+                ('tab_m', vp), ('tab_v', vp), ('dense_m', vp), ('dense_v', vp)]
+
+
+# name -> (restype, argtypes); must list every symbol include/satrans_b200.h declares
+PROTOTYPES = {
+    'sat_abi_version': (C.c_int, []),
+    'sat_last_error': (C.c_char_p, []),
+    'sat_workspace_sizes': (C.c_int, [C.POINTER(SatModel), i32, i32, C.POINTER(i64), C.POINTER(i32)]),
+    'sat_gather_fwd': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, i32, vp, vp, vp]),
+    'sat_bucket_by_domain': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), i32, vp]),
+    'sat_encoder_fwd': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_encoder_bwd': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_forward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, vp]),
+    'sat_backward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, vp]),
+    'sat_rows_mark': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
+    'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp, vp]),
+    'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
+    'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, vp]),
+}
+
+_lib = None
+
+
+class SatError(RuntimeError):
+    pass
+
+
+def build(verbose=False, jobs=None):
+    """Compile satrans_b200/csrc/*.cu for sm_100a into satrans_b200/lib/libsatrans_b200.so (make)."""
+    jobs = jobs or os.cpu_count() or 4
+    r = subprocess.run(['make', '-C', CSRC, '-j%d' % jobs], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise SatError('building libsatrans_b200.so failed')
+    return LIB_PATH
+
+
+def lib():
+    """The loaded shared library with prototypes attached; raises SatError if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SatError('%s not found: build it first (make -C satrans_b200/csrc); there is no CPU fallback'
+                           % LIB_PATH)
+        import torch  # noqa: F401  (makes sure libcudart is already resolvable / loaded in-process)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        if l.sat_abi_version() != 1:
+            raise SatError('libsatrans_b200.so ABI version mismatch')
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise SatError('%s failed (%d): %s' % (what, rc, lib().sat_last_error().decode()))

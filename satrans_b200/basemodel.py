@@ -1,0 +1,459 @@
+"""BaseModel: the trainer / scorer half of the drop-in API.
+
+Mirrors `models/meta_basemodel.py:124-686` of the reference (identical public surface to
+`models/basemodel.py:125-128`): constructor arguments, `compile`, `fit`, `evaluate`, `predict`,
+`input_from_feature_columns`, `compute_input_dim`, `add_regularization_weight`,
+`get_regularization_loss`, `add_auxiliary_loss`, and the attributes `feature_index`,
+`embedding_dict`, `history`, `metrics_names`, `stop_training`.
+
+What differs underneath: `fit`/`predict` keep the input matrix resident in HBM, run each batch through the
+fused sm_100a kernels (satrans_b200/csrc) instead of ~4.7 k ATen dispatches, fuse L2 + Adam into the
+kernels, and compute the per-step host metrics from asynchronously copied predictions.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .inputs import DenseFeat, SparseFeat, VarLenSparseFeat, build_input_features
+
+
+class History(object):
+    """keras-style History callback (the reference takes it from deepctr_torch.callbacks)."""
+
+    def __init__(self):
+        self.epoch, self.history, self.model = [], {}, None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_train_begin(self, logs=None):
+        self.epoch, self.history = [], {}
+
+    def on_train_end(self, logs=None):
+        pass
+
+    def on_epoch_begin(self, epoch, logs=None):
+        pass
+
+    def on_epoch_end(self, epoch, logs=None):
+        self.epoch.append(epoch)
+        for k, v in (logs or {}).items():
+            self.history.setdefault(k, []).append(v)
+
+
+class CallbackList(object):
+    """The hooks of keras' CallbackList that `fit` drives (reference meta_basemodel.py:283-294,379-383)."""
+
+    def __init__(self, callbacks=None):
+        self.callbacks, self.model = list(callbacks or []), None
+
+    def set_model(self, model):
+        self.model = model
+        for c in self.callbacks:
+            if hasattr(c, 'set_model'):
+                c.set_model(model)
+
+    def _call(self, name, *a):
+        for c in self.callbacks:
+            fn = getattr(c, name, None)
+            if fn is not None:
+                fn(*a)
+
+    def on_train_begin(self, logs=None):
+        self._call('on_train_begin', logs)
+
+    def on_train_end(self, logs=None):
+        self._call('on_train_end', logs)
+
+    def on_epoch_begin(self, epoch, logs=None):
+        self._call('on_epoch_begin', epoch, logs)
+
+    def on_epoch_end(self, epoch, logs=None):
+        self._call('on_epoch_end', epoch, logs)
+
+
+class PredictionLayer(nn.Module):
+    """Bias + sigmoid (deepctr PredictionLayer).  SATrans never calls it (reference satrans.py:255 uses
+    torch.sigmoid directly) but `out.bias` is part of the state dict."""
+
+    def __init__(self, task='binary', use_bias=True):
+        if task not in ["binary", "multiclass", "regression"]:
+            raise ValueError("task must be binary,multiclass or regression")
+        super().__init__()
+        self.use_bias, self.task = use_bias, task
+        if use_bias:
+            self.bias = nn.Parameter(torch.zeros((1,)))
+
+    def forward(self, X):
+        out = X + self.bias if self.use_bias else X
+        return torch.sigmoid(out) if self.task == "binary" else out
+
+
+class Linear(nn.Module):
+    """The per-feature dim-1 tables of the linear part (reference meta_basemodel.py:34-92).  SATrans.forward
+    never evaluates it (use_linear is ignored, l2_reg_linear=0), it only carries state-dict entries."""
+
+    def __init__(self, feature_columns, feature_index, init_std=0.0001, device='cpu'):
+        super().__init__()
+        self.feature_index = feature_index
+        sparse = [f for f in feature_columns if isinstance(f, SparseFeat)]
+        dense = [f for f in feature_columns if isinstance(f, DenseFeat)]
+        self.embedding_dict = nn.ModuleDict({f.embedding_name: nn.Embedding(f.vocabulary_size, 1) for f in sparse})
+        for t in self.embedding_dict.values():
+            nn.init.normal_(t.weight, mean=0, std=init_std)
+        if dense:
+            self.weight = nn.Parameter(torch.empty(sum(f.dimension for f in dense), 1))
+            nn.init.normal_(self.weight, mean=0, std=init_std)
+        self.to(device)
+
+
+def _auc(y_true, y_score):
+    from sklearn.metrics import roc_auc_score
+    return roc_auc_score(y_true, y_score)
+
+
+def _logloss(y_true, y_score):
+    from sklearn.metrics import log_loss
+    return log_loss(y_true, y_score)
+
+
+def _mse(y_true, y_score):
+    return float(np.mean((np.asarray(y_true, dtype=np.float64).ravel() - np.asarray(y_score).ravel()) ** 2))
+
+
+def _acc(y_true, y_score):
+    return float(np.mean(np.asarray(y_true).ravel() == np.where(np.asarray(y_score).ravel() > 0.5, 1, 0)))
+
+
+class BaseModel(nn.Module):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5,
+                 init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None,
+                 flag=None, domain_column=None, num_domains=None, meta_dnn_hidden_units=(32, 64, 32)):
+        super().__init__()
+        if any(isinstance(f, VarLenSparseFeat) for f in list(linear_feature_columns) + list(dnn_feature_columns)):
+            raise NotImplementedError("VarLenSparseFeat is not on the SATrans path (reference main.py:103,146)")
+        if domain_column:
+            raise NotImplementedError("BaseModel(domain_column=...) is the 'metatrans' hook of the single-task "
+                                      "baselines (reference basemodel.py:191-199), outside the SATrans path")
+        self.flag = flag
+        torch.manual_seed(int(seed))                                  # reference meta_basemodel.py:153
+        self.dnn_feature_columns = dnn_feature_columns
+        self.device = device
+        self.gpus = gpus
+        if gpus and str(self.gpus[0]) not in self.device:              # reference meta_basemodel.py:160-162
+            raise ValueError("`gpus[0]` should be the same gpu with `device`")
+        if gpus and len(gpus) > 1:
+            raise NotImplementedError("single-process nn.DataParallel is replaced by one process per GPU: "
+                                      "launch with torchrun and use satrans_b200.dist (see DESIGN.md)")
+        self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
+        self.reg_loss = torch.zeros((1,), device=device)
+        self.aux_loss = torch.zeros((1,), device=device)
+
+        # ---- embedding tables: ONE [total_rows, d] buffer, every nn.Embedding.weight is a view of it -----
+        sparse = [f for f in dnn_feature_columns if isinstance(f, SparseFeat)]
+        d = self.embedding_size
+        self._sparse_feats = sparse
+        self._row_off = np.concatenate([[0], np.cumsum([f.vocabulary_size for f in sparse])]).astype(np.int64)
+        self._tables = torch.empty((int(self._row_off[-1]), d), dtype=torch.float32, device=device)
+        if not (flag and 'noembinit' in flag):                           # reference meta_basemodel.py:114-119
+            self._tables.normal_(mean=0.0, std=init_std)
+        else:
+            self._tables.normal_(mean=0.0, std=1.0)
+        self.embedding_dict = nn.ModuleDict()
+        for i, f in enumerate(sparse):
+            emb = nn.Embedding(f.vocabulary_size, d, device='meta')
+            emb.weight = nn.Parameter(self._tables[int(self._row_off[i]):int(self._row_off[i + 1])])
+            self.embedding_dict[f.embedding_name] = emb
+
+        self.linear_model = Linear(linear_feature_columns, self.feature_index, device=device)
+        self.regularization_weight = []
+        self.add_regularization_weight(self.embedding_dict.parameters(), l2=l2_reg_embedding)
+        self.add_regularization_weight(self.linear_model.parameters(), l2=l2_reg_linear)
+        self.l2_reg_embedding = l2_reg_embedding
+        self.out = PredictionLayer(task).to(device)
+
+        self._is_graph_network = True
+        self._ckpt_saved_epoch = False
+        self.history = History()
+        self.stop_training = False
+        self._engine = None
+
+    # ---- introspection helpers kept from the reference ------------------------------------------------
+    @property
+    def embedding_size(self):
+        sizes = set(f.embedding_dim for f in self.dnn_feature_columns if isinstance(f, SparseFeat))
+        if len(sizes) > 1:
+            raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
+        return list(sizes)[0]
+
+    def compute_input_dim(self, feature_columns, include_sparse=True, include_dense=True, feature_group=False):
+        sparse = [f for f in feature_columns if isinstance(f, SparseFeat)]
+        dense = [f for f in feature_columns if isinstance(f, DenseFeat)]
+        dense_dim = sum(f.dimension for f in dense)
+        sparse_dim = len(sparse) if feature_group else sum(f.embedding_dim for f in sparse)
+        return (sparse_dim if include_sparse else 0) + (dense_dim if include_dense else 0)
+
+    def add_regularization_weight(self, weight_list, l1=0.0, l2=0.0):
+        if isinstance(weight_list, torch.nn.parameter.Parameter):
+            weight_list = [weight_list]
+        else:
+            weight_list = list(weight_list)
+        self.regularization_weight.append((weight_list, l1, l2))
+
+    def add_auxiliary_loss(self, aux_loss, alpha):
+        self.aux_loss = aux_loss * alpha
+
+    def get_regularization_loss(self):
+        """l2 * sum(square(w)) over the registered weights as a (1,) tensor (reference
+        meta_basemodel.py:577-593).  `fit` never calls this: the fused optimiser sweep produces the same
+        number as a by-product; it is kept for API compatibility and evaluated with torch ops."""
+        total = torch.zeros((1,), device=self._tables.device)
+        for weight_list, l1, l2 in self.regularization_weight:
+            for w in weight_list:
+                p = w[1] if isinstance(w, tuple) else w
+                if l1 > 0:
+                    total = total + torch.sum(l1 * torch.abs(p))
+                if l2 > 0:
+                    total = total + torch.sum(l2 * torch.square(p))
+        return total
+
+    def input_from_feature_columns(self, X, feature_columns, embedding_dict, support_dense=True):
+        """(list of F (B,1,d) embeddings, list of (B,k) dense slices) — reference meta_basemodel.py:519-545.
+        The F lookups are ONE launch of the multi-field gather kernel; the list entries are views."""
+        sparse = [f for f in feature_columns if isinstance(f, SparseFeat)]
+        dense = [f for f in feature_columns if isinstance(f, DenseFeat)]
+        if not support_dense and len(dense) > 0:
+            raise ValueError("DenseFeat is not supported in dnn_feature_columns")
+        if embedding_dict is not self.embedding_dict or [f.name for f in sparse] != [f.name for f in self._sparse_feats]:
+            raise NotImplementedError("only the model's own embedding_dict / dnn_feature_columns are supported")
+        E = self.engine.gather(self._as_device_matrix(X))
+        embs = [E[:, i:i + 1, :] for i in range(E.shape[1])]
+        dense_vals = [X[:, self.feature_index[f.name][0]:self.feature_index[f.name][1]] for f in dense]
+        return embs, dense_vals
+
+    # ---- engine plumbing ------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self)
+        return self._engine
+
+    def _as_device_matrix(self, X):
+        if not torch.is_tensor(X):
+            X = torch.as_tensor(np.ascontiguousarray(X))
+        if X.dtype not in (torch.float32, torch.int32, torch.int64):
+            X = X.float()
+        return X.to(self._tables.device, non_blocking=True).contiguous()
+
+    # ---- compile -----------------------------------------------------------------------------------------
+    def compile(self, optimizer, loss=None, metrics=None):
+        """Same contract as the reference (meta_basemodel.py:598-610).  The optimiser may be a string or a
+        torch.optim instance built over `model.parameters()`; its hyper-parameters are read and the update
+        itself runs inside the fused kernels (Adam: tables + dense parameters)."""
+        self.metrics_names = ["loss"]
+        self.optim = self._get_optim(optimizer)
+        self.loss_func = self._get_loss_func(loss)
+        self.metrics = self._get_metrics(metrics)
+
+    def _get_optim(self, optimizer):
+        if isinstance(optimizer, str):
+            if optimizer == "adam":
+                self._opt_hparams = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+            elif optimizer in ("sgd", "adagrad", "rmsprop"):
+                raise NotImplementedError("the fused B200 path implements Adam (the reference's optimiser, "
+                                          "main.py:343); '%s' is not available" % optimizer)
+            else:
+                raise NotImplementedError
+            return optimizer
+        if isinstance(optimizer, torch.optim.Adam):
+            g = optimizer.param_groups[0]
+            if g.get('amsgrad') or g.get('weight_decay', 0) != 0 or g.get('maximize'):
+                raise NotImplementedError("Adam with amsgrad / weight_decay / maximize is not on the SATrans path")
+            self._opt_hparams = dict(lr=g['lr'], betas=tuple(g['betas']), eps=g['eps'])
+            return optimizer
+        raise NotImplementedError("the fused B200 path implements torch.optim.Adam (reference main.py:343)")
+
+    def _get_loss_func(self, loss):
+        if isinstance(loss, str):
+            if loss == "binary_crossentropy":
+                return "binary_crossentropy"
+            if loss in ("mse", "mae"):
+                raise NotImplementedError("the fused B200 path implements binary_crossentropy "
+                                          "(reference main.py:343-344)")
+            raise NotImplementedError
+        raise NotImplementedError("custom loss callables are not supported by the fused path")
+
+    def _get_metrics(self, metrics, set_eps=False):
+        metrics_ = {}
+        if metrics:
+            for metric in metrics:
+                if metric in ("binary_crossentropy", "logloss"):
+                    metrics_[metric] = _logloss
+                if metric == "auc":
+                    metrics_[metric] = _auc
+                if metric == "mse":
+                    metrics_[metric] = _mse
+                if metric in ("accuracy", "acc"):
+                    metrics_[metric] = _acc
+                self.metrics_names.append(metric)
+        return metrics_
+
+    # ---- data staging ------------------------------------------------------------------------------------
+    def _stack_inputs(self, x):
+        """dict / list of 1-D columns -> (N, n_cols) matrix in feature_index order (reference
+        meta_basemodel.py:221-222,257-264).  float32 exactly like the reference when any column is
+        non-integer; int32 otherwise (exact for ids >= 2**24, which the fp32 route cannot represent)."""
+        if isinstance(x, dict):
+            x = [x[feature] for feature in self.feature_index]
+        cols = [np.asarray(c) for c in x]
+        cols = [c.reshape(len(c), -1) for c in cols]
+        all_int = all(np.issubdtype(c.dtype, np.integer) for c in cols)
+        if all_int and all(c.size == 0 or (c.min() >= -2 ** 31 and c.max() < 2 ** 31) for c in cols):
+            return np.concatenate([c.astype(np.int32, copy=False) for c in cols], axis=-1)
+        for c in cols:
+            if np.issubdtype(c.dtype, np.integer) and c.size and c.max() >= 2 ** 24:
+                raise ValueError("ids >= 2**24 cannot travel through the reference's float32 input matrix; "
+                                 "pass integer columns only (no dense features) to use the int32 path")
+        return np.concatenate([c.astype(np.float32, copy=False) for c in cols], axis=-1)
+
+    # ---- fit ---------------------------------------------------------------------------------------------
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, valid_cnt_per_epoch=1, verbose=1, initial_epoch=0,
+            validation_split=0., validation_data=None, shuffle=True, callbacks=None):
+        """Same signature / History contract as the reference (meta_basemodel.py:200-385)."""
+        if isinstance(x, dict) and getattr(self, 'domain_column_list', None):
+            self.domain_id_offset = x[self.domain_column_list[0]].min()        # reference :218
+        do_validation = False
+        val_x, val_y = [], []
+        if validation_data:
+            do_validation = True
+            if len(validation_data) == 2:
+                val_x, val_y = validation_data
+            elif len(validation_data) == 3:
+                val_x, val_y, _ = validation_data
+            else:
+                raise ValueError('When passing a `validation_data` argument, it must contain either 2 items '
+                                 '(x_val, y_val), or 3 items (x_val, y_val, val_sample_weights)')
+        X = self._stack_inputs(x)
+        y = np.asarray(y).reshape(len(X), -1)[:, 0]
+        if not validation_data and validation_split and 0. < validation_split < 1.:
+            do_validation = True
+            split_at = int(len(X) * (1. - validation_split))
+            X, val_x = X[:split_at], X[split_at:]
+            y, val_y = y[:split_at], y[split_at:]
+        if batch_size is None:
+            batch_size = 256
+        self.train()
+        eng = self.engine
+        dev = self._tables.device
+        hp = self._opt_hparams
+        sample_num = len(X)
+        steps_per_epoch = (sample_num - 1) // batch_size + 1
+        steps_to_valid = steps_per_epoch // valid_cnt_per_epoch + 1
+
+        callbacks = CallbackList((callbacks or []) + [self.history])
+        callbacks.set_model(self)
+        callbacks.on_train_begin()
+        self.stop_training = False
+
+        # the whole training matrix lives in HBM for the epoch; labels too
+        Xd = torch.as_tensor(np.ascontiguousarray(X)).to(dev)
+        yd = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)).to(dev)
+        want_metrics = verbose > 0 and len(self.metrics) > 0
+        if verbose > 0:
+            print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(
+                sample_num, len(val_y), steps_per_epoch))
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(torch.initial_seed() & (2 ** 63 - 1))
+        for epoch in range(initial_epoch, epochs):
+            callbacks.on_epoch_begin(epoch)
+            epoch_logs = {}
+            start_time = time.time()
+            order = torch.randperm(sample_num, generator=gen).to(dev) if shuffle else None
+            preds = torch.empty(sample_num, dtype=torch.float32, device=dev) if want_metrics else None
+            losses = torch.zeros((steps_per_epoch, 2), dtype=torch.float32, device=dev)
+            step_num = 0
+            for s0 in range(0, sample_num, batch_size):
+                s1 = min(s0 + batch_size, sample_num)
+                if order is not None:
+                    idx = order[s0:s1]
+                    xb, yb = Xd.index_select(0, idx).contiguous(), yd.index_select(0, idx).contiguous()
+                else:
+                    xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
+                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
+                                           l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                           training=True, dropout_p=self.dropout_rate,
+                                           seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
+                losses[step_num].copy_(w['scalars'][0:2])
+                if want_metrics:
+                    preds[s0:s1] = y_pred
+                step_num += 1
+                if valid_cnt_per_epoch > 1 and step_num % steps_to_valid == 0 and do_validation:
+                    eval_result = self.evaluate(val_x, val_y, batch_size)
+                    self.train()
+                    print('Step: %d/%d, %s' % (step_num, steps_per_epoch, ''.join(
+                        " - %s: %.4f" % (k, v) for k, v in eval_result.items())))
+            eng.check_errors(eng.workspace(1, True))
+            lh = losses.double().cpu().numpy()
+            epoch_logs["loss"] = float(lh.sum()) / sample_num                 # (bce + reg) summed / N (:353)
+            if want_metrics:
+                ph = preds.cpu().numpy().astype("float64")
+                yh = (yd.index_select(0, order) if order is not None else yd).cpu().numpy()
+                train_result = {name: [] for name in self.metrics}
+                for s0 in range(0, sample_num, batch_size):
+                    s1 = min(s0 + batch_size, sample_num)
+                    for name, fn in self.metrics.items():
+                        try:
+                            train_result[name].append(fn(yh[s0:s1], ph[s0:s1]))
+                        except ValueError:          # e.g. AUC of a single-class batch: the reference would raise
+                            train_result[name].append(float('nan'))
+                for name, result in train_result.items():
+                    epoch_logs[name] = np.sum(result) / steps_per_epoch
+            if do_validation:
+                eval_result = self.evaluate(val_x, val_y, batch_size)
+                self.train()
+                for name, result in eval_result.items():
+                    epoch_logs["val_" + name] = result
+            if verbose > 0:
+                epoch_time = int(time.time() - start_time)
+                print('Epoch {0}/{1}'.format(epoch + 1, epochs))
+                eval_str = "{0}s - loss: {1: .4f}".format(epoch_time, epoch_logs["loss"])
+                for name in self.metrics:
+                    if name in epoch_logs:
+                        eval_str += " - " + name + ": {0: .4f}".format(epoch_logs[name])
+                if do_validation:
+                    for name in self.metrics:
+                        eval_str += " - val_" + name + ": {0: .4f}".format(epoch_logs["val_" + name])
+                print(eval_str)
+            callbacks.on_epoch_end(epoch, epoch_logs)
+            if self.stop_training:
+                break
+        callbacks.on_train_end()
+        return self.history
+
+    # ---- evaluate / predict ------------------------------------------------------------------------------
+    def evaluate(self, x, y, batch_size=256):
+        pred_ans = self.predict(x, batch_size, y)
+        return {name: fn(y, pred_ans) for name, fn in self.metrics.items()}
+
+    def predict(self, x, batch_size=256, y=None, domain_ids=None):
+        """(N, 1) float64 predictions, eval mode (reference meta_basemodel.py:401-517; the 'showattn' /
+        'instattn' analysis dumps are not part of the scoring path and are not implemented)."""
+        self.eval()
+        X = self._stack_inputs(x)
+        dev = self._tables.device
+        eng = self.engine
+        n = len(X)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        Xd = torch.as_tensor(np.ascontiguousarray(X)).to(dev)
+        for s0 in range(0, n, batch_size):
+            s1 = min(s0 + batch_size, n)
+            out[s0:s1] = eng.forward(Xd[s0:s1].contiguous(), training=False)
+        if n:
+            eng.check_errors(eng.workspace(1, False))
+        return out.cpu().numpy().astype("float64").reshape(-1, 1)
+
+    def _in_multi_worker_mode(self):
+        return None

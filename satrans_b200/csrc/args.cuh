@@ -1,0 +1,60 @@
+// Argument blocks shared by the per-head-count instantiations of the token kernels and their dispatchers.
+#pragma once
+#include "common.cuh"
+
+namespace sat {
+
+struct FwdArgs {
+    SatModel m;
+    const void* x;
+    int id_kind, ld;
+    const float* y;            // labels in original sample order, or NULL
+    const int32_t* perm;
+    const int32_t* tiles;
+    int32_t* counters;
+    const float* theta;
+    float* acts;               // [L][5][act_stride] + [act_stride]
+    long long act_stride;      // cap_B * F * 32 floats
+    float* dz;
+    double* loss_part;
+    float* y_pred;
+    float p_drop;
+    unsigned long long seed;
+};
+
+enum { ACT_X = 0, ACT_ZQ = 1, ACT_ZK = 2, ACT_V = 3, ACT_R = 4, ACT_PER_LAYER = 5 };
+
+struct BwdArgs {
+    SatModel m;
+    const void* x;
+    int id_kind, ld;
+    const int32_t* perm;
+    const int32_t* tiles;
+    int32_t* counters;
+    const float* theta;
+    float* dtheta;
+    const float* acts;
+    long long act_stride;
+    const float* dz;
+    float* dx;                 // [tok][32] gradient w.r.t. the current layer's output / input (in place)
+    float* dqkv;               // [3][act_stride]
+    float* dgrad;
+    const uint32_t* bitmap;
+    const int32_t* word_rank;
+    float* row_grad;
+    int layer;
+    float p_drop;
+    unsigned long long seed;
+};
+
+}  // namespace sat
+
+// one translation unit per head count H (compiled with -DSAT_INST_H=H); defined in forward.cu / backward_attn.cu
+#define SAT_DECL_H(H)                                                                          \
+    int sat_launch_forward_h##H(const sat::FwdArgs& a, int grid, int training, cudaStream_t s); \
+    int sat_launch_bwd_attn_h##H(const sat::BwdArgs& a, int grid, cudaStream_t s);
+SAT_DECL_H(1)
+SAT_DECL_H(2)
+SAT_DECL_H(4)
+SAT_DECL_H(8)
+#undef SAT_DECL_H

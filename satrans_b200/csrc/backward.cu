@@ -1,0 +1,335 @@
+// Fused SATrans backward (replaces torch autograd over the graph of reference satrans.py:197-256).
+//
+// Same mapping as the forward: one thread = one field token, a CTA = whole samples of one scenario.
+// Per layer, two kernels:
+//   k_bwd_attn : LayerNorm-out bwd, out-projection bwd (+dW_out), attention bwd -> dQ', dK', dV
+//   k_bwd_meta : MetaNet-LayerNorm bwd, MetaNet bwd (+d theta), QKV projection bwd (+dW_q/k/v) -> dX
+// Data gradients are thread-local GEMVs against weights in shared memory (as in the forward).  Weight
+// gradients are reductions over tokens: the two operands are staged as [token][36] shared tiles and every
+// thread owns a 4x4 block of the 32x32 product (64 blocks x 3 token groups = 192 threads), accumulated
+// into shared-memory accumulators that are flushed to HBM with one atomicAdd per element per CTA.
+// Attention uses the FlashAttention identity  sum_j P_ij dP_ij = dR_i . R_i  so no (F x F) tensor is
+// stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
+#include "bwd_common.cuh"
+
+namespace sat {
+
+
+// =====================================================================================================
+// head backward: dOut_L[tok][c] = dz[b] * w_head[f*32+c];  dW_head, db_head.   (reference satrans.py:244-255)
+// =====================================================================================================
+__global__ void __launch_bounds__(NT) k_bwd_head(const BwdArgs a) {
+    __shared__ __align__(16) float sT[NT * KV_LD];
+    __shared__ float sDz[NT];
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, F = m.F, L = m.L;
+    const int n_tiles = a.counters[CNT_NTILES];
+    const int s = tid / F, f = tid - s * F;
+    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    // thread (ff, chunk) owns dW_head[ff*32 + chunk*4 .. +4) for ff = tid/8 (+24 per pass)
+    float4 accw[2];
+    accw[0] = make_float4(0.f, 0.f, 0.f, 0.f); accw[1] = accw[0];
+    float accb = 0.f, accd = 0.f;      // bias grad; dense-feature weight grad (thread k < n_dense)
+    for (int t = t0; t < t1; ++t) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int p = start + s;
+        const long long tokpos = ((long long)p * F + f) * D;
+        __syncthreads();
+        if (valid) {
+            const float dzv = a.dz[p];
+            float xl[D], dout[D];
+            load_row(a.acts + (long long)L * ACT_PER_LAYER * a.act_stride + tokpos, xl);
+            const float* hw = m.dense + m.off_headw + f * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { dout[i] = dzv * __ldg(hw + i); xl[i] *= dzv; }
+            store_row(a.dx + tokpos, dout);
+            sts_row(sT + tid * KV_LD, xl);
+            if (f == 0) sDz[s] = dzv;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 2; ++pass) {
+            const int ff = (tid >> 3) + pass * (NT / 8), ch = (tid & 7) * 4;
+            if (ff < F) {
+                for (int ss = 0; ss < cnt; ++ss) {
+                    const float4 v = *reinterpret_cast<const float4*>(sT + (ss * F + ff) * KV_LD + ch);
+                    accw[pass].x += v.x; accw[pass].y += v.y; accw[pass].z += v.z; accw[pass].w += v.w;
+                }
+            }
+        }
+        if (tid == 0) for (int ss = 0; ss < cnt; ++ss) accb += sDz[ss];
+        if (tid >= 32 && tid < 32 + m.n_dense) {
+            const int k = tid - 32;
+            for (int ss = 0; ss < cnt; ++ss) {
+                const int b = a.perm[start + ss];
+                accd = fmaf(sDz[ss], load_dense(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.dense_cols + k)), accd);
+            }
+        }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ff = (tid >> 3) + pass * (NT / 8), ch = (tid & 7) * 4;
+        if (ff < F) {
+            float* d = a.dgrad + m.off_headw + ff * D + ch;
+            atomicAdd(d + 0, accw[pass].x); atomicAdd(d + 1, accw[pass].y);
+            atomicAdd(d + 2, accw[pass].z); atomicAdd(d + 3, accw[pass].w);
+        }
+    }
+    if (tid == 0) atomicAdd(a.dgrad + m.off_headb, accb);
+    if (tid >= 32 && tid < 32 + m.n_dense) atomicAdd(a.dgrad + m.off_headw + F * D + (tid - 32), accd);
+}
+
+// =====================================================================================================
+// kernel B: MetaNet LayerNorm bwd + MetaNet bwd + QKV projection bwd; layer 0 scatters dE0 to table rows.
+// =====================================================================================================
+constexpr int BWDB_SMEM_FLOATS = 3072 /*WQ WK WV*/ + 3072 /*dWQ dWK dWV*/ + 192 /*LN params*/ + 128 /*dLN q,k*/ +
+                                 2 * PSZ /*theta q,k*/ + 2 * PSZ /*dtheta q,k*/ + 2 * NT * KV_LD;
+
+// One MetaNet side (Q or K).  On entry dqp holds dLoss/dQ' (post-LN); on exit dLoss/d(x @ W) .
+// All threads of the CTA must call this (it contains __syncthreads()).
+__device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta, bool valid, int ntok, int tid, int lane,
+                                                 const float* __restrict__ sWp,      // projection weight [32][32]
+                                                 const float* __restrict__ sTh,      // W1|W2
+                                                 float* __restrict__ sdTh,           // their gradient accumulators
+                                                 const float* __restrict__ lng,      // LN gamma (smem)
+                                                 float* __restrict__ sdLNg,          // dgamma[32] | dbeta[32]
+                                                 float* __restrict__ sdWp,           // projection weight gradient
+                                                 float* __restrict__ sA, float* __restrict__ sG,
+                                                 const float* __restrict__ act_x, const float* __restrict__ act_z,
+                                                 long long tokpos, const DropCtx& dc, float (&dqp)[D]) {
+    float qp[D];
+    zero(qp);
+    if (has_meta) {
+        float zh[D];
+        float rstd = 0.f;
+        if (valid) { load_row(act_z + tokpos, zh); rstd = normalize32(zh); } else zero(zh);
+        layernorm_bwd32(dqp, zh, rstd, lng, sdLNg, sdLNg + 32, lane, valid);        // dqp := dLoss/dz
+        float dm[D];
+        if (valid) {
+            float xin[D];
+            load_row(act_x + tokpos, xin);
+            vm_outer<D, D, D>(sWp, xin, qp);                                         // recompute qp = x @ W
+#pragma unroll
+            for (int i = 0; i < D; ++i) dm[i] = dqp[i] * drop_factor(dc, i);
+        } else zero(dm);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t mask = 0;
+            {
+                float h[D];
+                zero(h);
+                if (valid) {
+#pragma unroll
+                    for (int c0 = 0; c0 < D; c0 += 16) {
+                        float hc[16];
+                        zero(hc);
+                        vm_outer<D, 16, HID>(sTh + half * D + c0, qp, hc);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            h[c0 + c] = fmaxf(hc[c], 0.f);
+                            if (hc[c] > 0.f) mask |= 1u << (c0 + c);
+                        }
+                    }
+                    sts_row(sA + tid * KV_LD, h);
+                    sts_row(sG + tid * KV_LD, dm);
+                }
+            }
+            __syncthreads();
+            wgrad32(sA, sG, ntok, sdTh + D * HID + half * D * D, D, tid);       // dW2[half*32 + c][j] += h[c] dm[j]
+            __syncthreads();
+            float dh[D];
+            zero(dh);
+            if (valid) {
+#pragma unroll
+                for (int c0 = 0; c0 < D; c0 += 16) {
+                    float dhc[16];
+                    zero(dhc);
+                    vm_dot<D, 16, D>(sTh + D * HID + (half * D + c0) * D, dm, dhc);   // dh[c] = sum_j dm[j] W2[c][j]
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) dh[c0 + c] = ((mask >> (c0 + c)) & 1u) ? dhc[c] : 0.f;
+                }
+                sts_row(sA + tid * KV_LD, qp);
+                sts_row(sG + tid * KV_LD, dh);
+            }
+            __syncthreads();
+            wgrad32(sA, sG, ntok, sdTh + half * D, HID, tid);                     // dW1[i][half*32 + c] += qp[i] dh[c]
+            __syncthreads();
+            if (valid) vm_dot<D, D, HID>(sTh + half * D, dh, dqp);                 // dqp[i] += sum_c dh[c] W1[i][half*32+c]
+        }
+    }
+    // projection weight gradient: dW[i][j] += x[i] dqp[j]
+    if (valid) {
+        float xin[D];
+        load_row(act_x + tokpos, xin);
+        sts_row(sA + tid * KV_LD, xin);
+        sts_row(sG + tid * KV_LD, dqp);
+    }
+    __syncthreads();
+    wgrad32(sA, sG, ntok, sdWp, D, tid);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                    // WQ WK WV
+    float* sdW = sW + 3072;
+    float* sLN = sdW + 3072;             // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
+    float* sdLN = sLN + 192;             // dQLN_G dQLN_B dKLN_G dKLN_B
+    float* sThQ = sdLN + 128;
+    float* sThK = sThQ + PSZ;
+    float* sdThQ = sThK + PSZ;
+    float* sdThK = sdThQ + PSZ;
+    float* sA = sdThK + PSZ;
+    float* sG = sA + NT * KV_LD;
+
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, lane = tid & 31, F = m.F, L = m.L, l = a.layer;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const int n_tiles = a.counters[CNT_NTILES];
+    const int s = tid / F, f = tid - s * F;
+    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
+    const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
+
+    copy_to_smem(sW, lay, 3072, tid, NT);
+    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NT);
+    for (int i = tid; i < 3072; i += NT) sdW[i] = 0.f;
+    for (int i = tid; i < 2 * PSZ; i += NT) sdThQ[i] = 0.f;      // sdThQ and sdThK are contiguous
+    if (tid < 128) sdLN[tid] = 0.f;
+    int cur_q = -1, cur_k = -1;
+    float* sdLNk = pos ? sdLN + 64 : sdLN;                     // without 'pos' K shares Q's MetaNet LayerNorm
+    const float* klng = pos ? sLN + 128 : sLN + 64;
+    float* sdThKuse = pos ? sdThK : sdThQ;                     // ... and Q's generated weights
+
+    for (int t = t0; t < t1; ++t) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int g = td.x, start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int ntok = cnt * F;
+        const int p = start + s;
+        const int b = valid ? a.perm[p] : 0;
+        const long long tokpos = ((long long)p * F + f) * D;
+        const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
+        const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
+        __syncthreads();
+        if (kq != cur_q) {
+            if (cur_q >= 0) flush_add(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
+            copy_to_smem(sThQ, a.theta + (long long)kq * PSZ, PSZ, tid, NT);
+            cur_q = kq;
+        }
+        if (pos && kk != cur_k) {
+            if (cur_k >= 0) flush_add(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+            copy_to_smem(sThK, a.theta + (long long)kk * PSZ, PSZ, tid, NT);
+            cur_k = kk;
+        }
+        __syncthreads();
+        const float* thK = pos ? sThK : sThQ;
+
+        float dxa[D];                       // accumulates dLoss/dX of this token
+        if (valid) load_row(a.dx + tokpos, dxa); else zero(dxa);
+        {   // ---- Q side ---------------------------------------------------------------------------------
+            float dqp[D];
+            if (valid) load_row(a.dqkv + 0 * a.act_stride + tokpos, dqp); else zero(dqp);
+            metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLN, sdW + OFF_WQ, sA,
+                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride, tokpos,
+                             make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, true), dqp);
+            if (valid) vm_dot<D, D, D>(sW + OFF_WQ, dqp, dxa);          // dX[i] += sum_j dqp[j] WQ[i][j]
+        }
+        {   // ---- K side ---------------------------------------------------------------------------------
+            float dkp[D];
+            if (valid) load_row(a.dqkv + 1 * a.act_stride + tokpos, dkp); else zero(dkp);
+            metanet_side_bwd(a, meta_k, valid, ntok, tid, lane, sW + OFF_WK, thK, sdThKuse, klng, sdLNk, sdW + OFF_WK, sA,
+                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZK * a.act_stride, tokpos,
+                             make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, true), dkp);
+            if (valid) vm_dot<D, D, D>(sW + OFF_WK, dkp, dxa);
+        }
+        {   // ---- V side ---------------------------------------------------------------------------------
+            float dv[D];
+            if (valid) {
+                float xin[D];
+                load_row(a.dqkv + 2 * a.act_stride + tokpos, dv);
+                load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
+                sts_row(sA + tid * KV_LD, xin);
+                sts_row(sG + tid * KV_LD, dv);
+            }
+            __syncthreads();
+            wgrad32(sA, sG, ntok, sdW + OFF_WV, D, tid);
+            __syncthreads();
+            if (valid) vm_dot<D, D, D>(sW + OFF_WV, dv, dxa);
+        }
+        if (valid) {
+            if (l > 0) {
+                store_row(a.dx + tokpos, dxa);
+            } else {
+                // layer 0: dLoss/dE0 -> accumulated per unique touched table row (rank through the bitmap)
+                long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
+                const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
+                if (id < 0 || id >= hi - lo) id = 0;
+                const long long row = lo + id;
+                const uint32_t wbits = __ldg(a.bitmap + (row >> 5));
+                const int slot = __ldg(a.word_rank + (row >> 5)) + __popc(wbits & ((1u << (row & 31)) - 1u));
+                float* dst = a.row_grad + (long long)slot * D;
+#pragma unroll
+                for (int i = 0; i < D; i += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
+            }
+        }
+    }
+    __syncthreads();
+    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
+    flush_add(dlay, sdW, 3072, tid);
+    flush_add(dlay + OFF_QLN_G, sdLN, 128, tid);
+    if (cur_q >= 0) flush_add(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
+    if (pos && cur_k >= 0) flush_add(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+}
+
+}  // namespace sat
+
+using namespace sat;
+
+extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
+                            uint64_t seed, void* stream) {
+    if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->row_grad)
+        return sat_host::fail(SAT_EINVAL, "sat_backward: null argument / workspace not sized for training");
+    if (w->B == 0) return SAT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_keys = (m->flags & SAT_FLAG_POS) ? m->n_dom * m->L * 2 : m->n_dom;
+    if (cudaMemsetAsync(w->dgrad, 0, (size_t)m->n_dense_params * sizeof(float), s) != cudaSuccess ||
+        cudaMemsetAsync(w->dtheta, 0, (size_t)n_keys * PSZ * sizeof(float), s) != cudaSuccess)
+        return sat_host::fail(SAT_ECUDA, "sat_backward: memset failed");
+    BwdArgs a;
+    a.m = *m; a.x = x; a.id_kind = id_kind; a.ld = ld; a.perm = w->perm; a.tiles = w->tiles; a.counters = w->counters;
+    a.theta = w->theta; a.dtheta = w->dtheta; a.acts = w->acts; a.act_stride = (long long)w->cap_B * m->F * D;
+    a.dz = w->dz; a.dx = w->dx; a.dqkv = w->dqkv; a.dgrad = w->dgrad; a.bitmap = w->bitmap; a.word_rank = w->word_rank;
+    a.row_grad = w->row_grad; a.layer = 0; a.p_drop = dropout_p; a.seed = seed;
+    const int spt = NT / m->F;
+    const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
+    const int grid2 = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
+    const int grid1 = max_tiles < 148 ? max_tiles : 148;
+    static bool configured_b = false;
+    const size_t smem_b = BWDB_SMEM_FLOATS * sizeof(float);
+    if (!configured_b) {
+        if (cudaFuncSetAttribute(k_bwd_meta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem_b);
+        configured_b = true;
+    }
+    k_bwd_head<<<grid2, NT, 0, s>>>(a);
+    int rc = sat_host::check_launch("k_bwd_head");
+    if (rc) return rc;
+    for (int l = m->L - 1; l >= 0; --l) {
+        a.layer = l;
+        switch (m->H) {
+            case 1: rc = sat_launch_bwd_attn_h1(a, grid2, s); break;
+            case 2: rc = sat_launch_bwd_attn_h2(a, grid2, s); break;
+            case 4: rc = sat_launch_bwd_attn_h4(a, grid2, s); break;
+            case 8: rc = sat_launch_bwd_attn_h8(a, grid2, s); break;
+            default: return sat_host::fail(SAT_EINVAL, "sat_backward: heads=%d not in {1,2,4,8}", m->H);
+        }
+        if (rc) return rc;
+        k_bwd_meta<<<grid1, NT, smem_b, s>>>(a);
+        rc = sat_host::check_launch("k_bwd_meta");
+        if (rc) return rc;
+    }
+    return sat_encoder_bwd(m, w, stream);
+}

@@ -1,0 +1,254 @@
+// Fused SATrans backward (replaces torch autograd over the graph of reference satrans.py:197-256).
+//
+// Same mapping as the forward: one thread = one field token, a CTA = whole samples of one scenario.
+// Per layer, two kernels:
+//   k_bwd_attn : LayerNorm-out bwd, out-projection bwd (+dW_out), attention bwd -> dQ', dK', dV
+//   k_bwd_meta : MetaNet-LayerNorm bwd, MetaNet bwd (+d theta), QKV projection bwd (+dW_q/k/v) -> dX
+// Data gradients are thread-local GEMVs against weights in shared memory (as in the forward).  Weight
+// gradients are reductions over tokens: the two operands are staged as [token][36] shared tiles and every
+// thread owns a 4x4 block of the 32x32 product (64 blocks x 3 token groups = 192 threads), accumulated
+// into shared-memory accumulators that are flushed to HBM with one atomicAdd per element per CTA.
+// Attention uses the FlashAttention identity  sum_j P_ij dP_ij = dR_i . R_i  so no (F x F) tensor is
+// stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
+#include "bwd_common.cuh"
+
+namespace sat {
+
+// =====================================================================================================
+// kernel A: LayerNorm-out bwd, out-projection bwd, attention bwd.
+// =====================================================================================================
+constexpr int BWDA_SMEM_FLOATS = 1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ +
+                                 2 * NT * KV_LD /*tiles*/ + NT * 24 /*mx,sum,Dh per head*/;
+
+template <int H>
+__global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
+    constexpr int DH = D / H;
+    extern __shared__ __align__(16) float smem[];
+    float* sWO = smem;
+    float* sdWO = sWO + 1024;
+    float* sLN = sdWO + 1024;           // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
+    float* sdLN = sLN + 192;            // dgamma[32] dbeta[32] of the layer's output LayerNorm
+    float* sT0 = sdLN + 64;             // [NT][36]  r / K' / Q'
+    float* sT1 = sT0 + NT * KV_LD;      // [NT][36]  dO / V / dR
+    float* sSt = sT1 + NT * KV_LD;      // [NT][24]  per head: row max, row sum, D = dR.R
+
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, lane = tid & 31, F = m.F, l = a.layer;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
+    const int n_tiles = a.counters[CNT_NTILES];
+    const int s = tid / F, f = tid - s * F;
+    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
+    const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
+    const float sqrt_dh = sqrtf((float)DH);
+
+    copy_to_smem(sWO, lay + OFF_WO, 1024, tid, NT);
+    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NT);
+    for (int i = tid; i < 1024 + 0; i += NT) sdWO[i] = 0.f;
+    if (tid < 64) sdLN[tid] = 0.f;
+    const float* qln = sLN + 64;
+    const float* kln = pos ? sLN + 128 : sLN + 64;
+
+    for (int t = t0; t < t1; ++t) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int ntok = cnt * F;
+        const int p = start + s;
+        const int b = valid ? a.perm[p] : 0;
+        const long long tokpos = ((long long)p * F + f) * D;
+        const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
+        __syncthreads();                                   // smem init / previous tile done
+
+        float dr[D];
+        float Dh[H];
+        {   // ---- phase 1: y = drop(act(r @ WO^T)) + x ; LN bwd ; dO ; dR -------------------------------
+            float r[D], dy[D], o[D];
+            zero(o);
+            uint32_t relu_mask = 0xffffffffu;
+            float rstd = 0.f;
+            if (valid) {
+                load_row(act_l + ACT_R * a.act_stride + tokpos, r);
+                vm_dot<D, D, D>(sWO, r, o);
+                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
+                float xin[D];
+                load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    if (relu_out && o[i] <= 0.f) relu_mask &= ~(1u << i);
+                    float v = relu_out ? fmaxf(o[i], 0.f) : o[i];
+                    v *= drop_factor(dco, i);
+                    o[i] = use_res ? v + xin[i] : v;      // o := y (pre-LN)
+                }
+                rstd = normalize32(o);                     // o := yhat
+                load_row(a.dx + tokpos, dy);
+            } else {
+                zero(r); zero(dy);
+            }
+            layernorm_bwd32(dy, o, rstd, sLN, sdLN, sdLN + 32, lane, valid);     // dy := dLoss/dy
+            if (valid) {
+                if (use_res) store_row(a.dx + tokpos, dy);                  // residual branch of dX
+                else { float zr[D]; zero(zr); store_row(a.dx + tokpos, zr); }
+                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
+#pragma unroll
+                for (int i = 0; i < D; ++i) dy[i] = ((relu_mask >> i) & 1u) ? dy[i] * drop_factor(dco, i) : 0.f;   // dy := dO
+                zero(dr);
+                vm_outer<D, D, D>(sWO, dy, dr);            // dR[i] = sum_j dO[j] WO[j][i]
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < DH; ++c) acc = fmaf(dr[h * DH + c], r[h * DH + c], acc);
+                    Dh[h] = acc;
+                }
+                sts_row(sT0 + tid * KV_LD, r);
+                sts_row(sT1 + tid * KV_LD, dy);
+            }
+        }
+        __syncthreads();
+        wgrad32(sT1, sT0, ntok, sdWO, D, tid);             // dWO[j][i] += dO[j] r[i]   (A = dO, G = r)
+        __syncthreads();
+
+        // ---- phase 2: recompute Q' K' V, stage K'/V ----------------------------------------------------
+        float q[D];
+        if (valid) {
+            float k[D];
+            load_row(act_l + ACT_ZK * a.act_stride + tokpos, k);
+            if (meta_k) { float mean, rstd; layernorm32(k, kln, kln + 32, mean, rstd); }
+            sts_row(sT0 + tid * KV_LD, k);
+            load_row(act_l + ACT_V * a.act_stride + tokpos, k);
+            sts_row(sT1 + tid * KV_LD, k);
+            load_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+            if (meta_q) { float mean, rstd; layernorm32(q, qln, qln + 32, mean, rstd); }
+        }
+        __syncthreads();
+        // ---- query-role pass: dQ'_i = sum_j dS_ij K'_j / sqrt(dh) ------------------------------------
+        if (valid) {
+            float dq[D];
+            zero(dq);
+            const DropCtx dca = make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, true);
+            const int sbase = s * F;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float sc[SAT_MAXF];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < SAT_MAXF; ++j) {
+                    if (j < F) {
+                        const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int c = 0; c < DH; c += 4) {
+                            const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                            acc = fmaf(q[h * DH + c + 0], kk.x, acc); acc = fmaf(q[h * DH + c + 1], kk.y, acc);
+                            acc = fmaf(q[h * DH + c + 2], kk.z, acc); acc = fmaf(q[h * DH + c + 3], kk.w, acc);
+                        }
+                        sc[j] = acc / sqrt_dh;
+                        mx = fmaxf(mx, sc[j]);
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < SAT_MAXF; ++j)
+                    if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+                sSt[tid * 24 + h] = mx; sSt[tid * 24 + 8 + h] = sum; sSt[tid * 24 + 16 + h] = Dh[h];
+#pragma unroll
+                for (int j = 0; j < SAT_MAXF; ++j) {
+                    if (j < F) {
+                        const float pj = sc[j] / sum;
+                        const float* vr = sT1 + (sbase + j) * KV_LD + h * DH;
+                        const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
+                        float dAd = 0.f;
+#pragma unroll
+                        for (int c = 0; c < DH; c += 4) {
+                            const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+                            dAd = fmaf(dr[h * DH + c + 0], vv.x, dAd); dAd = fmaf(dr[h * DH + c + 1], vv.y, dAd);
+                            dAd = fmaf(dr[h * DH + c + 2], vv.z, dAd); dAd = fmaf(dr[h * DH + c + 3], vv.w, dAd);
+                        }
+                        const float dsc = pj * (dAd * drop_factor(dca, h * SAT_MAXF + j) - Dh[h]) / sqrt_dh;
+#pragma unroll
+                        for (int c = 0; c < DH; c += 4) {
+                            const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                            dq[h * DH + c + 0] = fmaf(dsc, kk.x, dq[h * DH + c + 0]); dq[h * DH + c + 1] = fmaf(dsc, kk.y, dq[h * DH + c + 1]);
+                            dq[h * DH + c + 2] = fmaf(dsc, kk.z, dq[h * DH + c + 2]); dq[h * DH + c + 3] = fmaf(dsc, kk.w, dq[h * DH + c + 3]);
+                        }
+                    }
+                }
+            }
+            store_row(a.dqkv + 0 * a.act_stride + tokpos, dq);
+        }
+        // ---- swap roles: own K', V to registers, tiles <- Q', dR ----------------------------------------
+        float kreg[D], vreg[D];
+        if (valid) { lds_row(sT0 + tid * KV_LD, kreg); lds_row(sT1 + tid * KV_LD, vreg); }
+        __syncthreads();
+        if (valid) { sts_row(sT0 + tid * KV_LD, q); sts_row(sT1 + tid * KV_LD, dr); }
+        __syncthreads();
+        // ---- key-role pass: dK'_j = sum_i dS_ij Q'_i / sqrt(dh) ; dV_j = sum_i Pd_ij dR_i ----------------
+        if (valid) {
+            float dk[D], dv[D];
+            zero(dk); zero(dv);
+            const int sbase = s * F;
+            for (int i = 0; i < F; ++i) {
+                const DropCtx dci = make_drop(a.seed, (uint32_t)b * (uint32_t)F + (uint32_t)i, l, SITE_ATT, a.p_drop, true);
+                const float* qr = sT0 + (sbase + i) * KV_LD;
+                const float* dR = sT1 + (sbase + i) * KV_LD;
+                const float* st = sSt + (sbase + i) * 24;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float acc = 0.f, dAd = 0.f;
+                    float qq[DH], dd[DH];
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 q4 = *reinterpret_cast<const float4*>(qr + h * DH + c);
+                        const float4 d4 = *reinterpret_cast<const float4*>(dR + h * DH + c);
+                        qq[c] = q4.x; qq[c + 1] = q4.y; qq[c + 2] = q4.z; qq[c + 3] = q4.w;
+                        dd[c] = d4.x; dd[c + 1] = d4.y; dd[c + 2] = d4.z; dd[c + 3] = d4.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kreg[h * DH + c], acc); dAd = fmaf(dd[c], vreg[h * DH + c], dAd); }
+                    const float pij = expf(acc / sqrt_dh - st[h]) / st[8 + h];
+                    const float df = drop_factor(dci, h * SAT_MAXF + f);
+                    const float dsc = pij * (dAd * df - st[16 + h]) / sqrt_dh;
+                    const float pd = pij * df;
+#pragma unroll
+                    for (int c = 0; c < DH; ++c) {
+                        dk[h * DH + c] = fmaf(dsc, qq[c], dk[h * DH + c]);
+                        dv[h * DH + c] = fmaf(pd, dd[c], dv[h * DH + c]);
+                    }
+                }
+            }
+            store_row(a.dqkv + 1 * a.act_stride + tokpos, dk);
+            store_row(a.dqkv + 2 * a.act_stride + tokpos, dv);
+        }
+    }
+    __syncthreads();
+    // flush: dWO and the output-LayerNorm parameter gradients
+    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
+    flush_add(dlay + OFF_WO, sdWO, 1024, tid);
+    flush_add(dlay + OFF_LN_G, sdLN, 64, tid);
+}
+
+}  // namespace sat
+
+using namespace sat;
+
+#ifndef SAT_INST_H
+#error "compile backward_attn.cu with -DSAT_INST_H={1,2,4,8}"
+#endif
+#define SAT_CAT_(a, b) a##b
+#define SAT_CAT(a, b) SAT_CAT_(a, b)
+
+int SAT_CAT(sat_launch_bwd_attn_h, SAT_INST_H)(const BwdArgs& a, int grid, cudaStream_t s) {
+    constexpr int H = SAT_INST_H;
+    const size_t smem = BWDA_SMEM_FLOATS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_bwd_attn<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
+        configured = true;
+    }
+    k_bwd_attn<H><<<grid, NT, smem, s>>>(a);
+    return sat_host::check_launch("k_bwd_attn");
+}

@@ -1,0 +1,90 @@
+// Device helpers shared by the backward kernels.
+#pragma once
+#include "args.cuh"
+
+namespace sat {
+
+// ---- warp reduce-scatter: on return lane L holds sum over the 32 lanes of v[L] (in v[0]) -------------
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[D], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// LayerNorm backward for one token.  xhat = normalised input, g = gamma (smem).  dy is overwritten by dx.
+// dgam/dbet (smem, 32 floats each) receive the token-summed parameter gradients.
+__device__ __forceinline__ void layernorm_bwd32(float (&dy)[D], const float (&xhat)[D], float rstd,
+                                                const float* __restrict__ g, float* __restrict__ dgam,
+                                                float* __restrict__ dbet, int lane, bool valid) {
+    float t1[D], t2[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { t1[i] = valid ? dy[i] * xhat[i] : 0.f; t2[i] = valid ? dy[i] : 0.f; }
+    const float sg = warp_reduce_scatter32(t1, lane);
+    const float sb = warp_reduce_scatter32(t2, lane);
+    atomicAdd(dgam + lane, sg);
+    atomicAdd(dbet + lane, sb);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { dy[i] *= g[i]; m1 += dy[i]; m2 = fmaf(dy[i], xhat[i], m2); }
+    m1 *= (1.f / D); m2 *= (1.f / D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) dy[i] = rstd * (dy[i] - m1 - xhat[i] * m2);
+}
+
+// normalise in place, return rstd (no affine)
+__device__ __forceinline__ float normalize32(float (&v)[D]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += v[i];
+    const float mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] *= rstd;
+    return rstd;
+}
+
+// acc[(ia+r)*ldacc + jg+c] += sum_{t<ntok} A[t][ia+r] * G[t][jg+c]  -- 32x32 product, A/G tiles [tok][36].
+__device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float* __restrict__ G, int ntok,
+                                        float* __restrict__ acc, int ldacc, int tid) {
+    const int blk = tid & 63, grp = tid >> 6;
+    const int ia = (blk >> 3) * 4, jg = (blk & 7) * 4;
+    float c[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
+    for (int t = grp; t < ntok; t += NT / 64) {
+        const float4 a = *reinterpret_cast<const float4*>(A + t * KV_LD + ia);
+        const float4 g = *reinterpret_cast<const float4*>(G + t * KV_LD + jg);
+        c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
+        c[1][0] = fmaf(a.y, g.x, c[1][0]); c[1][1] = fmaf(a.y, g.y, c[1][1]); c[1][2] = fmaf(a.y, g.z, c[1][2]); c[1][3] = fmaf(a.y, g.w, c[1][3]);
+        c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
+        c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) atomicAdd(acc + (ia + r) * ldacc + jg + cc, c[r][cc]);
+}
+
+__device__ __forceinline__ void flush_add(float* __restrict__ dst, float* __restrict__ sacc, int n, int tid) {
+    for (int i = tid; i < n; i += NT) {
+        const float v = sacc[i];
+        if (v != 0.f) atomicAdd(dst + i, v);
+        sacc[i] = 0.f;
+    }
+}
+
+
+}  // namespace sat

@@ -1,0 +1,93 @@
+// C-ABI plumbing: error reporting and workspace sizing.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sat_host {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SAT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    return SAT_OK;
+}
+
+}  // namespace sat_host
+
+extern "C" int sat_abi_version(void) { return SAT_ABI_VERSION; }
+extern "C" const char* sat_last_error(void) { return sat_host::g_err; }
+
+extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t training, int64_t* sz, int32_t* max_tiles_host) {
+    if (!m || !sz || cap_B <= 0 || m->F <= 0 || m->F > SAT_MAXF)
+        return sat_host::fail(SAT_EINVAL, "sat_workspace_sizes: bad argument");
+    const int64_t spt = sat::NT / m->F;
+    const int64_t max_tiles = (cap_B + spt - 1) / spt + m->n_dom;
+    const int64_t n_keys = (m->flags & SAT_FLAG_POS) ? (int64_t)m->n_dom * m->L * 2 : m->n_dom;
+    const int64_t tok = (int64_t)cap_B * m->F;
+    const int64_t words = (m->total_rows + 31) / 32;
+    int i = 0;
+    sz[i++] = cap_B * 4;                                   // perm
+    sz[i++] = cap_B * 4;                                   // dom
+    sz[i++] = max_tiles * 16;                              // tiles
+    sz[i++] = 64 * 4;                                      // counters
+    sz[i++] = n_keys * SAT_P * 4;                          // theta
+    sz[i++] = training ? n_keys * SAT_P * 4 : 0;           // dtheta
+    sz[i++] = training ? n_keys * 64 * 4 : 0;              // enc_du
+    sz[i++] = training ? ((int64_t)m->L * 5 + 1) * tok * SAT_D * 4 : 0;   // acts
+    sz[i++] = cap_B * 4;                                   // dz
+    sz[i++] = training ? tok * SAT_D * 4 : 0;              // dx
+    sz[i++] = training ? 3 * tok * SAT_D * 4 : 0;          // dqkv
+    sz[i++] = max_tiles * 8;                               // loss_part
+    sz[i++] = training ? m->n_dense_params * 4 : 0;        // dgrad
+    sz[i++] = training ? words * 4 : 0;                    // bitmap
+    sz[i++] = training ? words * 4 : 0;                    // word_rank
+    sz[i++] = training ? ((words + 1023) / 1024 + 1) * 4 : 0;   // block_sums
+    sz[i++] = training ? tok * 4 : 0;                      // uniq_rows
+    sz[i++] = training ? tok * SAT_D * 4 : 0;              // row_grad
+    sz[i++] = SAT_REG_PARTS * 8;                           // reg_part
+    sz[i++] = 8 * 4;                                       // scalars
+    if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
+    return SAT_OK;
+}
+
+// ---- sat_forward: argument marshalling + dispatch on the head count ---------------------------------
+#include "args.cuh"
+
+extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
+                           float* y_pred, int32_t training, float dropout_p, uint64_t seed, void* stream) {
+    using namespace sat;
+    if (!m || !x || !w || !y_pred) return sat_host::fail(SAT_EINVAL, "sat_forward: null argument");
+    if (m->F <= 0 || m->F > SAT_MAXF) return sat_host::fail(SAT_EINVAL, "sat_forward: F=%d not in 1..%d", m->F, SAT_MAXF);
+    if (m->n_dense > 64) return sat_host::fail(SAT_EINVAL, "sat_forward: n_dense=%d > 64", m->n_dense);
+    if (training && !w->acts) return sat_host::fail(SAT_EINVAL, "sat_forward: training needs w->acts");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return sat_host::fail(SAT_EINVAL, "sat_forward: dropout_p=%f", dropout_p);
+    if (w->B == 0) return SAT_OK;
+    if (w->B > w->cap_B) return sat_host::fail(SAT_EINVAL, "sat_forward: B=%d > workspace capacity %d", w->B, w->cap_B);
+    FwdArgs a;
+    a.m = *m; a.x = x; a.id_kind = id_kind; a.ld = ld; a.y = y; a.perm = w->perm; a.tiles = w->tiles;
+    a.counters = w->counters; a.theta = w->theta; a.acts = w->acts;
+    a.act_stride = (long long)w->cap_B * m->F * D;
+    a.dz = w->dz; a.loss_part = w->loss_part; a.y_pred = y_pred; a.p_drop = dropout_p; a.seed = seed;
+    const int spt = NT / m->F;
+    const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
+    const int grid = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (m->H) {
+        case 1: return sat_launch_forward_h1(a, grid, training, s);
+        case 2: return sat_launch_forward_h2(a, grid, training, s);
+        case 4: return sat_launch_forward_h4(a, grid, training, s);
+        case 8: return sat_launch_forward_h8(a, grid, training, s);
+        default: return sat_host::fail(SAT_EINVAL, "sat_forward: heads=%d not in {1,2,4,8}", m->H);
+    }
+}

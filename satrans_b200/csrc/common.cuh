@@ -1,0 +1,176 @@
+// Shared device helpers for the SATrans sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "satrans_b200.h"
+
+namespace sat {
+
+constexpr int D = SAT_D;          // embedding dim
+constexpr int HID = SAT_HID;      // MetaNet hidden width
+constexpr int PSZ = SAT_P;        // generated weights per key
+constexpr int NT = 192;           // threads per CTA of the token kernels (one thread = one field token)
+constexpr int KV_LD = 36;         // padded row stride (floats) of [token][36] smem tiles: conflict-free STS.128
+constexpr int LAYER_FLOATS = SAT_LAYER_FLOATS;
+constexpr int OFF_WQ = 0, OFF_WK = 1024, OFF_WV = 2048, OFF_WO = 3072;
+constexpr int OFF_LN_G = 4096, OFF_LN_B = 4128, OFF_QLN_G = 4160, OFF_QLN_B = 4192, OFF_KLN_G = 4224,
+              OFF_KLN_B = 4256;
+constexpr float LN_EPS = 1e-6f;   // nn.LayerNorm(d, eps=1e-6): reference satrans.py:40, submodules.py:75
+
+// counters[] slots of SatWork
+constexpr int CNT_NTILES = 0, CNT_ERR = 1, CNT_NUNIQ = 2, CNT_HIST = 8;
+constexpr int MAX_KEYS_HIST = 48;  // scenario ids supported by the single-block bucketing kernel
+
+// dropout sites inside one Meta_Transformer_Layer (reference submodules.py:99, satrans.py:87,92-94)
+constexpr uint32_t SITE_Q = 0, SITE_K = 1, SITE_ATT = 2, SITE_OUT = 3;
+
+// ------------------------------------------------------------------------------------------------
+// ids: integers stored in the (B, ld) input matrix as f32 / i32 / i64 (reference meta_basemodel.py:
+// 533-535 casts the fp32 column with .long(): truncation toward zero).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long load_id(const void* __restrict__ x, int kind, long long idx) {
+    if (kind == SAT_IDS_F32) return __float2ll_rz(__ldg(reinterpret_cast<const float*>(x) + idx));
+    if (kind == SAT_IDS_I32) return (long long)__ldg(reinterpret_cast<const int32_t*>(x) + idx);
+    return __ldg(reinterpret_cast<const long long*>(x) + idx);
+}
+__device__ __forceinline__ float load_dense(const void* __restrict__ x, int kind, long long idx) {
+    if (kind == SAT_IDS_F32) return __ldg(reinterpret_cast<const float*>(x) + idx);
+    if (kind == SAT_IDS_I32) return (float)__ldg(reinterpret_cast<const int32_t*>(x) + idx);
+    return (float)__ldg(reinterpret_cast<const long long*>(x) + idx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG for dropout: two 16-bit uniforms per 32-bit hash.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+struct DropCtx {
+    uint32_t key;     // per (seed, token, layer, site)
+    uint32_t thr;     // drop if u16 < thr
+    float scale;      // 1/(1-p)
+    bool on;
+};
+__device__ __forceinline__ DropCtx make_drop(uint64_t seed, uint32_t token_gid, uint32_t layer, uint32_t site,
+                                             float p, bool training) {
+    DropCtx c;
+    c.on = training && p > 0.f;
+    c.thr = (uint32_t)(p * 65536.f + 0.5f);
+    c.scale = 1.f / (1.f - p);
+    uint32_t s = (uint32_t)seed ^ (uint32_t)(seed >> 32) * 0x9E3779B1U;
+    c.key = mix32(s + token_gid * 0x9E3779B1U) ^ ((layer * 4u + site + 1u) * 0x85EBCA77U);
+    return c;
+}
+// keep-mask factor (0 or 1/(1-p)) of element e
+__device__ __forceinline__ float drop_factor(const DropCtx& c, uint32_t e) {
+    if (!c.on) return 1.f;
+    uint32_t r = mix32(c.key + (e >> 1) * 0xC2B2AE35U);
+    uint32_t u = (e & 1u) ? (r >> 16) : (r & 0xFFFFu);
+    return u < c.thr ? 0.f : c.scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// thread-local small GEMV against a matrix in shared memory (all lanes read the same address:
+// LDS.128 broadcasts).  a[] and y[] are registers.
+//   vm_outer : y[j] += sum_i a[i] * M[i*LD + j]        (M is [NIN][LD], "x @ W")
+//   vm_dot   : y[j] += sum_i a[i] * M[j*LD + i]        (M is [NOUT][LD], "x @ W^T")
+// ------------------------------------------------------------------------------------------------
+template <int NIN, int NOUT, int LD>
+__device__ __forceinline__ void vm_outer(const float* __restrict__ M, const float (&a)[NIN], float (&y)[NOUT]) {
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) {
+#pragma unroll
+        for (int j = 0; j < NOUT; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(M + i * LD + j);
+            y[j + 0] = fmaf(a[i], w.x, y[j + 0]);
+            y[j + 1] = fmaf(a[i], w.y, y[j + 1]);
+            y[j + 2] = fmaf(a[i], w.z, y[j + 2]);
+            y[j + 3] = fmaf(a[i], w.w, y[j + 3]);
+        }
+    }
+}
+template <int NIN, int NOUT, int LD>
+__device__ __forceinline__ void vm_dot(const float* __restrict__ M, const float (&a)[NIN], float (&y)[NOUT]) {
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) {
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NIN; i += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(M + j * LD + i);
+            acc0 = fmaf(a[i + 0], w.x, acc0);
+            acc1 = fmaf(a[i + 1], w.y, acc1);
+            acc0 = fmaf(a[i + 2], w.z, acc0);
+            acc1 = fmaf(a[i + 3], w.w, acc1);
+        }
+        y[j] += acc0 + acc1;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void zero(float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = 0.f;
+}
+
+// LayerNorm over the 32 channels a thread owns.  g/b in shared memory.  Returns mean / rstd for the backward.
+__device__ __forceinline__ void layernorm32(float (&v)[D], const float* __restrict__ g, const float* __restrict__ b,
+                                            float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) s += v[i];
+    mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { const float t = v[i] - mean; q = fmaf(t, t, q); }
+    rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+}
+
+// 128-byte row load/store helpers (global, 16 B aligned)
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+
+// 128-byte row <-> shared memory ([token][36] tiles: conflict-free 16 B accesses)
+__device__ __forceinline__ void sts_row(float* __restrict__ dst, const float (&v)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+__device__ __forceinline__ void lds_row(const float* __restrict__ src, float (&v)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
+// cooperative global -> shared copy of n floats (n % 4 == 0, both 16 B aligned)
+__device__ __forceinline__ void copy_to_smem(float* __restrict__ dst, const float* __restrict__ src, int n, int tid,
+                                             int nthreads) {
+    for (int i = tid * 4; i < n; i += nthreads * 4)
+        *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+}
+
+// key of the generated-weight table row used by (domain g, layer l, q/k side)
+__device__ __forceinline__ int theta_key(int g, int l, int side, int L, bool pos) {
+    return pos ? ((g * L + l) * 2 + side) : g;
+}
+
+}  // namespace sat
+
+// host-side error plumbing (defined in capi.cu)
+namespace sat_host {
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+}  // namespace sat_host

@@ -1,0 +1,270 @@
+// Fused SATrans forward: embedding gather + L x Meta_Transformer_Layer + logit head + sigmoid (+ BCE).
+//
+// Replaces, per batch, the ~1.2 k ATen dispatches of SATrans.forward (reference satrans.py:197-256),
+// Meta_Transformer_Layer.forward (satrans.py:50-100) and MetaNet.forward (submodules.py:77-103).
+//
+// Mapping: one thread = one field token (sample b, field f); its 32-channel vector lives in registers
+// from the table row to the logit.  A CTA holds floor(192/F) whole samples of ONE scenario (tiles come
+// from sat_bucket_by_domain), so the layer weights and that scenario's generated MetaNet weights are
+// CTA-uniform: they sit in shared memory and every weight read is a broadcast LDS.128 feeding 4 FFMAs.
+// Only K' and V cross threads (attention over the F tokens of a sample): they are staged in padded
+// [token][36] shared tiles.  LayerNorm / softmax are thread-local register reductions.
+// Nothing of shape (B,4096), (H,B,F,F) or (B,F,32)-per-op is ever materialised in HBM (inference), and
+// training saves only what the backward kernels re-use (x, pre-LN q/k, v, attention output).
+#include "args.cuh"
+
+namespace sat {
+
+
+constexpr int FWD_SMEM_FLOATS = 4096 + 192 + 2 * PSZ + 2 * NT * KV_LD + NT;
+
+// MetaNet (reference submodules.py:77-103) on one token: z = dropout(relu(q @ W1) @ W2) + q.
+// th = [W1 (32x64) | W2 (64x32)] in shared memory.  Hidden units are produced and consumed 16 at a time.
+__device__ __forceinline__ void metanet_fwd(const float (&q)[D], const float* __restrict__ th, const DropCtx& dc,
+                                            float (&z)[D]) {
+    float mo[D];
+    zero(mo);
+#pragma unroll
+    for (int c0 = 0; c0 < HID; c0 += 16) {
+        float h[16];
+        zero(h);
+        vm_outer<D, 16, HID>(th + c0, q, h);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) h[c] = fmaxf(h[c], 0.f);
+        vm_outer<16, D, D>(th + D * HID + c0 * D, h, mo);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = fmaf(mo[i], drop_factor(dc, i), q[i]);
+}
+
+// Multi-head attention of one query token against the F tokens of its sample (reference satrans.py:75-90).
+// K'/V rows of the sample start at row `sbase` of the [token][36] tiles.
+template <int H>
+__device__ __forceinline__ void attention_fwd(const float (&q)[D], const float* __restrict__ sK,
+                                              const float* __restrict__ sV, int sbase, int F, const DropCtx& dc,
+                                              float (&r)[D]) {
+    constexpr int DH = D / H;
+    const float sqrt_dh = sqrtf((float)DH);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float sc[SAT_MAXF];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j) {
+            if (j < F) {
+                const float* kr = sK + (sbase + j) * KV_LD + h * DH;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                    acc = fmaf(q[h * DH + c + 0], kk.x, acc);
+                    acc = fmaf(q[h * DH + c + 1], kk.y, acc);
+                    acc = fmaf(q[h * DH + c + 2], kk.z, acc);
+                    acc = fmaf(q[h * DH + c + 3], kk.w, acc);
+                }
+                sc[j] = acc / sqrt_dh;                    // inner_product /= dh ** 0.5   (satrans.py:85-86)
+                mx = fmaxf(mx, sc[j]);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j)
+            if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+        float o[DH];
+        zero(o);
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j) {
+            if (j < F) {
+                const float pj = (sc[j] / sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
+                const float* vr = sV + (sbase + j) * KV_LD + h * DH;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+                    o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
+                    o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
+                    o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
+                    o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < DH; ++c) r[h * DH + c] = o[c];
+    }
+}
+
+template <int H, bool TRAIN>
+__global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;                    // WQ | WK | WV | WO           (4096)
+    float* sLN = sW + 4096;              // 6 x 32 LayerNorm vectors    (192)  -- contiguous with sW in the layer block
+    float* sThQ = sLN + 192;             // generated W1|W2 for the Q side
+    float* sThK = sThQ + PSZ;            // ... K side (ENP only)
+    float* sK = sThK + PSZ;              // [NT][36]
+    float* sV = sK + NT * KV_LD;         // [NT][36]
+    float* sRed = sV + NT * KV_LD;       // [NT]
+    __shared__ double s_loss;
+
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x;
+    const int F = m.F, L = m.L;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
+    const int n_tiles = a.counters[CNT_NTILES];
+    const int s = tid / F, f = tid - s * F;
+    int cur_q = -1, cur_k = -1;
+
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int g = td.x, start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int p = start + s;
+        const int b = valid ? a.perm[p] : 0;
+        const long long tokpos = ((long long)p * F + f) * D;
+        const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
+
+        // ---- gather: x = T_f[id]  (reference meta_basemodel.py:533-535) -------------------------------
+        float x[D];
+        zero(x);
+        if (valid) {
+            long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
+            const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
+            if (id < 0 || id >= hi - lo) { atomicOr(&a.counters[CNT_ERR], 1); id = 0; }
+            load_row(m.tables + (lo + id) * D, x);
+        }
+        if (tid == 0) s_loss = 0.0;
+
+        for (int l = 0; l < L; ++l) {
+            __syncthreads();
+            copy_to_smem(sW, m.dense + m.off_layers + (long long)l * LAYER_FLOATS, LAYER_FLOATS, tid, NT);
+            const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
+            if (kq != cur_q) { copy_to_smem(sThQ, a.theta + (long long)kq * PSZ, PSZ, tid, NT); cur_q = kq; }
+            if (pos && kk != cur_k) { copy_to_smem(sThK, a.theta + (long long)kk * PSZ, PSZ, tid, NT); cur_k = kk; }
+            __syncthreads();
+            const float* thK = pos ? sThK : sThQ;
+            const float* kln = pos ? sLN + 128 : sLN + 64;      // K-side MetaNet LayerNorm (aliases Q's without 'pos')
+            float* act_l = TRAIN ? a.acts + (long long)l * ACT_PER_LAYER * a.act_stride : nullptr;
+            float q[D];
+            if (valid) {
+                if (TRAIN) store_row(act_l + ACT_X * a.act_stride + tokpos, x);
+                float mean, rstd;
+                {   // K' = LN(MetaNet(x @ W_Key))            (satrans.py:56,67-73)
+                    float kp[D];
+                    zero(kp);
+                    vm_outer<D, D, D>(sW + OFF_WK, x, kp);
+                    if (meta_k) {
+                        float z[D];
+                        metanet_fwd(kp, thK, make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, TRAIN), z);
+                        if (TRAIN) store_row(act_l + ACT_ZK * a.act_stride + tokpos, z);
+                        layernorm32(z, kln, kln + 32, mean, rstd);
+                        sts_row(sK + tid * KV_LD, z);
+                    } else {
+                        if (TRAIN) store_row(act_l + ACT_ZK * a.act_stride + tokpos, kp);
+                        sts_row(sK + tid * KV_LD, kp);
+                    }
+                }
+                {   // V = x @ W_Value                         (satrans.py:57)
+                    float v[D];
+                    zero(v);
+                    vm_outer<D, D, D>(sW + OFF_WV, x, v);
+                    if (TRAIN) store_row(act_l + ACT_V * a.act_stride + tokpos, v);
+                    sts_row(sV + tid * KV_LD, v);
+                }
+                {   // Q' = LN(MetaNet(x @ W_Query))           (satrans.py:55,60-66)
+                    float qp[D];
+                    zero(qp);
+                    vm_outer<D, D, D>(sW + OFF_WQ, x, qp);
+                    if (meta_q) {
+                        metanet_fwd(qp, sThQ, make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, TRAIN), q);
+                        if (TRAIN) store_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+                        layernorm32(q, sLN + 64, sLN + 96, mean, rstd);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) q[i] = qp[i];
+                        if (TRAIN) store_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+                    }
+                }
+            }
+            __syncthreads();
+            if (valid) {
+                float r[D];
+                attention_fwd<H>(q, sK, sV, s * F, F, make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, TRAIN), r);
+                if (TRAIN) store_row(act_l + ACT_R * a.act_stride + tokpos, r);
+                // O = dropout(act(R @ W_out^T)); x = LN(O + x)   (satrans.py:91-99)
+                float o[D];
+                zero(o);
+                vm_dot<D, D, D>(sW + OFF_WO, r, o);
+                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float v = relu_out ? fmaxf(o[i], 0.f) : o[i];
+                    v *= drop_factor(dco, i);
+                    x[i] = use_res ? v + x[i] : v;
+                }
+                float mean, rstd;
+                layernorm32(x, sLN, sLN + 32, mean, rstd);
+            }
+        }
+
+        // ---- logit head + sigmoid (+ BCE)  (satrans.py:244-255, meta_basemodel.py:317) ---------------
+        float part = 0.f;
+        if (valid) {
+            if (TRAIN) store_row(a.acts + (long long)L * ACT_PER_LAYER * a.act_stride + tokpos, x);
+            const float* hw = m.dense + m.off_headw + f * D;
+#pragma unroll
+            for (int i = 0; i < D; i += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(hw + i));
+                part = fmaf(x[i], w4.x, part); part = fmaf(x[i + 1], w4.y, part);
+                part = fmaf(x[i + 2], w4.z, part); part = fmaf(x[i + 3], w4.w, part);
+            }
+        }
+        sRed[tid] = part;
+        __syncthreads();
+        if (valid && f == 0) {
+            float z = 0.f;
+            for (int j = 0; j < F; ++j) z += sRed[tid + j];
+            for (int k = 0; k < m.n_dense; ++k)
+                z = fmaf(load_dense(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.dense_cols + k)),
+                         __ldg(m.dense + m.off_headw + F * D + k), z);
+            z += __ldg(m.dense + m.off_headb);
+            const float yp = 1.f / (1.f + expf(-z));
+            a.y_pred[b] = yp;
+            if (a.y) {
+                const float yt = __ldg(a.y + b);
+                // F.binary_cross_entropy(reduction='sum'): logs clamped at -100
+                const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
+                atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
+                // autograd of BCE then sigmoid: (p - y) / max((1-p) p, 1e-12) * (1-p) p
+                const float pq = (1.f - yp) * yp;
+                a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && a.loss_part) a.loss_part[t] = s_loss;
+    }
+}
+
+}  // namespace sat
+
+using namespace sat;
+
+#ifndef SAT_INST_H
+#error "compile forward.cu with -DSAT_INST_H={1,2,4,8}"
+#endif
+#define SAT_CAT_(a, b) a##b
+#define SAT_CAT(a, b) SAT_CAT_(a, b)
+
+int SAT_CAT(sat_launch_forward_h, SAT_INST_H)(const FwdArgs& a, int grid, int training, cudaStream_t s) {
+    constexpr int H = SAT_INST_H;
+    const size_t smem = FWD_SMEM_FLOATS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_forward<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_forward<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_forward: cannot raise dynamic shared memory to %zu", smem);
+        configured = true;
+    }
+    if (training) k_forward<H, true><<<grid, NT, smem, s>>>(a);
+    else k_forward<H, false><<<grid, NT, smem, s>>>(a);
+    return sat_host::check_launch("k_forward");
+}

@@ -1,0 +1,265 @@
+"""Host-side driver of the fused SATrans kernels: owns the C-ABI descriptors, per-batch workspaces and
+stream choreography.  PyTorch is used only for device memory, streams and events.
+
+One training step (reference meta_basemodel.py:311-328: forward, BCE(sum), dense L2, backward,
+dense Adam) becomes, on two streams:
+
+    main : bucket-by-scenario -> encoder -> mark+rank touched rows --E1--> fused forward(+BCE, dLogit)
+           -> head bwd -> L x (attention bwd, MetaNet/QKV bwd [layer 0 scatters dE0 to touched rows])
+           -> encoder bwd -> Adam on touched rows -> Adam on the flat dense buffer --(join E2)--> finalize
+    sweep: wait E1 -> L2 + Adam over every UNTOUCHED table row (HBM-bound, 6 x table bytes) --E2-->
+
+The sweep never touches a row the batch reads, so it overlaps the compute-bound forward/backward.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SatAdam, SatModel, SatWork, check, lib
+
+_BUF_DTYPES = {'perm': torch.int32, 'dom': torch.int32, 'tiles': torch.int32, 'counters': torch.int32,
+               'loss_part': torch.float64, 'reg_part': torch.float64, 'bitmap': torch.int32,
+               'word_rank': torch.int32, 'block_sums': torch.int32, 'uniq_rows': torch.int32}
+
+
+def _id_kind(X):
+    if X.dtype == torch.float32:
+        return _lib.IDS_F32
+    if X.dtype == torch.int32:
+        return _lib.IDS_I32
+    if X.dtype == torch.int64:
+        return _lib.IDS_I64
+    raise TypeError('input matrix must be float32, int32 or int64, got %s' % X.dtype)
+
+
+class Workspace:
+    """Caller-owned device buffers of one SatWork (sized by sat_workspace_sizes)."""
+
+    def __init__(self, engine, cap_B, training):
+        self.cap_B, self.training = int(cap_B), bool(training)
+        sizes = (C.c_int64 * _lib.SAT_WORK_BUFFERS)()
+        mt = C.c_int32()
+        check(lib().sat_workspace_sizes(C.byref(engine.desc), self.cap_B, int(training), sizes, C.byref(mt)),
+              'sat_workspace_sizes')
+        self.max_tiles = mt.value
+        self.bufs = {}
+        self.c = SatWork()
+        self.c.B, self.c.cap_B = 0, self.cap_B
+        dev = engine.device
+        for name, nbytes in zip(_lib.WORK_BUFFERS, sizes):
+            if nbytes == 0:
+                setattr(self.c, name, None)
+                continue
+            dt = _BUF_DTYPES.get(name, torch.float32)
+            n = (nbytes + dt.itemsize - 1) // dt.itemsize
+            t = torch.zeros(n, dtype=dt, device=dev)
+            self.bufs[name] = t
+            setattr(self.c, name, t.data_ptr())
+
+    def __getitem__(self, k):
+        return self.bufs[k]
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.desc = SatModel()
+        self._bound_ptrs = None
+        self._work = {}
+        self._adam = None
+        self._sweep_stream = None
+        self._ev_marked = None
+        self._ev_swept = None
+        self.step_count = 0
+        self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
+
+    # ------------------------------------------------------------------------------------------
+    def bind(self):
+        """(Re)build the SatModel descriptor if the model's buffers moved."""
+        m = self.model
+        m._ensure_flat()
+        ptrs = (m._tables.data_ptr(), m._dense.data_ptr())
+        if self._bound_ptrs == ptrs:
+            return
+        if not m._tables.is_cuda:
+            raise _lib.SatError('the SATrans B200 path needs the model on a CUDA device (got %s); there is no '
+                                'CPU fallback' % m._tables.device)
+        lib()
+        self.device = m._tables.device
+        lay = m._layout
+        d = self.desc
+        d.F, d.L, d.H = lay['F'], lay['L'], lay['H']
+        d.n_dom, d.n_dense, d.n_cols = lay['n_dom'], lay['n_dense'], lay['n_cols']
+        d.flags, d.enc_in, d.dom_col = lay['flags'], lay['enc_in'], lay['dom_col']
+        d.n_dense_params = lay['n_dense_params']
+        for k in ('off_dom', 'off_lid', 'off_qkv', 'off_encw', 'off_encb', 'off_layers', 'off_headw', 'off_headb'):
+            setattr(d, k, lay[k])
+        d.total_rows = lay['total_rows']
+        self._row_off = torch.tensor(lay['row_off'], dtype=torch.int64, device=self.device)
+        self._sparse_cols = torch.tensor(lay['sparse_cols'], dtype=torch.int32, device=self.device)
+        self._dense_cols = torch.tensor(lay['dense_cols'] or [0], dtype=torch.int32, device=self.device)
+        d.row_off, d.sparse_cols = self._row_off.data_ptr(), self._sparse_cols.data_ptr()
+        d.dense_cols = self._dense_cols.data_ptr()
+        d.tables, d.dense = ptrs
+        self._bound_ptrs = ptrs
+        self._work = {}
+        self._adam = None
+
+    def workspace(self, B, training):
+        key = bool(training)
+        w = self._work.get(key)
+        if w is None or w.cap_B < B:
+            cap = max(int(B), w.cap_B if w else 0)
+            w = Workspace(self, cap, training)
+            self._work[key] = w
+        w.c.B = int(B)
+        return w
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _check_x(self, X):
+        if not (X.is_cuda and X.dim() == 2 and X.is_contiguous() and X.shape[1] == self.desc.n_cols):
+            raise ValueError('expected a contiguous CUDA (B, %d) input matrix, got %s on %s'
+                             % (self.desc.n_cols, tuple(X.shape), X.device))
+        return _id_kind(X)
+
+    # ------------------------------------------------------------------------------------------
+    def gather(self, X):
+        """(B, F, 32) field embeddings of the batch — input_from_feature_columns + cat."""
+        self.bind()
+        kind = self._check_x(X)
+        B = X.shape[0]
+        out = torch.empty((B, self.desc.F, _lib.SAT_D), dtype=torch.float32, device=self.device)
+        w = self.workspace(max(B, 1), False)
+        check(lib().sat_gather_fwd(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], B, out.data_ptr(),
+                                   w['counters'].data_ptr() + 4, self._stream()), 'sat_gather_fwd')
+        self.launches += 1
+        return out
+
+    def _prepare(self, X, w, kind):
+        s = self._stream()
+        l = lib()
+        w['counters'].zero_()
+        check(l.sat_bucket_by_domain(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), 0, s),
+              'sat_bucket_by_domain')
+        check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
+        self.launches += 3
+
+    def forward(self, X, y=None, training=False, dropout_p=0.1, seed=0):
+        """y_pred (B,) in sample order.  With y: also leaves BCE partials / dLogit in the workspace."""
+        self.bind()
+        kind = self._check_x(X)
+        B = X.shape[0]
+        y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        if B == 0:
+            return y_pred
+        w = self.workspace(B, training)
+        self._prepare(X, w, kind)
+        check(lib().sat_forward(C.byref(self.desc), X.data_ptr(), kind, X.shape[1],
+                                y.data_ptr() if y is not None else None, C.byref(w.c), y_pred.data_ptr(),
+                                int(training), float(dropout_p), int(seed) & (2 ** 64 - 1), self._stream()),
+              'sat_forward')
+        self.launches += 1
+        return y_pred
+
+    def check_errors(self, w):
+        """Raise like the reference's nn.Embedding would for ids outside their table (device->host sync)."""
+        flags = int(w['counters'][1].item())
+        if flags & _lib.ERR_BAD_ID:
+            raise IndexError('a sparse feature id is outside its embedding table (index out of range in self)')
+        if flags & _lib.ERR_BAD_DOMAIN:
+            raise IndexError('a scenario id is outside [0, num_domains] (index out of range in self)')
+
+    # ------------------------------------------------------------------------------------------
+    def loss_and_grads(self, X, y, training=True, dropout_p=0.1, seed=0, l2_emb=0.0, with_reg=True):
+        """forward + BCE(sum) + backward.  Afterwards: w['dgrad'] = flat dense-parameter gradient,
+        w['row_grad'][:n_unique] / w['uniq_rows'][:n_unique] = dBCE/d(table row) of the touched rows
+        (the 2*l2*w regulariser term is added inside the optimiser), w['scalars'][0:2] = (bce, reg)."""
+        self.bind()
+        kind = self._check_x(X)
+        B = X.shape[0]
+        w = self.workspace(B, True)
+        l, s, d = lib(), self._stream(), C.byref(self.desc)
+        self._prepare(X, w, kind)
+        check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
+                            1 if training else 2, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s),
+              'sat_forward')
+        check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c),
+                             float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s), 'sat_backward')
+        self.launches += 4 + 1 + 1 + 2 * self.desc.L + 2
+        if with_reg:
+            check(l.sat_tables_sumsq(d, C.byref(w.c), s), 'sat_tables_sumsq')
+            self.launches += 1
+        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        self.launches += 1
+        return y_pred, w
+
+    # ------------------------------------------------------------------------------------------
+    def _adam_state(self):
+        if self._adam is None:
+            m = self.model
+            self._adam = {
+                'tab_m': torch.zeros_like(m._tables), 'tab_v': torch.zeros_like(m._tables),
+                'dense_m': torch.zeros_like(m._dense), 'dense_v': torch.zeros_like(m._dense),
+            }
+        return self._adam
+
+    def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
+                   dropout_p=0.1, seed=0, overlap=True):
+        """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
+        (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
+        finalize kernel (read them with .item() only when needed: that synchronises)."""
+        self.bind()
+        kind = self._check_x(X)
+        B = X.shape[0]
+        w = self.workspace(B, True)
+        st = self._adam_state()
+        self.step_count += 1
+        a = SatAdam()
+        a.lr, a.beta1, a.beta2, a.eps, a.l2_emb = float(lr), float(betas[0]), float(betas[1]), float(eps), float(l2_emb)
+        a.step, a.dense_mode = self.step_count, int(bool(dense_mode))
+        a.tab_m, a.tab_v = st['tab_m'].data_ptr(), st['tab_v'].data_ptr()
+        a.dense_m, a.dense_v = st['dense_m'].data_ptr(), st['dense_v'].data_ptr()
+        l, d = lib(), C.byref(self.desc)
+        main = torch.cuda.current_stream()
+        s = main.cuda_stream
+        if self._sweep_stream is None:
+            self._sweep_stream = torch.cuda.Stream(device=self.device)
+            self._ev_marked = torch.cuda.Event()
+            self._ev_swept = torch.cuda.Event()
+        sd = int(seed) & (2 ** 64 - 1)
+        p = float(dropout_p if training else 0.0)
+        self._prepare(X, w, kind)
+        check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        sweep_on_side = bool(dense_mode and overlap)
+        if sweep_on_side:
+            self._ev_marked.record(main)
+            self._sweep_stream.wait_event(self._ev_marked)
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), None, self._sweep_stream.cuda_stream), 'sat_tables_adam')
+            self._ev_swept.record(self._sweep_stream)
+        y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
+                            1 if training else 2, p, sd, s), 'sat_forward')
+        check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
+        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), s, None if sweep_on_side or not dense_mode else s),
+              'sat_tables_adam')
+        check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
+        if sweep_on_side:
+            main.wait_event(self._ev_swept)
+        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        self.launches += 3 + 4 + 1 + (1 + 2 * self.desc.L + 2 + 2) + 1 + (1 if dense_mode else 0) + 1 + 1
+        return y_pred, w
+
+    def adam_state(self):
+        return self._adam_state()
+
+    def reset_optimizer(self):
+        self._adam = None
+        self.step_count = 0

@@ -1,0 +1,116 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors dumped from the unmodified
+reference and against the CPU oracle on the same seeded inputs.  Tolerances (SURVEY.md §8c, fp32 noise floor
+of the reference itself): gathered rows bit-exact; y_pred atol 2e-6; BCE / reg rtol 1e-5; gradients
+max-norm rtol 1e-4 (+1e-9 abs); post-Adam parameters per `assert_adam_close`."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, FORWARD_ONLY_CASES, Golden, subsample
+from oracle import satrans_oracle as O
+from test_oracle_golden import assert_adam_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(t):
+    return t.cuda().contiguous()
+
+
+@pytest.mark.parametrize('name', CASES + FORWARD_ONLY_CASES)
+def test_gather_bit_exact(name):
+    from gpu_util import model_from_golden
+    g = Golden(name)
+    model = model_from_golden(g)
+    E = model.engine.gather(_dev(g.X()))
+    assert torch.equal(E.cpu(), g.arr('E0'))
+    # integer id paths give the same rows (dense-free schemas only: a mixed matrix has to be float)
+    if not g.cfg.dense_names:
+        for dt in (torch.int32, torch.int64):
+            assert torch.equal(model.engine.gather(_dev(g.X().to(dt))).cpu(), g.arr('E0'))
+    # the API-level call returns the reference's list-of-(B,1,d) structure
+    embs, dense = model.input_from_feature_columns(_dev(g.X()), model.dnn_feature_columns, model.embedding_dict)
+    assert len(embs) == len(g.cfg.sparse_names) and embs[0].shape == (g.B, 1, 32)
+    assert torch.equal(torch.cat(embs, dim=1).cpu(), g.arr('E0'))
+    assert len(dense) == len(g.cfg.dense_names)
+
+
+@pytest.mark.parametrize('name', CASES + FORWARD_ONLY_CASES)
+def test_forward_eval_matches_reference(name):
+    from gpu_util import model_from_golden
+    g = Golden(name)
+    model = model_from_golden(g).eval()
+    yp = model(_dev(g.X()))
+    assert yp.shape == (g.B, 1)
+    assert torch.allclose(yp.cpu(), g.arr('y_pred'), atol=2e-6, rtol=0), (yp.cpu() - g.arr('y_pred')).abs().max()
+    pred = model.predict(g.x_dict(), batch_size=37)
+    assert pred.dtype == np.float64 and pred.shape == (g.B, 1)
+    assert np.allclose(pred, g.z['predict'], atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_loss_and_gradients_match_reference(name):
+    from gpu_util import dense_grads, model_from_golden, table_grads
+    g = Golden(name)
+    model = model_from_golden(g)
+    l2 = g.cfg.l2_reg_embedding
+    yp, w = model.engine.loss_and_grads(_dev(g.X()), _dev(g.y()), training=False, l2_emb=l2)
+    torch.cuda.synchronize()
+    bce, reg = float(w['scalars'][0]), float(w['scalars'][1])
+    assert abs(bce - float(g.z['bce'])) <= 1e-5 * abs(float(g.z['bce']))
+    assert abs(reg - float(g.z['reg'])) <= 1e-5 * abs(float(g.z['reg']))
+    grads = dense_grads(model, w)
+    tg, _ = table_grads(model, w, l2)
+    grads.update(tg)
+    for k in O.trainable_keys(g.cfg):
+        ref = g.arr('grad/' + k)
+        got = grads[k][subsample(k)]
+        tol = 1e-4 * ref.abs().max().item() + 1e-9
+        err = (got - ref).abs().max().item()
+        assert err <= tol, (k, err, tol)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_dense_adam_steps_match_reference(name):
+    from gpu_util import model_from_golden
+    g = Golden(name)
+    model = model_from_golden(g)
+    lr = float(g.z['lr'])
+    eng = model.engine
+    for step in range(1, 4):
+        eng.train_step(_dev(g.X(step - 1)), _dev(g.y(step - 1)), lr=lr, l2_emb=g.cfg.l2_reg_embedding,
+                       dense_mode=True, training=False)
+        if step in (1, 3):
+            torch.cuda.synchronize()
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            for k in O.trainable_keys(g.cfg):
+                assert_adam_close(sd[k][subsample(k)], g.arr('step%d/%s' % (step, k)), lr, step, k)
+    # Adam moments after 3 steps
+    st = eng.adam_state()
+    names = {id(p): n for n, p in model.named_parameters()}
+    m_flat, v_flat = st['dense_m'].cpu(), st['dense_v'].cpu()
+    for p, off in model._flat_slots():
+        k = names[id(p)]
+        if k.endswith('K_meta_mlp.ffn_layer_norm.bias'):
+            continue
+        m_ref, v_ref = g.arr('step3_m/' + k), g.arr('step3_v/' + k)
+        m_got = m_flat[off:off + p.numel()].view(p.shape)[subsample(k)]
+        v_got = v_flat[off:off + p.numel()].view(p.shape)[subsample(k)]
+        assert (m_got - m_ref).abs().max().item() <= 1e-4 * m_ref.abs().max().item() + 1e-9, k
+        assert (v_got - v_ref).abs().max().item() <= 1e-4 * v_ref.abs().max().item() + 1e-12, k
+    tm, tv = st['tab_m'].cpu(), st['tab_v'].cpu()
+    for f, a, b in zip(model._sparse_feats, model._row_off[:-1], model._row_off[1:]):
+        k = 'embedding_dict.%s.weight' % f.embedding_name
+        m_ref, v_ref = g.arr('step3_m/' + k), g.arr('step3_v/' + k)
+        assert (tm[int(a):int(b)] - m_ref).abs().max().item() <= 1e-4 * m_ref.abs().max().item() + 1e-9, k
+        assert (tv[int(a):int(b)] - v_ref).abs().max().item() <= 1e-4 * v_ref.abs().max().item() + 1e-12, k
+
+
+def test_reg_and_loss_reported_by_train_step():
+    from gpu_util import model_from_golden
+    g = Golden('en_small')
+    model = model_from_golden(g)
+    _, w = model.engine.train_step(_dev(g.X()), _dev(g.y()), lr=1e-3, l2_emb=g.cfg.l2_reg_embedding, training=False)
+    torch.cuda.synchronize()
+    assert abs(float(w['scalars'][0]) - float(g.z['bce'])) <= 1e-5 * abs(float(g.z['bce']))
+    assert abs(float(w['scalars'][1]) - float(g.z['reg'])) <= 1e-5 * abs(float(g.z['reg']))
