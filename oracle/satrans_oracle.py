@@ -152,9 +152,12 @@ def _layer_norm(x, w, b):                   # nn.LayerNorm(d, eps=1e-6): satrans
 
 
 def _drop(x, p, masks, name):
-    """Inverted dropout with an injected keep-mask (1 = keep); identity when masks is None."""
+    """Inverted dropout: identity when masks is None (eval mode); `masks == 'rng'` draws from torch's RNG
+    exactly like the reference's nn.Dropout in train mode; a dict injects keep-masks (1 = keep)."""
     if masks is None or p == 0.0:
         return x
+    if isinstance(masks, str):
+        return F.dropout(x, p, training=True)
     return x * masks[name].to(x.dtype) / (1.0 - p)
 
 
@@ -312,6 +315,34 @@ def train_step(st, X, y, cfg: OracleConfig, opt, lr: float, masks=None):
     yp, bce, reg, grads = loss_and_grads(st, X, y, cfg, masks)
     adam_apply(st, grads, opt, lr)
     return yp, bce, reg
+
+
+class Trainer:
+    """The reference's training step on CPU, shaped like meta_basemodel.py:311-328 + main.py:343: leaf parameters,
+    train-mode forward (dropout from torch's RNG), BCE(sum) + dense L2, autograd backward (dense table
+    gradients), torch.optim.Adam over every parameter.  Used as the timed CPU baseline."""
+
+    def __init__(self, st, cfg: OracleConfig, lr: float):
+        self.cfg = cfg
+        self.state = dict(st)
+        self.params = {k: st[k].detach().clone().requires_grad_(True) for k in trainable_keys(cfg)}
+        self.state.update(self.params)
+        self.optim = torch.optim.Adam(list(self.params.values()), lr=lr)
+
+    def step(self, X, y, train_mode=True):
+        yp = forward(self.state, X, self.cfg, masks='rng' if train_mode else None).squeeze(-1)
+        self.optim.zero_grad()
+        loss = F.binary_cross_entropy(yp, y.reshape(-1), reduction='sum')
+        reg = reg_loss(self.state, self.cfg)
+        total = loss + reg
+        loss_v, total_v = loss.item(), total.item()          # the reference's two .item() calls (:324-325)
+        total.backward()
+        self.optim.step()
+        return loss_v, total_v - loss_v
+
+    @torch.no_grad()
+    def predict(self, X):
+        return forward(self.state, X, self.cfg)
 
 
 # --------------------------------------------------------------------------------------

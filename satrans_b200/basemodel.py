@@ -433,6 +433,26 @@ class BaseModel(nn.Module):
         callbacks.on_train_end()
         return self.history
 
+    def train_on_batch(self, x, y):
+        """One optimiser step on one batch given as HOST data (dict / list of columns or an (B, n_cols) array)
+        and labels; returns (bce_sum, reg_loss) as Python floats — the per-step body of `fit`
+        (reference meta_basemodel.py:311-328, incl. its `.item()` synchronisation)."""
+        X = x if (isinstance(x, np.ndarray) and x.ndim == 2) or torch.is_tensor(x) else self._stack_inputs(x)
+        dev = self._tables.device
+        Xd = torch.as_tensor(X).to(dev, non_blocking=True)
+        yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)
+        hp = self._opt_hparams
+        eng = self.engine
+        self.train()
+        _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
+                              l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
+                              dropout_p=self.dropout_rate,
+                              seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
+        sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()
+        if sc[3] != 0:
+            eng.check_errors(w)
+        return sc[0], sc[1]
+
     # ---- evaluate / predict ------------------------------------------------------------------------------
     def evaluate(self, x, y, batch_size=256):
         pred_ans = self.predict(x, batch_size, y)

@@ -75,6 +75,27 @@ class Engine:
         self._ev_swept = None
         self.step_count = 0
         self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
+        self.timing = None         # set to {} to collect CUDA-event pairs per phase: {name: [(start, end), ...]}
+
+    def _tic(self, name, stream=None):
+        if self.timing is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        return (name, ev, stream)
+
+    def _toc(self, tok):
+        if tok is None:
+            return
+        name, ev0, stream = tok
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(stream if stream is not None else torch.cuda.current_stream())
+        self.timing.setdefault(name, []).append((ev0, ev1))
+
+    def timing_ms(self):
+        """{phase: mean milliseconds} of the collected event pairs (synchronises)."""
+        torch.cuda.synchronize()
+        return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in (self.timing or {}).items()}
 
     # ------------------------------------------------------------------------------------------
     def bind(self):
@@ -148,7 +169,6 @@ class Engine:
         check(l.sat_bucket_by_domain(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), 0, s),
               'sat_bucket_by_domain')
         check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
-        self.launches += 3
 
     def forward(self, X, y=None, training=False, dropout_p=0.1, seed=0):
         """y_pred (B,) in sample order.  With y: also leaves BCE partials / dLogit in the workspace."""
@@ -164,7 +184,7 @@ class Engine:
                                 y.data_ptr() if y is not None else None, C.byref(w.c), y_pred.data_ptr(),
                                 int(training), float(dropout_p), int(seed) & (2 ** 64 - 1), self._stream()),
               'sat_forward')
-        self.launches += 1
+        self.launches += 3
         return y_pred
 
     def check_errors(self, w):
@@ -188,12 +208,13 @@ class Engine:
         self._prepare(X, w, kind)
         check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        w['row_grad'].zero_()
         check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
-                            1 if training else 2, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s),
+                            1, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s),
               'sat_forward')
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c),
                              float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s), 'sat_backward')
-        self.launches += 4 + 1 + 1 + 2 * self.desc.L + 2
+        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2)
         if with_reg:
             check(l.sat_tables_sumsq(d, C.byref(w.c), s), 'sat_tables_sumsq')
             self.launches += 1
@@ -236,25 +257,42 @@ class Engine:
             self._ev_swept = torch.cuda.Event()
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
+        t = self._tic('prepare')
         self._prepare(X, w, kind)
         check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        self._toc(t)
         sweep_on_side = bool(dense_mode and overlap)
         if sweep_on_side:
             self._ev_marked.record(main)
             self._sweep_stream.wait_event(self._ev_marked)
+            t = self._tic('adam_sweep', self._sweep_stream)
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), None, self._sweep_stream.cuda_stream), 'sat_tables_adam')
+            self._toc(t)
             self._ev_swept.record(self._sweep_stream)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
+        t = self._tic('forward')
         check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
-                            1 if training else 2, p, sd, s), 'sat_forward')
+                            1, p, sd, s), 'sat_forward')
+        self._toc(t)
+        t = self._tic('backward')
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
-        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), s, None if sweep_on_side or not dense_mode else s),
-              'sat_tables_adam')
+        self._toc(t)
+        t = self._tic('adam_rows')
+        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), s, None), 'sat_tables_adam')
+        self._toc(t)
+        if dense_mode and not sweep_on_side:
+            t = self._tic('adam_sweep')
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), None, s), 'sat_tables_adam')
+            self._toc(t)
+        t = self._tic('adam_dense')
         check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
+        self._toc(t)
         if sweep_on_side:
             main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
-        self.launches += 3 + 4 + 1 + (1 + 2 * self.desc.L + 2 + 2) + 1 + (1 if dense_mode else 0) + 1 + 1
+        # own kernels per step: bucket 1, encoder 1, mark+rank 3, forward 1, head bwd 1, 2 per layer, encoder bwd 2,
+        # adam rows 1, sweep 0/1, dense adam 1, finalize 1
+        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2) + 1 + (1 if dense_mode else 0) + 1 + 1
         return y_pred, w
 
     def adam_state(self):
