@@ -181,9 +181,12 @@ int sat_rows_mark(const SatModel* m, const void* x, int32_t id_kind, int32_t ld,
 
 /* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
  *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */
-/* touched rows on stream_rows (NULL = skip), untouched rows on stream_sweep (NULL or dense_mode==0 = skip);
- * the two kernels write disjoint rows and may run concurrently. */
-int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream_rows, void* stream_sweep);
+/* which = SAT_ADAM_TOUCHED (rows read by the batch: g = dE + 2*l2*w), SAT_ADAM_UNTOUCHED (every other row:
+ * g = 2*l2*w; skipped when dense_mode == 0) or both.  The two kernels write disjoint rows, so they may be
+ * issued on different streams and run concurrently with each other and with forward/backward. */
+#define SAT_ADAM_TOUCHED 1
+#define SAT_ADAM_UNTOUCHED 2
+int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, int32_t which, void* stream);
 int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
 /* sum of squares of all table rows into w->reg_part (regulariser without an optimiser step). */
 int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream);

@@ -17,6 +17,7 @@ SAT_WORK_BUFFERS = 20
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
 ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
+ADAM_TOUCHED, ADAM_UNTOUCHED = 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -59,7 +60,7 @@ PROTOTYPES = {
     'sat_forward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, vp]),
     'sat_backward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, vp]),
     'sat_rows_mark': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
-    'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp, vp]),
+    'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, vp]),

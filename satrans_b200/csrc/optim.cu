@@ -176,20 +176,21 @@ static AdamConst make_const(const SatAdam* a, bool with_l2) {
 }
 
 // reg_part layout: [0, SWEEP_BLOCKS) sweep partials, [SWEEP_BLOCKS, SWEEP_BLOCKS + ROWS_BLOCKS) touched-row partials
-extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream_rows, void* stream_sweep) {
+extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, int32_t which, void* stream) {
     if (!m || !w || !a || !a->tab_m || !a->tab_v || !w->reg_part) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: null argument");
     if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: step must be >= 1");
     const AdamConst c = make_const(a, true);
     const long long n_vec = m->total_rows * 8;
-    if (stream_rows) {
-        k_adam_rows<<<ROWS_BLOCKS, ROWS_THREADS, 0, (cudaStream_t)stream_rows>>>(
+    cudaStream_t s = (cudaStream_t)stream;
+    if (which & SAT_ADAM_TOUCHED) {
+        k_adam_rows<<<ROWS_BLOCKS, ROWS_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
             w->uniq_rows, reinterpret_cast<float4*>(w->row_grad), w->counters, c, w->reg_part + SWEEP_BLOCKS);
         int rc = sat_host::check_launch("k_adam_rows");
         if (rc) return rc;
     }
-    if (stream_sweep && a->dense_mode) {
-        k_adam_sweep<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, (cudaStream_t)stream_sweep>>>(
+    if ((which & SAT_ADAM_UNTOUCHED) && a->dense_mode) {
+        k_adam_sweep<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
             w->bitmap, n_vec, c, w->reg_part);
         int rc = sat_host::check_launch("k_adam_sweep");

@@ -266,7 +266,8 @@ class Engine:
             self._ev_marked.record(main)
             self._sweep_stream.wait_event(self._ev_marked)
             t = self._tic('adam_sweep', self._sweep_stream)
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), None, self._sweep_stream.cuda_stream), 'sat_tables_adam')
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, self._sweep_stream.cuda_stream),
+                  'sat_tables_adam')
             self._toc(t)
             self._ev_swept.record(self._sweep_stream)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -278,11 +279,11 @@ class Engine:
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
         self._toc(t)
         t = self._tic('adam_rows')
-        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), s, None), 'sat_tables_adam')
+        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, s), 'sat_tables_adam')
         self._toc(t)
         if dense_mode and not sweep_on_side:
             t = self._tic('adam_sweep')
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), None, s), 'sat_tables_adam')
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
             self._toc(t)
         t = self._tic('adam_dense')
         check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
