@@ -1,0 +1,156 @@
+"""CPU-only tests: host-side logic of the drop-in API and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden
+from satrans_b200 import DenseFeat, SATrans, SparseFeat, build_input_features, get_feature_names, synth
+from satrans_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(g, device='cpu'):
+    m = g.meta
+    cols = ([SparseFeat(n, v, 32) for n, v in zip(m['sparse_names'], m['vocab_sizes'])] +
+            [DenseFeat(n, 1) for n in m['dense_names']])
+    return SATrans(cols, cols, [m['domain_col']], [m['num_domains']], att_layer_num=0,
+                   domain_att_layer_num=m['domain_att_layer_num'], att_head_num=m['att_head_num'],
+                   meta_mode=m['meta_mode'], seed='1021', device=device, flag=m['flag'])
+
+
+def test_header_symbols_exported_and_bound():
+    hdr = open(os.path.join(ROOT, 'include', 'satrans_b200.h')).read()
+    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(sat_\w+)\s*\(', hdr, flags=re.M))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(l, name), name
+    assert l.sat_abi_version() == 1
+    # struct mirrors: sizes implied by the header layout
+    assert ctypes.sizeof(_lib.SatModel) == 10 * 4 + 10 * 8 + 5 * 8
+    assert ctypes.sizeof(_lib.SatWork) == 8 + _lib.SAT_WORK_BUFFERS * 8
+    assert ctypes.sizeof(_lib.SatAdam) == 32 + 4 * 8
+
+
+def test_workspace_sizes_host_only():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    l = _lib.lib()
+    d = _lib.SatModel()
+    d.F, d.L, d.H, d.n_dom, d.total_rows, d.n_dense_params, d.flags = 19, 3, 4, 4, 6571961, 148580, 0
+    sizes = (ctypes.c_int64 * _lib.SAT_WORK_BUFFERS)()
+    mt = ctypes.c_int32()
+    assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 1, sizes, ctypes.byref(mt)) == 0
+    s = dict(zip(_lib.WORK_BUFFERS, sizes))
+    assert s['acts'] == (3 * 5 + 1) * 8192 * 19 * 32 * 4
+    assert s['bitmap'] == (6571961 + 31) // 32 * 4
+    assert mt.value == (8192 + 9) // 10 + 4
+    assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 0, sizes, ctypes.byref(mt)) == 0
+    assert dict(zip(_lib.WORK_BUFFERS, sizes))['acts'] == 0
+    d.F = 40
+    assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 1, sizes, ctypes.byref(mt)) != 0
+    assert b'bad argument' in l.sat_last_error()
+
+
+def test_feature_columns_and_index():
+    cols = [SparseFeat('a', 10, 32), SparseFeat('b', 5, 32), DenseFeat('p', 1)]
+    fi = build_input_features(cols + cols)
+    assert list(fi.items()) == [('a', (0, 1)), ('b', (1, 2)), ('p', (2, 3))]
+    assert get_feature_names(cols) == ['a', 'b', 'p']
+    assert SparseFeat('x', 100, 'auto').embedding_dim == 6 * int(pow(100, 0.25))
+    assert SparseFeat('x', 7).embedding_name == 'x'
+
+
+@pytest.mark.parametrize('name', ['en_small', 'enp_small'])
+def test_state_dict_is_reference_compatible(name):
+    g = Golden(name)
+    model = _model(g)
+    full = g.full_state_dict()
+    sd = model.state_dict()
+    assert set(sd) == set(full)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(full[k].shape), k
+    model.load_state_dict(full)
+    # every kernel-visible parameter is a view into the flat buffer / the concatenated table
+    for p, off in model._flat_slots():
+        assert p.data_ptr() == model._dense.data_ptr() + 4 * off
+    o = model._layout['off_layers']
+    assert torch.equal(model._dense[o:o + 1024].view(32, 32), full['domain_int_layers.0.W_Query'])
+    first = g.cfg.sparse_names[0]
+    assert torch.equal(model._tables[:g.cfg.vocab_sizes[0]], full['embedding_dict.%s.weight' % first])
+    # aliases stay aliases (reference satrans.py:44-47,179-180)
+    assert model.domain_map_dnn_K is model.domain_map_dnn_Q
+    lay0 = model.domain_int_layers[0]
+    assert (lay0.K_meta_mlp is lay0.Q_meta_mlp) == ('pos' not in g.meta['flag'])
+    # .to() keeps the views intact
+    model.to('cpu')
+    model._ensure_flat()
+    for p, off in model._flat_slots():
+        assert p.data_ptr() == model._dense.data_ptr() + 4 * off
+
+
+def test_init_follows_reference_distributions():
+    g = Golden('en_small')
+    model = _model(g)
+    lay = model.domain_int_layers[0]
+    assert abs(lay.layer_norm.weight.mean().item()) < 0.05          # N(0, .05), not ones (satrans.py:42-43)
+    assert torch.equal(lay.Q_meta_mlp.ffn_layer_norm.weight, torch.ones(32))
+    assert model._tables.std().item() < 2e-4
+    assert model.domain_map_dnn_Q.linears[0].weight.std().item() < 2e-4
+
+
+def test_errors_match_reference_contract():
+    cols = [SparseFeat('a', 10, 32), SparseFeat('301', 5, 32)]
+    with pytest.raises(ValueError):
+        SATrans(cols, cols, ['301'], [3], att_head_num=0, flag='sota')
+    with pytest.raises(ValueError):
+        SATrans(cols, cols, ['301'], [3], att_head_num=3, flag='sota')
+    with pytest.raises(TypeError):
+        SATrans(cols, cols, ['301'], [3], att_head_num=2, flag=None)
+    with pytest.raises(ValueError):
+        SATrans([SparseFeat('a', 10, 32), SparseFeat('301', 5, 16)], [SparseFeat('a', 10, 32), SparseFeat('301', 5, 16)],
+                ['301'], [3], flag='sota')
+    m = SATrans(cols, cols, ['301'], [3], att_head_num=2, flag='sota')
+    with pytest.raises(NotImplementedError):
+        m.compile('nadam', 'binary_crossentropy')
+    with pytest.raises(NotImplementedError):
+        m.compile('adam', 'hinge')
+    m.compile(torch.optim.Adam(m.parameters(), lr=0.005), 'binary_crossentropy', metrics=['binary_crossentropy', 'auc'])
+    assert m._opt_hparams['lr'] == 0.005 and m.metrics_names == ['loss', 'binary_crossentropy', 'auc']
+    # no CPU fallback: using the engine off-GPU fails loudly
+    with pytest.raises(Exception):
+        m(torch.zeros((2, 2)))
+
+
+def test_stack_inputs_layouts():
+    cols = [SparseFeat('a', 10, 32), SparseFeat('301', 5, 32), DenseFeat('p', 1)]
+    m = SATrans(cols, cols, ['301'], [3], att_head_num=2, flag='sota')
+    x = {'a': np.array([1, 2, 3]), '301': np.array([1, 2, 3]), 'p': np.array([.5, .25, 1.], dtype=np.float32)}
+    X = m._stack_inputs(x)
+    assert X.dtype == np.float32 and X.shape == (3, 3) and X[1, 2] == 0.25
+    cols2 = cols[:2]
+    m2 = SATrans(cols2, cols2, ['301'], [3], att_head_num=2, flag='sota')
+    X2 = m2._stack_inputs({'a': np.array([1, 2 ** 25]), '301': np.array([1, 2])})
+    assert X2.dtype == np.int32 and X2[1, 0] == 2 ** 25            # exact beyond 2**24 on the integer path
+    with pytest.raises(ValueError):
+        m._stack_inputs({'a': np.array([2 ** 25]), '301': np.array([1]), 'p': np.array([.5], dtype=np.float32)})
+
+
+def test_synth_schemas():
+    s = synth.aliccp_schema()
+    assert s.total_rows == 6571961 and len(s.fields) == 19 and s.num_domains == 3
+    x, y = synth.make_inputs(synth.aliccp_schema(1e-3), 1000, seed=1)
+    assert set(np.unique(x['301'])) <= {1, 2, 3} and y.shape == (1000,)
+    a = synth.alimama_schema()
+    assert len(a.fields) == 15 and a.dense == ['price'] and a.num_domains == 4
+    xz, _ = synth.make_inputs(synth.aliccp_schema(1e-2), 1000, seed=1, dist='zipf')
+    for f in s.fields:
+        assert xz[f].min() >= 0
