@@ -112,7 +112,7 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
 #pragma unroll
             for (int i = 0; i < D; ++i) dm[i] = dqp[i] * drop_factor(dc, i);
         } else zero(dm);
-#pragma unroll
+#pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             uint32_t mask = 0;
             {

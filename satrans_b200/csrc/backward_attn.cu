@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
     const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
     const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
-    const float sqrt_dh = sqrtf((float)DH);
+    const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
 
     copy_to_smem(sWO, lay + OFF_WO, 1024, tid, NT);
     copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NT);
@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
         __syncthreads();                                   // smem init / previous tile done
 
         float dr[D];
-        float Dh[H];
         {   // ---- phase 1: y = drop(act(r @ WO^T)) + x ; LN bwd ; dO ; dR -------------------------------
             float r[D], dy[D], o[D];
             zero(o);
@@ -101,7 +100,7 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
                     float acc = 0.f;
 #pragma unroll
                     for (int c = 0; c < DH; ++c) acc = fmaf(dr[h * DH + c], r[h * DH + c], acc);
-                    Dh[h] = acc;
+                    sSt[tid * 24 + 16 + h] = acc;               // D_i[h] = dR_i . R_i  (own row, read back below)
                 }
                 sts_row(sT0 + tid * KV_LD, r);
                 sts_row(sT1 + tid * KV_LD, dy);
@@ -130,10 +129,12 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
             zero(dq);
             const DropCtx dca = make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, true);
             const int sbase = s * F;
-#pragma unroll
+            // rolled over heads: q / dr / dq are rotated by DH per head (compact code, see common.cuh)
+#pragma unroll 1
             for (int h = 0; h < H; ++h) {
                 float sc[SAT_MAXF];
                 float mx = -INFINITY;
+                const float Dhh = sSt[tid * 24 + 16 + h];
 #pragma unroll
                 for (int j = 0; j < SAT_MAXF; ++j) {
                     if (j < F) {
@@ -142,10 +143,10 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
 #pragma unroll
                         for (int c = 0; c < DH; c += 4) {
                             const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                            acc = fmaf(q[h * DH + c + 0], kk.x, acc); acc = fmaf(q[h * DH + c + 1], kk.y, acc);
-                            acc = fmaf(q[h * DH + c + 2], kk.z, acc); acc = fmaf(q[h * DH + c + 3], kk.w, acc);
+                            acc = fmaf(q[c + 0], kk.x, acc); acc = fmaf(q[c + 1], kk.y, acc);
+                            acc = fmaf(q[c + 2], kk.z, acc); acc = fmaf(q[c + 3], kk.w, acc);
                         }
-                        sc[j] = acc / sqrt_dh;
+                        sc[j] = acc * inv_sqrt_dh;
                         mx = fmaxf(mx, sc[j]);
                     }
                 }
@@ -153,29 +154,31 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
 #pragma unroll
                 for (int j = 0; j < SAT_MAXF; ++j)
                     if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-                sSt[tid * 24 + h] = mx; sSt[tid * 24 + 8 + h] = sum; sSt[tid * 24 + 16 + h] = Dh[h];
+                const float inv_sum = 1.f / sum;
+                sSt[tid * 24 + h] = mx; sSt[tid * 24 + 8 + h] = inv_sum;
 #pragma unroll
                 for (int j = 0; j < SAT_MAXF; ++j) {
                     if (j < F) {
-                        const float pj = sc[j] / sum;
+                        const float pj = sc[j] * inv_sum;
                         const float* vr = sT1 + (sbase + j) * KV_LD + h * DH;
                         const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
                         float dAd = 0.f;
 #pragma unroll
                         for (int c = 0; c < DH; c += 4) {
                             const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                            dAd = fmaf(dr[h * DH + c + 0], vv.x, dAd); dAd = fmaf(dr[h * DH + c + 1], vv.y, dAd);
-                            dAd = fmaf(dr[h * DH + c + 2], vv.z, dAd); dAd = fmaf(dr[h * DH + c + 3], vv.w, dAd);
+                            dAd = fmaf(dr[c + 0], vv.x, dAd); dAd = fmaf(dr[c + 1], vv.y, dAd);
+                            dAd = fmaf(dr[c + 2], vv.z, dAd); dAd = fmaf(dr[c + 3], vv.w, dAd);
                         }
-                        const float dsc = pj * (dAd * drop_factor(dca, h * SAT_MAXF + j) - Dh[h]) / sqrt_dh;
+                        const float dsc = pj * (dAd * drop_factor(dca, h * SAT_MAXF + j) - Dhh) * inv_sqrt_dh;
 #pragma unroll
                         for (int c = 0; c < DH; c += 4) {
                             const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                            dq[h * DH + c + 0] = fmaf(dsc, kk.x, dq[h * DH + c + 0]); dq[h * DH + c + 1] = fmaf(dsc, kk.y, dq[h * DH + c + 1]);
-                            dq[h * DH + c + 2] = fmaf(dsc, kk.z, dq[h * DH + c + 2]); dq[h * DH + c + 3] = fmaf(dsc, kk.w, dq[h * DH + c + 3]);
+                            dq[c + 0] = fmaf(dsc, kk.x, dq[c + 0]); dq[c + 1] = fmaf(dsc, kk.y, dq[c + 1]);
+                            dq[c + 2] = fmaf(dsc, kk.z, dq[c + 2]); dq[c + 3] = fmaf(dsc, kk.w, dq[c + 3]);
                         }
                     }
                 }
+                if (H > 1) { rotate_regs<D, DH>(q); rotate_regs<D, DH>(dr); rotate_regs<D, DH>(dq); }
             }
             store_row(a.dqkv + 0 * a.act_stride + tokpos, dq);
         }
@@ -208,9 +211,9 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
                     }
 #pragma unroll
                     for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kreg[h * DH + c], acc); dAd = fmaf(dd[c], vreg[h * DH + c], dAd); }
-                    const float pij = expf(acc / sqrt_dh - st[h]) / st[8 + h];
+                    const float pij = expf(acc * inv_sqrt_dh - st[h]) * st[8 + h];
                     const float df = drop_factor(dci, h * SAT_MAXF + f);
-                    const float dsc = pij * (dAd * df - st[16 + h]) / sqrt_dh;
+                    const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;
                     const float pd = pij * df;
 #pragma unroll
                     for (int c = 0; c < DH; ++c) {

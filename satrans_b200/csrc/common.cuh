@@ -77,34 +77,63 @@ __device__ __forceinline__ float drop_factor(const DropCtx& c, uint32_t e) {
 //   vm_outer : y[j] += sum_i a[i] * M[i*LD + j]        (M is [NIN][LD], "x @ W")
 //   vm_dot   : y[j] += sum_i a[i] * M[j*LD + i]        (M is [NOUT][LD], "x @ W^T")
 // ------------------------------------------------------------------------------------------------
+// rotate a register array left by R positions (compile-time indices only: pure register moves)
+template <int N, int R>
+__device__ __forceinline__ void rotate_regs(float (&v)[N]) {
+    float t[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) t[i] = v[i];
+#pragma unroll
+    for (int i = 0; i < N - R; ++i) v[i] = v[i + R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[N - R + i] = t[i];
+}
+
+// The GEMVs are ROLLED loops over chunks of CH inputs (vm_outer) / CH outputs (vm_dot); the register array that
+// would need a run-time index is rotated by CH after every chunk instead (N/CH rotations restore it).  A fully
+// unrolled layer body is ~30 k SASS instructions and was instruction-fetch bound (ncu: stall_no_instruction #1).
 template <int NIN, int NOUT, int LD>
-__device__ __forceinline__ void vm_outer(const float* __restrict__ M, const float (&a)[NIN], float (&y)[NOUT]) {
+__device__ __forceinline__ void vm_outer(const float* __restrict__ M, float (&a)[NIN], float (&y)[NOUT]) {
+    constexpr int CH = (NIN * NOUT >= 512) ? ((NOUT >= 32) ? 8 : 16) : NIN;
+    static_assert(NIN % CH == 0, "chunking");
+#pragma unroll 1
+    for (int c = 0; c < NIN / CH; ++c) {
+        const float* Mc = M + c * CH * LD;
 #pragma unroll
-    for (int i = 0; i < NIN; ++i) {
+        for (int i = 0; i < CH; ++i) {
 #pragma unroll
-        for (int j = 0; j < NOUT; j += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(M + i * LD + j);
-            y[j + 0] = fmaf(a[i], w.x, y[j + 0]);
-            y[j + 1] = fmaf(a[i], w.y, y[j + 1]);
-            y[j + 2] = fmaf(a[i], w.z, y[j + 2]);
-            y[j + 3] = fmaf(a[i], w.w, y[j + 3]);
+            for (int j = 0; j < NOUT; j += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(Mc + i * LD + j);
+                y[j + 0] = fmaf(a[i], w.x, y[j + 0]);
+                y[j + 1] = fmaf(a[i], w.y, y[j + 1]);
+                y[j + 2] = fmaf(a[i], w.z, y[j + 2]);
+                y[j + 3] = fmaf(a[i], w.w, y[j + 3]);
+            }
         }
+        if (CH < NIN) rotate_regs<NIN, CH>(a);
     }
 }
 template <int NIN, int NOUT, int LD>
 __device__ __forceinline__ void vm_dot(const float* __restrict__ M, const float (&a)[NIN], float (&y)[NOUT]) {
+    constexpr int CH = (NIN * NOUT >= 512) ? ((NIN >= 32) ? 8 : 16) : NOUT;
+    static_assert(NOUT % CH == 0, "chunking");
+#pragma unroll 1
+    for (int c = 0; c < NOUT / CH; ++c) {
+        const float* Mc = M + c * CH * LD;
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) {
-        float acc0 = 0.f, acc1 = 0.f;
+        for (int j = 0; j < CH; ++j) {
+            float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < NIN; i += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(M + j * LD + i);
-            acc0 = fmaf(a[i + 0], w.x, acc0);
-            acc1 = fmaf(a[i + 1], w.y, acc1);
-            acc0 = fmaf(a[i + 2], w.z, acc0);
-            acc1 = fmaf(a[i + 3], w.w, acc1);
+            for (int i = 0; i < NIN; i += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(Mc + j * LD + i);
+                acc0 = fmaf(a[i + 0], w.x, acc0);
+                acc1 = fmaf(a[i + 1], w.y, acc1);
+                acc0 = fmaf(a[i + 2], w.z, acc0);
+                acc1 = fmaf(a[i + 3], w.w, acc1);
+            }
+            y[j] += acc0 + acc1;
         }
-        y[j] += acc0 + acc1;
+        if (CH < NOUT) rotate_regs<NOUT, CH>(y);
     }
 }
 

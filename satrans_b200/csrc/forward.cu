@@ -20,11 +20,11 @@ constexpr int FWD_SMEM_FLOATS = 4096 + 192 + 2 * PSZ + 2 * NT * KV_LD + NT;
 
 // MetaNet (reference submodules.py:77-103) on one token: z = dropout(relu(q @ W1) @ W2) + q.
 // th = [W1 (32x64) | W2 (64x32)] in shared memory.  Hidden units are produced and consumed 16 at a time.
-__device__ __forceinline__ void metanet_fwd(const float (&q)[D], const float* __restrict__ th, const DropCtx& dc,
+__device__ __forceinline__ void metanet_fwd(float (&q)[D], const float* __restrict__ th, const DropCtx& dc,
                                             float (&z)[D]) {
     float mo[D];
     zero(mo);
-#pragma unroll
+#pragma unroll 1
     for (int c0 = 0; c0 < HID; c0 += 16) {
         float h[16];
         zero(h);
@@ -39,13 +39,14 @@ __device__ __forceinline__ void metanet_fwd(const float (&q)[D], const float* __
 
 // Multi-head attention of one query token against the F tokens of its sample (reference satrans.py:75-90).
 // K'/V rows of the sample start at row `sbase` of the [token][36] tiles.
+// Rolled over heads: q is rotated by DH per head so that the head's channels are always q[0..DH) (compact code).
 template <int H>
-__device__ __forceinline__ void attention_fwd(const float (&q)[D], const float* __restrict__ sK,
+__device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __restrict__ sK,
                                               const float* __restrict__ sV, int sbase, int F, const DropCtx& dc,
                                               float (&r)[D]) {
     constexpr int DH = D / H;
-    const float sqrt_dh = sqrtf((float)DH);
-#pragma unroll
+    const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+#pragma unroll 1
     for (int h = 0; h < H; ++h) {
         float sc[SAT_MAXF];
         float mx = -INFINITY;
@@ -57,12 +58,12 @@ __device__ __forceinline__ void attention_fwd(const float (&q)[D], const float* 
 #pragma unroll
                 for (int c = 0; c < DH; c += 4) {
                     const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                    acc = fmaf(q[h * DH + c + 0], kk.x, acc);
-                    acc = fmaf(q[h * DH + c + 1], kk.y, acc);
-                    acc = fmaf(q[h * DH + c + 2], kk.z, acc);
-                    acc = fmaf(q[h * DH + c + 3], kk.w, acc);
+                    acc = fmaf(q[c + 0], kk.x, acc);
+                    acc = fmaf(q[c + 1], kk.y, acc);
+                    acc = fmaf(q[c + 2], kk.z, acc);
+                    acc = fmaf(q[c + 3], kk.w, acc);
                 }
-                sc[j] = acc / sqrt_dh;                    // inner_product /= dh ** 0.5   (satrans.py:85-86)
+                sc[j] = acc * inv_sqrt_dh;                // inner_product /= dh ** 0.5   (satrans.py:85-86)
                 mx = fmaxf(mx, sc[j]);
             }
         }
@@ -72,10 +73,11 @@ __device__ __forceinline__ void attention_fwd(const float (&q)[D], const float* 
             if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
         float o[DH];
         zero(o);
+        const float inv_sum = 1.f / sum;
 #pragma unroll
         for (int j = 0; j < SAT_MAXF; ++j) {
             if (j < F) {
-                const float pj = (sc[j] / sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
+                const float pj = (sc[j] * inv_sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
                 const float* vr = sV + (sbase + j) * KV_LD + h * DH;
 #pragma unroll
                 for (int c = 0; c < DH; c += 4) {
@@ -87,8 +89,10 @@ __device__ __forceinline__ void attention_fwd(const float (&q)[D], const float* 
                 }
             }
         }
+        // r[h*DH + c] = o[c]: write the head's slot, then rotate so that after H heads r is in channel order
 #pragma unroll
-        for (int c = 0; c < DH; ++c) r[h * DH + c] = o[c];
+        for (int c = 0; c < DH; ++c) r[c] = o[c];
+        if (H > 1) { rotate_regs<D, DH>(r); rotate_regs<D, DH>(q); }
     }
 }
 
