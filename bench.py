@@ -194,12 +194,16 @@ def run_b200(args):
     schema = synth.aliccp_schema(args.vocab_scale)
     cols = schema.feature_columns(32)
     model = SATrans(cols, cols, ['301'], [3], att_layer_num=0, domain_att_layer_num=3, att_head_num=4, meta_mode='QK',
-                    seed=1021, device=dev, flag='sota')
+                    seed=1021, device=dev, flag='sota', table_shard=(rank, world) if world > 1 else None)
     model.dense_table_updates = not args.lazy
     model.compile(torch.optim.Adam(model.parameters(), lr=0.005), "binary_crossentropy",
                   metrics=["binary_crossentropy", "auc"])
     eng = model.engine
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    if world > 1:
+        from satrans_b200.dist import DistContext
+        eng.attach_dist(DistContext())
+        eng.prepare_training(B)
     n_batches = 16
     xs, ys = synth.make_inputs(schema, n_batches * B, seed=1021 + rank, dist=args.ids, ctr=0.04)
     X_host = torch.from_numpy(synth.stack_columns(xs, schema.fields)).pin_memory()
@@ -267,11 +271,12 @@ def run_b200(args):
            "api": "SATrans.train_on_batch(x_host, y_host) -> (bce, reg)"}
     if rank != 0:
         if world > 1:
+            dist.barrier()          # keep this rank's table shard mapped until rank 0 is done with the extras
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel: the dense L2+Adam sweep (HBM-bound) ---------------------------------
-    rows = schema.total_rows
+    rows = model._tables.shape[0]                                    # rows of this rank's shard
     sweep_bytes = (rows - n_unique) * 6 * 128 + (rows / 8)           # p,m,v read + written once; bitmap read
     roof = None
     if 'adam_sweep' in phases:
@@ -335,6 +340,7 @@ def run_b200(args):
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

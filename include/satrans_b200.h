@@ -40,6 +40,7 @@ extern "C" {
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
 #define SAT_WORK_BUFFERS 20  /* pointer members of SatWork */
+#define SAT_MAX_SHARDS 8     /* processes (GPUs) of one node sharing the row-sharded tables */
 #define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
 #define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
 
@@ -89,12 +90,22 @@ typedef struct SatModel {
     int32_t pad0;
     int64_t n_dense_params; /* floats in the flat dense buffer                              */
     int64_t off_dom, off_lid, off_qkv, off_encw, off_encb, off_layers, off_headw, off_headb;
-    int64_t total_rows;   /* rows of the concatenated embedding table                       */
+    int64_t total_rows;   /* rows of the concatenated embedding table (all shards)          */
     const int64_t* row_off;   /* [F+1] first row of each field's table in `tables`          */
     const int32_t* sparse_cols; /* [F] input-matrix column of each sparse field             */
     const int32_t* dense_cols;  /* [n_dense] input-matrix column of each dense feature      */
-    float* tables;        /* [total_rows][32] all embedding_dict tables back to back        */
+    float* tables;        /* [local_rows][32] this process' rows of the concatenated table  */
     float* dense;         /* flat dense parameter buffer                                    */
+    /* Row sharding across the R processes of one node (R = 1: everything local).  Global row g of the
+     * concatenated table lives on shard g % R at local row g / R.  Every shard_* array holds the R peer-mapped
+     * base pointers (CUDA IPC, NVLink P2P); entry [shard_rank] is this process' own buffer. */
+    int32_t n_shards;     /* R                                                              */
+    int32_t shard_rank;   /* this process                                                   */
+    int64_t local_rows;   /* rows held by this process: ceil((total_rows - shard_rank) / R) */
+    float* shard_tables[SAT_MAX_SHARDS];
+    uint32_t* shard_bitmap[SAT_MAX_SHARDS];     /* SatWork.bitmap of every shard            */
+    int32_t* shard_word_rank[SAT_MAX_SHARDS];   /* SatWork.word_rank of every shard         */
+    float* shard_row_grad[SAT_MAX_SHARDS];      /* SatWork.row_grad of every shard          */
 } SatModel;
 
 /* Per-batch workspace, caller-allocated (sizes from sat_workspace_sizes).  */
@@ -176,8 +187,16 @@ int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, c
 int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
                  float dropout_p, uint64_t seed, void* stream);
 
-/* ---- touched-row bookkeeping: mark + rank the rows this batch reads ------------------------- */
+/* ---- touched-row bookkeeping.  sat_rows_clear zeroes this shard's bitmap; sat_rows_mark sets one bit per
+ *      row the batch reads IN THE OWNING SHARD's bitmap (remote atomics over NVLink when R > 1);
+ *      sat_rows_rank turns this shard's bitmap into ranks + the sorted unique row list.  With R > 1 the caller
+ *      separates the three calls with a cross-process barrier; sat_rows_mark_and_rank does all three (R = 1). */
+int sat_rows_clear(const SatModel* m, SatWork* w, void* stream);
 int sat_rows_mark(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
+int sat_rows_rank(const SatModel* m, SatWork* w, void* stream);
+int sat_rows_mark_and_rank(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent). */
+int sat_enable_peer_access(int32_t peer_device);
 
 /* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
  *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */

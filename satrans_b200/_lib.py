@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 8 + 148 * 4
 SAT_WORK_BUFFERS = 20
+SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
 ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
@@ -29,7 +30,10 @@ class SatModel(C.Structure):
                 ('off_dom', i64), ('off_lid', i64), ('off_qkv', i64), ('off_encw', i64), ('off_encb', i64),
                 ('off_layers', i64), ('off_headw', i64), ('off_headb', i64),
                 ('total_rows', i64),
-                ('row_off', vp), ('sparse_cols', vp), ('dense_cols', vp), ('tables', vp), ('dense', vp)]
+                ('row_off', vp), ('sparse_cols', vp), ('dense_cols', vp), ('tables', vp), ('dense', vp),
+                ('n_shards', i32), ('shard_rank', i32), ('local_rows', i64),
+                ('shard_tables', vp * 8), ('shard_bitmap', vp * 8), ('shard_word_rank', vp * 8),
+                ('shard_row_grad', vp * 8)]
 
 
 WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
@@ -59,7 +63,11 @@ PROTOTYPES = {
     'sat_encoder_bwd': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_forward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, vp]),
     'sat_backward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, vp]),
+    'sat_rows_clear': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_rows_mark': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
+    'sat_rows_rank': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_rows_mark_and_rank': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
+    'sat_enable_peer_access': (C.c_int, [i32]),
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),

@@ -130,7 +130,8 @@ def _acc(y_true, y_score):
 class BaseModel(nn.Module):
     def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5,
                  init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None,
-                 flag=None, domain_column=None, num_domains=None, meta_dnn_hidden_units=(32, 64, 32)):
+                 flag=None, domain_column=None, num_domains=None, meta_dnn_hidden_units=(32, 64, 32),
+                 table_shard=None):
         super().__init__()
         if any(isinstance(f, VarLenSparseFeat) for f in list(linear_feature_columns) + list(dnn_feature_columns)):
             raise NotImplementedError("VarLenSparseFeat is not on the SATrans path (reference main.py:103,146)")
@@ -156,7 +157,11 @@ class BaseModel(nn.Module):
         d = self.embedding_size
         self._sparse_feats = sparse
         self._row_off = np.concatenate([[0], np.cumsum([f.vocabulary_size for f in sparse])]).astype(np.int64)
-        self._tables = torch.empty((int(self._row_off[-1]), d), dtype=torch.float32, device=device)
+        # table_shard = (rank, world): this process holds only rows g with g % world == rank (satrans_b200/dist.py)
+        self._shard = (0, 1) if table_shard is None else (int(table_shard[0]), int(table_shard[1]))
+        total_rows = int(self._row_off[-1])
+        n_local = (total_rows - self._shard[0] + self._shard[1] - 1) // self._shard[1]
+        self._tables = torch.empty((n_local, d), dtype=torch.float32, device=device)
         if not (flag and 'noembinit' in flag):                           # reference meta_basemodel.py:114-119
             self._tables.normal_(mean=0.0, std=init_std)
         else:
@@ -164,7 +169,10 @@ class BaseModel(nn.Module):
         self.embedding_dict = nn.ModuleDict()
         for i, f in enumerate(sparse):
             emb = nn.Embedding(f.vocabulary_size, d, device='meta')
-            emb.weight = nn.Parameter(self._tables[int(self._row_off[i]):int(self._row_off[i + 1])])
+            if self._shard[1] == 1:
+                emb.weight = nn.Parameter(self._tables[int(self._row_off[i]):int(self._row_off[i + 1])])
+            else:       # rows of one field are strided over the ranks: no per-field view exists (see gather_tables)
+                emb.weight = nn.Parameter(torch.empty((0, d), dtype=torch.float32, device=device))
             self.embedding_dict[f.embedding_name] = emb
 
         self.linear_model = Linear(linear_feature_columns, self.feature_index, device=device)
@@ -232,6 +240,32 @@ class BaseModel(nn.Module):
         embs = [E[:, i:i + 1, :] for i in range(E.shape[1])]
         dense_vals = [X[:, self.feature_index[f.name][0]:self.feature_index[f.name][1]] for f in dense]
         return embs, dense_vals
+
+    # ---- row-sharded tables (multi-GPU) ---------------------------------------------------------------
+    def load_full_tables(self, full):
+        """Copy this process' rows out of a full [total_rows, d] table (rows g with g % world == rank)."""
+        rank, world = self._shard
+        with torch.no_grad():
+            self._tables.copy_(torch.as_tensor(full)[rank::world].to(self._tables.device))
+
+    def gather_tables(self, group=None):
+        """Full [total_rows, d] table on every rank (all-gather of the shards) — e.g. to write a reference-
+        compatible checkpoint from a sharded run."""
+        rank, world = self._shard
+        if world == 1:
+            return self._tables.detach().clone()
+        import torch.distributed as tdist
+        total = int(self._row_off[-1])
+        n_max = (total + world - 1) // world
+        pad = torch.zeros((n_max, self._tables.shape[1]), dtype=torch.float32, device=self._tables.device)
+        pad[:self._tables.shape[0]] = self._tables.detach()
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        tdist.all_gather(parts, pad, group=group)
+        full = torch.empty((total, self._tables.shape[1]), dtype=torch.float32, device=self._tables.device)
+        for r in range(world):
+            n_r = (total - r + world - 1) // world
+            full[r::world] = parts[r][:n_r]
+        return full
 
     # ---- engine plumbing ------------------------------------------------------------------------------
     @property

@@ -267,12 +267,21 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
                 const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
                 if (id < 0 || id >= hi - lo) id = 0;
                 const long long row = lo + id;
-                const uint32_t wbits = __ldg(a.bitmap + (row >> 5));
-                const int slot = __ldg(a.word_rank + (row >> 5)) + __popc(wbits & ((1u << (row & 31)) - 1u));
-                float* dst = a.row_grad + (long long)slot * D;
+                const int owner = (int)(row % m.n_shards);
+                const long long lrow = row / m.n_shards;
+                // volatile loads: the owner's bitmap / ranks may live in a peer GPU's memory
+                const uint32_t wbits = *reinterpret_cast<const volatile uint32_t*>(m.shard_bitmap[owner] + (lrow >> 5));
+                const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
+                                 __popc(wbits & ((1u << (lrow & 31)) - 1u));
+                float* dst = m.shard_row_grad[owner] + (long long)slot * D;
+                if (owner == m.shard_rank) {
 #pragma unroll
-                for (int i = 0; i < D; i += 4)
-                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
+                    for (int i = 0; i < D; i += 4)
+                        atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) atomicAdd(dst + i, dxa[i]);       // scalar reductions over NVLink
+                }
             }
         }
     }

@@ -29,13 +29,15 @@ extern "C" int sat_abi_version(void) { return SAT_ABI_VERSION; }
 extern "C" const char* sat_last_error(void) { return sat_host::g_err; }
 
 extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t training, int64_t* sz, int32_t* max_tiles_host) {
-    if (!m || !sz || cap_B <= 0 || m->F <= 0 || m->F > SAT_MAXF)
+    if (!m || !sz || cap_B <= 0 || m->F <= 0 || m->F > SAT_MAXF || m->n_shards < 1 || m->n_shards > SAT_MAX_SHARDS)
         return sat_host::fail(SAT_EINVAL, "sat_workspace_sizes: bad argument");
     const int64_t spt = sat::NT / m->F;
     const int64_t max_tiles = (cap_B + spt - 1) / spt + m->n_dom;
     const int64_t n_keys = (m->flags & SAT_FLAG_POS) ? (int64_t)m->n_dom * m->L * 2 : m->n_dom;
     const int64_t tok = (int64_t)cap_B * m->F;
-    const int64_t words = (m->total_rows + 31) / 32;
+    const int64_t words = (m->local_rows + 31) / 32;
+    int64_t touched_cap = tok * (m->n_shards > 0 ? m->n_shards : 1);      // rows of this shard any process may touch
+    if (touched_cap > m->local_rows) touched_cap = m->local_rows;
     int i = 0;
     sz[i++] = cap_B * 4;                                   // perm
     sz[i++] = cap_B * 4;                                   // dom
@@ -53,8 +55,8 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = training ? words * 4 : 0;                    // bitmap
     sz[i++] = training ? words * 4 : 0;                    // word_rank
     sz[i++] = training ? ((words + 1023) / 1024 + 1) * 4 : 0;   // block_sums
-    sz[i++] = training ? tok * 4 : 0;                      // uniq_rows
-    sz[i++] = training ? tok * SAT_D * 4 : 0;              // row_grad
+    sz[i++] = training ? touched_cap * 4 : 0;              // uniq_rows
+    sz[i++] = training ? touched_cap * SAT_D * 4 : 0;      // row_grad
     sz[i++] = SAT_REG_PARTS * 8;                           // reg_part
     sz[i++] = 8 * 4;                                       // scalars
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;

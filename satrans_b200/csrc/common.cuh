@@ -191,6 +191,13 @@ __device__ __forceinline__ void copy_to_smem(float* __restrict__ dst, const floa
         *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
 }
 
+// address of global table row `row` (row-sharded: shard = row % R, local row = row / R)
+__device__ __forceinline__ const float* table_row(const SatModel& m, long long row) {
+    if (m.n_shards == 1) return m.tables + row * D;
+    const int owner = (int)(row % m.n_shards);
+    return m.shard_tables[owner] + (row / m.n_shards) * D;
+}
+
 // key of the generated-weight table row used by (domain g, layer l, q/k side)
 __device__ __forceinline__ int theta_key(int g, int l, int side, int L, bool pos) {
     return pos ? ((g * L + l) * 2 + side) : g;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
             long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
             const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
             if (id < 0 || id >= hi - lo) { atomicOr(&a.counters[CNT_ERR], 1); id = 0; }
-            load_row(m.tables + (lo + id) * D, x);
+            load_row(table_row(m, lo + id), x);
         }
         if (tid == 0) s_loss = 0.0;
 

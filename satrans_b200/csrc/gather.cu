@@ -15,8 +15,10 @@ constexpr int GATHER_UNROLL = 4;
 
 template <int KIND>
 __global__ void __launch_bounds__(GATHER_THREADS)
-k_gather(const float* __restrict__ tables, const int64_t* __restrict__ row_off, const int32_t* __restrict__ cols,
-         const void* __restrict__ x, int ld, int B, int F, float* __restrict__ out, int32_t* __restrict__ err) {
+k_gather(const SatModel m, const void* __restrict__ x, int ld, int B, float* __restrict__ out, int32_t* __restrict__ err) {
+    const int64_t* __restrict__ row_off = m.row_off;
+    const int32_t* __restrict__ cols = m.sparse_cols;
+    const int F = m.F;
     const int lane8 = threadIdx.x & 7;                       // which float4 of the row
     const long long n_items = (long long)B * F;
     const long long group = ((long long)blockIdx.x * GATHER_THREADS + threadIdx.x) >> 3;   // row slot of this thread
@@ -34,7 +36,7 @@ k_gather(const float* __restrict__ tables, const int64_t* __restrict__ row_off, 
                 long long id = load_id(x, KIND, (long long)b * ld + __ldg(cols + f));
                 const long long lo = __ldg(row_off + f), hi = __ldg(row_off + f + 1);
                 if (id < 0 || id >= hi - lo) { bad = true; id = 0; }
-                src[u] = tables + (lo + id) * D + lane8 * 4;
+                src[u] = table_row(m, lo + id) + lane8 * 4;
             }
         }
         float4 v[GATHER_UNROLL];
@@ -52,8 +54,10 @@ k_gather(const float* __restrict__ tables, const int64_t* __restrict__ row_off, 
 // sweep skip them).
 template <int KIND>
 __global__ void __launch_bounds__(256)
-k_rows_mark(const int64_t* __restrict__ row_off, const int32_t* __restrict__ cols, const void* __restrict__ x, int ld,
-            int B, int F, uint32_t* __restrict__ bitmap) {
+k_rows_mark(const SatModel m, const void* __restrict__ x, int ld, int B) {
+    const int64_t* __restrict__ row_off = m.row_off;
+    const int32_t* __restrict__ cols = m.sparse_cols;
+    const int F = m.F;
     const long long n_items = (long long)B * F;
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n_items;
          it += (long long)gridDim.x * blockDim.x) {
@@ -62,7 +66,8 @@ k_rows_mark(const int64_t* __restrict__ row_off, const int32_t* __restrict__ col
         const long long lo = __ldg(row_off + f), hi = __ldg(row_off + f + 1);
         if (id < 0 || id >= hi - lo) id = 0;
         const long long row = lo + id;
-        atomicOr(bitmap + (row >> 5), 1u << (row & 31));
+        const long long lrow = row / m.n_shards;
+        atomicOr(m.shard_bitmap[(int)(row % m.n_shards)] + (lrow >> 5), 1u << (lrow & 31));
     }
 }
 
@@ -160,16 +165,13 @@ extern "C" int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind,
     cudaStream_t s = (cudaStream_t)stream;
     switch (id_kind) {
         case SAT_IDS_F32:
-            k_gather<SAT_IDS_F32><<<(int)blocks, GATHER_THREADS, 0, s>>>(m->tables, m->row_off, m->sparse_cols, x, ld,
-                                                                        B, m->F, out, err_flag);
+            k_gather<SAT_IDS_F32><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
             break;
         case SAT_IDS_I32:
-            k_gather<SAT_IDS_I32><<<(int)blocks, GATHER_THREADS, 0, s>>>(m->tables, m->row_off, m->sparse_cols, x, ld,
-                                                                        B, m->F, out, err_flag);
+            k_gather<SAT_IDS_I32><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
             break;
         case SAT_IDS_I64:
-            k_gather<SAT_IDS_I64><<<(int)blocks, GATHER_THREADS, 0, s>>>(m->tables, m->row_off, m->sparse_cols, x, ld,
-                                                                        B, m->F, out, err_flag);
+            k_gather<SAT_IDS_I64><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
             break;
         default:
             return sat_host::fail(SAT_EINVAL, "sat_gather_fwd: id_kind %d", id_kind);
@@ -177,34 +179,70 @@ extern "C" int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind,
     return sat_host::check_launch("k_gather");
 }
 
+extern "C" int sat_rows_clear(const SatModel* m, SatWork* w, void* stream) {
+    if (!m || !w || !w->bitmap) return sat_host::fail(SAT_EINVAL, "sat_rows_clear: bad argument");
+    const long long n_words = (m->local_rows + 31) / 32;
+    if (cudaMemsetAsync(w->bitmap, 0, (size_t)n_words * 4, (cudaStream_t)stream) != cudaSuccess)
+        return sat_host::fail(SAT_ECUDA, "sat_rows_clear: memset failed");
+    return SAT_OK;
+}
+
 extern "C" int sat_rows_mark(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
                              void* stream) {
     if (!m || !x || !w || !w->bitmap) return sat_host::fail(SAT_EINVAL, "sat_rows_mark: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
-    const long long n_words = (m->total_rows + 31) / 32;
-    if (cudaMemsetAsync(w->bitmap, 0, (size_t)n_words * 4, s) != cudaSuccess)
-        return sat_host::fail(SAT_ECUDA, "sat_rows_mark: memset failed");
     const long long items = (long long)w->B * m->F;
     if (items > 0) {
         int blocks = (int)((items + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         switch (id_kind) {
             case SAT_IDS_F32:
-                k_rows_mark<SAT_IDS_F32><<<blocks, 256, 0, s>>>(m->row_off, m->sparse_cols, x, ld, w->B, m->F, w->bitmap);
+                k_rows_mark<SAT_IDS_F32><<<blocks, 256, 0, s>>>(*m, x, ld, w->B);
                 break;
             case SAT_IDS_I32:
-                k_rows_mark<SAT_IDS_I32><<<blocks, 256, 0, s>>>(m->row_off, m->sparse_cols, x, ld, w->B, m->F, w->bitmap);
+                k_rows_mark<SAT_IDS_I32><<<blocks, 256, 0, s>>>(*m, x, ld, w->B);
                 break;
             case SAT_IDS_I64:
-                k_rows_mark<SAT_IDS_I64><<<blocks, 256, 0, s>>>(m->row_off, m->sparse_cols, x, ld, w->B, m->F, w->bitmap);
+                k_rows_mark<SAT_IDS_I64><<<blocks, 256, 0, s>>>(*m, x, ld, w->B);
                 break;
             default:
                 return sat_host::fail(SAT_EINVAL, "sat_rows_mark: id_kind %d", id_kind);
         }
     }
+    return sat_host::check_launch("k_rows_mark");
+}
+
+extern "C" int sat_rows_rank(const SatModel* m, SatWork* w, void* stream) {
+    if (!m || !w || !w->bitmap || !w->word_rank || !w->block_sums || !w->uniq_rows)
+        return sat_host::fail(SAT_EINVAL, "sat_rows_rank: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n_words = (m->local_rows + 31) / 32;
     const int nb = (int)((n_words + 1023) / 1024);
     k_rank_blocksum<<<nb, 1024, 0, s>>>(w->bitmap, n_words, w->block_sums);
     k_rank_words<<<nb, 1024, 0, s>>>(w->bitmap, n_words, w->block_sums, w->word_rank, w->uniq_rows, w->counters,
                                      w->scalars);
-    return sat_host::check_launch("k_rows_mark/rank");
+    return sat_host::check_launch("k_rank_words");
+}
+
+extern "C" int sat_rows_mark_and_rank(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
+                                      void* stream) {
+    int rc = sat_rows_clear(m, w, stream);
+    if (rc) return rc;
+    rc = sat_rows_mark(m, x, id_kind, ld, w, stream);
+    if (rc) return rc;
+    return sat_rows_rank(m, w, stream);
+}
+
+extern "C" int sat_enable_peer_access(int32_t peer_device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) return sat_host::fail(SAT_ECUDA, "sat_enable_peer_access: cudaGetDevice failed");
+    if (cur == peer_device) return SAT_OK;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, cur, peer_device);
+    if (!can) return sat_host::fail(SAT_ECUDA, "device %d cannot access peer %d", cur, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return sat_host::fail(SAT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    cudaGetLastError();
+    return SAT_OK;
 }

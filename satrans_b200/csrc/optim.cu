@@ -180,7 +180,7 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
     if (!m || !w || !a || !a->tab_m || !a->tab_v || !w->reg_part) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: null argument");
     if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: step must be >= 1");
     const AdamConst c = make_const(a, true);
-    const long long n_vec = m->total_rows * 8;
+    const long long n_vec = m->local_rows * 8;
     cudaStream_t s = (cudaStream_t)stream;
     if (which & SAT_ADAM_TOUCHED) {
         k_adam_rows<<<ROWS_BLOCKS, ROWS_THREADS, 0, s>>>(
@@ -204,7 +204,7 @@ extern "C" int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(w->reg_part + SWEEP_BLOCKS, 0, ROWS_BLOCKS * sizeof(double), s) != cudaSuccess)
         return sat_host::fail(SAT_ECUDA, "sat_tables_sumsq: memset failed");
-    k_sumsq<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(reinterpret_cast<const float4*>(m->tables), m->total_rows * 8, w->reg_part);
+    k_sumsq<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(reinterpret_cast<const float4*>(m->tables), m->local_rows * 8, w->reg_part);
     return sat_host::check_launch("k_sumsq");
 }
 

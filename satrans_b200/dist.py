@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), `torch.distributed` over NCCL/NVLink.
+
+Partitioning (the reference has no counterpart — its only multi-device hook is the
+single-process nn.DataParallel of meta_basemodel.py:272-275, which replicates the tables):
+
+  * embedding tables: ROW-SHARDED.  Global row g of the concatenated table lives on rank g % R at local row
+    g // R.  Every rank maps every other rank's shard (and its touched-row bitmap / ranks / gradient
+    accumulators) through CUDA IPC, so the fused kernels gather rows and scatter-add row gradients DIRECTLY
+    over NVLink peer memory — no id all-to-all, no row all-to-all, no host-side split sizes.
+  * dense parameters (148,578 fp32 for EN): replicated; their flat gradient buffer is all-reduced (SUM) with
+    one NCCL call per step.  The loss is a SUM over samples (reference meta_basemodel.py:317), so per-rank
+    gradients add without re-weighting and R ranks x B samples == one step on the R*B global batch.
+  * L2 + Adam over untouched rows: local to each shard (no communication).
+
+Cross-rank ordering inside a step uses stream-ordered NCCL all-reduces of one element as barriers
+(no host synchronisation).
+"""
+import torch
+import torch.distributed as dist
+
+
+class DistContext:
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise NotImplementedError("row sharding spans the GPUs of ONE node (<= 8)")
+        self._flag = None
+        self._keep = []            # opened peer storages must stay alive
+
+    # ---- stream-ordered barrier ---------------------------------------------------------------------
+    def barrier(self, device):
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        dist.all_reduce(self._flag, group=self.group)
+
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    # ---- peer mapping of a CUDA tensor ---------------------------------------------------------------
+    def exchange_pointers(self, tensor):
+        """All ranks call this with their own tensor; returns the list of R device pointers (own entry = the
+        local pointer, the others = CUDA-IPC mappings of the peers' tensors)."""
+        from . import _lib
+        if tensor.device.type != 'cuda':
+            # host-side logic test path (gloo): pointers are only meaningful per process
+            objs = [None] * self.world
+            dist.all_gather_object(objs, ('cpu', tensor.data_ptr()), group=self.group)
+            return [tensor.data_ptr() if r == self.rank else 0 for r in range(self.world)]
+        st = tensor.untyped_storage()
+        handle = st._share_cuda_()
+        off = tensor.storage_offset() * tensor.element_size()
+        objs = [None] * self.world
+        dist.all_gather_object(objs, (handle, off), group=self.group)
+        ptrs = []
+        for r, (h, o) in enumerate(objs):
+            if r == self.rank:
+                ptrs.append(tensor.data_ptr())
+                continue
+            _lib.check(_lib.lib().sat_enable_peer_access(int(h[0])), 'sat_enable_peer_access')
+            peer = torch.UntypedStorage._new_shared_cuda(*h)
+            self._keep.append(peer)
+            ptrs.append(peer.data_ptr() + o)
+        return ptrs
+
+
+def local_rows(total_rows, rank, world):
+    """Rows of the concatenated table held by `rank` under row % world sharding."""
+    return (total_rows - rank + world - 1) // world
+
+
+def shard_of(row, world):
+    return row % world, row // world

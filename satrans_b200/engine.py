@@ -76,6 +76,45 @@ class Engine:
         self.step_count = 0
         self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
         self.timing = None         # set to {} to collect CUDA-event pairs per phase: {name: [(start, end), ...]}
+        self.dist = None           # satrans_b200.dist.DistContext when the tables are row-sharded over ranks
+        self._peer_tables = None
+
+    def attach_dist(self, ctx):
+        """Row-sharded multi-GPU mode (collective: every rank calls it).  The model must have been built with
+        table_shard=(ctx.rank, ctx.world)."""
+        if tuple(self.model._shard) != (ctx.rank, ctx.world):
+            raise ValueError('model.table_shard %s does not match the process group (%d, %d)'
+                             % (self.model._shard, ctx.rank, ctx.world))
+        self.dist = ctx
+        if ctx.world > 1:           # replicated dense parameters start identical on every rank
+            import torch.distributed as tdist
+            self.model._ensure_flat()
+            tdist.broadcast(self.model._dense, src=0, group=ctx.group)
+        self._bound_ptrs = None
+        self.bind()
+
+    def prepare_training(self, cap_B):
+        """Allocate the training workspace for batches of up to cap_B samples per rank and (sharded mode) map
+        the peers' touched-row buffers.  Collective in sharded mode."""
+        self.bind()
+        w = self._work.get(True)
+        if w is None or w.cap_B < cap_B:
+            w = Workspace(self, int(cap_B), True)
+            self._work[True] = w
+            self._wire_shards(w)
+        return w
+
+    def _wire_shards(self, w):
+        d = self.desc
+        r = d.shard_rank
+        if self.dist is None or self.dist.world == 1:
+            d.shard_bitmap[r] = w['bitmap'].data_ptr()
+            d.shard_word_rank[r] = w['word_rank'].data_ptr()
+            d.shard_row_grad[r] = w['row_grad'].data_ptr()
+            return
+        for name, field in (('bitmap', d.shard_bitmap), ('word_rank', d.shard_word_rank), ('row_grad', d.shard_row_grad)):
+            for k, ptr in enumerate(self.dist.exchange_pointers(w[name])):
+                field[k] = ptr
 
     def _tic(self, name, stream=None):
         if self.timing is None:
@@ -125,6 +164,22 @@ class Engine:
         d.row_off, d.sparse_cols = self._row_off.data_ptr(), self._sparse_cols.data_ptr()
         d.dense_cols = self._dense_cols.data_ptr()
         d.tables, d.dense = ptrs
+        rank, world = m._shard
+        d.n_shards, d.shard_rank = world, rank
+        d.local_rows = m._tables.shape[0]
+        for k in range(_lib.SAT_MAX_SHARDS):
+            d.shard_tables[k] = None
+            d.shard_bitmap[k] = None
+            d.shard_word_rank[k] = None
+            d.shard_row_grad[k] = None
+        if world == 1:
+            d.shard_tables[0] = ptrs[0]
+        else:
+            if self.dist is None:
+                raise _lib.SatError('model built with table_shard=%s: call engine.attach_dist(DistContext()) first'
+                                    % (m._shard,))
+            for k, ptr in enumerate(self.dist.exchange_pointers(m._tables)):
+                d.shard_tables[k] = ptr
         self._bound_ptrs = ptrs
         self._work = {}
         self._adam = None
@@ -133,9 +188,14 @@ class Engine:
         key = bool(training)
         w = self._work.get(key)
         if w is None or w.cap_B < B:
+            if training and self.dist is not None and self.dist.world > 1:
+                raise _lib.SatError('sharded mode: call engine.prepare_training(cap_B) (collective) before stepping '
+                                    'with a batch of %d samples' % B)
             cap = max(int(B), w.cap_B if w else 0)
             w = Workspace(self, cap, training)
             self._work[key] = w
+            if training:
+                self._wire_shards(w)
         w.c.B = int(B)
         return w
 
@@ -169,6 +229,19 @@ class Engine:
         check(l.sat_bucket_by_domain(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), 0, s),
               'sat_bucket_by_domain')
         check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
+
+    def _mark_rows(self, X, w, kind):
+        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomics) | barrier | rank | barrier."""
+        l, s, d = lib(), self._stream(), C.byref(self.desc)
+        if self.dist is None or self.dist.world == 1:
+            check(l.sat_rows_mark_and_rank(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark_and_rank')
+            return
+        check(l.sat_rows_clear(d, C.byref(w.c), s), 'sat_rows_clear')
+        self.dist.barrier(self.device)
+        check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        self.dist.barrier(self.device)
+        check(l.sat_rows_rank(d, C.byref(w.c), s), 'sat_rows_rank')
+        self.dist.barrier(self.device)
 
     def forward(self, X, y=None, training=False, dropout_p=0.1, seed=0):
         """y_pred (B,) in sample order.  With y: also leaves BCE partials / dLogit in the workspace."""
@@ -206,19 +279,25 @@ class Engine:
         w = self.workspace(B, True)
         l, s, d = lib(), self._stream(), C.byref(self.desc)
         self._prepare(X, w, kind)
-        check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        self._mark_rows(X, w, kind)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
         w['row_grad'].zero_()
+        if self.dist is not None and self.dist.world > 1:
+            self.dist.barrier(self.device)
         check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
                             1, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s),
               'sat_forward')
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c),
                              float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s), 'sat_backward')
         self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2)
+        if self.dist is not None and self.dist.world > 1:
+            self.dist.all_reduce_sum(w['dgrad'])            # also orders the peers' row-gradient atomics
         if with_reg:
             check(l.sat_tables_sumsq(d, C.byref(w.c), s), 'sat_tables_sumsq')
             self.launches += 1
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        if self.dist is not None and self.dist.world > 1:
+            self.dist.all_reduce_sum(w['scalars'][0:2])
         self.launches += 1
         return y_pred, w
 
@@ -259,7 +338,7 @@ class Engine:
         p = float(dropout_p if training else 0.0)
         t = self._tic('prepare')
         self._prepare(X, w, kind)
-        check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
+        self._mark_rows(X, w, kind)
         self._toc(t)
         sweep_on_side = bool(dense_mode and overlap)
         if sweep_on_side:
@@ -278,6 +357,10 @@ class Engine:
         t = self._tic('backward')
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
         self._toc(t)
+        if self.dist is not None and self.dist.world > 1:
+            t = self._tic('allreduce')
+            self.dist.all_reduce_sum(w['dgrad'])            # dense grads; also orders the peers' row-gradient atomics
+            self._toc(t)
         t = self._tic('adam_rows')
         check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, s), 'sat_tables_adam')
         self._toc(t)
@@ -291,6 +374,8 @@ class Engine:
         if sweep_on_side:
             main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        if self.dist is not None and self.dist.world > 1:
+            self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
         # own kernels per step: bucket 1, encoder 1, mark+rank 3, forward 1, head bwd 1, 2 per layer, encoder bwd 2,
         # adam rows 1, sweep 0/1, dense adam 1, finalize 1
         self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2) + 1 + (1 if dense_mode else 0) + 1 + 1

@@ -82,10 +82,10 @@ class SATrans(BaseModel):
                  meta_dnn_hidden_units=(64, 32),
                  meta_mode='Q',
                  l2_reg_dnn=0, l2_reg_embedding=1e-5, dnn_use_bn=False, dnn_dropout=0, init_std=0.0001, seed=1024,
-                 task='binary', device='cpu', gpus=None, flag=None):
+                 task='binary', device='cpu', gpus=None, flag=None, table_shard=None):
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=0,
                          l2_reg_embedding=l2_reg_embedding, init_std=init_std, seed=seed, task=task,
-                         device=device, gpus=gpus)
+                         device=device, gpus=gpus, table_shard=table_shard)
         if not isinstance(flag, str):
             raise TypeError("flag must be a str (the reference substring-tests it: satrans.py:46,158-173)")
         for unsupported in ('gate', 'bilinear', 'onlyemb'):
@@ -198,10 +198,12 @@ class SATrans(BaseModel):
         (after construction, `.to()`, `.cuda()` ...).  Values are preserved."""
         dev = self.dnn_linear.weight.device
         slots = self._flat_slots()
+        sharded = self._shard[1] > 1
         ok = (self._dense.device == dev and self._tables.device == dev and
               all(p.data_ptr() == self._dense.data_ptr() + 4 * off for p, off in slots) and
-              all(self.embedding_dict[f.embedding_name].weight.data_ptr() == self._tables.data_ptr() + 4 * _lib.SAT_D * int(r)
-                  for f, r in zip(self._sparse_feats, self._row_off[:-1])))
+              (sharded or
+               all(self.embedding_dict[f.embedding_name].weight.data_ptr() == self._tables.data_ptr() + 4 * _lib.SAT_D * int(r)
+                   for f, r in zip(self._sparse_feats, self._row_off[:-1]))))
         if ok:
             return
         flat = torch.zeros(self._layout['n_dense_params'], dtype=torch.float32, device=dev)
@@ -211,7 +213,9 @@ class SATrans(BaseModel):
                 view.copy_(p.data.to(dev, torch.float32))
                 p.data = view
             first = self.embedding_dict[self._sparse_feats[0].embedding_name].weight
-            if first.data_ptr() != self._tables.data_ptr() or self._tables.device != dev:
+            if sharded:
+                self._tables = self._tables.to(dev)
+            elif first.data_ptr() != self._tables.data_ptr() or self._tables.device != dev:
                 tables = torch.empty((int(self._row_off[-1]), _lib.SAT_D), dtype=torch.float32, device=dev)
                 for f, a, b in zip(self._sparse_feats, self._row_off[:-1], self._row_off[1:]):
                     w = self.embedding_dict[f.embedding_name].weight

@@ -35,7 +35,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(l, name), name
     assert l.sat_abi_version() == 1
     # struct mirrors: sizes implied by the header layout
-    assert ctypes.sizeof(_lib.SatModel) == 10 * 4 + 10 * 8 + 5 * 8
+    assert ctypes.sizeof(_lib.SatModel) == 10 * 4 + 10 * 8 + 5 * 8 + 8 + 8 + 4 * 8 * 8
     assert ctypes.sizeof(_lib.SatWork) == 8 + _lib.SAT_WORK_BUFFERS * 8
     assert ctypes.sizeof(_lib.SatAdam) == 32 + 4 * 8
 
@@ -46,6 +46,7 @@ def test_workspace_sizes_host_only():
     l = _lib.lib()
     d = _lib.SatModel()
     d.F, d.L, d.H, d.n_dom, d.total_rows, d.n_dense_params, d.flags = 19, 3, 4, 4, 6571961, 148580, 0
+    d.n_shards, d.shard_rank, d.local_rows = 1, 0, 6571961
     sizes = (ctypes.c_int64 * _lib.SAT_WORK_BUFFERS)()
     mt = ctypes.c_int32()
     assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 1, sizes, ctypes.byref(mt)) == 0
