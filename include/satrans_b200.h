@@ -197,6 +197,12 @@ int sat_rows_rank(const SatModel* m, SatWork* w, void* stream);
 int sat_rows_mark_and_rank(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent). */
 int sat_enable_peer_access(int32_t peer_device);
+/* Map a peer process' allocation (64-byte cudaIpcMemHandle_t, host memory) into the CURRENT device's address
+ * space with peer access over NVLink; *out_ptr_host receives the base pointer of the exporter's allocation. */
+int sat_ipc_open(const void* handle64_host, void** out_ptr_host);
+int sat_ipc_close(void* ptr);
+/* debugging aid: one thread touches *p (mode 0 store, 1 atomicOr, 2 atomicAdd f32, 3 atomicAdd float4, 4 load -> *out). */
+int sat_debug_poke(void* p, int32_t mode, float* out, void* stream);
 
 /* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
  *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */

@@ -68,6 +68,9 @@ PROTOTYPES = {
     'sat_rows_rank': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_rows_mark_and_rank': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
     'sat_enable_peer_access': (C.c_int, [i32]),
+    'sat_debug_poke': (C.c_int, [vp, i32, vp, vp]),
+    'sat_ipc_open': (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    'sat_ipc_close': (C.c_int, [vp]),
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
@@ -111,6 +114,15 @@ def lib():
     return _lib
 
 
+_DEBUG_SYNC = bool(os.environ.get('SAT_DEBUG_SYNC'))
+
+
 def check(rc, what=''):
     if rc != 0:
         raise SatError('%s failed (%d): %s' % (what, rc, lib().sat_last_error().decode()))
+    if _DEBUG_SYNC:          # debugging aid: surface asynchronous kernel faults at the call that caused them
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise SatError('%s: asynchronous CUDA failure: %s' % (what, e))

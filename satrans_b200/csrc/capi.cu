@@ -93,3 +93,36 @@ extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, in
         default: return sat_host::fail(SAT_EINVAL, "sat_forward: heads=%d not in {1,2,4,8}", m->H);
     }
 }
+
+// ---- debugging aid: touch one word of (possibly peer-mapped) memory in a given way -----------------------
+__global__ void k_debug_poke(void* p, int mode, float* out) {
+    if (mode == 0) *reinterpret_cast<volatile uint32_t*>(p) = 0x12345678u;
+    else if (mode == 1) atomicOr(reinterpret_cast<uint32_t*>(p), 0xF0u);
+    else if (mode == 2) atomicAdd(reinterpret_cast<float*>(p), 1.0f);
+    else if (mode == 3) atomicAdd(reinterpret_cast<float4*>(p), make_float4(1.f, 2.f, 3.f, 4.f));
+    else if (mode == 4) *out = *reinterpret_cast<volatile float*>(p);
+}
+extern "C" int sat_debug_poke(void* p, int32_t mode, float* out, void* stream) {
+    k_debug_poke<<<1, 1, 0, (cudaStream_t)stream>>>(p, mode, out);
+    return sat_host::check_launch("k_debug_poke");
+}
+
+// ---- CUDA IPC: map a peer process' allocation into THIS device's address space (NVLink P2P) ---------------
+extern "C" int sat_ipc_open(const void* handle64_host, void** out_ptr_host) {
+    if (!handle64_host || !out_ptr_host) return sat_host::fail(SAT_EINVAL, "sat_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sat_host::fail(SAT_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    *out_ptr_host = p;
+    return SAT_OK;
+}
+extern "C" int sat_ipc_close(void* ptr) {
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return sat_host::fail(SAT_ECUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e)); }
+    return SAT_OK;
+}

@@ -29,7 +29,8 @@ class DistContext:
         if self.world > 8:
             raise NotImplementedError("row sharding spans the GPUs of ONE node (<= 8)")
         self._flag = None
-        self._keep = []            # opened peer storages must stay alive
+        self._keep = []            # exported storages must stay alive
+        self._opened = {}          # (rank, ipc handle) -> base pointer mapped into this device's address space
 
     # ---- stream-ordered barrier ---------------------------------------------------------------------
     def barrier(self, device):
@@ -50,20 +51,36 @@ class DistContext:
             objs = [None] * self.world
             dist.all_gather_object(objs, ('cpu', tensor.data_ptr()), group=self.group)
             return [tensor.data_ptr() if r == self.rank else 0 for r in range(self.world)]
+        import ctypes
         st = tensor.untyped_storage()
-        handle = st._share_cuda_()
-        off = tensor.storage_offset() * tensor.element_size()
+        # (device, cudaIpcMemHandle bytes, storage bytes, offset of the storage inside the exporter's allocation, ...)
+        share = st._share_cuda_()
+        self._keep.append(st)
+        off = int(share[3]) + tensor.storage_offset() * tensor.element_size()
+        handle = bytes(share[1])
+        # newer torch prefixes [version byte][type byte] (type 'c' = plain cudaMalloc block, 'e' = expandable segment)
+        if len(handle) == 66 and handle[1:2] == b'c':
+            handle = handle[2:]
+        elif len(handle) == 65 and handle[:1] == b'c':
+            handle = handle[1:]
+        if len(handle) != 64:
+            raise RuntimeError('unsupported CUDA IPC handle (%d bytes, type %r): disable expandable_segments'
+                               % (len(handle), handle[:2]))
         objs = [None] * self.world
-        dist.all_gather_object(objs, (handle, off), group=self.group)
+        dist.all_gather_object(objs, (int(share[0]), handle, off), group=self.group)
         ptrs = []
-        for r, (h, o) in enumerate(objs):
+        for r, (peer_dev, handle, o) in enumerate(objs):
             if r == self.rank:
                 ptrs.append(tensor.data_ptr())
                 continue
-            _lib.check(_lib.lib().sat_enable_peer_access(int(h[0])), 'sat_enable_peer_access')
-            peer = torch.UntypedStorage._new_shared_cuda(*h)
-            self._keep.append(peer)
-            ptrs.append(peer.data_ptr() + o)
+            base = self._opened.get((r, handle))
+            if base is None:       # one cudaIpcOpenMemHandle per exporter allocation, with THIS device current
+                _lib.check(_lib.lib().sat_enable_peer_access(peer_dev), 'sat_enable_peer_access')
+                out = ctypes.c_void_p()
+                _lib.check(_lib.lib().sat_ipc_open(handle, ctypes.byref(out)), 'sat_ipc_open')
+                base = out.value
+                self._opened[(r, handle)] = base
+            ptrs.append(base + o)
         return ptrs
 
 

@@ -282,6 +282,7 @@ class Engine:
         self._mark_rows(X, w, kind)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
         w['row_grad'].zero_()
+        self._row_grad_dirty = True          # left populated for the caller; train_step clears it before reuse
         if self.dist is not None and self.dist.world > 1:
             self.dist.barrier(self.device)
         check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
@@ -337,6 +338,9 @@ class Engine:
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
         t = self._tic('prepare')
+        if getattr(self, '_row_grad_dirty', False):
+            w['row_grad'].zero_()
+            self._row_grad_dirty = False
         self._prepare(X, w, kind)
         self._mark_rows(X, w, kind)
         self._toc(t)
