@@ -41,7 +41,7 @@ def parse():
     ap.add_argument('--vocab-scale', type=float, default=1.0)
     ap.add_argument('--ids', default='uniform', choices=['uniform', 'zipf'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-overlap', action='store_true', help='run the dense optimiser sweep on the main stream')
+    ap.add_argument('--overlap', action='store_true', help='run the dense optimiser sweep on a second stream, concurrent with forward/backward (default: on the main stream)')
     ap.add_argument('--lazy', action='store_true', help='touched-rows-only table updates (NOT reference semantics)')
     ap.add_argument('--cpu-budget-s', type=float, default=25.0)
     return ap.parse_args()
@@ -212,7 +212,7 @@ def run_b200(args):
     hp = model._opt_hparams
     model.train()
 
-    def step(i, overlap=not args.no_overlap):
+    def step(i, overlap=args.overlap):
         k = i % n_batches
         return eng.train_step(Xd[k * B:(k + 1) * B], yd[k * B:(k + 1) * B], lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
                               l2_emb=1e-5, dense_mode=not args.lazy, training=True, dropout_p=0.1, seed=1021 + i,
@@ -285,7 +285,7 @@ def run_b200(args):
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": phases['adam_sweep'],
                 "note": "6 x 128 B per untouched table row; timed with CUDA events on its own stream while "
-                        "forward/backward run concurrently on the main stream" if not args.no_overlap else
+                        "forward/backward run concurrently on the main stream" if args.overlap else
                         "6 x 128 B per untouched table row; timed alone on the main stream"}
 
     # ---- extra: stand-alone gather GB/s and eval-mode scoring ----------------------------------------------

@@ -39,7 +39,7 @@ extern "C" {
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
-#define SAT_WORK_BUFFERS 20  /* pointer members of SatWork */
+#define SAT_WORK_BUFFERS 22  /* pointer members of SatWork */
 #define SAT_MAX_SHARDS 8     /* processes (GPUs) of one node sharing the row-sharded tables */
 #define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
 #define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
@@ -115,7 +115,7 @@ typedef struct SatWork {
     int32_t* perm;        /* [cap_B] sorted position -> sample index (bucketed by scenario) */
     int32_t* dom;         /* [cap_B] scenario id per sorted position                        */
     int32_t* tiles;       /* [max_tiles][4] (key/domain, start, count, pad)                 */
-    int32_t* counters;    /* [64] ints: [0]=n_tiles [1]=error flags [2..] group histogram   */
+    int32_t* counters;    /* [64] ints: [0]=n_tiles [1]=error flags [2]=n_unique [3]=n_tiles2 [8..] histogram */
     float* theta;         /* [n_keys][4096] generated MetaNet weights per key               */
     float* dtheta;        /* [n_keys][4096] their gradient                                  */
     float* enc_du;        /* [n_keys][64] gradient w.r.t. the encoder inputs                */
@@ -133,6 +133,8 @@ typedef struct SatWork {
     float* row_grad;      /* [cap_B*F][32] accumulated dE per unique touched row            */
     double* reg_part;     /* [SAT_REG_PARTS] partial sums of squares of the tables          */
     float* scalars;       /* [8] device results: [0]=bce sum [1]=reg loss [2]=n_unique rows [3]=error flags */
+    float* wpack;         /* [(L + n_keys)][8192] weights packed as tcgen05 B operands (hi | lo)         */
+    int32_t* tiles2;      /* tile list of the tensor-core forward (128 tokens per tile)                  */
 } SatWork;
 
 typedef struct SatAdam {
@@ -215,8 +217,16 @@ int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, int32_t whi
 int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
 /* sum of squares of all table rows into w->reg_part (regulariser without an optimiser step). */
 int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream);
-/* w->scalars[0] = BCE(sum) of the batch, [1] = l2_emb * sum(table^2), [3] = error flags. */
-int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, void* stream);
+/* w->scalars[0] = BCE(sum) of the batch, [1] = l2_emb * sum(table^2), [3] = error flags.
+ * tile_set: 0 if the last forward was sat_forward, 1 if it was sat_forward_tc. */
+int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, int32_t tile_set, void* stream);
+
+/* ---- tensor-core forward (tcgen05 / TMEM): same contract as sat_forward.  sat_pack_weights (after
+ *      sat_encoder_fwd) packs the layer weights and the generated MetaNet weights as UMMA B operands;
+ *      passes = 3: error-compensated 3xTF32 (fp32-level parity), passes = 1: plain TF32. -------------------- */
+int sat_pack_weights(const SatModel* m, SatWork* w, void* stream);
+int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
+                   float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream);
 
 #ifdef __cplusplus
 }

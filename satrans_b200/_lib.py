@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 8 + 148 * 4
-SAT_WORK_BUFFERS = 20
+SAT_WORK_BUFFERS = 22
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
@@ -38,7 +38,7 @@ class SatModel(C.Structure):
 
 WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
                 'loss_part', 'dgrad', 'bitmap', 'word_rank', 'block_sums', 'uniq_rows', 'row_grad', 'reg_part',
-                'scalars']
+                'scalars', 'wpack', 'tiles2']
 assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
 
 
@@ -74,7 +74,9 @@ PROTOTYPES = {
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
-    'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, vp]),
+    'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, i32, vp]),
+    'sat_pack_weights': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_forward_tc': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, i32, vp]),
 }
 
 _lib = None

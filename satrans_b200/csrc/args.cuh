@@ -11,6 +11,7 @@ struct FwdArgs {
     const float* y;            // labels in original sample order, or NULL
     const int32_t* perm;
     const int32_t* tiles;
+    const int32_t* ntiles_ptr; // number of tiles in `tiles`
     int32_t* counters;
     const float* theta;
     float* acts;               // [L][5][act_stride] + [act_stride]
@@ -52,9 +53,11 @@ struct BwdArgs {
 // one translation unit per head count H (compiled with -DSAT_INST_H=H); defined in forward.cu / backward_attn.cu
 #define SAT_DECL_H(H)                                                                          \
     int sat_launch_forward_h##H(const sat::FwdArgs& a, int grid, int training, cudaStream_t s); \
+    int sat_launch_forward_tc_h##H(const sat::FwdArgs& a, const float* wpack, int grid, int training, int passes, cudaStream_t s); \
     int sat_launch_bwd_attn_h##H(const sat::BwdArgs& a, int grid, cudaStream_t s);
 SAT_DECL_H(1)
 SAT_DECL_H(2)
 SAT_DECL_H(4)
 SAT_DECL_H(8)
 #undef SAT_DECL_H
+int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, cudaStream_t s);

@@ -17,10 +17,12 @@ namespace sat {
 template <int KIND>
 __global__ void __launch_bounds__(1024)
 k_bucket(const void* __restrict__ x, int ld, int dom_col, int B, int n_dom, int spt, int32_t* __restrict__ perm,
-         int32_t* __restrict__ dom, int32_t* __restrict__ tiles, int32_t* __restrict__ counters) {
+         int32_t* __restrict__ dom, int32_t* __restrict__ tiles, int32_t* __restrict__ counters, int spt2,
+         int32_t* __restrict__ tiles2) {
     __shared__ int s_hist[MAX_KEYS_HIST];
     __shared__ int s_base[MAX_KEYS_HIST];
     __shared__ int s_tile_base[MAX_KEYS_HIST + 1];
+    __shared__ int s_tile_base2[MAX_KEYS_HIST + 1];
     __shared__ int s_cnt[32][MAX_KEYS_HIST];
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -34,16 +36,20 @@ k_bucket(const void* __restrict__ x, int ld, int dom_col, int B, int n_dom, int 
     }
     __syncthreads();
     if (tid == 0) {
-        int acc = 0, tacc = 0;
+        int acc = 0, tacc = 0, tacc2 = 0;
         for (int k = 0; k < n_dom; ++k) {
             s_base[k] = acc;
             s_tile_base[k] = tacc;
+            s_tile_base2[k] = tacc2;
             acc += s_hist[k];
             tacc += (s_hist[k] + spt - 1) / spt;
+            tacc2 += (s_hist[k] + spt2 - 1) / spt2;
             counters[CNT_HIST + k] = s_hist[k];
         }
         s_tile_base[n_dom] = tacc;
+        s_tile_base2[n_dom] = tacc2;
         counters[CNT_NTILES] = tacc;
+        counters[CNT_NTILES2] = tiles2 ? tacc2 : 0;
         if (s_bad) atomicOr(&counters[CNT_ERR], 2);
     }
     __syncthreads();
@@ -55,6 +61,15 @@ k_bucket(const void* __restrict__ x, int ld, int dom_col, int B, int n_dom, int 
             const int start = s_base[k] + t * spt;
             const int cnt = min(spt, s_base[k] + s_hist[k] - start);
             e[0] = k; e[1] = start; e[2] = cnt; e[3] = 0;
+        }
+        if (tiles2) {
+            const int nt2 = s_tile_base2[k + 1] - s_tile_base2[k];
+            for (int t = tid; t < nt2; t += 1024) {
+                int32_t* e = tiles2 + 4 * (s_tile_base2[k] + t);
+                const int start = s_base[k] + t * spt2;
+                const int cnt = min(spt2, s_base[k] + s_hist[k] - start);
+                e[0] = k; e[1] = start; e[2] = cnt; e[3] = 0;
+            }
         }
     }
     // stable placement, 1024 samples at a time
@@ -224,13 +239,13 @@ extern "C" int sat_bucket_by_domain(const SatModel* m, const void* x, int32_t id
     cudaStream_t s = (cudaStream_t)stream;
     switch (id_kind) {
         case SAT_IDS_F32:
-            k_bucket<SAT_IDS_F32><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters);
+            k_bucket<SAT_IDS_F32><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters, NT2 / m->F, w->tiles2);
             break;
         case SAT_IDS_I32:
-            k_bucket<SAT_IDS_I32><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters);
+            k_bucket<SAT_IDS_I32><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters, NT2 / m->F, w->tiles2);
             break;
         case SAT_IDS_I64:
-            k_bucket<SAT_IDS_I64><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters);
+            k_bucket<SAT_IDS_I64><<<1, 1024, 0, s>>>(x, ld, m->dom_col, w->B, m->n_dom, samples_per_tile, w->perm, w->dom, w->tiles, w->counters, NT2 / m->F, w->tiles2);
             break;
         default:
             return sat_host::fail(SAT_EINVAL, "sat_bucket_by_domain: id_kind %d", id_kind);

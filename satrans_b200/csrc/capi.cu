@@ -33,6 +33,8 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
         return sat_host::fail(SAT_EINVAL, "sat_workspace_sizes: bad argument");
     const int64_t spt = sat::NT / m->F;
     const int64_t max_tiles = (cap_B + spt - 1) / spt + m->n_dom;
+    const int64_t spt2 = sat::NT2 / m->F;
+    const int64_t max_tiles2 = (cap_B + spt2 - 1) / spt2 + m->n_dom;
     const int64_t n_keys = (m->flags & SAT_FLAG_POS) ? (int64_t)m->n_dom * m->L * 2 : m->n_dom;
     const int64_t tok = (int64_t)cap_B * m->F;
     const int64_t words = (m->local_rows + 31) / 32;
@@ -50,7 +52,7 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = cap_B * 4;                                   // dz
     sz[i++] = training ? tok * SAT_D * 4 : 0;              // dx
     sz[i++] = training ? 3 * tok * SAT_D * 4 : 0;          // dqkv
-    sz[i++] = max_tiles * 8;                               // loss_part
+    sz[i++] = max_tiles2 * 8;                              // loss_part (sized for the finer tiling)
     sz[i++] = training ? m->n_dense_params * 4 : 0;        // dgrad
     sz[i++] = training ? words * 4 : 0;                    // bitmap
     sz[i++] = training ? words * 4 : 0;                    // word_rank
@@ -59,6 +61,8 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = training ? touched_cap * SAT_D * 4 : 0;      // row_grad
     sz[i++] = SAT_REG_PARTS * 8;                           // reg_part
     sz[i++] = 8 * 4;                                       // scalars
+    sz[i++] = ((int64_t)m->L + n_keys) * 8192 * 4;         // wpack (tensor-core B operands)
+    sz[i++] = max_tiles2 * 16;                             // tiles2
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
     return SAT_OK;
 }
@@ -78,6 +82,7 @@ extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, in
     if (w->B > w->cap_B) return sat_host::fail(SAT_EINVAL, "sat_forward: B=%d > workspace capacity %d", w->B, w->cap_B);
     FwdArgs a;
     a.m = *m; a.x = x; a.id_kind = id_kind; a.ld = ld; a.y = y; a.perm = w->perm; a.tiles = w->tiles;
+    a.ntiles_ptr = w->counters + CNT_NTILES;
     a.counters = w->counters; a.theta = w->theta; a.acts = w->acts;
     a.act_stride = (long long)w->cap_B * m->F * D;
     a.dz = w->dz; a.loss_part = w->loss_part; a.y_pred = y_pred; a.p_drop = dropout_p; a.seed = seed;
@@ -125,4 +130,40 @@ extern "C" int sat_ipc_close(void* ptr) {
     const cudaError_t e = cudaIpcCloseMemHandle(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return sat_host::fail(SAT_ECUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e)); }
     return SAT_OK;
+}
+
+// ---- tensor-core forward: pack the B operands, then the tcgen05 kernel ---------------------------------------
+extern "C" int sat_pack_weights(const SatModel* m, SatWork* w, void* stream) {
+    if (!m || !w || !w->theta || !w->wpack) return sat_host::fail(SAT_EINVAL, "sat_pack_weights: null argument");
+    const int n_keys = (m->flags & SAT_FLAG_POS) ? m->n_dom * m->L * 2 : m->n_dom;
+    return sat_launch_pack_weights(m, n_keys, w->theta, w->wpack, (cudaStream_t)stream);
+}
+
+extern "C" int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
+                              float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream) {
+    using namespace sat;
+    if (!m || !x || !w || !y_pred || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: null argument");
+    if (m->F <= 0 || m->F > SAT_MAXF) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: F=%d not in 1..%d", m->F, SAT_MAXF);
+    if (m->n_dense > 64) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: n_dense=%d > 64", m->n_dense);
+    if (training && !w->acts) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: training needs w->acts");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: dropout_p=%f", dropout_p);
+    if (w->B == 0) return SAT_OK;
+    if (w->B > w->cap_B) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: B=%d > workspace capacity %d", w->B, w->cap_B);
+    FwdArgs a;
+    a.m = *m; a.x = x; a.id_kind = id_kind; a.ld = ld; a.y = y; a.perm = w->perm; a.tiles = w->tiles2;
+    a.ntiles_ptr = w->counters + CNT_NTILES2;
+    a.counters = w->counters; a.theta = w->theta; a.acts = w->acts;
+    a.act_stride = (long long)w->cap_B * m->F * D;
+    a.dz = w->dz; a.loss_part = w->loss_part; a.y_pred = y_pred; a.p_drop = dropout_p; a.seed = seed;
+    const int spt = 128 / m->F;
+    const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
+    const int grid = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (m->H) {
+        case 1: return sat_launch_forward_tc_h1(a, w->wpack, grid, training, passes, s);
+        case 2: return sat_launch_forward_tc_h2(a, w->wpack, grid, training, passes, s);
+        case 4: return sat_launch_forward_tc_h4(a, w->wpack, grid, training, passes, s);
+        case 8: return sat_launch_forward_tc_h8(a, w->wpack, grid, training, passes, s);
+        default: return sat_host::fail(SAT_EINVAL, "sat_forward_tc: heads=%d not in {1,2,4,8}", m->H);
+    }
 }

@@ -19,7 +19,8 @@ constexpr int OFF_LN_G = 4096, OFF_LN_B = 4128, OFF_QLN_G = 4160, OFF_QLN_B = 41
 constexpr float LN_EPS = 1e-6f;   // nn.LayerNorm(d, eps=1e-6): reference satrans.py:40, submodules.py:75
 
 // counters[] slots of SatWork
-constexpr int CNT_NTILES = 0, CNT_ERR = 1, CNT_NUNIQ = 2, CNT_HIST = 8;
+constexpr int CNT_NTILES = 0, CNT_ERR = 1, CNT_NUNIQ = 2, CNT_NTILES2 = 3, CNT_HIST = 8;
+constexpr int NT2 = 128;          // threads per CTA of the tensor-core forward (= TMEM lanes)
 constexpr int MAX_KEYS_HIST = 48;  // scenario ids supported by the single-block bucketing kernel
 
 // dropout sites inside one Meta_Transformer_Layer (reference submodules.py:99, satrans.py:87,92-94)

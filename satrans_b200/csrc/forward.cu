@@ -11,7 +11,7 @@
 // [token][36] shared tiles.  LayerNorm / softmax are thread-local register reductions.
 // Nothing of shape (B,4096), (H,B,F,F) or (B,F,32)-per-op is ever materialised in HBM (inference), and
 // training saves only what the backward kernels re-use (x, pre-LN q/k, v, attention output).
-#include "args.cuh"
+#include "fwd_common.cuh"
 
 namespace sat {
 
@@ -37,65 +37,6 @@ __device__ __forceinline__ void metanet_fwd(float (&q)[D], const float* __restri
     for (int i = 0; i < D; ++i) z[i] = fmaf(mo[i], drop_factor(dc, i), q[i]);
 }
 
-// Multi-head attention of one query token against the F tokens of its sample (reference satrans.py:75-90).
-// K'/V rows of the sample start at row `sbase` of the [token][36] tiles.
-// Rolled over heads: q is rotated by DH per head so that the head's channels are always q[0..DH) (compact code).
-template <int H>
-__device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __restrict__ sK,
-                                              const float* __restrict__ sV, int sbase, int F, const DropCtx& dc,
-                                              float (&r)[D]) {
-    constexpr int DH = D / H;
-    const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
-#pragma unroll 1
-    for (int h = 0; h < H; ++h) {
-        float sc[SAT_MAXF];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j) {
-            if (j < F) {
-                const float* kr = sK + (sbase + j) * KV_LD + h * DH;
-                float acc = 0.f;
-#pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                    acc = fmaf(q[c + 0], kk.x, acc);
-                    acc = fmaf(q[c + 1], kk.y, acc);
-                    acc = fmaf(q[c + 2], kk.z, acc);
-                    acc = fmaf(q[c + 3], kk.w, acc);
-                }
-                sc[j] = acc * inv_sqrt_dh;                // inner_product /= dh ** 0.5   (satrans.py:85-86)
-                mx = fmaxf(mx, sc[j]);
-            }
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j)
-            if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-        float o[DH];
-        zero(o);
-        const float inv_sum = 1.f / sum;
-#pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j) {
-            if (j < F) {
-                const float pj = (sc[j] * inv_sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
-                const float* vr = sV + (sbase + j) * KV_LD + h * DH;
-#pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                    o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
-                    o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
-                    o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
-                    o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
-                }
-            }
-        }
-        // r[h*DH + c] = o[c]: write the head's slot, then rotate so that after H heads r is in channel order
-#pragma unroll
-        for (int c = 0; c < DH; ++c) r[c] = o[c];
-        if (H > 1) { rotate_regs<D, DH>(r); rotate_regs<D, DH>(q); }
-    }
-}
-
 template <int H, bool TRAIN>
 __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -114,7 +55,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
     const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
-    const int n_tiles = a.counters[CNT_NTILES];
+    const int n_tiles = *a.ntiles_ptr;
     const int s = tid / F, f = tid - s * F;
     int cur_q = -1, cur_k = -1;
 

@@ -1,0 +1,424 @@
+// Fused SATrans forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same mapping as forward.cu -- one thread = one field token, a CTA = whole samples of ONE scenario -- but a
+// CTA is 128 threads = the 128 TMEM lanes of a cta_group::1 MMA with M = 128: lane i IS token i.  Every
+// projection of the layer (QKV, the scenario-generated MetaNet W1/W2 of the Q and K sides, the output
+// projection) is a grouped GEMM  [128 tokens x K] @ [K x N]  issued by ONE thread as tcgen05.mma.kind::tf32:
+//   * A operand: the tokens' activations, written by their owning threads straight into TMEM
+//     (tcgen05.st 32x32b: thread t writes lane t) -- no shared-memory staging, no bank conflicts;
+//   * B operand: the CTA-uniform weights in shared memory in the canonical K-major no-swizzle UMMA layout,
+//     pre-packed once per step by k_pack_weights (and, for the MetaNet, once per scenario key);
+//   * D accumulator: TMEM; tcgen05.ld 32x32b hands each thread ITS token's output row back in registers,
+//     where LayerNorm / ReLU / residual / dropout / softmax stay thread-local exactly as in forward.cu.
+// Precision: PASSES = 3 is the error-compensated 3xTF32 scheme (x = hi + lo, D = A_hi B_hi + A_lo B_hi + A_hi B_lo),
+// which keeps fp32-level parity with the reference; PASSES = 1 is plain TF32 (fast mode, reported separately).
+// Attention over the F <= 32 tokens of a sample (9 % of the FLOPs, F x F x 8 per head) stays on the CUDA cores.
+#include "fwd_common.cuh"
+
+namespace sat {
+
+constexpr int TC_NT = 128;            // threads per CTA = TMEM lanes = tokens per tile
+constexpr int TC_COLS = 256;          // TMEM columns allocated per CTA (2 CTAs / SM)
+constexpr int TC_A = 0;               // [0,64)   A operand, K = 32: hi at +0, lo at +32
+constexpr int TC_H = 64;              // [64,128) A operand for one half of the MetaNet hidden layer
+constexpr int TC_D = 128;             // [128,224) accumulators: QKV 96 | hidden 64 + out 32 | out-proj 32
+constexpr int PACK_FLOATS = 8192;     // floats per packed layer block / per packed key block
+// packed layer block: [QKV hi 3072][QKV lo 3072][WO hi 1024][WO lo 1024]
+constexpr int PK_QKV_HI = 0, PK_QKV_LO = 3072, PK_WO_HI = 6144, PK_WO_LO = 7168;
+// packed key block:   [W1 hi 2048][W1 lo 2048][W2a hi 1024][W2a lo 1024][W2b hi 1024][W2b lo 1024]
+constexpr int PK_W1_HI = 0, PK_W1_LO = 2048, PK_W2A_HI = 4096, PK_W2A_LO = 5120, PK_W2B_HI = 6144, PK_W2B_LO = 7168;
+
+// offset (floats) of B[n][k] in the canonical K-major, no-swizzle UMMA layout for K = 32 fp32/tf32 elements:
+// core matrix = 8 rows (n) x 16 B (4 k); core matrices contiguous along k (LBO = 128 B), 8-row groups SBO = 1024 B apart
+__host__ __device__ __forceinline__ int b_off32(int n, int k) { return (n >> 3) * 256 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing: layer weights + generated MetaNet weights -> UMMA B operands (hi / lo split)
+// ---------------------------------------------------------------------------------------------------------
+#if SAT_INST_H == 4      // one copy of the packing kernel (this file is compiled once per head count)
+__global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_keys, const float* __restrict__ theta,
+                                                      float* __restrict__ wpack) {
+    const int total = (m.L + n_keys) * 4096;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int blk = e >> 12, i = e & 4095;
+        float v;
+        int off_hi, off_lo;
+        if (blk < m.L) {
+            const float* lay = m.dense + m.off_layers + (long long)blk * LAYER_FLOATS;
+            if (i < 3072) {                      // B[n][k] = W_{Q|K|V}[k][n']   (x @ W)
+                const int n = i >> 5, k = i & 31;
+                v = lay[(n >> 5) * 1024 + k * 32 + (n & 31)];
+                off_hi = PK_QKV_HI + b_off32(n, k); off_lo = PK_QKV_LO + b_off32(n, k);
+            } else {                             // B[n][k] = Out_linear.weight[n][k]   (r @ W^T)
+                const int j = i - 3072, n = j >> 5, k = j & 31;
+                v = lay[OFF_WO + n * 32 + k];
+                off_hi = PK_WO_HI + b_off32(n, k); off_lo = PK_WO_LO + b_off32(n, k);
+            }
+        } else {
+            const float* th = theta + (long long)(blk - m.L) * PSZ;
+            if (i < 2048) {                      // W1: B[n][k] = theta[k*64 + n], N = 64
+                const int n = i >> 5, k = i & 31;
+                v = th[k * HID + n];
+                off_hi = PK_W1_HI + b_off32(n, k); off_lo = PK_W1_LO + b_off32(n, k);
+            } else {                             // W2 halves: B[n][k] = theta[2048 + (half*32 + k)*32 + n], N = 32
+                const int j = i - 2048, half = j >> 10, jj = j & 1023, n = jj >> 5, k = jj & 31;
+                v = th[D * HID + (half * 32 + k) * D + n];
+                off_hi = (half ? PK_W2B_HI : PK_W2A_HI) + b_off32(n, k);
+                off_lo = (half ? PK_W2B_LO : PK_W2A_LO) + b_off32(n, k);
+            }
+        }
+        float* dst = wpack + (long long)blk * PACK_FLOATS;
+        const float hi = tf32_hi(v);
+        dst[off_hi] = hi;
+        dst[off_lo] = v - hi;
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMEM / mbarrier)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, M = 128
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t make_idesc(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                   "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+                   "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                   "r"(__float_as_uint(v[15])) : "memory");
+}
+// 32 floats of this thread's lane: columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[D]) {
+    tmem_ld16(taddr, &v[0]);
+    tmem_ld16(taddr + 16, &v[16]);
+}
+// write a 32-vector as A operand: hi at col, lo at col + 32 (PASSES == 3) or as is (PASSES == 1)
+template <int PASSES>
+__device__ __forceinline__ void tmem_st_operand(uint32_t taddr, const float (&v)[D]) {
+    if (PASSES == 1) {
+        tmem_st16(taddr, &v[0]);
+        tmem_st16(taddr + 16, &v[16]);
+    } else {
+        float hi[D], lo[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { hi[i] = tf32_hi(v[i]); lo[i] = v[i] - hi[i]; }
+        tmem_st16(taddr, &hi[0]);
+        tmem_st16(taddr + 16, &hi[16]);
+        tmem_st16(taddr + 32, &lo[0]);
+        tmem_st16(taddr + 48, &lo[16]);
+    }
+}
+
+// issue D[128 x N] (+)= A[128 x 32] @ B[N x 32]^T as 4 k-steps of K = 8 (x3 products with the hi/lo split)
+template <int PASSES>
+__device__ __forceinline__ void issue_gemm_k32(uint32_t d_tmem, uint32_t a_tmem, const float* b_hi, const float* b_lo, int N,
+                                               bool accumulate) {
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t dh = make_b_desc(bh + kk * 256, 128, 1024);
+        mma_ts_tf32(d_tmem, a_tmem + kk * 8, dh, idesc, acc);
+        acc = 1u;
+        if (PASSES == 3) {
+            const uint64_t dl = make_b_desc(bl + kk * 256, 128, 1024);
+            mma_ts_tf32(d_tmem, a_tmem + 32 + kk * 8, dh, idesc, 1u);
+            mma_ts_tf32(d_tmem, a_tmem + kk * 8, dl, idesc, 1u);
+        }
+    }
+}
+
+constexpr int TC_SMEM_FLOATS = 2 * PACK_FLOATS + 2 * TC_NT * KV_LD + 192 + TC_NT + 8;
+
+template <int H, bool TRAIN, int PASSES>
+__global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const float* __restrict__ wpack) {
+    extern __shared__ __align__(128) float smem[];
+    float* sBL = smem;                            // packed layer block   (32 KB)
+    float* sBT = sBL + PACK_FLOATS;               // packed key block     (32 KB)
+    float* sK = sBT + PACK_FLOATS;                // [128][36]
+    float* sV = sK + TC_NT * KV_LD;               // [128][36]
+    float* sLN = sV + TC_NT * KV_LD;              // 6 x 32 LayerNorm vectors
+    float* sRed = sLN + 192;                      // [128]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sRed + TC_NT);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
+    __shared__ double s_loss;
+
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int F = m.F, L = m.L;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
+    const int n_tiles = *a.ntiles_ptr;
+    const int s = tid / F, f = tid - s * F;
+
+    if (warp == 0) tmem_alloc(s_tmem, TC_COLS);
+    if (tid == 0) mbar_init(mbar, 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *s_tmem;
+    const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
+    uint32_t phase = 0;
+    int cur_key = -1;
+
+    // one MMA round trip: [operands stored by all] -> sync -> thread 0 issues + commits -> all wait
+#define SAT_TC_ROUND(ISSUE)                                  \
+    do {                                                     \
+        tc_wait_st();                                        \
+        tc_fence_before();                                   \
+        __syncthreads();                                     \
+        if (tid == 0) {                                      \
+            tc_fence_after();                                \
+            ISSUE;                                           \
+            mma_commit(mbar);                                \
+        }                                                    \
+        mbar_wait(mbar, phase);                              \
+        phase ^= 1u;                                         \
+        tc_fence_after();                                    \
+    } while (0)
+
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int g = td.x, start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int p = start + s;
+        const int b = valid ? a.perm[p] : 0;
+        const long long tokpos = ((long long)p * F + f) * D;
+        const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
+
+        float x[D];
+        zero(x);
+        if (valid) {
+            long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
+            const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
+            if (id < 0 || id >= hi - lo) { atomicOr(&a.counters[CNT_ERR], 1); id = 0; }
+            load_row(table_row(m, lo + id), x);
+        }
+        if (tid == 0) s_loss = 0.0;
+
+        for (int l = 0; l < L; ++l) {
+            __syncthreads();                      // previous users of sBL / sBT / sK / sV are done
+            copy_to_smem(sBL, wpack + (long long)l * PACK_FLOATS, PACK_FLOATS, tid, TC_NT);
+            copy_to_smem(sLN, m.dense + m.off_layers + (long long)l * LAYER_FLOATS + OFF_LN_G, 192, tid, TC_NT);
+            const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
+            // K side first: its generated weights go into sBT now, the Q side's (ENP) are swapped in later
+            if (kk != cur_key) { copy_to_smem(sBT, wpack + (long long)(L + kk) * PACK_FLOATS, PACK_FLOATS, tid, TC_NT); cur_key = kk; }
+            fence_async_smem();                   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            float* act_l = TRAIN ? a.acts + (long long)l * ACT_PER_LAYER * a.act_stride : nullptr;
+            if (TRAIN && valid) store_row(act_l + ACT_X * a.act_stride + tokpos, x);
+
+            // ---- round 1: [Q | K | V] = x @ [W_Q | W_K | W_V] ---------------------------------------------------
+            tmem_st_operand<PASSES>(tlane + TC_A, x);
+            SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D, tbase + TC_A, sBL + PK_QKV_HI, sBL + PK_QKV_LO, 96, false));
+            float q[D], k[D], v[D];
+            tmem_ld32(tlane + TC_D, q);
+            tmem_ld32(tlane + TC_D + 32, k);
+            tmem_ld32(tlane + TC_D + 64, v);
+            tc_wait_ld();
+            if (TRAIN && valid) store_row(act_l + ACT_V * a.act_stride + tokpos, v);
+            sts_row(sV + tid * KV_LD, v);
+
+            // ---- MetaNet on K then Q: z = dropout(relu(u @ W1) @ W2) + u ; LayerNorm ------------------------------
+#pragma unroll
+            for (int side = 1; side >= 0; --side) {
+                float (&u)[D] = side ? k : q;
+                const bool has_meta = side ? meta_k : meta_q;
+                if (side == 0 && pos && kq != cur_key) {          // ENP: swap in the Q side's generated weights
+                    __syncthreads();
+                    copy_to_smem(sBT, wpack + (long long)(L + kq) * PACK_FLOATS, PACK_FLOATS, tid, TC_NT);
+                    cur_key = kq;
+                    fence_async_smem();
+                }
+                if (has_meta) {
+                    tmem_st_operand<PASSES>(tlane + TC_A, u);
+                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D, tbase + TC_A, sBT + PK_W1_HI, sBT + PK_W1_LO, 64, false));
+                    float hbuf[D];
+                    tmem_ld32(tlane + TC_D, hbuf);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < D; ++i) hbuf[i] = fmaxf(hbuf[i], 0.f);
+                    tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
+                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2A_HI, sBT + PK_W2A_LO, 32, false));
+                    tmem_ld32(tlane + TC_D + 32, hbuf);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < D; ++i) hbuf[i] = fmaxf(hbuf[i], 0.f);
+                    tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
+                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2B_HI, sBT + PK_W2B_LO, 32, true));
+                    tmem_ld32(tlane + TC_D + 64, hbuf);
+                    tc_wait_ld();
+                    const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, TRAIN);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) u[i] = fmaf(hbuf[i], drop_factor(dc, i), u[i]);
+                }
+                if (TRAIN && valid) store_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, u);
+                if (has_meta) {
+                    const float* ln = (side && pos) ? sLN + 128 : sLN + 64;
+                    float mean, rstd;
+                    layernorm32(u, ln, ln + 32, mean, rstd);
+                }
+                if (side) sts_row(sK + tid * KV_LD, k);
+            }
+            __syncthreads();                      // K', V tiles complete
+
+            // ---- attention on the CUDA cores, then the output projection on the tensor core ------------------------
+            float r[D];
+            zero(r);
+            if (valid)
+                attention_fwd<H>(q, sK, sV, s * F, F, make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, TRAIN), r);
+            if (TRAIN && valid) store_row(act_l + ACT_R * a.act_stride + tokpos, r);
+            tmem_st_operand<PASSES>(tlane + TC_A, r);
+            SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D, tbase + TC_A, sBL + PK_WO_HI, sBL + PK_WO_LO, 32, false));
+            float o[D];
+            tmem_ld32(tlane + TC_D, o);
+            tc_wait_ld();
+            const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float vv = relu_out ? fmaxf(o[i], 0.f) : o[i];
+                vv *= drop_factor(dco, i);
+                x[i] = use_res ? vv + x[i] : vv;
+            }
+            float mean, rstd;
+            layernorm32(x, sLN, sLN + 32, mean, rstd);
+        }
+
+        // ---- logit head + sigmoid (+ BCE): identical to forward.cu ------------------------------------------------
+        float part = 0.f;
+        if (valid) {
+            if (TRAIN) store_row(a.acts + (long long)L * ACT_PER_LAYER * a.act_stride + tokpos, x);
+            const float* hw = m.dense + m.off_headw + f * D;
+#pragma unroll
+            for (int i = 0; i < D; i += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(hw + i));
+                part = fmaf(x[i], w4.x, part); part = fmaf(x[i + 1], w4.y, part);
+                part = fmaf(x[i + 2], w4.z, part); part = fmaf(x[i + 3], w4.w, part);
+            }
+        }
+        sRed[tid] = part;
+        __syncthreads();
+        if (valid && f == 0) {
+            float z = 0.f;
+            for (int j = 0; j < F; ++j) z += sRed[tid + j];
+            for (int kd = 0; kd < m.n_dense; ++kd)
+                z = fmaf(load_dense(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.dense_cols + kd)),
+                         __ldg(m.dense + m.off_headw + F * D + kd), z);
+            z += __ldg(m.dense + m.off_headb);
+            const float yp = 1.f / (1.f + expf(-z));
+            a.y_pred[b] = yp;
+            if (a.y) {
+                const float yt = __ldg(a.y + b);
+                const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
+                atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
+                const float pq = (1.f - yp) * yp;
+                a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && a.loss_part) a.loss_part[t] = s_loss;
+    }
+#undef SAT_TC_ROUND
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TC_COLS);
+}
+
+}  // namespace sat
+
+using namespace sat;
+
+#ifndef SAT_INST_H
+#error "compile forward_tc.cu with -DSAT_INST_H={1,2,4,8}"
+#endif
+#define SAT_CAT_(a, b) a##b
+#define SAT_CAT(a, b) SAT_CAT_(a, b)
+
+template <bool TRAIN, int PASSES>
+static int launch_tc(const FwdArgs& a, const float* wpack, int grid, cudaStream_t s) {
+    constexpr int H = SAT_INST_H;
+    const size_t smem = TC_SMEM_FLOATS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_forward_tc<H, TRAIN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_forward_tc: cannot raise dynamic shared memory to %zu", smem);
+        configured = true;
+    }
+    k_forward_tc<H, TRAIN, PASSES><<<grid, TC_NT, smem, s>>>(a, wpack);
+    return sat_host::check_launch("k_forward_tc");
+}
+
+int SAT_CAT(sat_launch_forward_tc_h, SAT_INST_H)(const FwdArgs& a, const float* wpack, int grid, int training, int passes,
+                                                 cudaStream_t s) {
+    if (passes == 3) return training ? launch_tc<true, 3>(a, wpack, grid, s) : launch_tc<false, 3>(a, wpack, grid, s);
+    if (passes == 1) return training ? launch_tc<true, 1>(a, wpack, grid, s) : launch_tc<false, 1>(a, wpack, grid, s);
+    return sat_host::fail(SAT_EINVAL, "sat_forward_tc: passes must be 1 (tf32) or 3 (3xtf32), got %d", passes);
+}
+
+#if SAT_INST_H == 4
+// one copy of the packing entry point (any H translation unit would do)
+int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, cudaStream_t s) {
+    const int total = (m->L + n_keys) * 4096;
+    k_pack_weights<<<(total + 255) / 256, 256, 0, s>>>(*m, n_keys, theta, wpack);
+    return sat_host::check_launch("k_pack_weights");
+}
+#endif

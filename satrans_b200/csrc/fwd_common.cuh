@@ -1,0 +1,66 @@
+// Device code shared by the CUDA-core forward (forward.cu) and the tcgen05 forward (forward_tc.cu).
+#pragma once
+#include "args.cuh"
+
+namespace sat {
+
+// Multi-head attention of one query token against the F tokens of its sample (reference satrans.py:75-90).
+// K'/V rows of the sample start at row `sbase` of the [token][36] tiles.
+// Rolled over heads: q is rotated by DH per head so that the head's channels are always q[0..DH) (compact code).
+template <int H>
+__device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __restrict__ sK,
+                                              const float* __restrict__ sV, int sbase, int F, const DropCtx& dc,
+                                              float (&r)[D]) {
+    constexpr int DH = D / H;
+    const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+#pragma unroll 1
+    for (int h = 0; h < H; ++h) {
+        float sc[SAT_MAXF];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j) {
+            if (j < F) {
+                const float* kr = sK + (sbase + j) * KV_LD + h * DH;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                    acc = fmaf(q[c + 0], kk.x, acc);
+                    acc = fmaf(q[c + 1], kk.y, acc);
+                    acc = fmaf(q[c + 2], kk.z, acc);
+                    acc = fmaf(q[c + 3], kk.w, acc);
+                }
+                sc[j] = acc * inv_sqrt_dh;                // inner_product /= dh ** 0.5   (satrans.py:85-86)
+                mx = fmaxf(mx, sc[j]);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j)
+            if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+        float o[DH];
+        zero(o);
+        const float inv_sum = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < SAT_MAXF; ++j) {
+            if (j < F) {
+                const float pj = (sc[j] * inv_sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
+                const float* vr = sV + (sbase + j) * KV_LD + h * DH;
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+                    o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
+                    o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
+                    o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
+                    o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                }
+            }
+        }
+        // r[h*DH + c] = o[c]: write the head's slot, then rotate so that after H heads r is in channel order
+#pragma unroll
+        for (int c = 0; c < DH; ++c) r[c] = o[c];
+        if (H > 1) { rotate_regs<D, DH>(r); rotate_regs<D, DH>(q); }
+    }
+}
+
+}  // namespace sat

@@ -129,10 +129,10 @@ k_adam_dense(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V
 // scalars[0] = sum of per-tile BCE partials; scalars[1] = l2 * (sum of squares partials); scalars[3] = error flags
 __global__ void __launch_bounds__(256)
 k_finalize(const double* __restrict__ loss_part, const int32_t* __restrict__ counters, const double* __restrict__ reg_part,
-           int n_reg_part, float l2, float* __restrict__ scalars) {
+           int n_reg_part, float l2, float* __restrict__ scalars, int tile_set) {
     __shared__ double s_out[2];
     double a = 0.0, r = 0.0;
-    const int n_tiles = counters[CNT_NTILES];
+    const int n_tiles = counters[tile_set ? CNT_NTILES2 : CNT_NTILES];
     for (int i = threadIdx.x; i < n_tiles; i += 256) a += loss_part[i];
     for (int i = threadIdx.x; i < n_reg_part; i += 256) r += reg_part[i];
     block_sum_to(a, &s_out[0]);
@@ -218,9 +218,9 @@ extern "C" int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, v
     return sat_host::check_launch("k_adam_dense");
 }
 
-extern "C" int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, void* stream) {
+extern "C" int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, int32_t tile_set, void* stream) {
     if (!m || !w || !w->scalars) return sat_host::fail(SAT_EINVAL, "sat_finalize_loss: null argument");
     k_finalize<<<1, 256, 0, (cudaStream_t)stream>>>(w->loss_part, w->counters, w->reg_part, SWEEP_BLOCKS + ROWS_BLOCKS, l2_emb,
-                                                    w->scalars);
+                                                    w->scalars, tile_set);
     return sat_host::check_launch("k_finalize");
 }

@@ -77,6 +77,9 @@ class Engine:
         self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
         self.timing = None         # set to {} to collect CUDA-event pairs per phase: {name: [(start, end), ...]}
         self.dist = None           # satrans_b200.dist.DistContext when the tables are row-sharded over ranks
+        # forward precision: 'fp32' = CUDA-core FFMA kernels; 'tf32x3' = tcgen05 tensor cores with the error-
+        # compensated 3xTF32 split (fp32-level parity); 'tf32' = tcgen05 plain TF32 (fast mode)
+        self.precision = 'fp32'
         self._peer_tables = None
 
     def attach_dist(self, ctx):
@@ -229,6 +232,24 @@ class Engine:
         check(l.sat_bucket_by_domain(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), 0, s),
               'sat_bucket_by_domain')
         check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
+        if self.precision != 'fp32':
+            check(l.sat_pack_weights(C.byref(self.desc), C.byref(w.c), s), 'sat_pack_weights')
+
+    def _passes(self):
+        try:
+            return {'fp32': 0, 'tf32x3': 3, 'tf32': 1}[self.precision]
+        except KeyError:
+            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32', got %r" % (self.precision,))
+
+    def _forward_call(self, X, kind, y_ptr, w, y_pred, training, p, seed, s):
+        l, d = lib(), C.byref(self.desc)
+        passes = self._passes()
+        if passes == 0:
+            check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y_ptr, C.byref(w.c), y_pred.data_ptr(),
+                                int(training), float(p), seed, s), 'sat_forward')
+        else:
+            check(l.sat_forward_tc(d, X.data_ptr(), kind, X.shape[1], y_ptr, C.byref(w.c), y_pred.data_ptr(),
+                                   int(training), float(p), seed, passes, s), 'sat_forward_tc')
 
     def _mark_rows(self, X, w, kind):
         """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomics) | barrier | rank | barrier."""
@@ -253,11 +274,9 @@ class Engine:
             return y_pred
         w = self.workspace(B, training)
         self._prepare(X, w, kind)
-        check(lib().sat_forward(C.byref(self.desc), X.data_ptr(), kind, X.shape[1],
-                                y.data_ptr() if y is not None else None, C.byref(w.c), y_pred.data_ptr(),
-                                int(training), float(dropout_p), int(seed) & (2 ** 64 - 1), self._stream()),
-              'sat_forward')
-        self.launches += 3
+        self._forward_call(X, kind, y.data_ptr() if y is not None else None, w, y_pred, training, dropout_p,
+                           int(seed) & (2 ** 64 - 1), self._stream())
+        self.launches += 3 + (1 if self.precision != 'fp32' else 0)
         return y_pred
 
     def check_errors(self, w):
@@ -285,9 +304,8 @@ class Engine:
         self._row_grad_dirty = True          # left populated for the caller; train_step clears it before reuse
         if self.dist is not None and self.dist.world > 1:
             self.dist.barrier(self.device)
-        check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
-                            1, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s),
-              'sat_forward')
+        self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, float(dropout_p if training else 0.0),
+                           int(seed) & (2 ** 64 - 1), s)
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c),
                              float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s), 'sat_backward')
         self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2)
@@ -296,7 +314,7 @@ class Engine:
         if with_reg:
             check(l.sat_tables_sumsq(d, C.byref(w.c), s), 'sat_tables_sumsq')
             self.launches += 1
-        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
         if self.dist is not None and self.dist.world > 1:
             self.dist.all_reduce_sum(w['scalars'][0:2])
         self.launches += 1
@@ -313,7 +331,7 @@ class Engine:
         return self._adam
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=True):
+                   dropout_p=0.1, seed=0, overlap=False):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
         finalize kernel (read them with .item() only when needed: that synchronises)."""
@@ -355,8 +373,7 @@ class Engine:
             self._ev_swept.record(self._sweep_stream)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
         t = self._tic('forward')
-        check(l.sat_forward(d, X.data_ptr(), kind, X.shape[1], y.data_ptr(), C.byref(w.c), y_pred.data_ptr(),
-                            1, p, sd, s), 'sat_forward')
+        self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
         self._toc(t)
         t = self._tic('backward')
         check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
@@ -377,12 +394,13 @@ class Engine:
         self._toc(t)
         if sweep_on_side:
             main.wait_event(self._ev_swept)
-        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), s), 'sat_finalize_loss')
+        check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
         if self.dist is not None and self.dist.world > 1:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
         # own kernels per step: bucket 1, encoder 1, mark+rank 3, forward 1, head bwd 1, 2 per layer, encoder bwd 2,
         # adam rows 1, sweep 0/1, dense adam 1, finalize 1
-        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2) + 1 + (1 if dense_mode else 0) + 1 + 1
+        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2) + 1 + (1 if dense_mode else 0) + 1 + 1 + \
+            (1 if self.precision != 'fp32' else 0)
         return y_pred, w
 
     def adam_state(self):

@@ -114,3 +114,38 @@ def test_reg_and_loss_reported_by_train_step():
     torch.cuda.synchronize()
     assert abs(float(w['scalars'][0]) - float(g.z['bce'])) <= 1e-5 * abs(float(g.z['bce']))
     assert abs(float(w['scalars'][1]) - float(g.z['reg'])) <= 1e-5 * abs(float(g.z['reg']))
+
+
+# ---- tensor-core (tcgen05) forward ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', CASES + FORWARD_ONLY_CASES)
+@pytest.mark.parametrize('precision,atol', [('tf32x3', 2e-6), ('tf32', 2e-3)])
+def test_tensor_core_forward_matches_reference(name, precision, atol):
+    """tcgen05 forward: 3xTF32 keeps the fp32 tolerance of the CUDA-core path; plain TF32 is the fast mode
+    (10-bit mantissa products: tolerance 2e-3 on probabilities)."""
+    from gpu_util import model_from_golden
+    g = Golden(name)
+    model = model_from_golden(g).eval()
+    model.engine.precision = precision
+    yp = model(_dev(g.X()))
+    err = (yp.cpu() - g.arr('y_pred')).abs().max().item()
+    assert err <= atol, (precision, err)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_tensor_core_forward_training_path(name):
+    """3xTF32 tensor-core forward feeding the (CUDA-core) backward: loss and gradients stay within the fp32 bars."""
+    from gpu_util import dense_grads, model_from_golden, table_grads
+    g = Golden(name)
+    model = model_from_golden(g)
+    model.engine.precision = 'tf32x3'
+    l2 = g.cfg.l2_reg_embedding
+    yp, w = model.engine.loss_and_grads(_dev(g.X()), _dev(g.y()), training=False, l2_emb=l2)
+    torch.cuda.synchronize()
+    assert abs(float(w['scalars'][0]) - float(g.z['bce'])) <= 1e-5 * abs(float(g.z['bce']))
+    grads = dense_grads(model, w)
+    tg, _ = table_grads(model, w, l2)
+    grads.update(tg)
+    for k in O.trainable_keys(g.cfg):
+        ref = g.arr('grad/' + k)
+        got = grads[k][subsample(k)]
+        assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, k
