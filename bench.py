@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--overlap', action='store_true', help='run the dense optimiser sweep on a second stream, concurrent with forward/backward (default: on the main stream)')
     ap.add_argument('--lazy', action='store_true', help='touched-rows-only table updates (NOT reference semantics)')
     ap.add_argument('--cpu-budget-s', type=float, default=25.0)
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'],
+                    help="forward GEMMs: fp32 CUDA cores | tcgen05 3xTF32 (fp32-level parity, default) | tcgen05 TF32")
     return ap.parse_args()
 
 
@@ -55,6 +57,8 @@ def workload_config(args, n_gpus):
             "optimizer": "Adam lr=0.005 + L2(emb)=1e-5, " + ("lazy touched-rows-only" if args.lazy else
                                                                "dense every-row (reference semantics)"),
             "dropout": 0.1, "l2": "inputs>L2 (3 x 841 MB swept per step, new batch every step)",
+            "forward_gemms": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 3xTF32 error-compensated (fp32-level parity)",
+                              "tf32": "tcgen05 TF32"}[args.precision],
             "parallelism": "1 GPU" if n_gpus == 1 else "row-sharded tables + dp%d dense" % n_gpus}
 
 
@@ -199,6 +203,7 @@ def run_b200(args):
     model.compile(torch.optim.Adam(model.parameters(), lr=0.005), "binary_crossentropy",
                   metrics=["binary_crossentropy", "auc"])
     eng = model.engine
+    eng.precision = args.precision
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     if world > 1:
         from satrans_b200.dist import DistContext
@@ -320,7 +325,22 @@ def run_b200(args):
         torch.cuda.synchronize()
         ims = g0.elapsed_time(g1) / 10
         extra["infer"] = {"batch": Bi, "ms": ims, "value": Bi / (ims * 1e-3), "unit": UNIT,
-                          "gflops": Bi * 1540672 / (ims * 1e-3) / 1e9}
+                          "gflops": Bi * 1540672 / (ims * 1e-3) / 1e9, "precision": args.precision}
+        for prec in ('fp32', 'tf32x3', 'tf32'):
+            if prec == args.precision:
+                continue
+            eng.precision = prec
+            for _ in range(3):
+                eng.forward(Xi, training=False)
+            torch.cuda.synchronize()
+            g0.record()
+            for _ in range(10):
+                eng.forward(Xi, training=False)
+            g1.record()
+            torch.cuda.synchronize()
+            pms = g0.elapsed_time(g1) / 10
+            extra["infer_" + prec] = {"batch": Bi, "ms": pms, "value": Bi / (pms * 1e-3), "unit": UNIT}
+        eng.precision = args.precision
     except Exception as e:  # the headline number must survive a failure of the extras
         extra["extra_error"] = repr(e)
 

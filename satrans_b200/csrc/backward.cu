@@ -96,6 +96,7 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
                                                  float* __restrict__ sdWp,           // projection weight gradient
                                                  float* __restrict__ sA, float* __restrict__ sG,
                                                  const float* __restrict__ act_x, const float* __restrict__ act_z,
+                                                 const uint32_t* __restrict__ relu_mask,   // 2 words of this token/side
                                                  long long tokpos, const DropCtx& dc, float (&dqp)[D]) {
     float qp[D];
     zero(qp);
@@ -114,7 +115,9 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
         } else zero(dm);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            uint32_t mask = 0;
+            // the forward's ReLU decisions (saved), not a re-evaluation: identical function even if the forward
+            // ran on the tensor cores
+            const uint32_t mask = valid ? __ldg(relu_mask + half) : 0u;
             {
                 float h[D];
                 zero(h);
@@ -125,10 +128,7 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
                         zero(hc);
                         vm_outer<D, 16, HID>(sTh + half * D + c0, qp, hc);
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            h[c0 + c] = fmaxf(hc[c], 0.f);
-                            if (hc[c] > 0.f) mask |= 1u << (c0 + c);
-                        }
+                        for (int c = 0; c < 16; ++c) h[c0 + c] = ((mask >> (c0 + c)) & 1u) ? hc[c] : 0.f;
                     }
                     sts_row(sA + tid * KV_LD, h);
                     sts_row(sG + tid * KV_LD, dm);
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
             float dqp[D];
             if (valid) load_row(a.dqkv + 0 * a.act_stride + tokpos, dqp); else zero(dqp);
             metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLN, sdW + OFF_WQ, sA,
-                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride, tokpos,
+                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride,
+                             relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 0, tokpos / D), tokpos,
                              make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, true), dqp);
             if (valid) vm_dot<D, D, D>(sW + OFF_WQ, dqp, dxa);          // dX[i] += sum_j dqp[j] WQ[i][j]
         }
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
             float dkp[D];
             if (valid) load_row(a.dqkv + 1 * a.act_stride + tokpos, dkp); else zero(dkp);
             metanet_side_bwd(a, meta_k, valid, ntok, tid, lane, sW + OFF_WK, thK, sdThKuse, klng, sdLNk, sdW + OFF_WK, sA,
-                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZK * a.act_stride, tokpos,
+                             sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZK * a.act_stride,
+                             relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 1, tokpos / D), tokpos,
                              make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, true), dkp);
             if (valid) vm_dot<D, D, D>(sW + OFF_WK, dkp, dxa);
         }

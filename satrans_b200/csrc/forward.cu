@@ -21,16 +21,19 @@ constexpr int FWD_SMEM_FLOATS = 4096 + 192 + 2 * PSZ + 2 * NT * KV_LD + NT;
 // MetaNet (reference submodules.py:77-103) on one token: z = dropout(relu(q @ W1) @ W2) + q.
 // th = [W1 (32x64) | W2 (64x32)] in shared memory.  Hidden units are produced and consumed 16 at a time.
 __device__ __forceinline__ void metanet_fwd(float (&q)[D], const float* __restrict__ th, const DropCtx& dc,
-                                            float (&z)[D]) {
+                                            float (&z)[D], uint32_t (&mask)[2]) {
     float mo[D];
     zero(mo);
+    mask[0] = mask[1] = 0u;
 #pragma unroll 1
     for (int c0 = 0; c0 < HID; c0 += 16) {
         float h[16];
         zero(h);
         vm_outer<D, 16, HID>(th + c0, q, h);
+        uint32_t bits = 0u;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) h[c] = fmaxf(h[c], 0.f);
+        for (int c = 0; c < 16; ++c) { if (h[c] > 0.f) bits |= 1u << c; h[c] = fmaxf(h[c], 0.f); }
+        if (c0 < 32) mask[0] |= bits << c0; else mask[1] |= bits << (c0 - 32);
         vm_outer<16, D, D>(th + D * HID + c0 * D, h, mo);
     }
 #pragma unroll
@@ -99,8 +102,12 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                     vm_outer<D, D, D>(sW + OFF_WK, x, kp);
                     if (meta_k) {
                         float z[D];
-                        metanet_fwd(kp, thK, make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, TRAIN), z);
-                        if (TRAIN) store_row(act_l + ACT_ZK * a.act_stride + tokpos, z);
+                        uint32_t mk[2];
+                        metanet_fwd(kp, thK, make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, TRAIN), z, mk);
+                        if (TRAIN) {
+                            store_row(act_l + ACT_ZK * a.act_stride + tokpos, z);
+                            *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, 1, tokpos / D)) = make_uint2(mk[0], mk[1]);
+                        }
                         layernorm32(z, kln, kln + 32, mean, rstd);
                         sts_row(sK + tid * KV_LD, z);
                     } else {
@@ -120,8 +127,12 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                     zero(qp);
                     vm_outer<D, D, D>(sW + OFF_WQ, x, qp);
                     if (meta_q) {
-                        metanet_fwd(qp, sThQ, make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, TRAIN), q);
-                        if (TRAIN) store_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+                        uint32_t mq[2];
+                        metanet_fwd(qp, sThQ, make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, TRAIN), q, mq);
+                        if (TRAIN) {
+                            store_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+                            *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, 0, tokpos / D)) = make_uint2(mq[0], mq[1]);
+                        }
                         layernorm32(q, sLN + 64, sLN + 96, mean, rstd);
                     } else {
 #pragma unroll

@@ -293,16 +293,19 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
                     tmem_st_operand<PASSES>(tlane + TC_A, u);
                     SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D, tbase + TC_A, sBT + PK_W1_HI, sBT + PK_W1_LO, 64, false));
                     float hbuf[D];
+                    uint32_t m0 = 0u, m1 = 0u;
                     tmem_ld32(tlane + TC_D, hbuf);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < D; ++i) hbuf[i] = fmaxf(hbuf[i], 0.f);
+                    for (int i = 0; i < D; ++i) { if (hbuf[i] > 0.f) m0 |= 1u << i; hbuf[i] = fmaxf(hbuf[i], 0.f); }
                     tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
                     SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2A_HI, sBT + PK_W2A_LO, 32, false));
                     tmem_ld32(tlane + TC_D + 32, hbuf);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < D; ++i) hbuf[i] = fmaxf(hbuf[i], 0.f);
+                    for (int i = 0; i < D; ++i) { if (hbuf[i] > 0.f) m1 |= 1u << i; hbuf[i] = fmaxf(hbuf[i], 0.f); }
+                    if (TRAIN && valid)
+                        *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, side, tokpos / D)) = make_uint2(m0, m1);
                     tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
                     SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2B_HI, sBT + PK_W2B_LO, 32, true));
                     tmem_ld32(tlane + TC_D + 64, hbuf);

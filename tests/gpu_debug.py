@@ -12,6 +12,7 @@ for name in CASES + FORWARD_ONLY_CASES:
     print('=====', name, g.meta['flag'], g.meta['meta_mode'], 'H', g.meta['att_head_num'], 'L', g.meta['domain_att_layer_num'], flush=True)
     try:
         model = model_from_golden(g)
+        model.engine.precision = os.environ.get('SAT_PRECISION', 'fp32')
         X, y = g.X().cuda().contiguous(), g.y().cuda().contiguous()
         E = model.engine.gather(X)
         print('gather exact:', torch.equal(E.cpu(), g.arr('E0')))
