@@ -340,6 +340,10 @@ class BaseModel(nn.Module):
         """dict / list of 1-D columns -> (N, n_cols) matrix in feature_index order (reference
         meta_basemodel.py:221-222,257-264).  float32 exactly like the reference when any column is
         non-integer; int32 otherwise (exact for ids >= 2**24, which the fp32 route cannot represent)."""
+        if isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] == len(self.feature_index):
+            return x if x.dtype in (np.float32, np.int32) else x.astype(np.float32)      # already stacked
+        if torch.is_tensor(x):
+            return x.detach().cpu().numpy()
         if isinstance(x, dict):
             x = [x[feature] for feature in self.feature_index]
         cols = [np.asarray(c) for c in x]

@@ -228,7 +228,7 @@ class Engine:
     def _prepare(self, X, w, kind):
         s = self._stream()
         l = lib()
-        w['counters'].zero_()
+        # counters[1] (error flags) is sticky until check_errors() reads and clears it
         check(l.sat_bucket_by_domain(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), 0, s),
               'sat_bucket_by_domain')
         check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
@@ -282,6 +282,8 @@ class Engine:
     def check_errors(self, w):
         """Raise like the reference's nn.Embedding would for ids outside their table (device->host sync)."""
         flags = int(w['counters'][1].item())
+        if flags:
+            w['counters'][1] = 0
         if flags & _lib.ERR_BAD_ID:
             raise IndexError('a sparse feature id is outside its embedding table (index out of range in self)')
         if flags & _lib.ERR_BAD_DOMAIN:

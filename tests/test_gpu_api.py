@@ -1,0 +1,208 @@
+"""GPU tests of the drop-in API (fit / predict / evaluate / train_on_batch) and of the edge cases the domain has:
+ragged last batch, B = 1, empty scenario buckets, out-of-range ids, lazy vs dense table updates, dropout."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import satrans_oracle as O
+from satrans_b200 import synth
+from test_oracle_golden import assert_adam_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(scale=2e-4, flag='sota', mode='QK', heads=4, layers=2, alimama=False, seed=3):
+    schema = (synth.alimama_schema if alimama else synth.aliccp_schema)(scale)
+    cfg = O.OracleConfig(sparse_names=schema.fields, vocab_sizes=schema.vocab_sizes, dense_names=schema.dense,
+                         domain_col=schema.domain_col, num_domains=schema.num_domains, layers=layers, heads=heads,
+                         meta_mode=mode, flag=flag)
+    st = O.init_state(cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    st['domain_map_dnn_Q.linears.0.weight'] = torch.randn(st['domain_map_dnn_Q.linears.0.weight'].shape, generator=g) * 0.05
+    for k in list(st):
+        if k.startswith('embedding_dict.'):
+            st[k] = torch.randn(st[k].shape, generator=g) * 0.3
+    return schema, cfg, st
+
+
+def _model(cfg, st):
+    from gpu_util import model_from_cfg
+    return model_from_cfg(cfg, {k: v.clone() for k, v in st.items()})
+
+
+def test_fit_matches_oracle_training_loop():
+    """fit(shuffle=False, dropout off) == the reference's loop (meta_basemodel.py:311-328) on successive batches,
+    including a ragged last batch; History carries the epoch loss = sum(bce + reg) / N."""
+    schema, cfg, st = _small()
+    n, bs, lr = 1000, 256, 0.005                       # 4 steps, last batch 232 samples
+    xs, ys = synth.make_inputs(schema, n, seed=11, ctr=0.3)
+    model = _model(cfg, st)
+    model.dropout_rate = 0.0
+    model.compile(torch.optim.Adam(model.parameters(), lr=lr), "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+    hist = model.fit(x=xs, y=ys, batch_size=bs, epochs=1, verbose=0, shuffle=False)
+    tr = O.Trainer({k: v.clone() for k, v in st.items()}, cfg, lr=lr)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense))
+    y = torch.from_numpy(ys.astype(np.float32))
+    tot = 0.0
+    for s0 in range(0, n, bs):
+        b, r = tr.step(X[s0:s0 + bs], y[s0:s0 + bs], train_mode=False)
+        tot += b + r
+    assert abs(hist.history['loss'][0] - tot / n) <= 1e-5 * abs(tot / n)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in O.trainable_keys(cfg):
+        assert_adam_close(sd[k], tr.params[k].detach(), lr, 4, k)
+
+
+def test_fit_verbose_metrics_and_validation(capsys):
+    schema, cfg, st = _small(layers=1)
+    xs, ys = synth.make_inputs(schema, 1500, seed=5, ctr=0.3)
+    model = _model(cfg, st)
+    model.compile("adam", "binary_crossentropy", metrics=["binary_crossentropy", "auc"])
+    hist = model.fit(x=xs, y=ys, batch_size=500, epochs=2, verbose=1, validation_split=0.2)
+    h = hist.history
+    assert set(h) >= {'loss', 'binary_crossentropy', 'auc', 'val_binary_crossentropy', 'val_auc'}
+    assert len(h['loss']) == 2 and all(np.isfinite(v) for v in h['loss'])
+    assert 0.0 <= h['val_auc'][-1] <= 1.0
+    out = capsys.readouterr().out
+    assert 'Epoch 2/2' in out and 'Train on 1200 samples, validate on 300 samples' in out
+    ev = model.evaluate({k: v[:300] for k, v in xs.items()}, ys[:300], batch_size=128)
+    assert set(ev) == {'binary_crossentropy', 'auc'}
+
+
+def test_training_learns_a_planted_signal():
+    """Train mode (dropout on): the BCE on a label that depends on one field drops well below the prior entropy."""
+    schema, cfg, st = _small(layers=2, seed=9)
+    rng = np.random.default_rng(0)
+    n = 8192
+    xs, _ = synth.make_inputs(schema, n, seed=2)
+    f = schema.fields[1]                                 # '121': 99 values
+    p = np.where(xs[f] % 2 == 0, 0.9, 0.1)
+    ys = (rng.random(n) < p).astype(np.int64)
+    model = _model(cfg, st)
+    model.compile(torch.optim.Adam(model.parameters(), lr=0.01), "binary_crossentropy", metrics=["binary_crossentropy"])
+    hist = model.fit(x=xs, y=ys, batch_size=512, epochs=6, verbose=0)
+    losses = hist.history['loss']
+    assert losses[-1] < 0.75 * losses[0], losses
+    pred = model.predict(xs, 2048)[:, 0]
+    acc = np.mean((pred > 0.5) == (ys == 1))
+    assert acc > 0.8, acc
+
+
+@pytest.mark.parametrize('alimama', [False, True])
+def test_predict_batch_invariance_and_single_sample(alimama):
+    schema, cfg, st = _small(flag='sota-pos' if alimama else 'sota', alimama=alimama)
+    xs, _ = synth.make_inputs(schema, 333, seed=4)
+    model = _model(cfg, st)
+    ref = model.predict(xs, 333)
+    assert ref.shape == (333, 1) and ref.dtype == np.float64
+    for bs in (1, 7, 100, 332):
+        assert np.array_equal(model.predict(xs, bs), ref), bs            # per-sample independent => bit-identical
+    one = model.predict({k: v[:1] for k, v in xs.items()}, 256)
+    assert np.array_equal(one, ref[:1])
+    with torch.no_grad():
+        X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense))
+        assert np.allclose(O.forward(st, X, cfg).numpy(), ref, atol=2e-6, rtol=0)
+    # permutation equivariance
+    perm = np.random.default_rng(1).permutation(333)
+    assert np.array_equal(model.predict({k: v[perm] for k, v in xs.items()}, 64), ref[perm])
+
+
+def test_single_scenario_batch_and_empty_buckets():
+    schema, cfg, st = _small()
+    xs, ys = synth.make_inputs(schema, 200, seed=6, ctr=0.3)
+    xs['301'][:] = 2                                       # buckets 0, 1 and 3 are empty
+    model = _model(cfg, st)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    yp, w = model.engine.loss_and_grads(X.cuda(), torch.from_numpy(ys.astype(np.float32)).cuda(), training=False,
+                                        l2_emb=1e-5)
+    o_yp, o_bce, _, o_g = O.loss_and_grads(st, X, torch.from_numpy(ys.astype(np.float32)), cfg)
+    assert torch.allclose(yp.cpu(), o_yp[:, 0], atol=2e-6, rtol=0)
+    assert abs(float(w['scalars'][0]) - o_bce.item()) <= 1e-5 * abs(o_bce.item())
+    from gpu_util import dense_grads
+    gr = dense_grads(model, w)
+    ref = o_g['domain_embeddings.weight']
+    assert torch.count_nonzero(gr['domain_embeddings.weight'][[0, 1, 3]]) == 0
+    assert (gr['domain_embeddings.weight'] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9
+
+
+def test_out_of_range_ids_raise_like_the_reference():
+    schema, cfg, st = _small()
+    xs, _ = synth.make_inputs(schema, 64, seed=8)
+    model = _model(cfg, st)
+    bad = dict(xs)
+    bad['101'] = xs['101'].copy()
+    bad['101'][5] = cfg.vocab_sizes[0] + 3
+    with pytest.raises(IndexError):
+        model.predict(bad, 32)
+    bad = dict(xs)
+    bad['301'] = xs['301'].copy()
+    bad['301'][0] = 9                                     # scenario id beyond num_domains
+    with pytest.raises(IndexError):
+        model.predict(bad, 32)
+
+
+def test_train_on_batch_host_api_and_lazy_mode():
+    schema, cfg, st = _small()
+    xs, ys = synth.make_inputs(schema, 256, seed=10, ctr=0.3)
+    X = synth.stack_columns(xs, schema.fields)
+    dense, lazy = _model(cfg, st), _model(cfg, st)
+    for m in (dense, lazy):
+        m.dropout_rate = 0.0
+        m.compile(torch.optim.Adam(m.parameters(), lr=0.005), "binary_crossentropy")
+    lazy.dense_table_updates = False
+    bce_d, reg_d = dense.train_on_batch(X, ys.astype(np.float32))
+    bce_l, reg_l = lazy.train_on_batch(X, ys.astype(np.float32))
+    _, o_bce, o_reg, _ = O.loss_and_grads(st, torch.from_numpy(X), torch.from_numpy(ys.astype(np.float32)), cfg)
+    assert abs(bce_d - o_bce.item()) <= 1e-5 * abs(o_bce.item()) and abs(bce_l - bce_d) <= 1e-6 * abs(bce_d)
+    assert abs(reg_d - o_reg.item()) <= 1e-5 * abs(o_reg.item())
+    # touched rows: identical update in both modes; untouched rows: moved by dense Adam+L2, frozen in lazy mode
+    w = dense.engine.workspace(1, True)
+    n_u = int(w['scalars'][2].item())
+    rows = w['uniq_rows'][:n_u].long()
+    t0 = torch.cat([st['embedding_dict.%s.weight' % f] for f in cfg.sparse_names]).cuda()
+    # (the row-gradient accumulation uses float atomics: summation order may differ between two runs)
+    assert torch.allclose(dense._tables[rows], lazy._tables[rows], atol=1e-6, rtol=0)
+    untouched = torch.ones(t0.shape[0], dtype=torch.bool, device='cuda')
+    untouched[rows] = False
+    assert torch.equal(lazy._tables[untouched], t0[untouched])
+    assert not torch.equal(dense._tables[untouched], t0[untouched])
+
+
+def test_dropout_is_seeded_and_unbiased():
+    schema, cfg, st = _small(layers=1)
+    xs, _ = synth.make_inputs(schema, 2048, seed=12)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields)).cuda()
+    model = _model(cfg, st)
+    eng = model.engine
+    ev = eng.forward(X, training=False)
+    a = eng.forward(X, training=True, dropout_p=0.1, seed=1)
+    b = eng.forward(X, training=True, dropout_p=0.1, seed=1)
+    c = eng.forward(X, training=True, dropout_p=0.1, seed=2)
+    z = eng.forward(X, training=True, dropout_p=0.0, seed=1)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.equal(z, ev)
+    # inverted dropout keeps expectations: averaging many masks approaches the eval-mode logit distribution
+    acc = torch.zeros_like(ev)
+    for sd in range(32):
+        acc += eng.forward(X, training=True, dropout_p=0.1, seed=100 + sd)
+    assert (acc / 32 - ev).abs().mean().item() < 0.25 * (a - ev).abs().mean().item() + 1e-4
+
+
+def test_gather_full_vocab_properties():
+    """BASELINE size: full Ali-CCP vocabulary (6.57 M rows), B = 8192 -- bit-exact vs torch indexing, int and
+    float id paths agree, rows of equal ids are equal."""
+    from satrans_b200 import SATrans
+    schema = synth.aliccp_schema()
+    cols = schema.feature_columns(32)
+    model = SATrans(cols, cols, ['301'], [3], att_layer_num=0, domain_att_layer_num=3, att_head_num=4, meta_mode='QK',
+                    seed=1021, device='cuda:0', flag='sota')
+    xs, _ = synth.make_inputs(schema, 8192, seed=1021)
+    Xf = torch.from_numpy(synth.stack_columns(xs, schema.fields)).cuda()
+    E = model.engine.gather(Xf)
+    ids = Xf.long()
+    off = torch.as_tensor(model._row_off[:-1], device='cuda')
+    ref = model._tables[(ids + off[None, :]).reshape(-1)].view(8192, 19, 32)
+    assert torch.equal(E, ref)
+    assert torch.equal(model.engine.gather(Xf.to(torch.int32)), ref)
+    yp = model.eval()(Xf)
+    assert yp.shape == (8192, 1) and torch.isfinite(yp).all() and (yp > 0).all() and (yp < 1).all()
