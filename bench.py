@@ -284,10 +284,17 @@ def run_b200(args):
     rows = model._tables.shape[0]                                    # rows of this rank's shard
     sweep_bytes = (rows - n_unique) * 6 * 128 + (rows / 8)           # p,m,v read + written once; bitmap read
     roof = None
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (profiles/)
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))['k_adam_sweep']
+        if world == 1 and args.vocab_scale == 1.0:
+            traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+    except Exception:
+        pass
     if 'adam_sweep' in phases:
         ach = sweep_bytes / (phases['adam_sweep'] * 1e-3) / 1e9
         roof = {"kernel": "k_adam_sweep", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": phases['adam_sweep'],
                 "note": "6 x 128 B per untouched table row; timed with CUDA events on its own stream while "
                         "forward/backward run concurrently on the main stream" if args.overlap else

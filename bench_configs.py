@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configurations that bench.py's single headline line does not cover
+(SURVEY.md §8d).  One JSON line per measurement on stdout; run on one B200:
+
+    python bench_configs.py [--only infer_sweep,alimama,zipf,lazy]
+
+  infer_sweep : config 5 — eval-mode scoring, batch 1 Ki .. 1 Mi, meta_mode QK and QKV (identical math in the
+                reference: satrans.py has no 'V' branch), fp32 CUDA-core vs tcgen05 3xTF32 vs tcgen05 TF32
+  alimama     : config 3 — ENP+MetaNet (flag 'sota-pos', scenario column shopping_level, dense price), train step B=8192
+  zipf        : config 2 with Zipf(1.05) ids instead of uniform (realistic skew: hot rows)
+  lazy        : config 2 with touched-rows-only table updates (NOT the reference's semantics; reported separately)
+
+All timings: CUDA events, >=3 warm-up iterations, inputs resident in HBM.
+"""
+import argparse
+import json
+import sys
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def timeit(fn, iters, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def build(schema, flag, mode, lr, precision):
+    import torch
+    from satrans_b200 import SATrans
+    cols = schema.feature_columns(32)
+    model = SATrans(cols, cols, [schema.domain_col], [schema.num_domains], att_layer_num=0, domain_att_layer_num=3,
+                    att_head_num=4, meta_mode=mode, seed=1021, device='cuda:0', flag=flag)
+    model.compile(torch.optim.Adam(model.parameters(), lr=lr), "binary_crossentropy")
+    model.engine.precision = precision
+    return model
+
+
+def train_bench(name, schema, flag, lr, ids, lazy, precision, B=8192, steps=20):
+    import torch
+    from satrans_b200 import synth
+    model = build(schema, flag, 'QK', lr, precision)
+    model.dense_table_updates = not lazy
+    nb = 8
+    xs, ys = synth.make_inputs(schema, nb * B, seed=1021, dist=ids, ctr=0.04)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense)).cuda()
+    y = torch.from_numpy(ys.astype(np.float32)).cuda()
+    eng, hp = model.engine, model._opt_hparams
+    it = [0]
+
+    def step():
+        k = it[0] % nb
+        it[0] += 1
+        eng.train_step(X[k * B:(k + 1) * B], y[k * B:(k + 1) * B], lr=hp['lr'], l2_emb=1e-5, dense_mode=not lazy,
+                       training=True, dropout_p=0.1, seed=it[0])
+    for _ in range(5):
+        step()
+    eng.timing = {}
+    ms = timeit(step, steps, warm=0)
+    phases = eng.timing_ms()
+    print(json.dumps({"bench": name, "metric": "train_samples_per_sec", "value": B / (ms * 1e-3), "unit": "samples/s",
+                      "ms_per_step": ms, "batch": B, "rows": schema.total_rows, "fields": len(schema.fields),
+                      "flag": flag, "ids": ids, "table_updates": "lazy" if lazy else "dense (reference semantics)",
+                      "precision": precision, "phases_ms": phases}), flush=True)
+    del model
+    torch.cuda.empty_cache()
+
+
+def infer_sweep(precisions):
+    import torch
+    from satrans_b200 import synth
+    schema = synth.aliccp_schema()
+    for mode in ('QK', 'QKV'):
+        model = build(schema, 'sota', mode, 0.005, 'fp32').eval()
+        for B in (1024, 4096, 16384, 65536, 262144, 1048576):
+            xs, _ = synth.make_inputs(schema, B, seed=7)
+            X = torch.from_numpy(np.stack([xs[f].astype(np.int32) for f in schema.fields], axis=1)).cuda()
+            for prec in precisions:
+                model.engine.precision = prec
+                ms = timeit(lambda: model.engine.forward(X, training=False), 10 if B <= 65536 else 4)
+                print(json.dumps({"bench": "infer_sweep", "metric": "infer_samples_per_sec", "value": B / (ms * 1e-3),
+                                  "unit": "samples/s", "ms": ms, "batch": B, "meta_mode": mode, "precision": prec,
+                                  "gflops": B * 1540672 / (ms * 1e-3) / 1e9,
+                                  "hbm_gbs_algorithmic": B * 2508 / (ms * 1e-3) / 1e9}), flush=True)
+            del X
+        del model
+        torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default='infer_sweep,alimama,zipf,lazy')
+    args = ap.parse_args()
+    from satrans_b200 import synth
+    only = set(args.only.split(','))
+    if 'alimama' in only:
+        for prec in ('tf32x3', 'fp32'):
+            train_bench('alimama_enp_train', synth.alimama_schema(), 'sota-pos', 0.001, 'uniform', False, prec)
+    if 'zipf' in only:
+        train_bench('aliccp_en_train_zipf', synth.aliccp_schema(), 'sota', 0.005, 'zipf', False, 'tf32x3')
+    if 'lazy' in only:
+        train_bench('aliccp_en_train_lazy', synth.aliccp_schema(), 'sota', 0.005, 'uniform', True, 'tf32x3')
+    if 'infer_sweep' in only:
+        infer_sweep(('fp32', 'tf32x3', 'tf32'))
+
+
+if __name__ == '__main__':
+    main()
