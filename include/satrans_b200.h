@@ -55,6 +55,8 @@ extern "C" {
 #define SAT_FLAG_META_K 4    /* 'K' in meta_mode                                                          */
 #define SAT_FLAG_RELU 8      /* 'relu' in flag: ReLU on the output projection                             */
 #define SAT_FLAG_RES 16      /* att_res: residual connection                                              */
+#define SAT_FLAG_LOSS_MSE 32 /* loss = F.mse_loss(y_pred, y, 'sum') instead of binary cross-entropy (meta_basemodel.py:627-640) */
+#define SAT_FLAG_LOSS_MAE 64 /* loss = F.l1_loss(y_pred, y, 'sum')                                         */
 
 /*
  * Model description.  All dense (non-table) parameters live in ONE flat fp32 buffer `dense`
@@ -137,6 +139,12 @@ typedef struct SatWork {
     int32_t* tiles2;      /* tile list of the tensor-core forward (128 tokens per tile)                  */
 } SatWork;
 
+/* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */
+#define SAT_OPT_ADAM 0      /* m, v */
+#define SAT_OPT_SGD 1       /* p -= lr*g                                  (no state)               */
+#define SAT_OPT_ADAGRAD 2   /* v += g*g; p -= lr*g/(sqrt(v)+eps)          (v = state_sum)          */
+#define SAT_OPT_RMSPROP 3   /* v = a*v+(1-a)*g*g; p -= lr*g/(sqrt(v)+eps) (v = square_avg, a=beta2) */
+
 typedef struct SatAdam {
     float lr, beta1, beta2, eps;
     float l2_emb;         /* l2_reg_embedding (reference satrans.py:117, meta_basemodel.py:179) */
@@ -144,8 +152,8 @@ typedef struct SatAdam {
     int32_t dense_mode;   /* 1 = reference semantics (every table row gets L2 + Adam every step,
                              reference meta_basemodel.py:577-593 + main.py:343);
                              0 = touched rows only (lazy/sparse Adam)                           */
-    int32_t pad0;
-    float* tab_m; float* tab_v;       /* [total_rows][32] Adam moments of the tables            */
+    int32_t kind;         /* SAT_OPT_*                                                           */
+    float* tab_m; float* tab_v;       /* [local_rows][32] optimiser state of the tables (unused ones may be NULL) */
     float* dense_m; float* dense_v;   /* [n_dense_params]                                       */
 } SatAdam;
 

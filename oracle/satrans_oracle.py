@@ -267,7 +267,13 @@ def reg_loss(st, cfg: OracleConfig):
     return tot
 
 
-def loss_and_grads(st, X, y, cfg: OracleConfig, masks=None, with_reg: bool = True):
+def _loss(yp, y, kind='binary_crossentropy'):
+    """loss strings of BaseModel._get_loss_func (meta_basemodel.py:627-640), reduction='sum' as fit uses them (:317)."""
+    fn = {'binary_crossentropy': F.binary_cross_entropy, 'mse': F.mse_loss, 'mae': F.l1_loss}[kind]
+    return fn(yp, y, reduction='sum')
+
+
+def loss_and_grads(st, X, y, cfg: OracleConfig, masks=None, with_reg: bool = True, loss: str = 'binary_crossentropy'):
     """One forward + BCE(sum) + reg + backward (meta_basemodel.py:311-327) through torch autograd.
     Returns (y_pred (B,1), bce_sum, reg, {canonical key: grad})."""
     keys = trainable_keys(cfg)
@@ -275,7 +281,7 @@ def loss_and_grads(st, X, y, cfg: OracleConfig, masks=None, with_reg: bool = Tru
     work = dict(st)
     work.update(leaves)
     yp = forward(work, X, cfg, masks)
-    bce = F.binary_cross_entropy(yp.squeeze(-1), y.to(yp.dtype).reshape(-1), reduction='sum')   # :317
+    bce = _loss(yp.squeeze(-1), y.to(yp.dtype).reshape(-1), loss)                               # :317
     reg = reg_loss(work, cfg) if with_reg else torch.zeros((), dtype=yp.dtype)
     total = bce + reg                                                                           # :320
     total.backward()
@@ -322,17 +328,20 @@ class Trainer:
     train-mode forward (dropout from torch's RNG), BCE(sum) + dense L2, autograd backward (dense table
     gradients), torch.optim.Adam over every parameter.  Used as the timed CPU baseline."""
 
-    def __init__(self, st, cfg: OracleConfig, lr: float):
+    def __init__(self, st, cfg: OracleConfig, lr: float, optimizer: str = 'adam', loss: str = 'binary_crossentropy'):
         self.cfg = cfg
+        self.loss = loss
         self.state = dict(st)
         self.params = {k: st[k].detach().clone().requires_grad_(True) for k in trainable_keys(cfg)}
         self.state.update(self.params)
-        self.optim = torch.optim.Adam(list(self.params.values()), lr=lr)
+        cls = {'adam': torch.optim.Adam, 'sgd': torch.optim.SGD, 'adagrad': torch.optim.Adagrad,
+               'rmsprop': torch.optim.RMSprop}[optimizer]                     # meta_basemodel.py:612-625
+        self.optim = cls(list(self.params.values()), lr=lr)
 
     def step(self, X, y, train_mode=True):
         yp = forward(self.state, X, self.cfg, masks='rng' if train_mode else None).squeeze(-1)
         self.optim.zero_grad()
-        loss = F.binary_cross_entropy(yp, y.reshape(-1), reduction='sum')
+        loss = _loss(yp, y.reshape(-1), self.loss)
         reg = reg_loss(self.state, self.cfg)
         total = loss + reg
         loss_v, total_v = loss.item(), total.item()          # the reference's two .item() calls (:324-325)

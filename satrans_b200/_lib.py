@@ -17,6 +17,8 @@ SAT_WORK_BUFFERS = 22
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
+FLAG_LOSS_MSE, FLAG_LOSS_MAE = 32, 64
+OPT_ADAM, OPT_SGD, OPT_ADAGRAD, OPT_RMSPROP = 0, 1, 2, 3
 ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
 ADAM_TOUCHED, ADAM_UNTOUCHED = 1, 2
 
@@ -48,7 +50,7 @@ class SatWork(C.Structure):
 
 class SatAdam(C.Structure):
     _fields_ = [('lr', f32), ('beta1', f32), ('beta2', f32), ('eps', f32), ('l2_emb', f32),
-                ('step', i32), ('dense_mode', i32), ('pad0', i32),
+                ('step', i32), ('dense_mode', i32), ('kind', i32),
                 ('tab_m', vp), ('tab_v', vp), ('dense_m', vp), ('dense_v', vp)]
 
 

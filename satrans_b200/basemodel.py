@@ -293,30 +293,50 @@ class BaseModel(nn.Module):
         self.metrics = self._get_metrics(metrics)
 
     def _get_optim(self, optimizer):
+        """String or torch.optim instance -> hyper-parameters of the fused update (reference meta_basemodel.py:
+        612-625: sgd lr=0.01, adam, adagrad, rmsprop with torch defaults).  Only the plain variants exist in the
+        kernels (no momentum / weight decay / amsgrad / centering); anything else raises."""
+        from . import _lib
         if isinstance(optimizer, str):
-            if optimizer == "adam":
-                self._opt_hparams = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
-            elif optimizer in ("sgd", "adagrad", "rmsprop"):
-                raise NotImplementedError("the fused B200 path implements Adam (the reference's optimiser, "
-                                          "main.py:343); '%s' is not available" % optimizer)
-            else:
+            table = {"sgd": dict(kind=_lib.OPT_SGD, lr=0.01, betas=(0.0, 0.0), eps=0.0),
+                     "adam": dict(kind=_lib.OPT_ADAM, lr=1e-3, betas=(0.9, 0.999), eps=1e-8),
+                     "adagrad": dict(kind=_lib.OPT_ADAGRAD, lr=0.01, betas=(0.0, 0.0), eps=1e-10),
+                     "rmsprop": dict(kind=_lib.OPT_RMSPROP, lr=0.01, betas=(0.0, 0.99), eps=1e-8)}
+            if optimizer not in table:
                 raise NotImplementedError
+            self._opt_hparams = table[optimizer]
             return optimizer
+        g = optimizer.param_groups[0] if hasattr(optimizer, 'param_groups') else None
         if isinstance(optimizer, torch.optim.Adam):
-            g = optimizer.param_groups[0]
             if g.get('amsgrad') or g.get('weight_decay', 0) != 0 or g.get('maximize'):
                 raise NotImplementedError("Adam with amsgrad / weight_decay / maximize is not on the SATrans path")
-            self._opt_hparams = dict(lr=g['lr'], betas=tuple(g['betas']), eps=g['eps'])
-            return optimizer
-        raise NotImplementedError("the fused B200 path implements torch.optim.Adam (reference main.py:343)")
+            self._opt_hparams = dict(kind=_lib.OPT_ADAM, lr=g['lr'], betas=tuple(g['betas']), eps=g['eps'])
+        elif isinstance(optimizer, torch.optim.SGD):
+            if g.get('momentum', 0) != 0 or g.get('weight_decay', 0) != 0 or g.get('nesterov') or g.get('maximize'):
+                raise NotImplementedError("SGD with momentum / weight_decay / nesterov is not built")
+            self._opt_hparams = dict(kind=_lib.OPT_SGD, lr=g['lr'], betas=(0.0, 0.0), eps=0.0)
+        elif isinstance(optimizer, torch.optim.Adagrad):
+            if g.get('lr_decay', 0) != 0 or g.get('weight_decay', 0) != 0 or g.get('initial_accumulator_value', 0) != 0:
+                raise NotImplementedError("Adagrad with lr_decay / weight_decay / initial accumulator is not built")
+            self._opt_hparams = dict(kind=_lib.OPT_ADAGRAD, lr=g['lr'], betas=(0.0, 0.0), eps=g['eps'])
+        elif isinstance(optimizer, torch.optim.RMSprop):
+            if g.get('momentum', 0) != 0 or g.get('centered') or g.get('weight_decay', 0) != 0:
+                raise NotImplementedError("RMSprop with momentum / centered / weight_decay is not built")
+            self._opt_hparams = dict(kind=_lib.OPT_RMSPROP, lr=g['lr'], betas=(0.0, g['alpha']), eps=g['eps'])
+        else:
+            raise NotImplementedError("optimizer must be 'sgd' | 'adam' | 'adagrad' | 'rmsprop' or the matching "
+                                      "torch.optim instance (reference meta_basemodel.py:612-625)")
+        return optimizer
 
     def _get_loss_func(self, loss):
+        """'binary_crossentropy' | 'mse' | 'mae' (reference meta_basemodel.py:627-640), fused into the forward
+        kernel's logit head; custom callables are not supported."""
         if isinstance(loss, str):
-            if loss == "binary_crossentropy":
-                return "binary_crossentropy"
-            if loss in ("mse", "mae"):
-                raise NotImplementedError("the fused B200 path implements binary_crossentropy "
-                                          "(reference main.py:343-344)")
+            if loss in ("binary_crossentropy", "mse", "mae"):
+                self._loss_kind = loss
+                if getattr(self, '_engine', None) is not None:
+                    self._engine._bound_ptrs = None       # loss kind travels in the model descriptor
+                return loss
             raise NotImplementedError
         raise NotImplementedError("custom loss callables are not supported by the fused path")
 
@@ -420,7 +440,7 @@ class BaseModel(nn.Module):
                     xb, yb = Xd.index_select(0, idx).contiguous(), yd.index_select(0, idx).contiguous()
                 else:
                     xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
-                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
+                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], kind=hp['kind'],
                                            l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                            training=True, dropout_p=self.dropout_rate,
                                            seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
@@ -483,7 +503,7 @@ class BaseModel(nn.Module):
         eng = self.engine
         self.train()
         _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
-                              l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
+                              kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
                               dropout_p=self.dropout_rate,
                               seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
         sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()

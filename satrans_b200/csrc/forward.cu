@@ -187,12 +187,22 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
             a.y_pred[b] = yp;
             if (a.y) {
                 const float yt = __ldg(a.y + b);
-                // F.binary_cross_entropy(reduction='sum'): logs clamped at -100
-                const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
-                atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
-                // autograd of BCE then sigmoid: (p - y) / max((1-p) p, 1e-12) * (1-p) p
-                const float pq = (1.f - yp) * yp;
-                a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
+                const float pq = (1.f - yp) * yp;            // d sigmoid / d logit
+                if (m.flags & SAT_FLAG_LOSS_MSE) {           // F.mse_loss(reduction='sum')
+                    const float d = yp - yt;
+                    atomicAdd(&s_loss, (double)(d * d));
+                    a.dz[p] = 2.f * d * pq;
+                } else if (m.flags & SAT_FLAG_LOSS_MAE) {    // F.l1_loss(reduction='sum')
+                    const float d = yp - yt;
+                    atomicAdd(&s_loss, (double)fabsf(d));
+                    a.dz[p] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * pq;
+                } else {
+                    // F.binary_cross_entropy(reduction='sum'): logs clamped at -100; autograd of BCE then sigmoid:
+                    // (p - y) / max((1-p) p, 1e-12) * (1-p) p
+                    const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
+                    atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
+                    a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
+                }
             }
         }
         __syncthreads();

@@ -20,14 +20,26 @@
 namespace sat {
 
 struct AdamConst {
-    float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, two_l2;
+    float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, two_l2, lr;
+    int kind;
 };
 
+// one parameter element; follows the op order of torch.optim's single-tensor implementations
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, const AdamConst& c) {
-    m = fmaf(g - m, c.one_minus_b1, m);
-    v = fmaf(c.one_minus_b2 * g, g, v * c.b2);
-    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-    p = p - c.step_size * (m / denom);
+    if (c.kind == SAT_OPT_ADAM) {
+        m = fmaf(g - m, c.one_minus_b1, m);
+        v = fmaf(c.one_minus_b2 * g, g, v * c.b2);
+        const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+        p = p - c.step_size * (m / denom);
+    } else if (c.kind == SAT_OPT_SGD) {
+        p = p - c.lr * g;
+    } else if (c.kind == SAT_OPT_ADAGRAD) {
+        v = fmaf(g, g, v);
+        p = p - c.lr * (g / (sqrtf(v) + c.eps));
+    } else {    // RMSprop, alpha in b2
+        v = fmaf(c.one_minus_b2 * g, g, v * c.b2);
+        p = p - c.lr * (g / (sqrtf(v) + c.eps));
+    }
 }
 
 __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const float4& g, const AdamConst& c) {
@@ -72,7 +84,11 @@ k_adam_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict_
                 const long long row = i >> 3;
                 act[u] = !((__ldg(bitmap + (row >> 5)) >> (row & 31)) & 1u);
             }
-            if (act[u]) { p[u] = __ldcs(P + i); m[u] = __ldcs(M + i); v[u] = __ldcs(V + i); }
+            if (act[u]) {
+                p[u] = __ldcs(P + i);
+                if (c.kind == SAT_OPT_ADAM) m[u] = __ldcs(M + i);
+                if (c.kind != SAT_OPT_SGD) v[u] = __ldcs(V + i);
+            }
         }
 #pragma unroll
         for (int u = 0; u < SWEEP_UNROLL; ++u) {
@@ -82,7 +98,9 @@ k_adam_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict_
                 sq = fmaf(p[u].z, p[u].z, sq); sq = fmaf(p[u].w, p[u].w, sq);
                 const float4 g = make_float4(c.two_l2 * p[u].x, c.two_l2 * p[u].y, c.two_l2 * p[u].z, c.two_l2 * p[u].w);
                 adam4(p[u], m[u], v[u], g, c);
-                __stcs(P + i, p[u]); __stcs(M + i, m[u]); __stcs(V + i, v[u]);
+                __stcs(P + i, p[u]);
+                if (c.kind == SAT_OPT_ADAM) __stcs(M + i, m[u]);
+                if (c.kind != SAT_OPT_SGD) __stcs(V + i, v[u]);
             }
         }
     }
@@ -103,14 +121,18 @@ k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__
          i += (long long)gridDim.x * ROWS_THREADS) {
         const long long slot = i >> 3;
         const long long e = (long long)__ldg(uniq_rows + slot) * 8 + (i & 7);
-        float4 p = P[e], m = M[e], v = V[e];
+        float4 p = P[e], m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
+        if (c.kind == SAT_OPT_ADAM) m = M[e];
+        if (c.kind != SAT_OPT_SGD) v = V[e];
         float4 g = row_grad[i];
         row_grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         sq = fmaf(p.x, p.x, sq); sq = fmaf(p.y, p.y, sq); sq = fmaf(p.z, p.z, sq); sq = fmaf(p.w, p.w, sq);
         g.x = fmaf(c.two_l2, p.x, g.x); g.y = fmaf(c.two_l2, p.y, g.y);
         g.z = fmaf(c.two_l2, p.z, g.z); g.w = fmaf(c.two_l2, p.w, g.w);
         adam4(p, m, v, g, c);
-        P[e] = p; M[e] = m; V[e] = v;
+        P[e] = p;
+        if (c.kind == SAT_OPT_ADAM) M[e] = m;
+        if (c.kind != SAT_OPT_SGD) V[e] = v;
     }
     block_sum_to((double)sq, reg_part + blockIdx.x);
 }
@@ -120,9 +142,13 @@ __global__ void __launch_bounds__(256)
 k_adam_dense(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V, const float* __restrict__ G, long long n,
              AdamConst c) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        float p = P[i], m = M[i], v = V[i];
+        float p = P[i], m = 0.f, v = 0.f;
+        if (c.kind == SAT_OPT_ADAM) m = M[i];
+        if (c.kind != SAT_OPT_SGD) v = V[i];
         adam1(p, m, v, G[i], c);
-        P[i] = p; M[i] = m; V[i] = v;
+        P[i] = p;
+        if (c.kind == SAT_OPT_ADAM) M[i] = m;
+        if (c.kind != SAT_OPT_SGD) V[i] = v;
     }
 }
 
@@ -172,12 +198,16 @@ static AdamConst make_const(const SatAdam* a, bool with_l2) {
     c.bc2_sqrt = (float)sqrt(bc2);
     c.eps = a->eps;
     c.two_l2 = with_l2 ? 2.f * a->l2_emb : 0.f;
+    c.lr = a->lr;
+    c.kind = a->kind;
     return c;
 }
 
 // reg_part layout: [0, SWEEP_BLOCKS) sweep partials, [SWEEP_BLOCKS, SWEEP_BLOCKS + ROWS_BLOCKS) touched-row partials
 extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, int32_t which, void* stream) {
-    if (!m || !w || !a || !a->tab_m || !a->tab_v || !w->reg_part) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: null argument");
+    if (!m || !w || !a || !w->reg_part || (a->kind == SAT_OPT_ADAM && !a->tab_m) || (a->kind != SAT_OPT_SGD && !a->tab_v) ||
+        a->kind < 0 || a->kind > SAT_OPT_RMSPROP)
+        return sat_host::fail(SAT_EINVAL, "sat_tables_adam: null argument / bad optimiser kind");
     if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: step must be >= 1");
     const AdamConst c = make_const(a, true);
     const long long n_vec = m->local_rows * 8;
@@ -209,7 +239,8 @@ extern "C" int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream) {
 }
 
 extern "C" int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream) {
-    if (!m || !w || !a || !a->dense_m || !a->dense_v || !w->dgrad) return sat_host::fail(SAT_EINVAL, "sat_dense_adam: null argument");
+    if (!m || !w || !a || !w->dgrad || (a->kind == SAT_OPT_ADAM && !a->dense_m) || (a->kind != SAT_OPT_SGD && !a->dense_v))
+        return sat_host::fail(SAT_EINVAL, "sat_dense_adam: null argument");
     if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_dense_adam: step must be >= 1");
     const AdamConst c = make_const(a, false);
     int blocks = (int)((m->n_dense_params + 255) / 256);

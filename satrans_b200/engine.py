@@ -156,7 +156,9 @@ class Engine:
         d = self.desc
         d.F, d.L, d.H = lay['F'], lay['L'], lay['H']
         d.n_dom, d.n_dense, d.n_cols = lay['n_dom'], lay['n_dense'], lay['n_cols']
-        d.flags, d.enc_in, d.dom_col = lay['flags'], lay['enc_in'], lay['dom_col']
+        loss_kind = getattr(m, '_loss_kind', 'binary_crossentropy')
+        d.flags = lay['flags'] | {'binary_crossentropy': 0, 'mse': _lib.FLAG_LOSS_MSE, 'mae': _lib.FLAG_LOSS_MAE}[loss_kind]
+        d.enc_in, d.dom_col = lay['enc_in'], lay['dom_col']
         d.n_dense_params = lay['n_dense_params']
         for k in ('off_dom', 'off_lid', 'off_qkv', 'off_encw', 'off_encb', 'off_layers', 'off_headw', 'off_headb'):
             setattr(d, k, lay[k])
@@ -323,17 +325,22 @@ class Engine:
         return y_pred, w
 
     # ------------------------------------------------------------------------------------------
-    def _adam_state(self):
-        if self._adam is None:
+    def _adam_state(self, kind=0):
+        """Optimiser state buffers: Adam m+v, Adagrad / RMSprop v only, SGD none."""
+        if self._adam is None or self._adam.get('kind') != kind:
             m = self.model
+            need_m, need_v = kind == _lib.OPT_ADAM, kind != _lib.OPT_SGD
             self._adam = {
-                'tab_m': torch.zeros_like(m._tables), 'tab_v': torch.zeros_like(m._tables),
-                'dense_m': torch.zeros_like(m._dense), 'dense_v': torch.zeros_like(m._dense),
+                'kind': kind,
+                'tab_m': torch.zeros_like(m._tables) if need_m else None,
+                'tab_v': torch.zeros_like(m._tables) if need_v else None,
+                'dense_m': torch.zeros_like(m._dense) if need_m else None,
+                'dense_v': torch.zeros_like(m._dense) if need_v else None,
             }
         return self._adam
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=False):
+                   dropout_p=0.1, seed=0, overlap=False, kind=0):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
         finalize kernel (read them with .item() only when needed: that synchronises)."""
@@ -341,13 +348,16 @@ class Engine:
         kind = self._check_x(X)
         B = X.shape[0]
         w = self.workspace(B, True)
-        st = self._adam_state()
+        st = self._adam_state(kind)
         self.step_count += 1
         a = SatAdam()
+        a.kind = int(kind)
         a.lr, a.beta1, a.beta2, a.eps, a.l2_emb = float(lr), float(betas[0]), float(betas[1]), float(eps), float(l2_emb)
         a.step, a.dense_mode = self.step_count, int(bool(dense_mode))
-        a.tab_m, a.tab_v = st['tab_m'].data_ptr(), st['tab_v'].data_ptr()
-        a.dense_m, a.dense_v = st['dense_m'].data_ptr(), st['dense_v'].data_ptr()
+        a.tab_m = st['tab_m'].data_ptr() if st['tab_m'] is not None else None
+        a.tab_v = st['tab_v'].data_ptr() if st['tab_v'] is not None else None
+        a.dense_m = st['dense_m'].data_ptr() if st['dense_m'] is not None else None
+        a.dense_v = st['dense_v'].data_ptr() if st['dense_v'] is not None else None
         l, d = lib(), C.byref(self.desc)
         main = torch.cuda.current_stream()
         s = main.cuda_stream
@@ -406,7 +416,7 @@ class Engine:
         return y_pred, w
 
     def adam_state(self):
-        return self._adam_state()
+        return self._adam_state(self._adam['kind'] if self._adam else 0)
 
     def reset_optimizer(self):
         self._adam = None

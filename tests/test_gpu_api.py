@@ -206,3 +206,49 @@ def test_gather_full_vocab_properties():
     assert torch.equal(model.engine.gather(Xf.to(torch.int32)), ref)
     yp = model.eval()(Xf)
     assert yp.shape == (8192, 1) and torch.isfinite(yp).all() and (yp > 0).all() and (yp < 1).all()
+
+
+@pytest.mark.parametrize('opt,lr', [('sgd', 0.01), ('adagrad', 0.01), ('rmsprop', 0.001)])
+def test_other_optimizers_match_torch(opt, lr):
+    """compile('sgd' | 'adagrad' | 'rmsprop') (reference meta_basemodel.py:612-625): 3 fused steps == torch.optim."""
+    schema, cfg, st = _small(layers=1)
+    xs, ys = synth.make_inputs(schema, 3 * 128, seed=21, ctr=0.3)
+    X = synth.stack_columns(xs, schema.fields)
+    y = ys.astype(np.float32)
+    model = _model(cfg, st)
+    model.dropout_rate = 0.0
+    cls = {'sgd': torch.optim.SGD, 'adagrad': torch.optim.Adagrad, 'rmsprop': torch.optim.RMSprop}[opt]
+    model.compile(cls(model.parameters(), lr=lr), "binary_crossentropy")
+    tr = O.Trainer({k: v.clone() for k, v in st.items()}, cfg, lr=lr, optimizer=opt)
+    for k in range(3):
+        model.train_on_batch(X[k * 128:(k + 1) * 128], y[k * 128:(k + 1) * 128])
+        tr.step(torch.from_numpy(X[k * 128:(k + 1) * 128]), torch.from_numpy(y[k * 128:(k + 1) * 128]), train_mode=False)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in O.trainable_keys(cfg):
+        ref = tr.params[k].detach()
+        err = (sd[k] - ref).abs()
+        tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
+        assert (err <= tight).float().mean().item() >= 0.995, (k, opt)
+        assert err.max().item() <= 0.05 * max(lr, 1e-3) * 3 * (10 if opt != 'sgd' else 1), (k, opt, err.max().item())
+
+
+@pytest.mark.parametrize('loss', ['mse', 'mae'])
+def test_other_losses_match_torch(loss):
+    """compile(loss='mse' | 'mae') (reference meta_basemodel.py:627-640): loss value and every gradient."""
+    from gpu_util import dense_grads, table_grads
+    schema, cfg, st = _small(layers=1)
+    xs, ys = synth.make_inputs(schema, 200, seed=22, ctr=0.4)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    y = torch.from_numpy(ys.astype(np.float32))
+    model = _model(cfg, st)
+    model.compile('adam', loss)
+    yp, w = model.engine.loss_and_grads(X.cuda(), y.cuda(), training=False, l2_emb=cfg.l2_reg_embedding)
+    torch.cuda.synchronize()
+    o_yp, o_loss, _, o_g = O.loss_and_grads(st, X, y, cfg, loss=loss)
+    assert abs(float(w['scalars'][0]) - o_loss.item()) <= 1e-5 * abs(o_loss.item())
+    grads = dense_grads(model, w)
+    tg, _ = table_grads(model, w, cfg.l2_reg_embedding)
+    grads.update(tg)
+    for k in O.trainable_keys(cfg):
+        ref = o_g[k]
+        assert (grads[k] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, k

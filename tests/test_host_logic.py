@@ -122,6 +122,12 @@ def test_errors_match_reference_contract():
     m = SATrans(cols, cols, ['301'], [3], att_head_num=2, flag='sota')
     with pytest.raises(NotImplementedError):
         m.compile('nadam', 'binary_crossentropy')
+    for name in ('sgd', 'adam', 'adagrad', 'rmsprop'):
+        m.compile(name, 'binary_crossentropy')
+    for loss in ('mse', 'mae'):
+        m.compile('adam', loss)
+    with pytest.raises(NotImplementedError):
+        m.compile(torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9), 'binary_crossentropy')
     with pytest.raises(NotImplementedError):
         m.compile('adam', 'hinge')
     m.compile(torch.optim.Adam(m.parameters(), lr=0.005), 'binary_crossentropy', metrics=['binary_crossentropy', 'auc'])
