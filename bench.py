@@ -220,7 +220,7 @@ def run_b200(args):
     def step(i, overlap=args.overlap):
         k = i % n_batches
         return eng.train_step(Xd[k * B:(k + 1) * B], yd[k * B:(k + 1) * B], lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
-                              kind=hp['kind'], l2_emb=1e-5, dense_mode=not args.lazy, training=True, dropout_p=0.1, seed=1021 + i,
+                              opt_kind=hp['kind'], l2_emb=1e-5, dense_mode=not args.lazy, training=True, dropout_p=0.1, seed=1021 + i,
                               overlap=overlap)
 
     def barrier():

@@ -236,6 +236,12 @@ int sat_pack_weights(const SatModel* m, SatWork* w, void* stream);
 int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
                    float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream);
 
+/* ---- "next" row: SelfAttention_Layer.forward (reference submodules.py:178-238) through the same
+ *      per-sample field-attention code.  x, out: [B][F][32]; W_*: [32][32] used as x @ W; forward only. ---------- */
+int sat_selfatt_fwd(const float* x, float* out, const float* wq, const float* wk, const float* wv, const float* wres,
+                    const float* ln_g, const float* ln_b, int32_t B, int32_t F, int32_t H, int32_t use_res,
+                    int32_t training, float dropout_p, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,8 +195,40 @@ def build_case(name):
     return out
 
 
+def build_selfatt():
+    """SelfAttention_Layer of the unmodified reference (submodules.py:178-238): eval-mode forward goldens."""
+    sys.path.insert(0, ROOT)
+    from oracle import satrans_oracle as O
+    import_reference()
+    from models.submodules import SelfAttention_Layer
+    out = {}
+    g = torch.Generator().manual_seed(3)
+    for heads, Fn, res in ((4, 19, True), (2, 15, True), (4, 7, False)):
+        layer = SelfAttention_Layer(32, heads, use_res=res).eval()
+        with torch.no_grad():
+            layer.layer_norm.weight.add_(1.0)          # N(0, .05) gamma would squash the output to ~0
+        x = torch.randn((24, Fn, 32), generator=g) * 0.5
+        with torch.no_grad():
+            y = layer(x)
+        tag = 'h%d_f%d_r%d' % (heads, Fn, int(res))
+        out[tag + '/x'] = x.numpy()
+        out[tag + '/y'] = y.numpy()
+        sd = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+        for k, v in sd.items():
+            out[tag + '/state/' + k] = v.numpy()
+        with torch.no_grad():
+            o = O.self_attention_layer(x, sd, heads, res)
+        assert torch.allclose(o, y, atol=1e-6, rtol=0), (o - y).abs().max()
+    return out
+
+
 def main():
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
+    path = os.path.join(ROOT, 'tests', 'golden', 'selfatt_layer.npz')
+    np.savez_compressed(path, **build_selfatt())
+    print('selfatt_layer ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+    if os.environ.get('SAT_GOLDEN_ONLY_SELFATT'):
+        return
     for name in CASES:
         out = build_case(name)
         path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')

@@ -257,6 +257,24 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
     return (y, aux) if return_aux else y
 
 
+def self_attention_layer(x, p, heads: int, use_res: bool = True, masks=None):
+    """SelfAttention_Layer.forward, submodules.py:208-238 ("next" row: AutoInt / STAR-Trans style front-end).
+    p: dict with W_Query, W_Key, W_Value, W_Res, layer_norm.weight, layer_norm.bias (W_Out is never used)."""
+    B_, F_, d = x.shape
+    dh = d // heads
+    q, k, v = x @ p['W_Query'], x @ p['W_Key'], x @ p['W_Value']
+    qh = q.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    kh = k.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    vh = v.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    a = F.softmax(torch.matmul(qh, kh.transpose(-1, -2)) / (dh ** 0.5), dim=-1)     # :222-225
+    a = _drop(a, 0.1, masks, 'att')
+    r = torch.matmul(a, vh).permute(1, 2, 0, 3).reshape(B_, F_, d)                   # :227-230
+    r = _drop(r, 0.1, masks, 'out')                                                 # :231
+    if use_res:
+        r = r + x @ p['W_Res']                                                      # :232-233
+    return _layer_norm(F.relu(r), p['layer_norm.weight'], p['layer_norm.bias'])     # :234-235
+
+
 def reg_loss(st, cfg: OracleConfig):
     """get_regularization_loss, meta_basemodel.py:577-593: l2 * sum(square(w)) over the embedding
     tables only (linear_model is registered with l2=0, satrans.py:120)."""

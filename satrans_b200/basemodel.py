@@ -440,7 +440,7 @@ class BaseModel(nn.Module):
                     xb, yb = Xd.index_select(0, idx).contiguous(), yd.index_select(0, idx).contiguous()
                 else:
                     xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
-                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], kind=hp['kind'],
+                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                            l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                            training=True, dropout_p=self.dropout_rate,
                                            seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
@@ -503,7 +503,7 @@ class BaseModel(nn.Module):
         eng = self.engine
         self.train()
         _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
-                              kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
+                              opt_kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
                               dropout_p=self.dropout_rate,
                               seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
         sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()

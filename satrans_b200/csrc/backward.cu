@@ -276,14 +276,10 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
                 const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
                                  __popc(wbits & ((1u << (lrow & 31)) - 1u));
                 float* dst = m.shard_row_grad[owner] + (long long)slot * D;
-                if (owner == m.shard_rank) {
+                // 16-byte vector reductions, local or over NVLink peer memory (verified: tests/p2p_probe.py mode 3)
 #pragma unroll
-                    for (int i = 0; i < D; i += 4)
-                        atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) atomicAdd(dst + i, dxa[i]);       // scalar reductions over NVLink
-                }
+                for (int i = 0; i < D; i += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
             }
         }
     }

@@ -340,7 +340,7 @@ class Engine:
         return self._adam
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=False, kind=0):
+                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
         finalize kernel (read them with .item() only when needed: that synchronises)."""
@@ -348,10 +348,10 @@ class Engine:
         kind = self._check_x(X)
         B = X.shape[0]
         w = self.workspace(B, True)
-        st = self._adam_state(kind)
+        st = self._adam_state(opt_kind)
         self.step_count += 1
         a = SatAdam()
-        a.kind = int(kind)
+        a.kind = int(opt_kind)
         a.lr, a.beta1, a.beta2, a.eps, a.l2_emb = float(lr), float(betas[0]), float(betas[1]), float(eps), float(l2_emb)
         a.step, a.dense_mode = self.step_count, int(bool(dense_mode))
         a.tab_m = st['tab_m'].data_ptr() if st['tab_m'] is not None else None

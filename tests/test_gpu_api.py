@@ -252,3 +252,21 @@ def test_other_losses_match_torch(loss):
     for k in O.trainable_keys(cfg):
         ref = o_g[k]
         assert (grads[k] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, k
+
+
+def test_selfattention_layer_matches_reference():
+    """'next' row: SelfAttention_Layer through the shared field-attention kernel code vs vectors
+    dumped from the reference's own module (submodules.py:178-238)."""
+    import os
+    from satrans_b200 import SelfAttention_Layer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'selfatt_layer.npz'))
+    for tag, heads, res in (('h4_f19_r1', 4, True), ('h2_f15_r1', 2, True), ('h4_f7_r0', 4, False)):
+        layer = SelfAttention_Layer(32, heads, use_res=res, device='cuda:0').eval()
+        sd = {k[len(tag) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + '/state/')}
+        assert set(sd) == set(layer.state_dict())
+        layer.load_state_dict(sd)
+        y = layer(torch.from_numpy(z[tag + '/x']).cuda())
+        assert torch.allclose(y.cpu(), torch.from_numpy(z[tag + '/y']), atol=2e-6, rtol=0), tag
+        layer.train()
+        yt = layer(torch.from_numpy(z[tag + '/x']).cuda())
+        assert torch.isfinite(yt).all() and not torch.equal(yt, y)

@@ -84,3 +84,15 @@ def test_mask_injection_matches_eval_when_all_kept():
         b = O.forward(st, g.X(), g.cfg, masks={k: torch.ones_like(v) for k, v in masks.items()})
     # all-kept masks still rescale by 1/(1-p): outputs differ, but finite and in (0,1)
     assert torch.isfinite(b).all() and (b > 0).all() and (b < 1).all() and a.shape == b.shape
+
+
+def test_selfattention_layer_oracle_vs_reference():
+    """'next' row: SelfAttention_Layer restatement against vectors from the reference's own module."""
+    import numpy as np
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'selfatt_layer.npz'))
+    for tag, heads, res in (('h4_f19_r1', 4, True), ('h2_f15_r1', 2, True), ('h4_f7_r0', 4, False)):
+        p = {k[len(tag) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + '/state/')}
+        with torch.no_grad():
+            y = O.self_attention_layer(torch.from_numpy(z[tag + '/x']), p, heads, res)
+        assert torch.allclose(y, torch.from_numpy(z[tag + '/y']), atol=1e-6, rtol=0)
