@@ -235,6 +235,9 @@ int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, int32_t tile_
 int sat_pack_weights(const SatModel* m, SatWork* w, void* stream);
 int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
                    float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream);
+/* sat_backward with the MetaNet / QKV data-gradient projections on the tensor cores (same contract, same outputs). */
+int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
+                    uint64_t seed, int32_t passes, void* stream);
 
 /* ---- "next" row: SelfAttention_Layer.forward (reference submodules.py:178-238) through the same
  *      per-sample field-attention code.  x, out: [B][F][32]; W_*: [32][32] used as x @ W; forward only. ---------- */

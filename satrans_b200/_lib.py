@@ -65,6 +65,7 @@ PROTOTYPES = {
     'sat_encoder_bwd': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_forward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, vp]),
     'sat_backward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, vp]),
+    'sat_backward_tc': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, i32, vp]),
     'sat_rows_clear': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_rows_mark': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
     'sat_rows_rank': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),

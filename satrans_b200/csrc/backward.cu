@@ -295,8 +295,11 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
 
 using namespace sat;
 
-extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
-                            uint64_t seed, void* stream) {
+int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
+
+// passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
+static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
+                         uint64_t seed, int passes, void* stream) {
     if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->row_grad)
         return sat_host::fail(SAT_EINVAL, "sat_backward: null argument / workspace not sized for training");
     if (w->B == 0) return SAT_OK;
@@ -334,9 +337,29 @@ extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, i
             default: return sat_host::fail(SAT_EINVAL, "sat_backward: heads=%d not in {1,2,4,8}", m->H);
         }
         if (rc) return rc;
-        k_bwd_meta<<<grid1, NT, smem_b, s>>>(a);
-        rc = sat_host::check_launch("k_bwd_meta");
+        if (passes == 0) {
+            k_bwd_meta<<<grid1, NT, smem_b, s>>>(a);
+            rc = sat_host::check_launch("k_bwd_meta");
+        } else {
+            BwdArgs a2 = a;
+            a2.tiles = w->tiles2;
+            const int spt2 = NT2 / m->F;
+            const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
+            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2, passes, s);
+        }
         if (rc) return rc;
     }
     return sat_encoder_bwd(m, w, stream);
+}
+
+extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
+                            uint64_t seed, void* stream) {
+    return backward_impl(m, x, id_kind, ld, w, dropout_p, seed, 0, stream);
+}
+
+extern "C" int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
+                               uint64_t seed, int32_t passes, void* stream) {
+    if (passes != 1 && passes != 3) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: passes must be 1 or 3, got %d", passes);
+    if (!w || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: workspace has no packed weights");
+    return backward_impl(m, x, id_kind, ld, w, dropout_p, seed, passes, stream);
 }

@@ -1,0 +1,268 @@
+// Tensor-core version of k_bwd_meta (MetaNet-LayerNorm bwd + MetaNet bwd + QKV projection bwd), sm_100a.
+//
+// Same thread-per-token / 128-lane mapping as forward_tc.cu.  Every DATA-gradient / recompute projection is a
+// tcgen05.mma.kind::tf32 grouped GEMM with the tokens' vectors as A operand in TMEM and pre-packed weights (the
+// backward blocks of k_pack_weights) as B operand in shared memory:
+//     u = x W                (recompute)        pre = u W1            (recompute, ReLU decisions come from the forward)
+//     dh = dm W2^T                              du += dh W1^T                              dX += [du_q|du_k|dv] [W_Q|W_K|W_V]^T
+// WEIGHT gradients (reductions over tokens) stay on the CUDA cores: operands staged as [token][36] tiles, 4x4 register
+// blocks, shared-memory accumulators flushed once per CTA (wgrad32, as in backward.cu).
+#include "bwd_common.cuh"
+#include "tc_common.cuh"
+
+namespace sat {
+
+constexpr int TCB_A = 0, TCB_H = 64, TCB_D = 128, TCB_H2 = 192;          // TMEM column map (256 columns)
+constexpr int TCB_SB = 6144;                                             // floats of the B-operand staging buffer
+constexpr int TCB_SMEM_FLOATS = TCB_SB + 2 * TC_NT * KV_LD + 192 + 3072 + 128 + 2 * PSZ + 8;
+
+// copy n floats of packed operand into sB (all threads), generic->async proxy fence included
+__device__ __forceinline__ void load_b(float* __restrict__ sB, const float* __restrict__ src, int n, int tid) {
+    copy_to_smem(sB, src, n, tid, TC_NT);
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const float* __restrict__ wpack, int n_keys) {
+    extern __shared__ __align__(128) float smem[];
+    float* sB = smem;                         // B operands of the current round (<= 24 KB)
+    float* sA = sB + TCB_SB;                  // [128][36] weight-gradient operand A
+    float* sG = sA + TC_NT * KV_LD;           // [128][36] weight-gradient operand G
+    float* sLN = sG + TC_NT * KV_LD;          // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
+    float* sdW = sLN + 192;                   // dWQ dWK dWV
+    float* sdLN = sdW + 3072;                 // dQLN_G dQLN_B dKLN_G dKLN_B
+    float* sdThQ = sdLN + 128;
+    float* sdThK = sdThQ + PSZ;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThK + PSZ);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = m.F, L = m.L, l = a.layer;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const int n_tiles = a.counters[CNT_NTILES2];
+    const int s = tid / F, f = tid - s * F;
+    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
+    const int nblk = L + n_keys;
+    const float* pk_lf = wpack + (long long)l * PACK_FLOATS;                    // forward layer block
+    const float* pk_lb = wpack + (long long)(nblk + l) * PACK_FLOATS;           // backward layer block
+
+    copy_to_smem(sLN, m.dense + m.off_layers + (long long)l * LAYER_FLOATS + OFF_LN_G, 192, tid, TC_NT);
+    for (int i = tid; i < 3072; i += TC_NT) sdW[i] = 0.f;
+    for (int i = tid; i < 2 * PSZ; i += TC_NT) sdThQ[i] = 0.f;
+    if (tid < 128) sdLN[tid] = 0.f;
+    if (warp == 0) tmem_alloc(s_tmem, TC_COLS);
+    if (tid == 0) mbar_init(mbar, 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *s_tmem;
+    const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    int cur_q = -1, cur_k = -1;
+
+#define SAT_TC_ROUND(ISSUE)                                  \
+    do {                                                     \
+        fence_async_smem();                                  \
+        tc_wait_st();                                        \
+        tc_fence_before();                                   \
+        __syncthreads();                                     \
+        if (tid == 0) {                                      \
+            tc_fence_after();                                \
+            ISSUE;                                           \
+            mma_commit(mbar);                                \
+        }                                                    \
+        mbar_wait(mbar, phase);                              \
+        phase ^= 1u;                                         \
+        tc_fence_after();                                    \
+    } while (0)
+
+    for (int t = t0; t < t1; ++t) {
+        const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
+        const int g = td.x, start = td.y, cnt = td.z;
+        const bool valid = s < cnt;
+        const int ntok = cnt * F;
+        const int p = start + s;
+        const int b = valid ? a.perm[p] : 0;
+        const long long tokpos = ((long long)p * F + f) * D;
+        const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
+        const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
+        __syncthreads();
+        if (kq != cur_q) {
+            if (cur_q >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
+            cur_q = kq;
+        }
+        if (pos && kk != cur_k) {
+            if (cur_k >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+            cur_k = kk;
+        }
+
+        float keep_q[D], keep_k[D];          // d(x W_Q), d(x W_K): A operands of the final dX round
+        zero(keep_q); zero(keep_k);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const bool has_meta = side ? meta_k : meta_q;
+            const int key = side ? kk : kq;
+            const float* pk_kf = wpack + (long long)(L + key) * PACK_FLOATS;             // forward key block
+            const float* pk_kb = wpack + (long long)(nblk + L + key) * PACK_FLOATS;      // backward key block
+            float* sdTh = (side && pos) ? sdThK : sdThQ;
+            const float* lng = (side && pos) ? sLN + 128 : sLN + 64;
+            float* sdLNs = (side && pos) ? sdLN + 64 : sdLN;
+            float (&du)[D] = side ? keep_k : keep_q;
+
+            if (valid) load_row(a.dqkv + (long long)side * a.act_stride + tokpos, du);     // dLoss/dQ' (post-LN)
+            if (has_meta) {
+                float u[D];                                                                // u = x @ W (recomputed)
+                {
+                    float xin[D];
+                    if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, xin); else zero(xin);
+                    load_b(sB, pk_lf + PK_QKV_HI + side * 1024, 1024, tid);
+                    load_b(sB + 1024, pk_lf + PK_QKV_LO + side * 1024, 1024, tid);
+                    tmem_st_operand<PASSES>(tlane + TCB_A, xin);
+                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB, sB + 1024, 32, false));
+                    tmem_ld32(tlane + TCB_D, u);
+                    tc_wait_ld();
+                }
+                float dm[D];
+                {   // LayerNorm backward of the MetaNet output
+                    float zh[D];
+                    float rstd = 0.f;
+                    if (valid) { load_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, zh); rstd = normalize32(zh); }
+                    else zero(zh);
+                    layernorm_bwd32(du, zh, rstd, lng, sdLNs, sdLNs + 32, lane, valid);     // du := dLoss/dz
+                    const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dm[i] = valid ? du[i] * drop_factor(dc, i) : 0.f;
+                }
+                uint2 mk = make_uint2(0u, 0u);
+                if (valid) mk = *reinterpret_cast<const uint2*>(relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, side, tokpos / D));
+
+                // ---- pre = u @ W1 (N = 64): hidden activations for dW2 ------------------------------------------------
+                load_b(sB, pk_kf + PK_W1_HI, 4096, tid);
+                tmem_st_operand<PASSES>(tlane + TCB_A, u);
+                SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PK_W1_HI, sB + PK_W1_LO, 64, false));
+                if (valid) sts_row(sG + tid * KV_LD, dm);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float h[D];
+                    tmem_ld32(tlane + TCB_D + half * 32, h);
+                    tc_wait_ld();
+                    const uint32_t mb = half ? mk.y : mk.x;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) h[i] = ((mb >> i) & 1u) ? h[i] : 0.f;
+                    if (valid) sts_row(sA + tid * KV_LD, h);
+                    __syncthreads();
+                    wgrad32<TC_NT>(sA, sG, ntok, sdTh + D * HID + half * D * D, D, tid);    // dW2[half*32 + c][j] += h[c] dm[j]
+                    __syncthreads();
+                }
+                // ---- dh = dm @ W2^T (N = 64), masked; dW1 += u^T dh; du += dh @ W1^T -----------------------------------
+                load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid);
+                tmem_st_operand<PASSES>(tlane + TCB_A, dm);
+                SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_W2T_HI, sB + PKB_W2T_LO, 64, false));
+                if (valid) sts_row(sA + tid * KV_LD, u);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float dh[D];
+                    tmem_ld32(tlane + TCB_D + half * 32, dh);
+                    tc_wait_ld();
+                    const uint32_t mb = half ? mk.y : mk.x;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dh[i] = ((mb >> i) & 1u) ? dh[i] : 0.f;
+                    tmem_st_operand<PASSES>(tlane + (half ? TCB_H2 : TCB_H), dh);
+                    if (valid) sts_row(sG + tid * KV_LD, dh);
+                    __syncthreads();
+                    wgrad32<TC_NT>(sA, sG, ntok, sdTh + half * D, HID, tid);               // dW1[i][half*32 + c] += u[i] dh[c]
+                    __syncthreads();
+                }
+                load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid);
+                SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB, sB + 1024, 32, false),
+                              issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + 2048, sB + 3072, 32, true)));
+                {
+                    float add[D];
+                    tmem_ld32(tlane + TCB_D, add);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < D; ++i) du[i] += add[i];
+                }
+            }
+            // ---- projection weight gradient: dW[i][j] += x[i] du[j] ----------------------------------------------------
+            if (valid) {
+                float xin[D];
+                load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
+                sts_row(sA + tid * KV_LD, xin);
+                sts_row(sG + tid * KV_LD, du);
+            }
+            __syncthreads();
+            wgrad32<TC_NT>(sA, sG, ntok, sdW + (side ? OFF_WK : OFF_WQ), D, tid);
+            __syncthreads();
+        }
+        // ---- V: dW_V += x^T dv ; then dX = dX_res + du_q W_Q^T + du_k W_K^T + dv W_V^T in ONE round --------------------
+        float dv[D];
+        if (valid) load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); else zero(dv);
+        if (valid) sts_row(sG + tid * KV_LD, dv);              // sA still holds x
+        __syncthreads();
+        wgrad32<TC_NT>(sA, sG, ntok, sdW + OFF_WV, D, tid);
+        load_b(sB, pk_lb, 6144, tid);
+        tmem_st_operand<PASSES>(tlane + TCB_A, keep_q);
+        tmem_st_operand<PASSES>(tlane + TCB_H, keep_k);
+        tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
+        SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_WQN_HI, sB + PKB_WQN_LO, 32, false),
+                      issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB + PKB_WKN_HI, sB + PKB_WKN_LO, 32, true),
+                      issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + PKB_WVN_HI, sB + PKB_WVN_LO, 32, true)));
+        float dxa[D];
+        tmem_ld32(tlane + TCB_D, dxa);
+        tc_wait_ld();
+        if (valid) {
+            float res[D];
+            load_row(a.dx + tokpos, res);
+#pragma unroll
+            for (int i = 0; i < D; ++i) dxa[i] += res[i];
+            if (l > 0) {
+                store_row(a.dx + tokpos, dxa);
+            } else {
+                long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
+                const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
+                if (id < 0 || id >= hi - lo) id = 0;
+                const long long row = lo + id;
+                const int owner = (int)(row % m.n_shards);
+                const long long lrow = row / m.n_shards;
+                const uint32_t wbits = *reinterpret_cast<const volatile uint32_t*>(m.shard_bitmap[owner] + (lrow >> 5));
+                const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
+                                 __popc(wbits & ((1u << (lrow & 31)) - 1u));
+                float* dst = m.shard_row_grad[owner] + (long long)slot * D;
+#pragma unroll
+                for (int i = 0; i < D; i += 4)
+                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
+            }
+        }
+    }
+#undef SAT_TC_ROUND
+    __syncthreads();
+    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
+    flush_add<TC_NT>(dlay, sdW, 3072, tid);
+    flush_add<TC_NT>(dlay + OFF_QLN_G, sdLN, 128, tid);
+    if (cur_q >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
+    if (pos && cur_k >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TC_COLS);
+}
+
+}  // namespace sat
+
+using namespace sat;
+
+int sat_launch_bwd_meta_tc(const BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s) {
+    const size_t smem = TCB_SMEM_FLOATS * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_bwd_meta_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_bwd_meta_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
+        configured = true;
+    }
+    if (passes == 3) k_bwd_meta_tc<3><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
+    else k_bwd_meta_tc<1><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
+    return sat_host::check_launch("k_bwd_meta_tc");
+}

@@ -55,6 +55,7 @@ __device__ __forceinline__ float normalize32(float (&v)[D]) {
 }
 
 // acc[(ia+r)*ldacc + jg+c] += sum_{t<ntok} A[t][ia+r] * G[t][jg+c]  -- 32x32 product, A/G tiles [tok][36].
+template <int NTHREADS = NT>
 __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float* __restrict__ G, int ntok,
                                         float* __restrict__ acc, int ldacc, int tid) {
     const int blk = tid & 63, grp = tid >> 6;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
-    for (int t = grp; t < ntok; t += NT / 64) {
+    for (int t = grp; t < ntok; t += NTHREADS / 64) {
         const float4 a = *reinterpret_cast<const float4*>(A + t * KV_LD + ia);
         const float4 g = *reinterpret_cast<const float4*>(G + t * KV_LD + jg);
         c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
@@ -78,8 +79,9 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
         for (int cc = 0; cc < 4; ++cc) atomicAdd(acc + (ia + r) * ldacc + jg + cc, c[r][cc]);
 }
 
+template <int NTHREADS = NT>
 __device__ __forceinline__ void flush_add(float* __restrict__ dst, float* __restrict__ sacc, int n, int tid) {
-    for (int i = tid; i < n; i += NT) {
+    for (int i = tid; i < n; i += NTHREADS) {
         const float v = sacc[i];
         if (v != 0.f) atomicAdd(dst + i, v);
         sacc[i] = 0.f;

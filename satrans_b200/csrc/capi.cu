@@ -61,7 +61,7 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = training ? touched_cap * SAT_D * 4 : 0;      // row_grad
     sz[i++] = SAT_REG_PARTS * 8;                           // reg_part
     sz[i++] = 8 * 4;                                       // scalars
-    sz[i++] = ((int64_t)m->L + n_keys) * 8192 * 4;         // wpack (tensor-core B operands)
+    sz[i++] = 2 * ((int64_t)m->L + n_keys) * 8192 * 4;     // wpack (tensor-core B operands: forward + backward blocks)
     sz[i++] = max_tiles2 * 16;                             // tiles2
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
     return SAT_OK;

@@ -14,25 +14,10 @@
 // which keeps fp32-level parity with the reference; PASSES = 1 is plain TF32 (fast mode, reported separately).
 // Attention over the F <= 32 tokens of a sample (9 % of the FLOPs, F x F x 8 per head) stays on the CUDA cores.
 #include "fwd_common.cuh"
+#include "tc_common.cuh"
 
 namespace sat {
 
-constexpr int TC_NT = 128;            // threads per CTA = TMEM lanes = tokens per tile
-constexpr int TC_COLS = 256;          // TMEM columns allocated per CTA (2 CTAs / SM)
-constexpr int TC_A = 0;               // [0,64)   A operand, K = 32: hi at +0, lo at +32
-constexpr int TC_H = 64;              // [64,128) A operand for one half of the MetaNet hidden layer
-constexpr int TC_D = 128;             // [128,224) accumulators: QKV 96 | hidden 64 + out 32 | out-proj 32
-constexpr int PACK_FLOATS = 8192;     // floats per packed layer block / per packed key block
-// packed layer block: [QKV hi 3072][QKV lo 3072][WO hi 1024][WO lo 1024]
-constexpr int PK_QKV_HI = 0, PK_QKV_LO = 3072, PK_WO_HI = 6144, PK_WO_LO = 7168;
-// packed key block:   [W1 hi 2048][W1 lo 2048][W2a hi 1024][W2a lo 1024][W2b hi 1024][W2b lo 1024]
-constexpr int PK_W1_HI = 0, PK_W1_LO = 2048, PK_W2A_HI = 4096, PK_W2A_LO = 5120, PK_W2B_HI = 6144, PK_W2B_LO = 7168;
-
-// offset (floats) of B[n][k] in the canonical K-major, no-swizzle UMMA layout for K = 32 fp32/tf32 elements:
-// core matrix = 8 rows (n) x 16 B (4 k); core matrices contiguous along k (LBO = 128 B), 8-row groups SBO = 1024 B apart
-__host__ __device__ __forceinline__ int b_off32(int n, int k) { return (n >> 3) * 256 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
-
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // ---------------------------------------------------------------------------------------------------------
 // weight packing: layer weights + generated MetaNet weights -> UMMA B operands (hi / lo split)
@@ -40,7 +25,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 #if SAT_INST_H == 4      // one copy of the packing kernel (this file is compiled once per head count)
 __global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_keys, const float* __restrict__ theta,
                                                       float* __restrict__ wpack) {
-    const int total = (m.L + n_keys) * 4096;
+    const int nblk = m.L + n_keys;
+    const int total = 2 * nblk * 4096;
     for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         const int blk = e >> 12, i = e & 4095;
         float v;
@@ -56,7 +42,7 @@ __global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_ke
                 v = lay[OFF_WO + n * 32 + k];
                 off_hi = PK_WO_HI + b_off32(n, k); off_lo = PK_WO_LO + b_off32(n, k);
             }
-        } else {
+        } else if (blk < nblk) {
             const float* th = theta + (long long)(blk - m.L) * PSZ;
             if (i < 2048) {                      // W1: B[n][k] = theta[k*64 + n], N = 64
                 const int n = i >> 5, k = i & 31;
@@ -68,6 +54,28 @@ __global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_ke
                 off_hi = (half ? PK_W2B_HI : PK_W2A_HI) + b_off32(n, k);
                 off_lo = (half ? PK_W2B_LO : PK_W2A_LO) + b_off32(n, k);
             }
+        } else if (blk < nblk + m.L) {           // backward layer block
+            const float* lay = m.dense + m.off_layers + (long long)(blk - nblk) * LAYER_FLOATS;
+            const int which = i >> 10, j = i & 1023, n = j >> 5, k = j & 31;
+            if (which < 3) {                     // B[n=i][k=j] = W[i][j]
+                v = lay[which * 1024 + n * 32 + k];
+                off_hi = which * 2048 + b_off32(n, k); off_lo = which * 2048 + 1024 + b_off32(n, k);
+            } else {                             // B[n=i][k=j] = W_out[j][i]
+                v = lay[OFF_WO + k * 32 + n];
+                off_hi = PKB_WOT_HI + b_off32(n, k); off_lo = PKB_WOT_LO + b_off32(n, k);
+            }
+        } else {                                 // backward key block
+            const float* th = theta + (long long)(blk - nblk - m.L) * PSZ;
+            if (i < 2048) {                      // W2T: B[n=c][k=j] = W2[c][j], N = 64
+                const int n = i >> 5, k = i & 31;
+                v = th[D * HID + n * D + k];
+                off_hi = PKB_W2T_HI + b_off32(n, k); off_lo = PKB_W2T_LO + b_off32(n, k);
+            } else {                             // W1N halves: B[n=i][k=c] = W1[i][half*32 + c]
+                const int j = i - 2048, half = j >> 10, jj = j & 1023, n = jj >> 5, k = jj & 31;
+                v = th[n * HID + half * 32 + k];
+                off_hi = (half ? PKB_W1N1_HI : PKB_W1N0_HI) + b_off32(n, k);
+                off_lo = (half ? PKB_W1N1_LO : PKB_W1N0_LO) + b_off32(n, k);
+            }
         }
         float* dst = wpack + (long long)blk * PACK_FLOATS;
         const float hi = tf32_hi(v);
@@ -77,115 +85,6 @@ __global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_ke
 }
 #endif
 
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers (tcgen05 / TMEM / mbarrier)
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-// all previously issued MMAs of this thread arrive on the mbarrier when they complete
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, M = 128
-__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
-__device__ __forceinline__ constexpr uint32_t make_idesc(int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-                   "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-                   "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-                   "r"(__float_as_uint(v[15])) : "memory");
-}
-// 32 floats of this thread's lane: columns [col, col+32)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[D]) {
-    tmem_ld16(taddr, &v[0]);
-    tmem_ld16(taddr + 16, &v[16]);
-}
-// write a 32-vector as A operand: hi at col, lo at col + 32 (PASSES == 3) or as is (PASSES == 1)
-template <int PASSES>
-__device__ __forceinline__ void tmem_st_operand(uint32_t taddr, const float (&v)[D]) {
-    if (PASSES == 1) {
-        tmem_st16(taddr, &v[0]);
-        tmem_st16(taddr + 16, &v[16]);
-    } else {
-        float hi[D], lo[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) { hi[i] = tf32_hi(v[i]); lo[i] = v[i] - hi[i]; }
-        tmem_st16(taddr, &hi[0]);
-        tmem_st16(taddr + 16, &hi[16]);
-        tmem_st16(taddr + 32, &lo[0]);
-        tmem_st16(taddr + 48, &lo[16]);
-    }
-}
-
-// issue D[128 x N] (+)= A[128 x 32] @ B[N x 32]^T as 4 k-steps of K = 8 (x3 products with the hi/lo split)
-template <int PASSES>
-__device__ __forceinline__ void issue_gemm_k32(uint32_t d_tmem, uint32_t a_tmem, const float* b_hi, const float* b_lo, int N,
-                                               bool accumulate) {
-    const uint32_t idesc = make_idesc(N);
-    const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-    uint32_t acc = accumulate ? 1u : 0u;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        const uint64_t dh = make_b_desc(bh + kk * 256, 128, 1024);
-        mma_ts_tf32(d_tmem, a_tmem + kk * 8, dh, idesc, acc);
-        acc = 1u;
-        if (PASSES == 3) {
-            const uint64_t dl = make_b_desc(bl + kk * 256, 128, 1024);
-            mma_ts_tf32(d_tmem, a_tmem + 32 + kk * 8, dh, idesc, 1u);
-            mma_ts_tf32(d_tmem, a_tmem + kk * 8, dl, idesc, 1u);
-        }
-    }
-}
 
 constexpr int TC_SMEM_FLOATS = 2 * PACK_FLOATS + 2 * TC_NT * KV_LD + 192 + TC_NT + 8;
 
@@ -432,7 +331,7 @@ int SAT_CAT(sat_launch_forward_tc_h, SAT_INST_H)(const FwdArgs& a, const float* 
 #if SAT_INST_H == 4
 // one copy of the packing entry point (any H translation unit would do)
 int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, cudaStream_t s) {
-    const int total = (m->L + n_keys) * 4096;
+    const int total = 2 * (m->L + n_keys) * 4096;
     k_pack_weights<<<(total + 255) / 256, 256, 0, s>>>(*m, n_keys, theta, wpack);
     return sat_host::check_launch("k_pack_weights");
 }

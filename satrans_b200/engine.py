@@ -80,6 +80,8 @@ class Engine:
         # forward precision: 'fp32' = CUDA-core FFMA kernels; 'tf32x3' = tcgen05 tensor cores with the error-
         # compensated 3xTF32 split (fp32-level parity); 'tf32' = tcgen05 plain TF32 (fast mode)
         self.precision = 'fp32'
+        # backward of the MetaNet/QKV block: None = follow `precision`; 'fp32' forces the CUDA-core kernel
+        self.backward_precision = None
         self._peer_tables = None
 
     def attach_dist(self, ctx):
@@ -253,6 +255,18 @@ class Engine:
             check(l.sat_forward_tc(d, X.data_ptr(), kind, X.shape[1], y_ptr, C.byref(w.c), y_pred.data_ptr(),
                                    int(training), float(p), seed, passes, s), 'sat_forward_tc')
 
+    def _backward_call(self, X, kind, w, p, seed, s):
+        l, d = lib(), C.byref(self.desc)
+        bp = self.backward_precision or self.precision
+        passes = {'fp32': 0, 'tf32x3': 3, 'tf32': 1}[bp]
+        if passes and self.precision == 'fp32':
+            raise ValueError("a tensor-core backward needs the packed weights of a tensor-core forward precision")
+        if passes == 0:
+            check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), float(p), seed, s), 'sat_backward')
+        else:
+            check(l.sat_backward_tc(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), float(p), seed, passes, s),
+                  'sat_backward_tc')
+
     def _mark_rows(self, X, w, kind):
         """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomics) | barrier | rank | barrier."""
         l, s, d = lib(), self._stream(), C.byref(self.desc)
@@ -310,8 +324,7 @@ class Engine:
             self.dist.barrier(self.device)
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, float(dropout_p if training else 0.0),
                            int(seed) & (2 ** 64 - 1), s)
-        check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c),
-                             float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s), 'sat_backward')
+        self._backward_call(X, kind, w, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s)
         self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2)
         if self.dist is not None and self.dist.world > 1:
             self.dist.all_reduce_sum(w['dgrad'])            # also orders the peers' row-gradient atomics
@@ -388,7 +401,7 @@ class Engine:
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
         self._toc(t)
         t = self._tic('backward')
-        check(l.sat_backward(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), p, sd, s), 'sat_backward')
+        self._backward_call(X, kind, w, p, sd, s)
         self._toc(t)
         if self.dist is not None and self.dist.world > 1:
             t = self._tic('allreduce')

@@ -131,8 +131,9 @@ def test_tensor_core_forward_matches_reference(name, precision, atol):
     assert err <= atol, (precision, err)
 
 
+@pytest.mark.parametrize('bwd', ['fp32', None])
 @pytest.mark.parametrize('name', CASES)
-def test_tensor_core_forward_training_path(name):
+def test_tensor_core_forward_training_path(name, bwd):
     """3xTF32 tensor-core forward feeding the (CUDA-core) backward.  y_pred / loss keep the fp32 bars.  Gradients:
     3xTF32 perturbs pre-activations by ~1e-7, which can flip the ReLU decision of a MetaNet hidden unit that the
     reference evaluated within ~1e-7 of zero (about one of the 5e5 units of a fixture; measured on enp_small) — both
@@ -143,6 +144,7 @@ def test_tensor_core_forward_training_path(name):
     g = Golden(name)
     model = model_from_golden(g)
     model.engine.precision = 'tf32x3'
+    model.engine.backward_precision = bwd          # 'fp32': CUDA-core k_bwd_meta; None: tensor-core k_bwd_meta_tc
     l2 = g.cfg.l2_reg_embedding
     yp, w = model.engine.loss_and_grads(_dev(g.X()), _dev(g.y()), training=False, l2_emb=l2)
     torch.cuda.synchronize()
