@@ -65,6 +65,7 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
+#pragma unroll 4
     for (int t = grp; t < ntok; t += NTHREADS / 64) {
         const float4 a = *reinterpret_cast<const float4*>(A + t * KV_LD + ia);
         const float4 g = *reinterpret_cast<const float4*>(G + t * KV_LD + jg);
