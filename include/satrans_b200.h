@@ -39,7 +39,7 @@ extern "C" {
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
-#define SAT_WORK_BUFFERS 22  /* pointer members of SatWork */
+#define SAT_WORK_BUFFERS 23  /* pointer members of SatWork */
 #define SAT_MAX_SHARDS 8     /* processes (GPUs) of one node sharing the row-sharded tables */
 #define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
 #define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
@@ -136,7 +136,8 @@ typedef struct SatWork {
     double* reg_part;     /* [SAT_REG_PARTS] partial sums of squares of the tables          */
     float* scalars;       /* [8] device results: [0]=bce sum [1]=reg loss [2]=n_unique rows [3]=error flags */
     float* wpack;         /* [(L + n_keys)][8192] weights packed as tcgen05 B operands (hi | lo)         */
-    int32_t* tiles2;      /* tile list of the tensor-core forward (128 tokens per tile)                  */
+    int32_t* tiles2;      /* tile list of the tensor-core kernels (128 tokens per tile)                  */
+    float* wacc;          /* [296][11264] CTA-private weight-gradient scratch of k_bwd_meta_tc           */
 } SatWork;
 
 /* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */
@@ -211,6 +212,10 @@ int sat_enable_peer_access(int32_t peer_device);
  * space with peer access over NVLink; *out_ptr_host receives the base pointer of the exporter's allocation. */
 int sat_ipc_open(const void* handle64_host, void** out_ptr_host);
 int sat_ipc_close(void* ptr);
+/* debugging aid: out[32][32] = A^T G (A, G: [128][32]) through the tensor-core weight-gradient path; raw: [128][32]. */
+int sat_debug_wgrad(const float* A, const float* G, float* out, float* raw, void* stream);
+/* debugging aid: raw[128][32] = P[128][128] Q[32][128]^T through SS tcgen05 MMAs with K-/MN-major staged operands. */
+int sat_debug_ss(const float* P, const float* Q, float* raw, int32_t a_mn, int32_t b_mn, int32_t swap, void* stream);
 /* debugging aid: one thread touches *p (mode 0 store, 1 atomicOr, 2 atomicAdd f32, 3 atomicAdd float4, 4 load -> *out). */
 int sat_debug_poke(void* p, int32_t mode, float* out, void* stream);
 
