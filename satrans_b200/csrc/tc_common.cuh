@@ -109,20 +109,29 @@ __device__ __forceinline__ void wg_stage_row(float* __restrict__ tile_hi, float*
         tile_lo[off] = v[c] - h;
     }
 }
-// D_w[128 x 32] = A^T G over the 128 tokens of the tile: 16 k-steps (8 tokens) x (hi*hi + lo*hi + hi*lo)
+// first MMA of a chain (overwrites D) / accumulating MMA: compile-time predicate, no setp
+__device__ __forceinline__ void mma_ss_tf32_first(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma_ss_tf32_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+// D_w[128 x 32] = A^T G over the 128 tokens of the tile: 16 k-steps (8 tokens) x (hi*hi + lo*hi + hi*lo).
+// Fully unrolled; the descriptor of k-step ks is the base descriptor + ks * (2*LBO/16) in the start-address field.
 __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, const float* a_hi, const float* a_lo, const float* g_hi, const float* g_lo) {
     const uint32_t idesc = make_idesc(32);
-    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), gh = smem_u32(g_hi), gl = smem_u32(g_lo);
-    uint32_t acc = 0u;
-#pragma unroll 1
+    const uint64_t dah = make_b_desc(smem_u32(a_hi), WG_LBO, WG_SBO), dal = make_b_desc(smem_u32(a_lo), WG_LBO, WG_SBO);
+    const uint64_t dgh = make_b_desc(smem_u32(g_hi), WG_LBO, WG_SBO), dgl = make_b_desc(smem_u32(g_lo), WG_LBO, WG_SBO);
+    constexpr uint64_t STEP = (2 * WG_LBO) >> 4;
+#pragma unroll
     for (int ks = 0; ks < 16; ++ks) {
-        const uint32_t o = ks * 2 * WG_LBO;
-        const uint64_t dah = make_b_desc(ah + o, WG_LBO, WG_SBO), dal = make_b_desc(al + o, WG_LBO, WG_SBO);
-        const uint64_t dgh = make_b_desc(gh + o, WG_LBO, WG_SBO), dgl = make_b_desc(gl + o, WG_LBO, WG_SBO);
-        mma_ss_tf32(d_tmem, dah, dgh, idesc, acc);
-        mma_ss_tf32(d_tmem, dal, dgh, idesc, 1u);
-        mma_ss_tf32(d_tmem, dah, dgl, idesc, 1u);
-        acc = 1u;
+        const uint64_t o = ks * STEP;
+        if (ks == 0) mma_ss_tf32_first(d_tmem, dah, dgh, idesc);
+        else mma_ss_tf32_acc(d_tmem, dah + o, dgh + o, idesc);
+        mma_ss_tf32_acc(d_tmem, dal + o, dgh + o, idesc);
+        mma_ss_tf32_acc(d_tmem, dah + o, dgl + o, idesc);
     }
 }
 
