@@ -39,7 +39,7 @@ extern "C" {
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
-#define SAT_WORK_BUFFERS 23  /* pointer members of SatWork */
+#define SAT_WORK_BUFFERS 22  /* pointer members of SatWork */
 #define SAT_MAX_SHARDS 8     /* processes (GPUs) of one node sharing the row-sharded tables */
 #define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
 #define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
@@ -137,7 +137,6 @@ typedef struct SatWork {
     float* scalars;       /* [8] device results: [0]=bce sum [1]=reg loss [2]=n_unique rows [3]=error flags */
     float* wpack;         /* [(L + n_keys)][8192] weights packed as tcgen05 B operands (hi | lo)         */
     int32_t* tiles2;      /* tile list of the tensor-core kernels (128 tokens per tile)                  */
-    float* wacc;          /* [296][11264] CTA-private weight-gradient scratch of k_bwd_meta_tc           */
 } SatWork;
 
 /* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */

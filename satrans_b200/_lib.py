@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 8 + 148 * 4
-SAT_WORK_BUFFERS = 23
+SAT_WORK_BUFFERS = 22
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
@@ -40,7 +40,7 @@ class SatModel(C.Structure):
 
 WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
                 'loss_part', 'dgrad', 'bitmap', 'word_rank', 'block_sums', 'uniq_rows', 'row_grad', 'reg_part',
-                'scalars', 'wpack', 'tiles2', 'wacc']
+                'scalars', 'wpack', 'tiles2']
 assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
 
 

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
 
 using namespace sat;
 
-int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, float* wacc, int grid, int passes, cudaStream_t s);
+int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
 
 // passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
 static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
@@ -345,7 +345,7 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
             a2.tiles = w->tiles2;
             const int spt2 = NT2 / m->F;
             const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
-            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, w->wacc, max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2, passes, s);
+            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2, passes, s);
         }
         if (rc) return rc;
     }
@@ -360,6 +360,6 @@ extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, i
 extern "C" int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
                                uint64_t seed, int32_t passes, void* stream) {
     if (passes != 1 && passes != 3) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: passes must be 1 or 3, got %d", passes);
-    if (!w || !w->wpack || !w->tiles2 || !w->wacc) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: workspace has no packed weights / scratch");
+    if (!w || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: workspace has no packed weights");
     return backward_impl(m, x, id_kind, ld, w, dropout_p, seed, passes, stream);
 }

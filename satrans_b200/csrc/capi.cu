@@ -63,7 +63,6 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = 8 * 4;                                       // scalars
     sz[i++] = 2 * ((int64_t)m->L + n_keys) * 8192 * 4;     // wpack (tensor-core B operands: forward + backward blocks)
     sz[i++] = max_tiles2 * 16;                             // tiles2
-    sz[i++] = training ? (int64_t)296 * 11264 * 4 : 0;     // wacc
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
     return SAT_OK;
 }
