@@ -111,7 +111,11 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
             load_row(act_x + tokpos, xin);
             vm_outer<D, D, D>(sWp, xin, qp);                                         // recompute qp = x @ W
 #pragma unroll
-            for (int i = 0; i < D; ++i) dm[i] = dqp[i] * drop_factor(dc, i);
+            for (int i = 0; i < D; i += 2) {
+                float f0, f1;
+                drop_pair(dc, i >> 1, f0, f1);
+                dm[i] = dqp[i] * f0; dm[i + 1] = dqp[i + 1] * f1;
+            }
         } else zero(dm);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -327,13 +331,26 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
     k_bwd_head<<<grid2, NT, 0, s>>>(a);
     int rc = sat_host::check_launch("k_bwd_head");
     if (rc) return rc;
+    // k_bwd_attn tiling (see backward_attn.cu): tuning knob, default chosen by measurement
+    static const int attn_variant_env = [] { const char* e = getenv("SAT_BWD_ATTN_VARIANT"); return e ? atoi(e) : 1; }();
+    const int attn_variant = w->tiles2 ? attn_variant_env : 0;
+    const int spt2 = NT2 / m->F;
+    const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
+    BwdArgs aa = a;                           // k_bwd_attn's view: its own tile set
+    int grid_a = grid2;
+    if (attn_variant != 0) {
+        aa.tiles = w->tiles2;
+        const int per_sm = attn_variant == 2 ? 3 : 2;
+        grid_a = max_tiles2 < 148 * per_sm ? max_tiles2 : 148 * per_sm;
+    }
     for (int l = m->L - 1; l >= 0; --l) {
         a.layer = l;
+        aa.layer = l;
         switch (m->H) {
-            case 1: rc = sat_launch_bwd_attn_h1(a, grid2, s); break;
-            case 2: rc = sat_launch_bwd_attn_h2(a, grid2, s); break;
-            case 4: rc = sat_launch_bwd_attn_h4(a, grid2, s); break;
-            case 8: rc = sat_launch_bwd_attn_h8(a, grid2, s); break;
+            case 1: rc = sat_launch_bwd_attn_h1(aa, attn_variant, grid_a, s); break;
+            case 2: rc = sat_launch_bwd_attn_h2(aa, attn_variant, grid_a, s); break;
+            case 4: rc = sat_launch_bwd_attn_h4(aa, attn_variant, grid_a, s); break;
+            case 8: rc = sat_launch_bwd_attn_h8(aa, attn_variant, grid_a, s); break;
             default: return sat_host::fail(SAT_EINVAL, "sat_backward: heads=%d not in {1,2,4,8}", m->H);
         }
         if (rc) return rc;
@@ -343,8 +360,6 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
         } else {
             BwdArgs a2 = a;
             a2.tiles = w->tiles2;
-            const int spt2 = NT2 / m->F;
-            const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
             rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2, passes, s);
         }
         if (rc) return rc;

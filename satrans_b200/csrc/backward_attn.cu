@@ -17,11 +17,16 @@ namespace sat {
 // =====================================================================================================
 // kernel A: LayerNorm-out bwd, out-projection bwd, attention bwd.
 // =====================================================================================================
-constexpr int BWDA_SMEM_FLOATS = 1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ +
-                                 2 * NT * KV_LD /*tiles*/ + NT * 24 /*mx,sum,Dh per head*/;
+constexpr int ST_LD = 25;              // row stride of the per-token softmax statistics (odd: conflict-free)
+constexpr int bwda_smem_floats(int nth) {
+    return 1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ + 2 * nth * KV_LD /*tiles*/ +
+           nth * ST_LD /*mx,sum,Dh per head + dropout key*/;
+}
 
-template <int H>
-__global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
+// NTH threads (= tokens) per CTA: 192 walks the `tiles` set of k_bucket, 128 the `tiles2` set; MINB = CTAs per SM the register
+// budget is sized for.
+template <int H, int NTH, int MINB>
+__global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
     constexpr int DH = D / H;
     extern __shared__ __align__(16) float smem[];
     float* sWO = smem;
@@ -29,24 +34,24 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
     float* sLN = sdWO + 1024;           // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
     float* sdLN = sLN + 192;            // dgamma[32] dbeta[32] of the layer's output LayerNorm
     float* sT0 = sdLN + 64;             // [NT][36]  r / K' / Q'
-    float* sT1 = sT0 + NT * KV_LD;      // [NT][36]  dO / V / dR
-    float* sSt = sT1 + NT * KV_LD;      // [NT][24]  per head: row max, row sum, D = dR.R
+    float* sT1 = sT0 + NTH * KV_LD;      // [NT][36]  dO / V / dR
+    float* sSt = sT1 + NTH * KV_LD;      // [NT][25]  per head: row max, 1/row sum, D = dR.R; [24] = attention-dropout key
 
     const SatModel& m = a.m;
     const int tid = threadIdx.x, lane = tid & 31, F = m.F, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
     const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
-    const int n_tiles = a.counters[CNT_NTILES];
+    const int n_tiles = a.counters[NTH == NT ? CNT_NTILES : CNT_NTILES2];
     const int s = tid / F, f = tid - s * F;
     const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
     const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
     const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
 
-    copy_to_smem(sWO, lay + OFF_WO, 1024, tid, NT);
-    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NT);
-    for (int i = tid; i < 1024 + 0; i += NT) sdWO[i] = 0.f;
+    copy_to_smem(sWO, lay + OFF_WO, 1024, tid, NTH);
+    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NTH);
+    for (int i = tid; i < 1024; i += NTH) sdWO[i] = 0.f;
     if (tid < 64) sdLN[tid] = 0.f;
     const float* qln = sLN + 64;
     const float* kln = pos ? sLN + 128 : sLN + 64;
@@ -71,15 +76,21 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
             if (valid) {
                 load_row(act_l + ACT_R * a.act_stride + tokpos, r);
                 vm_dot<D, D, D>(sWO, r, o);
+                sts_row(sT0 + tid * KV_LD, r);             // staged for dW_out now, re-read for D_i below (frees 32 registers)
                 const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
                 float xin[D];
                 load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    if (relu_out && o[i] <= 0.f) relu_mask &= ~(1u << i);
-                    float v = relu_out ? fmaxf(o[i], 0.f) : o[i];
-                    v *= drop_factor(dco, i);
-                    o[i] = use_res ? v + xin[i] : v;      // o := y (pre-LN)
+                for (int i = 0; i < D; i += 2) {
+                    float fk[2];
+                    drop_pair(dco, i >> 1, fk[0], fk[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (relu_out && o[i + e] <= 0.f) relu_mask &= ~(1u << (i + e));
+                        float v = relu_out ? fmaxf(o[i + e], 0.f) : o[i + e];
+                        v *= fk[e];
+                        o[i + e] = use_res ? v + xin[i + e] : v;      // o := y (pre-LN)
+                    }
                 }
                 rstd = normalize32(o);                     // o := yhat
                 load_row(a.dx + tokpos, dy);
@@ -92,22 +103,27 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
                 else { float zr[D]; zero(zr); store_row(a.dx + tokpos, zr); }
                 const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
 #pragma unroll
-                for (int i = 0; i < D; ++i) dy[i] = ((relu_mask >> i) & 1u) ? dy[i] * drop_factor(dco, i) : 0.f;   // dy := dO
+                for (int i = 0; i < D; i += 2) {                                                  // dy := dO
+                    float f0, f1;
+                    drop_pair(dco, i >> 1, f0, f1);
+                    dy[i] = ((relu_mask >> i) & 1u) ? dy[i] * f0 : 0.f;
+                    dy[i + 1] = ((relu_mask >> (i + 1)) & 1u) ? dy[i + 1] * f1 : 0.f;
+                }
                 zero(dr);
                 vm_outer<D, D, D>(sWO, dy, dr);            // dR[i] = sum_j dO[j] WO[j][i]
+                lds_row(sT0 + tid * KV_LD, r);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     float acc = 0.f;
 #pragma unroll
                     for (int c = 0; c < DH; ++c) acc = fmaf(dr[h * DH + c], r[h * DH + c], acc);
-                    sSt[tid * 24 + 16 + h] = acc;               // D_i[h] = dR_i . R_i  (own row, read back below)
+                    sSt[tid * ST_LD + 16 + h] = acc;               // D_i[h] = dR_i . R_i  (own row, read back below)
                 }
-                sts_row(sT0 + tid * KV_LD, r);
                 sts_row(sT1 + tid * KV_LD, dy);
             }
         }
         __syncthreads();
-        wgrad32(sT1, sT0, ntok, sdWO, D, tid);             // dWO[j][i] += dO[j] r[i]   (A = dO, G = r)
+        wgrad32<NTH>(sT1, sT0, ntok, sdWO, D, tid);             // dWO[j][i] += dO[j] r[i]   (A = dO, G = r)
         __syncthreads();
 
         // ---- phase 2: recompute Q' K' V, stage K'/V ----------------------------------------------------
@@ -129,12 +145,13 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
             zero(dq);
             const DropCtx dca = make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, true);
             const int sbase = s * F;
+            sSt[tid * ST_LD + 24] = __uint_as_float(dca.key);          // read back by the key-role pass of the other tokens
             // rolled over heads: q / dr / dq are rotated by DH per head (compact code, see common.cuh)
 #pragma unroll 1
             for (int h = 0; h < H; ++h) {
                 float sc[SAT_MAXF];
                 float mx = -INFINITY;
-                const float Dhh = sSt[tid * 24 + 16 + h];
+                const float Dhh = sSt[tid * ST_LD + 16 + h];
 #pragma unroll
                 for (int j = 0; j < SAT_MAXF; ++j) {
                     if (j < F) {
@@ -155,10 +172,12 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
                 for (int j = 0; j < SAT_MAXF; ++j)
                     if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
                 const float inv_sum = 1.f / sum;
-                sSt[tid * 24 + h] = mx; sSt[tid * 24 + 8 + h] = inv_sum;
+                sSt[tid * ST_LD + h] = mx; sSt[tid * ST_LD + 8 + h] = inv_sum;
+                float fd[2];
 #pragma unroll
                 for (int j = 0; j < SAT_MAXF; ++j) {
                     if (j < F) {
+                        if ((j & 1) == 0) drop_pair(dca, (h * SAT_MAXF + j) >> 1, fd[0], fd[1]);
                         const float pj = sc[j] * inv_sum;
                         const float* vr = sT1 + (sbase + j) * KV_LD + h * DH;
                         const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
@@ -169,7 +188,7 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
                             dAd = fmaf(dr[c + 0], vv.x, dAd); dAd = fmaf(dr[c + 1], vv.y, dAd);
                             dAd = fmaf(dr[c + 2], vv.z, dAd); dAd = fmaf(dr[c + 3], vv.w, dAd);
                         }
-                        const float dsc = pj * (dAd * drop_factor(dca, h * SAT_MAXF + j) - Dhh) * inv_sqrt_dh;
+                        const float dsc = pj * (dAd * fd[j & 1] - Dhh) * inv_sqrt_dh;
 #pragma unroll
                         for (int c = 0; c < DH; c += 4) {
                             const float4 kk = *reinterpret_cast<const float4*>(kr + c);
@@ -189,48 +208,59 @@ __global__ void __launch_bounds__(NT, 2) k_bwd_attn(const BwdArgs a) {
         if (valid) { sts_row(sT0 + tid * KV_LD, q); sts_row(sT1 + tid * KV_LD, dr); }
         __syncthreads();
         // ---- key-role pass: dK'_j = sum_i dS_ij Q'_i / sqrt(dh) ; dV_j = sum_i Pd_ij dR_i ----------------
+        // Head by head (rolled; kreg / vreg rotate by DH): the head's dK'/dV slices are complete after its F queries and go
+        // straight to HBM, so only 2*DH accumulators are live (32-wide dk/dv next to kreg/vreg spilled to local memory).
         if (valid) {
-            float dk[D], dv[D];
-            zero(dk); zero(dv);
             const int sbase = s * F;
-            for (int i = 0; i < F; ++i) {
-                const DropCtx dci = make_drop(a.seed, (uint32_t)b * (uint32_t)F + (uint32_t)i, l, SITE_ATT, a.p_drop, true);
-                const float* qr = sT0 + (sbase + i) * KV_LD;
-                const float* dR = sT1 + (sbase + i) * KV_LD;
-                const float* st = sSt + (sbase + i) * 24;
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    float acc = 0.f, dAd = 0.f;
+            float* dk_out = a.dqkv + 1 * a.act_stride + tokpos;
+            float* dv_out = a.dqkv + 2 * a.act_stride + tokpos;
+            DropCtx dci = make_drop(a.seed, 0u, l, SITE_ATT, a.p_drop, true);     // .key is replaced per query below
+#pragma unroll 1
+            for (int h = 0; h < H; ++h) {
+                float dk[DH], dv[DH];
+                zero(dk); zero(dv);
+                const uint32_t e = h * SAT_MAXF + f;
+#pragma unroll 2
+                for (int i = 0; i < F; ++i) {
+                    const float* qr = sT0 + (sbase + i) * KV_LD + h * DH;
+                    const float* dR = sT1 + (sbase + i) * KV_LD + h * DH;
+                    const float* st = sSt + (sbase + i) * ST_LD;
                     float qq[DH], dd[DH];
 #pragma unroll
                     for (int c = 0; c < DH; c += 4) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(qr + h * DH + c);
-                        const float4 d4 = *reinterpret_cast<const float4*>(dR + h * DH + c);
+                        const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
+                        const float4 d4 = *reinterpret_cast<const float4*>(dR + c);
                         qq[c] = q4.x; qq[c + 1] = q4.y; qq[c + 2] = q4.z; qq[c + 3] = q4.w;
                         dd[c] = d4.x; dd[c + 1] = d4.y; dd[c + 2] = d4.z; dd[c + 3] = d4.w;
                     }
+                    float acc = 0.f, dAd = 0.f;
 #pragma unroll
-                    for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kreg[h * DH + c], acc); dAd = fmaf(dd[c], vreg[h * DH + c], dAd); }
+                    for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kreg[c], acc); dAd = fmaf(dd[c], vreg[c], dAd); }
                     const float pij = expf(acc * inv_sqrt_dh - st[h]) * st[8 + h];
-                    const float df = drop_factor(dci, h * SAT_MAXF + f);
+                    dci.key = __float_as_uint(st[24]);
+                    const float df = drop_factor(dci, e);
                     const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;
                     const float pd = pij * df;
 #pragma unroll
                     for (int c = 0; c < DH; ++c) {
-                        dk[h * DH + c] = fmaf(dsc, qq[c], dk[h * DH + c]);
-                        dv[h * DH + c] = fmaf(pd, dd[c], dv[h * DH + c]);
+                        dk[c] = fmaf(dsc, qq[c], dk[c]);
+                        dv[c] = fmaf(pd, dd[c], dv[c]);
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    *reinterpret_cast<float4*>(dk_out + h * DH + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+                    *reinterpret_cast<float4*>(dv_out + h * DH + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+                }
+                if (H > 1) { rotate_regs<D, DH>(kreg); rotate_regs<D, DH>(vreg); }
             }
-            store_row(a.dqkv + 1 * a.act_stride + tokpos, dk);
-            store_row(a.dqkv + 2 * a.act_stride + tokpos, dv);
         }
     }
     __syncthreads();
     // flush: dWO and the output-LayerNorm parameter gradients
     float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
-    flush_add(dlay + OFF_WO, sdWO, 1024, tid);
-    flush_add(dlay + OFF_LN_G, sdLN, 64, tid);
+    flush_add<NTH>(dlay + OFF_WO, sdWO, 1024, tid);
+    flush_add<NTH>(dlay + OFF_LN_G, sdLN, 64, tid);
 }
 
 }  // namespace sat
@@ -243,15 +273,23 @@ using namespace sat;
 #define SAT_CAT_(a, b) a##b
 #define SAT_CAT(a, b) SAT_CAT_(a, b)
 
-int SAT_CAT(sat_launch_bwd_attn_h, SAT_INST_H)(const BwdArgs& a, int grid, cudaStream_t s) {
-    constexpr int H = SAT_INST_H;
-    const size_t smem = BWDA_SMEM_FLOATS * sizeof(float);
+template <int H, int NTH, int MINB>
+static int launch_variant(const BwdArgs& a, int grid, cudaStream_t s) {
+    const size_t smem = bwda_smem_floats(NTH) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_bwd_attn<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_bwd_attn<H, NTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
         configured = true;
     }
-    k_bwd_attn<H><<<grid, NT, smem, s>>>(a);
+    k_bwd_attn<H, NTH, MINB><<<grid, NTH, smem, s>>>(a);
     return sat_host::check_launch("k_bwd_attn");
+}
+
+// variant 0: 192 threads x 2 CTAs/SM over a.tiles; 1: 128 x 2 and 2: 128 x 3 over the 128-token tile set (caller passes it in a.tiles)
+int SAT_CAT(sat_launch_bwd_attn_h, SAT_INST_H)(const BwdArgs& a, int variant, int grid, cudaStream_t s) {
+    constexpr int H = SAT_INST_H;
+    if (variant == 1) return launch_variant<H, NT2, 2>(a, grid, s);
+    if (variant == 2) return launch_variant<H, NT2, 3>(a, grid, s);
+    return launch_variant<H, NT, 2>(a, grid, s);
 }

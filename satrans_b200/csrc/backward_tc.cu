@@ -13,10 +13,17 @@
 namespace sat {
 
 constexpr int TCB_A = 0, TCB_H = 64, TCB_D = 128, TCB_H2 = 192;          // TMEM column map (256 columns)
-constexpr int TCB_SB = 6144;                                             // floats of the B-operand staging buffer
-constexpr int TCB_SMEM_FLOATS = TCB_SB + 2 * TC_NT * KV_LD + 192 + 3072 + 128 + 2 * PSZ + 8;
+constexpr int TCB_SB = 4096;                                             // floats of the B-operand staging buffer (16 KB)
 
-// copy n floats of packed operand into sB (all threads), generic->async proxy fence included
+// Shared memory (floats): B staging | three [tile_rows][36] weight-gradient operand tiles | LN params | dW_Q/K/V | dLN | d theta
+// (one key block, two with per-position keys).  tile_rows = (128 / F) * F: rows past the last token of a full tile are never
+// touched.  F = 19: 95.6 KB (EN) / 112 KB (ENP) -> 2 CTAs per SM either way.
+static size_t tcb_smem_bytes(int F, bool pos) {
+    const int rows = (TC_NT / F) * F;
+    return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);
+}
+
+// copy n floats of packed operand into sB (all threads); the round macro issues the generic->async proxy fence
 __device__ __forceinline__ void load_b(float* __restrict__ sB, const float* __restrict__ src, int n, int tid) {
     copy_to_smem(sB, src, n, tid, TC_NT);
 }
@@ -24,22 +31,24 @@ __device__ __forceinline__ void load_b(float* __restrict__ sB, const float* __re
 template <int PASSES>
 __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const float* __restrict__ wpack, int n_keys) {
     extern __shared__ __align__(128) float smem[];
-    float* sB = smem;                         // B operands of the current round (<= 24 KB)
-    float* sA = sB + TCB_SB;                  // [128][36] weight-gradient operand A
-    float* sG = sA + TC_NT * KV_LD;           // [128][36] weight-gradient operand G
-    float* sLN = sG + TC_NT * KV_LD;          // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
-    float* sdW = sLN + 192;                   // dWQ dWK dWV
-    float* sdLN = sdW + 3072;                 // dQLN_G dQLN_B dKLN_G dKLN_B
-    float* sdThQ = sdLN + 128;
-    float* sdThK = sdThQ + PSZ;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThK + PSZ);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
-
     const SatModel& m = a.m;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, hsel = tid >> 6;
     const int F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const int tile_rows = (TC_NT / F) * F;
+    float* sB = smem;                         // B operands of the current round
+    float* sT0 = sB + TCB_SB;                 // weight-gradient operand tiles
+    float* sT1 = sT0 + tile_rows * KV_LD;
+    float* sT2 = sT1 + tile_rows * KV_LD;
+    float* sLN = sT2 + tile_rows * KV_LD;     // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
+    float* sdW = sLN + 192;                   // dWQ dWK dWV
+    float* sdLN = sdW + 3072;                 // dQLN_G dQLN_B dKLN_G dKLN_B
+    float* sdThQ = sdLN + 128;
+    float* sdThK = sdThQ + PSZ;               // only with per-position keys
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThQ + (pos ? 2 : 1) * PSZ);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
+
     const int n_tiles = a.counters[CNT_NTILES2];
     const int s = tid / F, f = tid - s * F;
     const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
@@ -50,7 +59,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
 
     copy_to_smem(sLN, m.dense + m.off_layers + (long long)l * LAYER_FLOATS + OFF_LN_G, 192, tid, TC_NT);
     for (int i = tid; i < 3072; i += TC_NT) sdW[i] = 0.f;
-    for (int i = tid; i < 2 * PSZ; i += TC_NT) sdThQ[i] = 0.f;
+    for (int i = tid; i < (pos ? 2 : 1) * PSZ; i += TC_NT) sdThQ[i] = 0.f;
     if (tid < 128) sdLN[tid] = 0.f;
     if (warp == 0) tmem_alloc(s_tmem, TC_COLS);
     if (tid == 0) mbar_init(mbar, 1);
@@ -61,6 +70,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     int cur_q = -1, cur_k = -1;
+    float* const sTh = hsel ? sT1 : sT0;      // this 64-thread half's tile in the paired weight-gradient phases
 
 #define SAT_TC_ROUND(ISSUE)                                  \
     do {                                                     \
@@ -88,7 +98,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         const long long tokpos = ((long long)p * F + f) * D;
         const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
         const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
-        __syncthreads();
+        __syncthreads();                       // previous tile's weight-gradient phases are done with the tiles / accumulators
         if (kq != cur_q) {
             if (cur_q >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
             cur_q = kq;
@@ -98,118 +108,126 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             cur_k = kk;
         }
 
-        float keep_q[D], keep_k[D];          // d(x W_Q), d(x W_K): A operands of the final dX round
-        zero(keep_q); zero(keep_k);
-#pragma unroll
+        // Rolled over the Q / K sides (half the code of an unrolled body: the kernel was instruction-fetch bound).  The
+        // side's d(x W) goes back to its dqkv slot in place and is re-read for the projection phase below.
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
             const bool has_meta = side ? meta_k : meta_q;
+            float* dqkv_s = a.dqkv + (long long)side * a.act_stride + tokpos;
+            if (!has_meta) continue;                                                        // dqkv slot already holds d(x W)
             const int key = side ? kk : kq;
             const float* pk_kf = wpack + (long long)(L + key) * PACK_FLOATS;             // forward key block
             const float* pk_kb = wpack + (long long)(nblk + L + key) * PACK_FLOATS;      // backward key block
             float* sdTh = (side && pos) ? sdThK : sdThQ;
             const float* lng = (side && pos) ? sLN + 128 : sLN + 64;
             float* sdLNs = (side && pos) ? sdLN + 64 : sdLN;
-            float (&du)[D] = side ? keep_k : keep_q;
 
-            if (valid) load_row(a.dqkv + (long long)side * a.act_stride + tokpos, du);     // dLoss/dQ' (post-LN)
-            if (has_meta) {
-                float u[D];                                                                // u = x @ W (recomputed)
-                {
-                    float xin[D];
-                    if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, xin); else zero(xin);
-                    load_b(sB, pk_lf + PK_QKV_HI + side * 1024, 1024, tid);
-                    load_b(sB + 1024, pk_lf + PK_QKV_LO + side * 1024, 1024, tid);
-                    tmem_st_operand<PASSES>(tlane + TCB_A, xin);
-                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB, sB + 1024, 32, false));
-                    tmem_ld32(tlane + TCB_D, u);
-                    tc_wait_ld();
-                }
-                float dm[D];
-                {   // LayerNorm backward of the MetaNet output
-                    float zh[D];
-                    float rstd = 0.f;
-                    if (valid) { load_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, zh); rstd = normalize32(zh); }
-                    else zero(zh);
-                    layernorm_bwd32(du, zh, rstd, lng, sdLNs, sdLNs + 32, lane, valid);     // du := dLoss/dz
-                    const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
-#pragma unroll
-                    for (int i = 0; i < D; ++i) dm[i] = valid ? du[i] * drop_factor(dc, i) : 0.f;
-                }
-                uint2 mk = make_uint2(0u, 0u);
-                if (valid) mk = *reinterpret_cast<const uint2*>(relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, side, tokpos / D));
-
-                // ---- pre = u @ W1 (N = 64): hidden activations for dW2 ------------------------------------------------
-                load_b(sB, pk_kf + PK_W1_HI, 4096, tid);
-                tmem_st_operand<PASSES>(tlane + TCB_A, u);
-                SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PK_W1_HI, sB + PK_W1_LO, 64, false));
-                if (valid) sts_row(sG + tid * KV_LD, dm);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float h[D];
-                    tmem_ld32(tlane + TCB_D + half * 32, h);
-                    tc_wait_ld();
-                    const uint32_t mb = half ? mk.y : mk.x;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) h[i] = ((mb >> i) & 1u) ? h[i] : 0.f;
-                    if (valid) sts_row(sA + tid * KV_LD, h);
-                    __syncthreads();
-                    wgrad32<TC_NT>(sA, sG, ntok, sdTh + D * HID + half * D * D, D, tid);    // dW2[half*32 + c][j] += h[c] dm[j]
-                    __syncthreads();
-                }
-                // ---- dh = dm @ W2^T (N = 64), masked; dW1 += u^T dh; du += dh @ W1^T -----------------------------------
-                load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid);
-                tmem_st_operand<PASSES>(tlane + TCB_A, dm);
-                SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_W2T_HI, sB + PKB_W2T_LO, 64, false));
-                if (valid) sts_row(sA + tid * KV_LD, u);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float dh[D];
-                    tmem_ld32(tlane + TCB_D + half * 32, dh);
-                    tc_wait_ld();
-                    const uint32_t mb = half ? mk.y : mk.x;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) dh[i] = ((mb >> i) & 1u) ? dh[i] : 0.f;
-                    tmem_st_operand<PASSES>(tlane + (half ? TCB_H2 : TCB_H), dh);
-                    if (valid) sts_row(sG + tid * KV_LD, dh);
-                    __syncthreads();
-                    wgrad32<TC_NT>(sA, sG, ntok, sdTh + half * D, HID, tid);               // dW1[i][half*32 + c] += u[i] dh[c]
-                    __syncthreads();
-                }
-                load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid);
-                SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB, sB + 1024, 32, false),
-                              issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + 2048, sB + 3072, 32, true)));
-                {
-                    float add[D];
-                    tmem_ld32(tlane + TCB_D, add);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < D; ++i) du[i] += add[i];
-                }
-            }
-            // ---- projection weight gradient: dW[i][j] += x[i] du[j] ----------------------------------------------------
-            if (valid) {
+            float du[D];
+            if (valid) load_row(dqkv_s, du); else zero(du);                                 // dLoss/dQ' (post-LN)
+            float u[D];                                                                    // u = x @ W (recomputed)
+            {
                 float xin[D];
-                load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
-                sts_row(sA + tid * KV_LD, xin);
-                sts_row(sG + tid * KV_LD, du);
+                if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, xin); else zero(xin);
+                load_b(sB, pk_lf + PK_QKV_HI + side * 1024, 1024, tid);
+                load_b(sB + 1024, pk_lf + PK_QKV_LO + side * 1024, 1024, tid);
+                tmem_st_operand<PASSES>(tlane + TCB_A, xin);
+                SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB, sB + 1024, 32, false));
+                tmem_ld32(tlane + TCB_D, u);
+                tc_wait_ld();
+            }
+            float dm[D];
+            {   // LayerNorm backward of the MetaNet output
+                float zh[D];
+                float rstd = 0.f;
+                if (valid) { load_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, zh); rstd = normalize32(zh); }
+                else zero(zh);
+                layernorm_bwd32(du, zh, rstd, lng, sdLNs, sdLNs + 32, lane, valid);         // du := dLoss/dz
+                const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
+#pragma unroll
+                for (int i = 0; i < D; i += 2) {
+                    float f0, f1;
+                    drop_pair(dc, i >> 1, f0, f1);
+                    dm[i] = valid ? du[i] * f0 : 0.f; dm[i + 1] = valid ? du[i + 1] * f1 : 0.f;
+                }
+            }
+            uint2 mk = make_uint2(0u, 0u);
+            if (valid) mk = *reinterpret_cast<const uint2*>(relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, side, tokpos / D));
+
+            // ---- pre = u @ W1 (N = 64): hidden activations; dW2[half*32 + c][j] += h[c] dm[j], both halves at once ------------
+            load_b(sB, pk_kf + PK_W1_HI, 4096, tid);
+            tmem_st_operand<PASSES>(tlane + TCB_A, u);
+            SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PK_W1_HI, sB + PK_W1_LO, 64, false));
+            if (valid) sts_row(sT2 + tid * KV_LD, dm);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float h[D];
+                tmem_ld32(tlane + TCB_D + hh * 32, h);
+                tc_wait_ld();
+                const uint32_t mb = hh ? mk.y : mk.x;
+#pragma unroll
+                for (int i = 0; i < D; ++i) h[i] = ((mb >> i) & 1u) ? h[i] : 0.f;
+                if (valid) sts_row((hh ? sT1 : sT0) + tid * KV_LD, h);
             }
             __syncthreads();
-            wgrad32<TC_NT>(sA, sG, ntok, sdW + (side ? OFF_WK : OFF_WQ), D, tid);
+            wgrad_half(sTh, sT2, ntok, sdTh + D * HID + hsel * D * D, D, tid);
+            // ---- dh = dm @ W2^T (N = 64), masked; dW1[i][half*32 + c] += u[i] dh[c]; du += dh @ W1^T ---------------------------
+            load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid);
+            tmem_st_operand<PASSES>(tlane + TCB_A, dm);
+            SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_W2T_HI, sB + PKB_W2T_LO, 64, false));
+            if (valid) sts_row(sT2 + tid * KV_LD, u);            // (the round's barrier: dW2 phase is done with the tiles)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float dh[D];
+                tmem_ld32(tlane + TCB_D + hh * 32, dh);
+                tc_wait_ld();
+                const uint32_t mb = hh ? mk.y : mk.x;
+#pragma unroll
+                for (int i = 0; i < D; ++i) dh[i] = ((mb >> i) & 1u) ? dh[i] : 0.f;
+                tmem_st_operand<PASSES>(tlane + (hh ? TCB_H2 : TCB_H), dh);
+                if (valid) sts_row((hh ? sT1 : sT0) + tid * KV_LD, dh);
+            }
             __syncthreads();
+            wgrad_half(sT2, sTh, ntok, sdTh + hsel * D, HID, tid);
+            load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid);
+            SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB, sB + 1024, 32, false),
+                          issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + 2048, sB + 3072, 32, true)));
+            {
+                float add[D];
+                tmem_ld32(tlane + TCB_D, add);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < D; ++i) du[i] += add[i];
+            }
+            if (valid) store_row(dqkv_s, du);
         }
-        // ---- V: dW_V += x^T dv ; then dX = dX_res + du_q W_Q^T + du_k W_K^T + dv W_V^T in ONE round --------------------
-        float dv[D];
-        if (valid) load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); else zero(dv);
-        if (valid) sts_row(sG + tid * KV_LD, dv);              // sA still holds x
+        // ---- projections: dW_Q += x^T du_q and dW_K += x^T du_k (paired), dW_V += x^T dv;
+        //      dX = dX_res + du_q W_Q^T + du_k W_K^T + dv W_V^T -----------------------------------------------------------------
+        __syncthreads();                                         // tiles free (a side without MetaNet has no round barrier)
+        {
+            float v[D];
+            if (valid) load_row(a.dqkv + tokpos, v); else zero(v);
+            if (valid) sts_row(sT0 + tid * KV_LD, v);
+            tmem_st_operand<PASSES>(tlane + TCB_A, v);
+            if (valid) load_row(a.dqkv + a.act_stride + tokpos, v); else zero(v);
+            if (valid) sts_row(sT1 + tid * KV_LD, v);
+            tmem_st_operand<PASSES>(tlane + TCB_H, v);
+            if (valid) { load_row(act_l + ACT_X * a.act_stride + tokpos, v); sts_row(sT2 + tid * KV_LD, v); }
+        }
+        load_b(sB, pk_lb + PKB_WQN_HI, 4096, tid);
         __syncthreads();
-        wgrad32<TC_NT>(sA, sG, ntok, sdW + OFF_WV, D, tid);
-        load_b(sB, pk_lb, 6144, tid);
-        tmem_st_operand<PASSES>(tlane + TCB_A, keep_q);
-        tmem_st_operand<PASSES>(tlane + TCB_H, keep_k);
-        tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
+        wgrad_half(sT2, sTh, ntok, sdW + (hsel ? OFF_WK : OFF_WQ), D, tid);
         SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_WQN_HI, sB + PKB_WQN_LO, 32, false),
-                      issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB + PKB_WKN_HI, sB + PKB_WKN_LO, 32, true),
-                      issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + PKB_WVN_HI, sB + PKB_WVN_LO, 32, true)));
+                      issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB + PKB_WKN_HI, sB + PKB_WKN_LO, 32, true)));
+        {
+            float dv[D];
+            if (valid) load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); else zero(dv);
+            if (valid) sts_row(sT0 + tid * KV_LD, dv);           // (the round's barrier: paired phase is done with sT0)
+            tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
+        }
+        load_b(sB, pk_lb + PKB_WVN_HI, 2048, tid);
+        __syncthreads();
+        wgrad32<TC_NT>(sT2, sT0, ntok, sdW + OFF_WV, D, tid);
+        SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB, sB + 1024, 32, true));
         float dxa[D];
         tmem_ld32(tlane + TCB_D, dxa);
         tc_wait_ld();
@@ -254,13 +272,13 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
 using namespace sat;
 
 int sat_launch_bwd_meta_tc(const BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s) {
-    const size_t smem = TCB_SMEM_FLOATS * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = tcb_smem_bytes(a.m.F, a.m.flags & SAT_FLAG_POS);
+    static size_t configured = 0;
+    if (smem > configured) {
         if (cudaFuncSetAttribute(k_bwd_meta_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(k_bwd_meta_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
-        configured = true;
+        configured = smem;
     }
     if (passes == 3) k_bwd_meta_tc<3><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
     else k_bwd_meta_tc<1><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);

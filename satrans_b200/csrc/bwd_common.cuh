@@ -80,6 +80,38 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
         for (int cc = 0; cc < 4; ++cc) atomicAdd(acc + (ia + r) * ldacc + jg + cc, c[r][cc]);
 }
 
+// Two 32x32 products at once in a 128-thread CTA: the caller hands each 64-thread half (tid >> 6, warp-uniform) its own
+// A / G / acc.  Every thread owns one 4x4 block over ALL tokens, so the shared-memory accumulator is updated with plain
+// 16 B read-modify-writes (fp32 atomicAdd on shared memory is a CAS loop: 17 % of k_bwd_meta_tc's stall samples before).
+__device__ __forceinline__ void wgrad_half(const float* __restrict__ A, const float* __restrict__ G, int ntok,
+                                           float* __restrict__ acc, int ldacc, int tid) {
+    const int blk = tid & 63;
+    const int ia = (blk >> 3) * 4, jg = (blk & 7) * 4;
+    float c[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
+    const float* pa = A + ia;
+    const float* pg = G + jg;
+#pragma unroll 4
+    for (int t = 0; t < ntok; ++t) {
+        const float4 a = *reinterpret_cast<const float4*>(pa + t * KV_LD);
+        const float4 g = *reinterpret_cast<const float4*>(pg + t * KV_LD);
+        c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
+        c[1][0] = fmaf(a.y, g.x, c[1][0]); c[1][1] = fmaf(a.y, g.y, c[1][1]); c[1][2] = fmaf(a.y, g.z, c[1][2]); c[1][3] = fmaf(a.y, g.w, c[1][3]);
+        c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
+        c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float4* p = reinterpret_cast<float4*>(acc + (ia + r) * ldacc + jg);
+        float4 v = *p;
+        v.x += c[r][0]; v.y += c[r][1]; v.z += c[r][2]; v.w += c[r][3];
+        *p = v;
+    }
+}
+
 template <int NTHREADS = NT>
 __device__ __forceinline__ void flush_add(float* __restrict__ dst, float* __restrict__ sacc, int n, int tid) {
     for (int i = tid; i < n; i += NTHREADS) {

@@ -71,6 +71,22 @@ __device__ __forceinline__ float drop_factor(const DropCtx& c, uint32_t e) {
     uint32_t u = (e & 1u) ? (r >> 16) : (r & 0xFFFFu);
     return u < c.thr ? 0.f : c.scale;
 }
+// keep-mask factors of elements 2*pair and 2*pair + 1 from ONE hash (same values as drop_factor)
+__device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t pair, float& f0, float& f1) {
+    if (!c.on) { f0 = 1.f; f1 = 1.f; return; }
+    const uint32_t r = mix32(c.key + pair * 0xC2B2AE35U);
+    f0 = (r & 0xFFFFu) < c.thr ? 0.f : c.scale;
+    f1 = (r >> 16) < c.thr ? 0.f : c.scale;
+}
+// v[i] *= keep-mask factor of element i, i < D
+__device__ __forceinline__ void drop_apply32(const DropCtx& c, float (&v)[SAT_D]) {
+#pragma unroll
+    for (int i = 0; i < SAT_D; i += 2) {
+        float f0, f1;
+        drop_pair(c, i >> 1, f0, f1);
+        v[i] *= f0; v[i + 1] *= f1;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // thread-local small GEMV against a matrix in shared memory (all lanes read the same address:

@@ -37,7 +37,11 @@ __device__ __forceinline__ void metanet_fwd(float (&q)[D], const float* __restri
         vm_outer<16, D, D>(th + D * HID + c0 * D, h, mo);
     }
 #pragma unroll
-    for (int i = 0; i < D; ++i) z[i] = fmaf(mo[i], drop_factor(dc, i), q[i]);
+    for (int i = 0; i < D; i += 2) {
+        float f0, f1;
+        drop_pair(dc, i >> 1, f0, f1);
+        z[i] = fmaf(mo[i], f0, q[i]); z[i + 1] = fmaf(mo[i + 1], f1, q[i + 1]);
+    }
 }
 
 template <int H, bool TRAIN>
@@ -152,10 +156,15 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                 vm_dot<D, D, D>(sW + OFF_WO, r, o);
                 const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    float v = relu_out ? fmaxf(o[i], 0.f) : o[i];
-                    v *= drop_factor(dco, i);
-                    x[i] = use_res ? v + x[i] : v;
+                for (int i = 0; i < D; i += 2) {
+                    float fk[2];
+                    drop_pair(dco, i >> 1, fk[0], fk[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float v = relu_out ? fmaxf(o[i + e], 0.f) : o[i + e];
+                        v *= fk[e];
+                        x[i + e] = use_res ? v + x[i + e] : v;
+                    }
                 }
                 float mean, rstd;
                 layernorm32(x, sLN, sLN + 32, mean, rstd);

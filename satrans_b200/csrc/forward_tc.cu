@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
                     tc_wait_ld();
                     const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, TRAIN);
 #pragma unroll
-                    for (int i = 0; i < D; ++i) u[i] = fmaf(hbuf[i], drop_factor(dc, i), u[i]);
+                    for (int i = 0; i < D; i += 2) {
+                        float f0, f1;
+                        drop_pair(dc, i >> 1, f0, f1);
+                        u[i] = fmaf(hbuf[i], f0, u[i]); u[i + 1] = fmaf(hbuf[i + 1], f1, u[i + 1]);
+                    }
                 }
                 if (TRAIN && valid) store_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, u);
                 if (has_meta) {
@@ -236,10 +240,15 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
             tc_wait_ld();
             const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                float vv = relu_out ? fmaxf(o[i], 0.f) : o[i];
-                vv *= drop_factor(dco, i);
-                x[i] = use_res ? vv + x[i] : vv;
+            for (int i = 0; i < D; i += 2) {
+                float f[2];
+                drop_pair(dco, i >> 1, f[0], f[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float vv = relu_out ? fmaxf(o[i + e], 0.f) : o[i + e];
+                    vv *= f[e];
+                    x[i + e] = use_res ? vv + x[i + e] : vv;
+                }
             }
             float mean, rstd;
             layernorm32(x, sLN, sLN + 32, mean, rstd);

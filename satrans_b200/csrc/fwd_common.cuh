@@ -41,10 +41,12 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
         float o[DH];
         zero(o);
         const float inv_sum = 1.f / sum;
+        float fd[2];
 #pragma unroll
         for (int j = 0; j < SAT_MAXF; ++j) {
             if (j < F) {
-                const float pj = (sc[j] * inv_sum) * drop_factor(dc, h * SAT_MAXF + j);     // softmax, attn_dropout
+                if ((j & 1) == 0) drop_pair(dc, (h * SAT_MAXF + j) >> 1, fd[0], fd[1]);   // one hash per two keys
+                const float pj = (sc[j] * inv_sum) * fd[j & 1];                             // softmax, attn_dropout
                 const float* vr = sV + (sbase + j) * KV_LD + h * DH;
 #pragma unroll
                 for (int c = 0; c < DH; c += 4) {
