@@ -8,7 +8,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libsatrans_b200.so')
+LIB_PATH = os.environ.get('SAT_LIB') or os.path.join(HERE, 'lib', 'libsatrans_b200.so')   # SAT_LIB: A/B builds of the same ABI
 CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288

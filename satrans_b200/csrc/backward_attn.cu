@@ -12,6 +12,13 @@
 // stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
 #include "bwd_common.cuh"
 
+#ifndef SAT_BWDA_JC
+#define SAT_BWDA_JC 4          // keys per basic block in the query-role pass
+#endif
+#ifndef SAT_BWDA_PREFETCH
+#define SAT_BWDA_PREFETCH 0    // 1: request the phase-2 rows before the dW_out phase (spills at 255 registers: slower)
+#endif
+
 namespace sat {
 
 // =====================================================================================================
@@ -122,20 +129,30 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
                 sts_row(sT1 + tid * KV_LD, dy);
             }
         }
+        // ---- phase 2: recompute Q' K' V, stage K'/V.  The rows are requested before the dW_out phase so that their HBM/L2
+        //      latency overlaps it. ------------------------------------------------------------------------
+        float q[D], kst[D], vst[D];
+#if SAT_BWDA_PREFETCH
+        if (valid) {
+            load_row(act_l + ACT_ZK * a.act_stride + tokpos, kst);
+            load_row(act_l + ACT_V * a.act_stride + tokpos, vst);
+            load_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+        }
+#endif
         __syncthreads();
         wgrad32<NTH>(sT1, sT0, ntok, sdWO, D, tid);             // dWO[j][i] += dO[j] r[i]   (A = dO, G = r)
         __syncthreads();
-
-        // ---- phase 2: recompute Q' K' V, stage K'/V ----------------------------------------------------
-        float q[D];
+#if !SAT_BWDA_PREFETCH
         if (valid) {
-            float k[D];
-            load_row(act_l + ACT_ZK * a.act_stride + tokpos, k);
-            if (meta_k) { float mean, rstd; layernorm32(k, kln, kln + 32, mean, rstd); }
-            sts_row(sT0 + tid * KV_LD, k);
-            load_row(act_l + ACT_V * a.act_stride + tokpos, k);
-            sts_row(sT1 + tid * KV_LD, k);
+            load_row(act_l + ACT_ZK * a.act_stride + tokpos, kst);
+            load_row(act_l + ACT_V * a.act_stride + tokpos, vst);
             load_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
+        }
+#endif
+        if (valid) {
+            if (meta_k) { float mean, rstd; layernorm32(kst, kln, kln + 32, mean, rstd); }
+            sts_row(sT0 + tid * KV_LD, kst);
+            sts_row(sT1 + tid * KV_LD, vst);
             if (meta_q) { float mean, rstd; layernorm32(q, qln, qln + 32, mean, rstd); }
         }
         __syncthreads();
@@ -149,51 +166,64 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
             // rolled over heads: q / dr / dq are rotated by DH per head (compact code, see common.cuh)
 #pragma unroll 1
             for (int h = 0; h < H; ++h) {
+                // keys in chunks of JC per basic block; keys past F read row F-1 with score -inf (see attention_fwd)
+                constexpr int JC = SAT_BWDA_JC;
                 float sc[SAT_MAXF];
                 float mx = -INFINITY;
                 const float Dhh = sSt[tid * ST_LD + 16 + h];
 #pragma unroll
-                for (int j = 0; j < SAT_MAXF; ++j) {
-                    if (j < F) {
-                        const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
-                        float acc = 0.f;
+                for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+                    if (j0 < F) {
 #pragma unroll
-                        for (int c = 0; c < DH; c += 4) {
-                            const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                            acc = fmaf(q[c + 0], kk.x, acc); acc = fmaf(q[c + 1], kk.y, acc);
-                            acc = fmaf(q[c + 2], kk.z, acc); acc = fmaf(q[c + 3], kk.w, acc);
+                        for (int j = j0; j < j0 + JC; ++j) {
+                            const float* kr = sT0 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            float acc = 0.f;
+#pragma unroll
+                            for (int c = 0; c < DH; c += 4) {
+                                const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                                acc = fmaf(q[c + 0], kk.x, acc); acc = fmaf(q[c + 1], kk.y, acc);
+                                acc = fmaf(q[c + 2], kk.z, acc); acc = fmaf(q[c + 3], kk.w, acc);
+                            }
+                            sc[j] = j < F ? acc * inv_sqrt_dh : -INFINITY;
+                            mx = fmaxf(mx, sc[j]);
                         }
-                        sc[j] = acc * inv_sqrt_dh;
-                        mx = fmaxf(mx, sc[j]);
                     }
                 }
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < SAT_MAXF; ++j)
-                    if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+                for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+                    if (j0 < F) {
+#pragma unroll
+                        for (int j = j0; j < j0 + JC; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+                    }
+                }
                 const float inv_sum = 1.f / sum;
                 sSt[tid * ST_LD + h] = mx; sSt[tid * ST_LD + 8 + h] = inv_sum;
-                float fd[2];
 #pragma unroll
-                for (int j = 0; j < SAT_MAXF; ++j) {
-                    if (j < F) {
-                        if ((j & 1) == 0) drop_pair(dca, (h * SAT_MAXF + j) >> 1, fd[0], fd[1]);
-                        const float pj = sc[j] * inv_sum;
-                        const float* vr = sT1 + (sbase + j) * KV_LD + h * DH;
-                        const float* kr = sT0 + (sbase + j) * KV_LD + h * DH;
-                        float dAd = 0.f;
+                for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+                    if (j0 < F) {
+                        float fd[JC];
 #pragma unroll
-                        for (int c = 0; c < DH; c += 4) {
-                            const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                            dAd = fmaf(dr[c + 0], vv.x, dAd); dAd = fmaf(dr[c + 1], vv.y, dAd);
-                            dAd = fmaf(dr[c + 2], vv.z, dAd); dAd = fmaf(dr[c + 3], vv.w, dAd);
-                        }
-                        const float dsc = pj * (dAd * fd[j & 1] - Dhh) * inv_sqrt_dh;
+                        for (int j = j0; j < j0 + JC; j += 2) drop_pair(dca, (h * SAT_MAXF + j) >> 1, fd[j - j0], fd[j - j0 + 1]);
 #pragma unroll
-                        for (int c = 0; c < DH; c += 4) {
-                            const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                            dq[c + 0] = fmaf(dsc, kk.x, dq[c + 0]); dq[c + 1] = fmaf(dsc, kk.y, dq[c + 1]);
-                            dq[c + 2] = fmaf(dsc, kk.z, dq[c + 2]); dq[c + 3] = fmaf(dsc, kk.w, dq[c + 3]);
+                        for (int j = j0; j < j0 + JC; ++j) {
+                            const float pj = sc[j] * inv_sum;                  // exactly 0 for the padding keys
+                            const float* vr = sT1 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            const float* kr = sT0 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            float dAd = 0.f;
+#pragma unroll
+                            for (int c = 0; c < DH; c += 4) {
+                                const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+                                dAd = fmaf(dr[c + 0], vv.x, dAd); dAd = fmaf(dr[c + 1], vv.y, dAd);
+                                dAd = fmaf(dr[c + 2], vv.z, dAd); dAd = fmaf(dr[c + 3], vv.w, dAd);
+                            }
+                            const float dsc = pj * (dAd * fd[j - j0] - Dhh) * inv_sqrt_dh;
+#pragma unroll
+                            for (int c = 0; c < DH; c += 4) {
+                                const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                                dq[c + 0] = fmaf(dsc, kk.x, dq[c + 0]); dq[c + 1] = fmaf(dsc, kk.y, dq[c + 1]);
+                                dq[c + 2] = fmaf(dsc, kk.z, dq[c + 2]); dq[c + 3] = fmaf(dsc, kk.w, dq[c + 3]);
+                            }
                         }
                     }
                 }

@@ -13,48 +13,63 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
                                               float (&r)[D]) {
     constexpr int DH = D / H;
     const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+    // Keys are processed in chunks of JC inside ONE basic block (a per-key `if (j < F)` made every key its own block and
+    // serialised the dot-product / hash / exp chains: "wait" was 41 % of the forward's stall samples).  Keys past F in the
+    // last chunk read row F-1 and get score -inf: probability exactly 0, so the sums are unchanged bit for bit.
+    constexpr int JC = 4;
 #pragma unroll 1
     for (int h = 0; h < H; ++h) {
         float sc[SAT_MAXF];
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j) {
-            if (j < F) {
-                const float* kr = sK + (sbase + j) * KV_LD + h * DH;
-                float acc = 0.f;
+        for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+            if (j0 < F) {
 #pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                    acc = fmaf(q[c + 0], kk.x, acc);
-                    acc = fmaf(q[c + 1], kk.y, acc);
-                    acc = fmaf(q[c + 2], kk.z, acc);
-                    acc = fmaf(q[c + 3], kk.w, acc);
+                for (int j = j0; j < j0 + JC; ++j) {
+                    const float* kr = sK + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+                        acc = fmaf(q[c + 0], kk.x, acc);
+                        acc = fmaf(q[c + 1], kk.y, acc);
+                        acc = fmaf(q[c + 2], kk.z, acc);
+                        acc = fmaf(q[c + 3], kk.w, acc);
+                    }
+                    sc[j] = j < F ? acc * inv_sqrt_dh : -INFINITY;     // inner_product /= dh ** 0.5   (satrans.py:85-86)
+                    mx = fmaxf(mx, sc[j]);
                 }
-                sc[j] = acc * inv_sqrt_dh;                // inner_product /= dh ** 0.5   (satrans.py:85-86)
-                mx = fmaxf(mx, sc[j]);
             }
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j)
-            if (j < F) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+        for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+            if (j0 < F) {
+#pragma unroll
+                for (int j = j0; j < j0 + JC; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+            }
+        }
         float o[DH];
         zero(o);
         const float inv_sum = 1.f / sum;
-        float fd[2];
 #pragma unroll
-        for (int j = 0; j < SAT_MAXF; ++j) {
-            if (j < F) {
-                if ((j & 1) == 0) drop_pair(dc, (h * SAT_MAXF + j) >> 1, fd[0], fd[1]);   // one hash per two keys
-                const float pj = (sc[j] * inv_sum) * fd[j & 1];                             // softmax, attn_dropout
-                const float* vr = sV + (sbase + j) * KV_LD + h * DH;
+        for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
+            if (j0 < F) {
+                float fd[JC];
 #pragma unroll
-                for (int c = 0; c < DH; c += 4) {
-                    const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                    o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
-                    o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
-                    o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
-                    o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                for (int j = j0; j < j0 + JC; j += 2) drop_pair(dc, (h * SAT_MAXF + j) >> 1, fd[j - j0], fd[j - j0 + 1]);
+#pragma unroll
+                for (int j = j0; j < j0 + JC; ++j) {
+                    const float pj = (sc[j] * inv_sum) * fd[j - j0];                        // softmax, attn_dropout
+                    const float* vr = sV + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 4) {
+                        const float4 vv = *reinterpret_cast<const float4*>(vr + c);
+                        o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
+                        o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
+                        o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
+                        o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                    }
                 }
             }
         }
