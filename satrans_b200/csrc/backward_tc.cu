@@ -16,10 +16,11 @@ constexpr int TCB_A = 0, TCB_H = 64, TCB_D = 128, TCB_H2 = 192;          // TMEM
 constexpr int TCB_SB = 4096;                                             // floats of the B-operand staging buffer (16 KB)
 
 // Shared memory (floats): B staging | three [tile_rows][36] weight-gradient operand tiles | LN params | dW_Q/K/V | dLN | d theta
-// (one key block, two with per-position keys).  tile_rows = (128 / F) * F: rows past the last token of a full tile are never
-// touched.  F = 19: 95.6 KB (EN) / 112 KB (ENP) -> 2 CTAs per SM either way.
+// (one key block, two with per-position keys).  tile_rows = (128 / F) * F rounded up to 4: the threads past a tile's last
+// token store zero rows, so the weight-gradient loops run over whole groups of 4 tokens.
+// F = 19: 96.4 KB (EN) / 112.9 KB (ENP) -> 2 CTAs per SM either way.
 static size_t tcb_smem_bytes(int F, bool pos) {
-    const int rows = (TC_NT / F) * F;
+    const int rows = ((TC_NT / F) * F + 3) & ~3;
     return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);
 }
 
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     const int F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
-    const int tile_rows = (TC_NT / F) * F;
+    const int tile_rows = ((TC_NT / F) * F + 3) & ~3;
     float* sB = smem;                         // B operands of the current round
     float* sT0 = sB + TCB_SB;                 // weight-gradient operand tiles
     float* sT1 = sT0 + tile_rows * KV_LD;
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
         const int g = td.x, start = td.y, cnt = td.z;
         const bool valid = s < cnt;
-        const int ntok = cnt * F;
+        const int ntok4 = (cnt * F + 3) & ~3;
+        const bool stage = tid < tile_rows;       // owns a row of the operand tiles (zeros past the last token)
         const int p = start + s;
         const int b = valid ? a.perm[p] : 0;
         const long long tokpos = ((long long)p * F + f) * D;
@@ -122,8 +124,11 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             const float* lng = (side && pos) ? sLN + 128 : sLN + 64;
             float* sdLNs = (side && pos) ? sdLN + 64 : sdLN;
 
-            float du[D];
-            if (valid) load_row(dqkv_s, du); else zero(du);                                 // dLoss/dQ' (post-LN)
+            float du[D], zh[D];
+            if (valid) {
+                load_row(dqkv_s, du);                                                       // dLoss/dQ' (post-LN)
+                load_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, zh);     // requested before the first round
+            } else { zero(du); zero(zh); }
             float u[D];                                                                    // u = x @ W (recomputed)
             {
                 float xin[D];
@@ -137,10 +142,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             }
             float dm[D];
             {   // LayerNorm backward of the MetaNet output
-                float zh[D];
                 float rstd = 0.f;
-                if (valid) { load_row(act_l + (side ? ACT_ZK : ACT_ZQ) * a.act_stride + tokpos, zh); rstd = normalize32(zh); }
-                else zero(zh);
+                if (valid) rstd = normalize32(zh);
                 layernorm_bwd32(du, zh, rstd, lng, sdLNs, sdLNs + 32, lane, valid);         // du := dLoss/dz
                 const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
 #pragma unroll
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             load_b(sB, pk_kf + PK_W1_HI, 4096, tid);
             tmem_st_operand<PASSES>(tlane + TCB_A, u);
             SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PK_W1_HI, sB + PK_W1_LO, 64, false));
-            if (valid) sts_row(sT2 + tid * KV_LD, dm);
+            if (stage) sts_row(sT2 + tid * KV_LD, dm);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 float h[D];
@@ -166,15 +169,15 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
                 const uint32_t mb = hh ? mk.y : mk.x;
 #pragma unroll
                 for (int i = 0; i < D; ++i) h[i] = ((mb >> i) & 1u) ? h[i] : 0.f;
-                if (valid) sts_row((hh ? sT1 : sT0) + tid * KV_LD, h);
+                if (stage) sts_row((hh ? sT1 : sT0) + tid * KV_LD, h);
             }
             __syncthreads();
-            wgrad_half(sTh, sT2, ntok, sdTh + D * HID + hsel * D * D, D, tid);
+            wgrad_half(sTh, sT2, ntok4, sdTh + D * HID + hsel * D * D, D, tid);
             // ---- dh = dm @ W2^T (N = 64), masked; dW1[i][half*32 + c] += u[i] dh[c]; du += dh @ W1^T ---------------------------
             load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid);
             tmem_st_operand<PASSES>(tlane + TCB_A, dm);
             SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_W2T_HI, sB + PKB_W2T_LO, 64, false));
-            if (valid) sts_row(sT2 + tid * KV_LD, u);            // (the round's barrier: dW2 phase is done with the tiles)
+            if (stage) sts_row(sT2 + tid * KV_LD, u);            // (the round's barrier: dW2 phase is done with the tiles)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 float dh[D];
@@ -184,10 +187,10 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
 #pragma unroll
                 for (int i = 0; i < D; ++i) dh[i] = ((mb >> i) & 1u) ? dh[i] : 0.f;
                 tmem_st_operand<PASSES>(tlane + (hh ? TCB_H2 : TCB_H), dh);
-                if (valid) sts_row((hh ? sT1 : sT0) + tid * KV_LD, dh);
+                if (stage) sts_row((hh ? sT1 : sT0) + tid * KV_LD, dh);
             }
             __syncthreads();
-            wgrad_half(sT2, sTh, ntok, sdTh + hsel * D, HID, tid);
+            wgrad_half(sT2, sTh, ntok4, sdTh + hsel * D, HID, tid);
             load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid);
             SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB, sB + 1024, 32, false),
                           issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + 2048, sB + 3072, 32, true)));
@@ -203,37 +206,54 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         // ---- projections: dW_Q += x^T du_q and dW_K += x^T du_k (paired), dW_V += x^T dv;
         //      dX = dX_res + du_q W_Q^T + du_k W_K^T + dv W_V^T -----------------------------------------------------------------
         __syncthreads();                                         // tiles free (a side without MetaNet has no round barrier)
+        float dv[D], res[D];                                     // requested now, used after the paired phase / at the end
         {
             float v[D];
             if (valid) load_row(a.dqkv + tokpos, v); else zero(v);
-            if (valid) sts_row(sT0 + tid * KV_LD, v);
+            if (stage) sts_row(sT0 + tid * KV_LD, v);
             tmem_st_operand<PASSES>(tlane + TCB_A, v);
             if (valid) load_row(a.dqkv + a.act_stride + tokpos, v); else zero(v);
-            if (valid) sts_row(sT1 + tid * KV_LD, v);
+            if (stage) sts_row(sT1 + tid * KV_LD, v);
             tmem_st_operand<PASSES>(tlane + TCB_H, v);
-            if (valid) { load_row(act_l + ACT_X * a.act_stride + tokpos, v); sts_row(sT2 + tid * KV_LD, v); }
+            if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, v); else zero(v);
+            if (stage) sts_row(sT2 + tid * KV_LD, v);
+            if (valid) { load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); load_row(a.dx + tokpos, res); }
+            else { zero(dv); zero(res); }
         }
         load_b(sB, pk_lb + PKB_WQN_HI, 4096, tid);
         __syncthreads();
-        wgrad_half(sT2, sTh, ntok, sdW + (hsel ? OFF_WK : OFF_WQ), D, tid);
+        wgrad_half(sT2, sTh, ntok4, sdW + (hsel ? OFF_WK : OFF_WQ), D, tid);
         SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_WQN_HI, sB + PKB_WQN_LO, 32, false),
                       issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB + PKB_WKN_HI, sB + PKB_WKN_LO, 32, true)));
-        {
-            float dv[D];
-            if (valid) load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); else zero(dv);
-            if (valid) sts_row(sT0 + tid * KV_LD, dv);           // (the round's barrier: paired phase is done with sT0)
-            tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
-        }
+        if (stage) sts_row(sT0 + tid * KV_LD, dv);               // (the round's barrier: paired phase is done with sT0)
+        tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
         load_b(sB, pk_lb + PKB_WVN_HI, 2048, tid);
         __syncthreads();
-        wgrad32<TC_NT>(sT2, sT0, ntok, sdW + OFF_WV, D, tid);
+        // dW_V: one product for 128 threads -> each half takes half of the token groups; the upper half parks its partial
+        // block in the free part of sB and the lower half adds both to the accumulator after the round's barrier
+        float cv[4][4];
+        {
+            const int mid = ((ntok4 >> 1) + 3) & ~3;
+            wgrad_block(sT2, sT0, hsel ? mid : 0, hsel ? ntok4 : mid, tid, cv);
+            if (hsel) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    *reinterpret_cast<float4*>(sB + 2048 + (tid & 63) * 16 + r * 4) = make_float4(cv[r][0], cv[r][1], cv[r][2], cv[r][3]);
+            }
+        }
         SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB, sB + 1024, 32, true));
+        if (!hsel) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 o = *reinterpret_cast<const float4*>(sB + 2048 + (tid & 63) * 16 + r * 4);
+                cv[r][0] += o.x; cv[r][1] += o.y; cv[r][2] += o.z; cv[r][3] += o.w;
+            }
+            wgrad_store(sdW + OFF_WV, D, tid, cv);
+        }
         float dxa[D];
         tmem_ld32(tlane + TCB_D, dxa);
         tc_wait_ld();
         if (valid) {
-            float res[D];
-            load_row(a.dx + tokpos, res);
 #pragma unroll
             for (int i = 0; i < D; ++i) dxa[i] += res[i];
             if (l > 0) {

@@ -80,29 +80,54 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
         for (int cc = 0; cc < 4; ++cc) atomicAdd(acc + (ia + r) * ldacc + jg + cc, c[r][cc]);
 }
 
-// Two 32x32 products at once in a 128-thread CTA: the caller hands each 64-thread half (tid >> 6, warp-uniform) its own
-// A / G / acc.  Every thread owns one 4x4 block over ALL tokens, so the shared-memory accumulator is updated with plain
-// 16 B read-modify-writes (fp32 atomicAdd on shared memory is a CAS loop: 17 % of k_bwd_meta_tc's stall samples before).
-__device__ __forceinline__ void wgrad_half(const float* __restrict__ A, const float* __restrict__ G, int ntok,
-                                           float* __restrict__ acc, int ldacc, int tid) {
+__device__ __forceinline__ void fma_block(float (&c)[4][4], const float4& a, const float4& g) {
+    c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
+    c[1][0] = fmaf(a.y, g.x, c[1][0]); c[1][1] = fmaf(a.y, g.y, c[1][1]); c[1][2] = fmaf(a.y, g.z, c[1][2]); c[1][3] = fmaf(a.y, g.w, c[1][3]);
+    c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
+    c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
+}
+
+// c[r][cc] = sum_{t in [tb, te)} A[t][ia + r] * G[t][jg + cc] for this thread's 4x4 block (blk = tid & 63) of a 32x32 product.
+// te - tb is a multiple of 4 (the tiles' rows past the last token are zero); tokens go four at a time with the next four
+// already requested from shared memory (software pipeline: the FMAs of one group hide the LDS latency of the next).
+__device__ __forceinline__ void wgrad_block(const float* __restrict__ A, const float* __restrict__ G, int tb, int te, int tid,
+                                            float (&c)[4][4]) {
     const int blk = tid & 63;
-    const int ia = (blk >> 3) * 4, jg = (blk & 7) * 4;
-    float c[4][4];
+    const float* pa = A + (blk >> 3) * 4 + tb * KV_LD;
+    const float* pg = G + (blk & 7) * 4 + tb * KV_LD;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
-    const float* pa = A + ia;
-    const float* pg = G + jg;
-#pragma unroll 4
-    for (int t = 0; t < ntok; ++t) {
-        const float4 a = *reinterpret_cast<const float4*>(pa + t * KV_LD);
-        const float4 g = *reinterpret_cast<const float4*>(pg + t * KV_LD);
-        c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
-        c[1][0] = fmaf(a.y, g.x, c[1][0]); c[1][1] = fmaf(a.y, g.y, c[1][1]); c[1][2] = fmaf(a.y, g.z, c[1][2]); c[1][3] = fmaf(a.y, g.w, c[1][3]);
-        c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
-        c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
+    if (te <= tb) return;
+    float4 a[4], g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = *reinterpret_cast<const float4*>(pa + k * KV_LD);
+        g[k] = *reinterpret_cast<const float4*>(pg + k * KV_LD);
     }
+#pragma unroll 1
+    for (int t = tb + 4; t < te; t += 4) {
+        pa += 4 * KV_LD; pg += 4 * KV_LD;
+        float4 na[4], ng[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            na[k] = *reinterpret_cast<const float4*>(pa + k * KV_LD);
+            ng[k] = *reinterpret_cast<const float4*>(pg + k * KV_LD);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fma_block(c, a[k], g[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] = na[k]; g[k] = ng[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fma_block(c, a[k], g[k]);
+}
+
+// acc[(ia + r) * ldacc + jg + cc] += c[r][cc] with plain 16 B read-modify-writes: the caller guarantees one owner per element
+__device__ __forceinline__ void wgrad_store(float* __restrict__ acc, int ldacc, int tid, const float (&c)[4][4]) {
+    const int blk = tid & 63;
+    const int ia = (blk >> 3) * 4, jg = (blk & 7) * 4;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         float4* p = reinterpret_cast<float4*>(acc + (ia + r) * ldacc + jg);
@@ -110,6 +135,16 @@ __device__ __forceinline__ void wgrad_half(const float* __restrict__ A, const fl
         v.x += c[r][0]; v.y += c[r][1]; v.z += c[r][2]; v.w += c[r][3];
         *p = v;
     }
+}
+
+// Two 32x32 products at once in a 128-thread CTA: the caller hands each 64-thread half (tid >> 6, warp-uniform) its own
+// A / G / acc.  Every thread owns one 4x4 block over ALL tokens, so the shared-memory accumulator is updated without
+// atomics (fp32 atomicAdd on shared memory is a CAS loop: 17 % of k_bwd_meta_tc's stall samples before).
+__device__ __forceinline__ void wgrad_half(const float* __restrict__ A, const float* __restrict__ G, int ntok4,
+                                           float* __restrict__ acc, int ldacc, int tid) {
+    float c[4][4];
+    wgrad_block(A, G, 0, ntok4, tid, c);
+    wgrad_store(acc, ldacc, tid, c);
 }
 
 template <int NTHREADS = NT>
