@@ -62,7 +62,7 @@ struct BwdArgs {
 #define SAT_DECL_H(H)                                                                          \
     int sat_launch_forward_h##H(const sat::FwdArgs& a, int grid, int training, cudaStream_t s); \
     int sat_launch_forward_tc_h##H(const sat::FwdArgs& a, const float* wpack, int grid, int training, int passes, cudaStream_t s); \
-    int sat_launch_bwd_attn_h##H(const sat::BwdArgs& a, int variant, int grid, cudaStream_t s);
+    int sat_launch_bwd_attn_h##H(const sat::BwdArgs& a, int grid, cudaStream_t s);
 SAT_DECL_H(1)
 SAT_DECL_H(2)
 SAT_DECL_H(4)

@@ -304,7 +304,7 @@ int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys
 // passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
 static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
                          uint64_t seed, int passes, void* stream) {
-    if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->row_grad)
+    if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->row_grad || !w->tiles2)
         return sat_host::fail(SAT_EINVAL, "sat_backward: null argument / workspace not sized for training");
     if (w->B == 0) return SAT_OK;
     cudaStream_t s = (cudaStream_t)stream;
@@ -331,26 +331,19 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
     k_bwd_head<<<grid2, NT, 0, s>>>(a);
     int rc = sat_host::check_launch("k_bwd_head");
     if (rc) return rc;
-    // k_bwd_attn tiling (see backward_attn.cu): tuning knob, default chosen by measurement
-    static const int attn_variant_env = [] { const char* e = getenv("SAT_BWD_ATTN_VARIANT"); return e ? atoi(e) : 1; }();
-    const int attn_variant = w->tiles2 ? attn_variant_env : 0;
     const int spt2 = NT2 / m->F;
     const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
-    BwdArgs aa = a;                           // k_bwd_attn's view: its own tile set
-    int grid_a = grid2;
-    if (attn_variant != 0) {
-        aa.tiles = w->tiles2;
-        const int per_sm = attn_variant == 2 ? 3 : 2;
-        grid_a = max_tiles2 < 148 * per_sm ? max_tiles2 : 148 * per_sm;
-    }
+    BwdArgs aa = a;                           // k_bwd_attn walks the 128-token tile set
+    aa.tiles = w->tiles2;
+    const int grid_a = max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2;
     for (int l = m->L - 1; l >= 0; --l) {
         a.layer = l;
         aa.layer = l;
         switch (m->H) {
-            case 1: rc = sat_launch_bwd_attn_h1(aa, attn_variant, grid_a, s); break;
-            case 2: rc = sat_launch_bwd_attn_h2(aa, attn_variant, grid_a, s); break;
-            case 4: rc = sat_launch_bwd_attn_h4(aa, attn_variant, grid_a, s); break;
-            case 8: rc = sat_launch_bwd_attn_h8(aa, attn_variant, grid_a, s); break;
+            case 1: rc = sat_launch_bwd_attn_h1(aa, grid_a, s); break;
+            case 2: rc = sat_launch_bwd_attn_h2(aa, grid_a, s); break;
+            case 4: rc = sat_launch_bwd_attn_h4(aa, grid_a, s); break;
+            case 8: rc = sat_launch_bwd_attn_h8(aa, grid_a, s); break;
             default: return sat_host::fail(SAT_EINVAL, "sat_backward: heads=%d not in {1,2,4,8}", m->H);
         }
         if (rc) return rc;

@@ -1,64 +1,80 @@
 // Fused SATrans backward (replaces torch autograd over the graph of reference satrans.py:197-256).
 //
-// Same mapping as the forward: one thread = one field token, a CTA = whole samples of one scenario.
-// Per layer, two kernels:
-//   k_bwd_attn : LayerNorm-out bwd, out-projection bwd (+dW_out), attention bwd -> dQ', dK', dV
+// Same mapping as the forward: one thread = one field token, a CTA = whole samples of one scenario
+// (128 threads, the 128-token tile set of k_bucket).  Per layer, two kernels:
+//   k_bwd_attn : LayerNorm-out bwd, out-projection bwd (+dW_out), attention bwd -> dQ', dK', dV      (this file)
 //   k_bwd_meta : MetaNet-LayerNorm bwd, MetaNet bwd (+d theta), QKV projection bwd (+dW_q/k/v) -> dX
-// Data gradients are thread-local GEMVs against weights in shared memory (as in the forward).  Weight
-// gradients are reductions over tokens: the two operands are staged as [token][36] shared tiles and every
-// thread owns a 4x4 block of the 32x32 product (64 blocks x 3 token groups = 192 threads), accumulated
-// into shared-memory accumulators that are flushed to HBM with one atomicAdd per element per CTA.
+// Data gradients are thread-local GEMVs against weights in shared memory (as in the forward).  The weight
+// gradient dW_out is a reduction over tokens: dO and r are staged as [token][36] shared tiles and every
+// thread owns a 4x4 block of the 32x32 product for half of the tokens (bwd_common.cuh).
 // Attention uses the FlashAttention identity  sum_j P_ij dP_ij = dR_i . R_i  so no (F x F) tensor is
 // stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
+//
+// Four operand tiles: T0 = r -> Q', T1 = dO -> dR, T2 = K', T3 = V.  The r / z_k / V rows of a tile are
+// fetched with cp.async at the top of the tile (no registers, all three latencies overlap the first phase).
 #include "bwd_common.cuh"
 
 #ifndef SAT_BWDA_JC
 #define SAT_BWDA_JC 4          // keys per basic block in the query-role pass
 #endif
-#ifndef SAT_BWDA_PREFETCH
-#define SAT_BWDA_PREFETCH 0    // 1: request the phase-2 rows before the dW_out phase (spills at 255 registers: slower)
+#ifndef SAT_BWDA_IC
+#define SAT_BWDA_IC 4          // queries per basic block in the key-role pass
 #endif
 
 namespace sat {
 
-// =====================================================================================================
-// kernel A: LayerNorm-out bwd, out-projection bwd, attention bwd.
-// =====================================================================================================
 constexpr int ST_LD = 25;              // row stride of the per-token softmax statistics (odd: conflict-free)
-constexpr int bwda_smem_floats(int nth) {
-    return 1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ + 2 * nth * KV_LD /*tiles*/ +
-           nth * ST_LD /*mx,sum,Dh per head + dropout key*/;
+constexpr int BA_NT = NT2;             // threads per CTA
+
+static size_t bwda_smem_bytes(int F) {
+    const int rows = ((BA_NT / F) * F + 3) & ~3;
+    return (size_t)(1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ + 2048 /*dWO partial blocks*/ +
+                    4 * rows * KV_LD /*tiles*/ + BA_NT * ST_LD /*mx,sum,Dh per head + dropout key*/) * sizeof(float);
 }
 
-// NTH threads (= tokens) per CTA: 192 walks the `tiles` set of k_bucket, 128 the `tiles2` set; MINB = CTAs per SM the register
-// budget is sized for.
-template <int H, int NTH, int MINB>
-__global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
+// one 128-byte row global -> shared, asynchronously (8 x 16 B)
+__device__ __forceinline__ void cp_async_row(float* __restrict__ dst, const float* __restrict__ src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+#pragma unroll
+    for (int i = 0; i < D; i += 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 4), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
     constexpr int DH = D / H;
     extern __shared__ __align__(16) float smem[];
+    const SatModel& m = a.m;
+    const int tid = threadIdx.x, lane = tid & 31, hsel = tid >> 6, F = m.F, l = a.layer;
+    const int tile_rows = ((BA_NT / F) * F + 3) & ~3;
     float* sWO = smem;
     float* sdWO = sWO + 1024;
     float* sLN = sdWO + 1024;           // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
     float* sdLN = sLN + 192;            // dgamma[32] dbeta[32] of the layer's output LayerNorm
-    float* sT0 = sdLN + 64;             // [NT][36]  r / K' / Q'
-    float* sT1 = sT0 + NTH * KV_LD;      // [NT][36]  dO / V / dR
-    float* sSt = sT1 + NTH * KV_LD;      // [NT][25]  per head: row max, 1/row sum, D = dR.R; [24] = attention-dropout key
+    float* sPart = sdLN + 64;           // [2][64][16] partial dW_out blocks of the two token halves
+    float* sT0 = sPart + 2048;          // [rows][36]  r  -> Q'
+    float* sT1 = sT0 + tile_rows * KV_LD;      //      dO -> dR
+    float* sT2 = sT1 + tile_rows * KV_LD;      //      K'
+    float* sT3 = sT2 + tile_rows * KV_LD;      //      V
+    float* sSt = sT3 + tile_rows * KV_LD;      // [128][25]  per head: row max, 1/row sum, D = dR.R; [24] = attention-dropout key
 
-    const SatModel& m = a.m;
-    const int tid = threadIdx.x, lane = tid & 31, F = m.F, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
     const bool relu_out = m.flags & SAT_FLAG_RELU, use_res = m.flags & SAT_FLAG_RES;
-    const int n_tiles = a.counters[NTH == NT ? CNT_NTILES : CNT_NTILES2];
+    const int n_tiles = a.counters[CNT_NTILES2];
     const int s = tid / F, f = tid - s * F;
     const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
     const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
     const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+    const bool stage = tid < tile_rows;                 // owns a row of the operand tiles (zeros past the last token)
 
-    copy_to_smem(sWO, lay + OFF_WO, 1024, tid, NTH);
-    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NTH);
-    for (int i = tid; i < 1024; i += NTH) sdWO[i] = 0.f;
+    copy_to_smem(sWO, lay + OFF_WO, 1024, tid, BA_NT);
+    copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, BA_NT);
+    for (int i = tid; i < 1024; i += BA_NT) sdWO[i] = 0.f;
     if (tid < 64) sdLN[tid] = 0.f;
     const float* qln = sLN + 64;
     const float* kln = pos ? sLN + 128 : sLN + 64;
@@ -67,13 +83,22 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
         const int4 td = *reinterpret_cast<const int4*>(a.tiles + 4 * t);
         const int start = td.y, cnt = td.z;
         const bool valid = s < cnt;
-        const int ntok = cnt * F;
+        const int ntok4 = (cnt * F + 3) & ~3;
         const int p = start + s;
         const int b = valid ? a.perm[p] : 0;
         const long long tokpos = ((long long)p * F + f) * D;
         const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
-        __syncthreads();                                   // smem init / previous tile done
+        __syncthreads();                                   // smem init / previous tile done with the tiles
 
+        if (valid) {
+            cp_async_row(sT0 + tid * KV_LD, act_l + ACT_R * a.act_stride + tokpos);
+            cp_async_row(sT2 + tid * KV_LD, act_l + ACT_ZK * a.act_stride + tokpos);
+            cp_async_row(sT3 + tid * KV_LD, act_l + ACT_V * a.act_stride + tokpos);
+        } else if (stage) {
+            float z[D];
+            zero(z);
+            sts_row(sT0 + tid * KV_LD, z);
+        }
         float dr[D];
         {   // ---- phase 1: y = drop(act(r @ WO^T)) + x ; LN bwd ; dO ; dR -------------------------------
             float r[D], dy[D], o[D];
@@ -81,12 +106,13 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
             uint32_t relu_mask = 0xffffffffu;
             float rstd = 0.f;
             if (valid) {
-                load_row(act_l + ACT_R * a.act_stride + tokpos, r);
-                vm_dot<D, D, D>(sWO, r, o);
-                sts_row(sT0 + tid * KV_LD, r);             // staged for dW_out now, re-read for D_i below (frees 32 registers)
-                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
                 float xin[D];
                 load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
+                load_row(a.dx + tokpos, dy);
+                cp_async_wait_all();                       // own rows of T0 / T2 / T3 have landed
+                lds_row(sT0 + tid * KV_LD, r);
+                vm_dot<D, D, D>(sWO, r, o);
+                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
 #pragma unroll
                 for (int i = 0; i < D; i += 2) {
                     float fk[2];
@@ -100,9 +126,8 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
                     }
                 }
                 rstd = normalize32(o);                     // o := yhat
-                load_row(a.dx + tokpos, dy);
             } else {
-                zero(r); zero(dy);
+                zero(dy);
             }
             layernorm_bwd32(dy, o, rstd, sLN, sdLN, sdLN + 32, lane, valid);     // dy := dLoss/dy
             if (valid) {
@@ -126,36 +151,32 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
                     for (int c = 0; c < DH; ++c) acc = fmaf(dr[h * DH + c], r[h * DH + c], acc);
                     sSt[tid * ST_LD + 16 + h] = acc;               // D_i[h] = dR_i . R_i  (own row, read back below)
                 }
-                sts_row(sT1 + tid * KV_LD, dy);
             }
+            if (stage) sts_row(sT1 + tid * KV_LD, dy);             // zeros past the last token
         }
-        // ---- phase 2: recompute Q' K' V, stage K'/V.  The rows are requested before the dW_out phase so that their HBM/L2
-        //      latency overlaps it. ------------------------------------------------------------------------
-        float q[D], kst[D], vst[D];
-#if SAT_BWDA_PREFETCH
+        // ---- phase 2: K' = LN(z_k) in place in T2 (own row); Q' to registers -------------------------------
+        float q[D];
         if (valid) {
-            load_row(act_l + ACT_ZK * a.act_stride + tokpos, kst);
-            load_row(act_l + ACT_V * a.act_stride + tokpos, vst);
+            if (meta_k) {
+                float k[D];
+                lds_row(sT2 + tid * KV_LD, k);
+                float mean, rstd;
+                layernorm32(k, kln, kln + 32, mean, rstd);
+                sts_row(sT2 + tid * KV_LD, k);
+            }
             load_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
-        }
-#endif
-        __syncthreads();
-        wgrad32<NTH>(sT1, sT0, ntok, sdWO, D, tid);             // dWO[j][i] += dO[j] r[i]   (A = dO, G = r)
-        __syncthreads();
-#if !SAT_BWDA_PREFETCH
-        if (valid) {
-            load_row(act_l + ACT_ZK * a.act_stride + tokpos, kst);
-            load_row(act_l + ACT_V * a.act_stride + tokpos, vst);
-            load_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
-        }
-#endif
-        if (valid) {
-            if (meta_k) { float mean, rstd; layernorm32(kst, kln, kln + 32, mean, rstd); }
-            sts_row(sT0 + tid * KV_LD, kst);
-            sts_row(sT1 + tid * KV_LD, vst);
             if (meta_q) { float mean, rstd; layernorm32(q, qln, qln + 32, mean, rstd); }
         }
-        __syncthreads();
+        __syncthreads();                                   // r, dO, K', V tiles complete
+        {   // dW_out[j][i] += dO[j] r[i]: each 64-thread half takes half of the token groups and parks its partial block
+            float cw[4][4];
+            const int mid = ((ntok4 >> 1) + 3) & ~3;
+            wgrad_block(sT1, sT0, hsel ? mid : 0, hsel ? ntok4 : mid, tid, cw);
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4)
+                *reinterpret_cast<float4*>(sPart + hsel * 1024 + (tid & 63) * 16 + r4 * 4) =
+                    make_float4(cw[r4][0], cw[r4][1], cw[r4][2], cw[r4][3]);
+        }
         // ---- query-role pass: dQ'_i = sum_j dS_ij K'_j / sqrt(dh) ------------------------------------
         if (valid) {
             float dq[D];
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
                     if (j0 < F) {
 #pragma unroll
                         for (int j = j0; j < j0 + JC; ++j) {
-                            const float* kr = sT0 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            const float* kr = sT2 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
                             float acc = 0.f;
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
@@ -208,8 +229,8 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
 #pragma unroll
                         for (int j = j0; j < j0 + JC; ++j) {
                             const float pj = sc[j] * inv_sum;                  // exactly 0 for the padding keys
-                            const float* vr = sT1 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
-                            const float* kr = sT0 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            const float* vr = sT3 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
+                            const float* kr = sT2 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
                             float dAd = 0.f;
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
@@ -231,50 +252,69 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
             }
             store_row(a.dqkv + 0 * a.act_stride + tokpos, dq);
         }
-        // ---- swap roles: own K', V to registers, tiles <- Q', dR ----------------------------------------
-        float kreg[D], vreg[D];
-        if (valid) { lds_row(sT0 + tid * KV_LD, kreg); lds_row(sT1 + tid * KV_LD, vreg); }
-        __syncthreads();
+        __syncthreads();                                   // dW_out phase is done with T0 / T1; partial blocks are visible
+        if (!hsel) {
+            float cw[4][4];
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const float4 lo = *reinterpret_cast<const float4*>(sPart + tid * 16 + r4 * 4);
+                const float4 hi = *reinterpret_cast<const float4*>(sPart + 1024 + tid * 16 + r4 * 4);
+                cw[r4][0] = lo.x + hi.x; cw[r4][1] = lo.y + hi.y; cw[r4][2] = lo.z + hi.z; cw[r4][3] = lo.w + hi.w;
+            }
+            wgrad_store(sdWO, D, tid, cw);
+        }
         if (valid) { sts_row(sT0 + tid * KV_LD, q); sts_row(sT1 + tid * KV_LD, dr); }
         __syncthreads();
         // ---- key-role pass: dK'_j = sum_i dS_ij Q'_i / sqrt(dh) ; dV_j = sum_i Pd_ij dR_i ----------------
-        // Head by head (rolled; kreg / vreg rotate by DH): the head's dK'/dV slices are complete after its F queries and go
-        // straight to HBM, so only 2*DH accumulators are live (32-wide dk/dv next to kreg/vreg spilled to local memory).
+        // Head by head (rolled): the head's dK'/dV slices are complete after its F queries and go straight to HBM; the own
+        // K'/V slices come from T2 / T3.  Queries in chunks of IC per basic block; queries past F read row F-1 with weight 0.
         if (valid) {
+            constexpr int IC = SAT_BWDA_IC;
             const int sbase = s * F;
             float* dk_out = a.dqkv + 1 * a.act_stride + tokpos;
             float* dv_out = a.dqkv + 2 * a.act_stride + tokpos;
             DropCtx dci = make_drop(a.seed, 0u, l, SITE_ATT, a.p_drop, true);     // .key is replaced per query below
 #pragma unroll 1
             for (int h = 0; h < H; ++h) {
-                float dk[DH], dv[DH];
+                float kh[DH], vh[DH], dk[DH], dv[DH];
+#pragma unroll
+                for (int c = 0; c < DH; c += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(sT2 + tid * KV_LD + h * DH + c);
+                    const float4 v4 = *reinterpret_cast<const float4*>(sT3 + tid * KV_LD + h * DH + c);
+                    kh[c] = k4.x; kh[c + 1] = k4.y; kh[c + 2] = k4.z; kh[c + 3] = k4.w;
+                    vh[c] = v4.x; vh[c + 1] = v4.y; vh[c + 2] = v4.z; vh[c + 3] = v4.w;
+                }
                 zero(dk); zero(dv);
                 const uint32_t e = h * SAT_MAXF + f;
-#pragma unroll 2
-                for (int i = 0; i < F; ++i) {
-                    const float* qr = sT0 + (sbase + i) * KV_LD + h * DH;
-                    const float* dR = sT1 + (sbase + i) * KV_LD + h * DH;
-                    const float* st = sSt + (sbase + i) * ST_LD;
-                    float qq[DH], dd[DH];
+#pragma unroll 1
+                for (int i0 = 0; i0 < F; i0 += IC) {
 #pragma unroll
-                    for (int c = 0; c < DH; c += 4) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
-                        const float4 d4 = *reinterpret_cast<const float4*>(dR + c);
-                        qq[c] = q4.x; qq[c + 1] = q4.y; qq[c + 2] = q4.z; qq[c + 3] = q4.w;
-                        dd[c] = d4.x; dd[c + 1] = d4.y; dd[c + 2] = d4.z; dd[c + 3] = d4.w;
-                    }
-                    float acc = 0.f, dAd = 0.f;
+                    for (int ii = 0; ii < IC; ++ii) {
+                        const int i = min(i0 + ii, F - 1);
+                        const float* qr = sT0 + (sbase + i) * KV_LD + h * DH;
+                        const float* dR = sT1 + (sbase + i) * KV_LD + h * DH;
+                        const float* st = sSt + (sbase + i) * ST_LD;
+                        float qq[DH], dd[DH];
 #pragma unroll
-                    for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kreg[c], acc); dAd = fmaf(dd[c], vreg[c], dAd); }
-                    const float pij = expf(acc * inv_sqrt_dh - st[h]) * st[8 + h];
-                    dci.key = __float_as_uint(st[24]);
-                    const float df = drop_factor(dci, e);
-                    const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;
-                    const float pd = pij * df;
+                        for (int c = 0; c < DH; c += 4) {
+                            const float4 q4 = *reinterpret_cast<const float4*>(qr + c);
+                            const float4 d4 = *reinterpret_cast<const float4*>(dR + c);
+                            qq[c] = q4.x; qq[c + 1] = q4.y; qq[c + 2] = q4.z; qq[c + 3] = q4.w;
+                            dd[c] = d4.x; dd[c + 1] = d4.y; dd[c + 2] = d4.z; dd[c + 3] = d4.w;
+                        }
+                        float acc = 0.f, dAd = 0.f;
 #pragma unroll
-                    for (int c = 0; c < DH; ++c) {
-                        dk[c] = fmaf(dsc, qq[c], dk[c]);
-                        dv[c] = fmaf(pd, dd[c], dv[c]);
+                        for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kh[c], acc); dAd = fmaf(dd[c], vh[c], dAd); }
+                        const float pij = (i0 + ii < F) ? expf(acc * inv_sqrt_dh - st[h]) * st[8 + h] : 0.f;
+                        dci.key = __float_as_uint(st[24]);
+                        const float df = drop_factor(dci, e);
+                        const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;
+                        const float pd = pij * df;
+#pragma unroll
+                        for (int c = 0; c < DH; ++c) {
+                            dk[c] = fmaf(dsc, qq[c], dk[c]);
+                            dv[c] = fmaf(pd, dd[c], dv[c]);
+                        }
                     }
                 }
 #pragma unroll
@@ -282,15 +322,14 @@ __global__ void __launch_bounds__(NTH, MINB) k_bwd_attn(const BwdArgs a) {
                     *reinterpret_cast<float4*>(dk_out + h * DH + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
                     *reinterpret_cast<float4*>(dv_out + h * DH + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
                 }
-                if (H > 1) { rotate_regs<D, DH>(kreg); rotate_regs<D, DH>(vreg); }
             }
         }
     }
     __syncthreads();
     // flush: dWO and the output-LayerNorm parameter gradients
     float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
-    flush_add<NTH>(dlay + OFF_WO, sdWO, 1024, tid);
-    flush_add<NTH>(dlay + OFF_LN_G, sdLN, 64, tid);
+    flush_add<BA_NT>(dlay + OFF_WO, sdWO, 1024, tid);
+    flush_add<BA_NT>(dlay + OFF_LN_G, sdLN, 64, tid);
 }
 
 }  // namespace sat
@@ -303,23 +342,16 @@ using namespace sat;
 #define SAT_CAT_(a, b) a##b
 #define SAT_CAT(a, b) SAT_CAT_(a, b)
 
-template <int H, int NTH, int MINB>
-static int launch_variant(const BwdArgs& a, int grid, cudaStream_t s) {
-    const size_t smem = bwda_smem_floats(NTH) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_bwd_attn<H, NTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
-        configured = true;
-    }
-    k_bwd_attn<H, NTH, MINB><<<grid, NTH, smem, s>>>(a);
-    return sat_host::check_launch("k_bwd_attn");
-}
-
-// variant 0: 192 threads x 2 CTAs/SM over a.tiles; 1: 128 x 2 and 2: 128 x 3 over the 128-token tile set (caller passes it in a.tiles)
-int SAT_CAT(sat_launch_bwd_attn_h, SAT_INST_H)(const BwdArgs& a, int variant, int grid, cudaStream_t s) {
+// a.tiles must be the 128-token tile set (SatWork.tiles2)
+int SAT_CAT(sat_launch_bwd_attn_h, SAT_INST_H)(const BwdArgs& a, int grid, cudaStream_t s) {
     constexpr int H = SAT_INST_H;
-    if (variant == 1) return launch_variant<H, NT2, 2>(a, grid, s);
-    if (variant == 2) return launch_variant<H, NT2, 3>(a, grid, s);
-    return launch_variant<H, NT, 2>(a, grid, s);
+    const size_t smem = bwda_smem_bytes(a.m.F);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_bwd_attn<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
+        configured = smem;
+    }
+    k_bwd_attn<H><<<grid, BA_NT, smem, s>>>(a);
+    return sat_host::check_launch("k_bwd_attn");
 }

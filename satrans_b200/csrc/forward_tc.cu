@@ -198,15 +198,17 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
 #pragma unroll
                     for (int i = 0; i < D; ++i) { if (hbuf[i] > 0.f) m0 |= 1u << i; hbuf[i] = fmaxf(hbuf[i], 0.f); }
                     tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
-                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2A_HI, sBT + PK_W2A_LO, 32, false));
                     tmem_ld32(tlane + TC_D + 32, hbuf);
                     tc_wait_ld();
 #pragma unroll
                     for (int i = 0; i < D; ++i) { if (hbuf[i] > 0.f) m1 |= 1u << i; hbuf[i] = fmaxf(hbuf[i], 0.f); }
                     if (TRAIN && valid)
                         *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, side, tokpos / D)) = make_uint2(m0, m1);
-                    tmem_st_operand<PASSES>(tlane + TC_H, hbuf);
-                    SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2B_HI, sBT + PK_W2B_LO, 32, true));
+                    // the hidden accumulator columns are free once both halves are in registers: the second half's operand
+                    // goes there, and both W2 halves run in ONE round
+                    tmem_st_operand<PASSES>(tlane + TC_D, hbuf);
+                    SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_H, sBT + PK_W2A_HI, sBT + PK_W2A_LO, 32, false),
+                                  issue_gemm_k32<PASSES>(tbase + TC_D + 64, tbase + TC_D, sBT + PK_W2B_HI, sBT + PK_W2B_LO, 32, true)));
                     tmem_ld32(tlane + TC_D + 64, hbuf);
                     tc_wait_ld();
                     const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, TRAIN);
