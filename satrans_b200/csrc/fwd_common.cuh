@@ -2,6 +2,10 @@
 #pragma once
 #include "args.cuh"
 
+#ifndef SAT_FWD_JC
+#define SAT_FWD_JC 4           // keys per basic block in attention_fwd
+#endif
+
 namespace sat {
 
 // Multi-head attention of one query token against the F tokens of its sample (reference satrans.py:75-90).
@@ -16,7 +20,7 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
     // Keys are processed in chunks of JC inside ONE basic block (a per-key `if (j < F)` made every key its own block and
     // serialised the dot-product / hash / exp chains: "wait" was 41 % of the forward's stall samples).  Keys past F in the
     // last chunk read row F-1 and get score -inf: probability exactly 0, so the sums are unchanged bit for bit.
-    constexpr int JC = 4;
+    constexpr int JC = SAT_FWD_JC;
 #pragma unroll 1
     for (int h = 0; h < H; ++h) {
         float sc[SAT_MAXF];
