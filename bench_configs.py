@@ -2,13 +2,16 @@
 """Secondary measurements for the BASELINE.json configurations that bench.py's single headline line does not cover
 (SURVEY.md §8d).  One JSON line per measurement on stdout; run on one B200:
 
-    python bench_configs.py [--only infer_sweep,alimama,zipf,lazy]
+    python bench_configs.py [--only infer_sweep,selfatt,alimama,zipf,lazy,config4,fit]
 
   infer_sweep : config 5 — eval-mode scoring, batch 1 Ki .. 1 Mi, meta_mode QK and QKV (identical math in the
                 reference: satrans.py has no 'V' branch), fp32 CUDA-core vs tcgen05 3xTF32 vs tcgen05 TF32
   alimama     : config 3 — ENP+MetaNet (flag 'sota-pos', scenario column shopping_level, dense price), train step B=8192
   zipf        : config 2 with Zipf(1.05) ids instead of uniform (realistic skew: hot rows)
   lazy        : config 2 with touched-rows-only table updates (NOT the reference's semantics; reported separately)
+  selfatt     : config 5's "SelfAttention_Layer x 3" (reference submodules.py:178-238) on (B, 19, 32) inputs, eval mode
+  config4     : config 4 on one GPU — vocab x16 (105 M rows, 13.5 GB of tables + 27 GB of Adam state), B=65,536, int32 ids
+  fit         : config 1(b) — fit() / predict() end to end from host numpy columns (verbose=0 and verbose=1 with sklearn metrics)
 
 All timings: CUDA events, >=3 warm-up iterations, inputs resident in HBM.
 """
@@ -48,14 +51,17 @@ def build(schema, flag, mode, lr, precision):
     return model
 
 
-def train_bench(name, schema, flag, lr, ids, lazy, precision, B=8192, steps=20):
+def train_bench(name, schema, flag, lr, ids, lazy, precision, B=8192, steps=20, int_ids=False, nb=8):
     import torch
     from satrans_b200 import synth
     model = build(schema, flag, 'QK', lr, precision)
     model.dense_table_updates = not lazy
-    nb = 8
     xs, ys = synth.make_inputs(schema, nb * B, seed=1021, dist=ids, ctr=0.04)
-    X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense)).cuda()
+    if int_ids:      # ids >= 2^24 are not exact in the reference's fp32 input matrix: int32 matrix instead
+        assert not schema.dense
+        X = torch.from_numpy(np.stack([xs[f].astype(np.int32) for f in schema.fields], axis=1)).cuda()
+    else:
+        X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense)).cuda()
     y = torch.from_numpy(ys.astype(np.float32)).cuda()
     eng, hp = model.engine, model._opt_hparams
     it = [0]
@@ -99,9 +105,60 @@ def infer_sweep(precisions):
         torch.cuda.empty_cache()
 
 
+def selfatt_sweep():
+    import torch
+    from satrans_b200 import SelfAttention_Layer
+    layers = [SelfAttention_Layer(32, head_num=2, use_res=True, device='cuda:0').eval() for _ in range(3)]
+    for B in (1024, 16384, 65536, 262144, 1048576):
+        x = torch.randn(B, 19, 32, device='cuda:0') * 0.05
+
+        def run():
+            h = x
+            for lay in layers:
+                h = lay(h)
+            return h
+        ms = timeit(run, 10 if B <= 65536 else 4)
+        print(json.dumps({"bench": "selfatt_x3", "metric": "infer_samples_per_sec", "value": B / (ms * 1e-3), "unit": "samples/s",
+                          "ms": ms, "batch": B, "fields": 19, "heads": 2,
+                          "hbm_gbs_algorithmic": 3 * 2 * B * 19 * 128 / (ms * 1e-3) / 1e9}), flush=True)
+        del x
+    torch.cuda.empty_cache()
+
+
+def fit_bench():
+    """fit() / predict() through the reference-facing API with host numpy columns (reference meta_basemodel.py:200-385,401-517)."""
+    import time
+    import torch
+    from satrans_b200 import synth
+    schema = synth.aliccp_schema()
+    model = build(schema, 'sota', 'QK', 0.005, 'tf32x3')
+    N = 32 * 8192
+    xs, ys = synth.make_inputs(schema, N, seed=1021, ctr=0.04)
+    model.fit(xs, ys, batch_size=8192, epochs=1, verbose=0, shuffle=False)            # warm-up epoch
+    for verbose in (0, 1):
+        model.compile(torch.optim.Adam(model.parameters(), lr=0.005), "binary_crossentropy",
+                      metrics=["binary_crossentropy", "auc"] if verbose else None)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.fit(xs, ys, batch_size=8192, epochs=1, verbose=verbose, shuffle=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"bench": "fit_e2e", "metric": "train_samples_per_sec", "value": N / dt, "unit": "samples/s",
+                          "rows": N, "batch": 8192, "verbose": verbose, "seconds": dt,
+                          "note": "host numpy dict -> fit(); includes column stacking, shuffling, H2D, per-epoch metrics"}), flush=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p = model.predict(xs, batch_size=32768)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"bench": "predict_e2e", "metric": "infer_samples_per_sec", "value": N / dt, "unit": "samples/s", "rows": N,
+                      "batch": 32768, "seconds": dt, "out": [list(p.shape), str(p.dtype)]}), flush=True)
+    del model
+    torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--only', default='infer_sweep,alimama,zipf,lazy')
+    ap.add_argument('--only', default='infer_sweep,selfatt,alimama,zipf,lazy,config4,fit')
     args = ap.parse_args()
     from satrans_b200 import synth
     only = set(args.only.split(','))
@@ -112,6 +169,13 @@ def main():
         train_bench('aliccp_en_train_zipf', synth.aliccp_schema(), 'sota', 0.005, 'zipf', False, 'tf32x3')
     if 'lazy' in only:
         train_bench('aliccp_en_train_lazy', synth.aliccp_schema(), 'sota', 0.005, 'uniform', True, 'tf32x3')
+    if 'config4' in only:
+        train_bench('aliccp_x16_config4_train', synth.aliccp_schema(16.0), 'sota', 0.005, 'uniform', False, 'tf32x3', B=65536,
+                    steps=8, int_ids=True, nb=2)
+    if 'fit' in only:
+        fit_bench()
+    if 'selfatt' in only:
+        selfatt_sweep()
     if 'infer_sweep' in only:
         infer_sweep(('fp32', 'tf32x3', 'tf32'))
 
