@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
                                 const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                                dq[c + 0] = fmaf(dsc, kk.x, dq[c + 0]); dq[c + 1] = fmaf(dsc, kk.y, dq[c + 1]);
-                                dq[c + 2] = fmaf(dsc, kk.z, dq[c + 2]); dq[c + 3] = fmaf(dsc, kk.w, dq[c + 3]);
+                                fma2(dq[c + 0], dq[c + 1], dsc, kk.x, kk.y);
+                                fma2(dq[c + 2], dq[c + 3], dsc, kk.z, kk.w);
                             }
                         }
                     }
@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                         const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;
                         const float pd = pij * df;
 #pragma unroll
-                        for (int c = 0; c < DH; ++c) {
-                            dk[c] = fmaf(dsc, qq[c], dk[c]);
-                            dv[c] = fmaf(pd, dd[c], dv[c]);
+                        for (int c = 0; c < DH; c += 2) {
+                            fma2(dk[c], dk[c + 1], dsc, qq[c], qq[c + 1]);
+                            fma2(dv[c], dv[c + 1], pd, dd[c], dd[c + 1]);
                         }
                     }
                 }

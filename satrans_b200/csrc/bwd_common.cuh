@@ -81,10 +81,10 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
 }
 
 __device__ __forceinline__ void fma_block(float (&c)[4][4], const float4& a, const float4& g) {
-    c[0][0] = fmaf(a.x, g.x, c[0][0]); c[0][1] = fmaf(a.x, g.y, c[0][1]); c[0][2] = fmaf(a.x, g.z, c[0][2]); c[0][3] = fmaf(a.x, g.w, c[0][3]);
-    c[1][0] = fmaf(a.y, g.x, c[1][0]); c[1][1] = fmaf(a.y, g.y, c[1][1]); c[1][2] = fmaf(a.y, g.z, c[1][2]); c[1][3] = fmaf(a.y, g.w, c[1][3]);
-    c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
-    c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
+    fma2(c[0][0], c[0][1], a.x, g.x, g.y); fma2(c[0][2], c[0][3], a.x, g.z, g.w);
+    fma2(c[1][0], c[1][1], a.y, g.x, g.y); fma2(c[1][2], c[1][3], a.y, g.z, g.w);
+    fma2(c[2][0], c[2][1], a.z, g.x, g.y); fma2(c[2][2], c[2][3], a.z, g.z, g.w);
+    fma2(c[3][0], c[3][1], a.w, g.x, g.y); fma2(c[3][2], c[3][3], a.w, g.z, g.w);
 }
 
 // c[r][cc] = sum_{t in [tb, te)} A[t][ia + r] * G[t][jg + cc] for this thread's 4x4 block (blk = tid & 63) of a 32x32 product.

@@ -88,6 +88,38 @@ __device__ __forceinline__ void drop_apply32(const DropCtx& c, float (&v)[SAT_D]
     }
 }
 
+// Packed fp32 FMA (sm_100a FFMA2): c0 += a * g0, c1 += a * g1 in ONE instruction; each lane is an IEEE fp32 FMA, so the
+// results are bit-identical to two fmaf().  ptxas folds the packing moves: the scalar is read as a broadcast operand and
+// (g0, g1) / (c0, c1) as aligned register pairs.
+#ifndef SAT_FFMA2
+#define SAT_FFMA2 1
+#endif
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a, float g0, float g1) {
+#if SAT_FFMA2
+    unsigned long long A, G, Cc, R;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a), "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(G) : "f"(g0), "f"(g1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(R) : "l"(A), "l"(G), "l"(Cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(R));
+#else
+    c0 = fmaf(a, g0, c0); c1 = fmaf(a, g1, c1);
+#endif
+}
+// c0 += a0 * g0, c1 += a1 * g1
+__device__ __forceinline__ void fma2v(float& c0, float& c1, float a0, float a1, float g0, float g1) {
+#if SAT_FFMA2
+    unsigned long long A, G, Cc, R;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(G) : "f"(g0), "f"(g1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(Cc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(R) : "l"(A), "l"(G), "l"(Cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(R));
+#else
+    c0 = fmaf(a0, g0, c0); c1 = fmaf(a1, g1, c1);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // thread-local small GEMV against a matrix in shared memory (all lanes read the same address:
 // LDS.128 broadcasts).  a[] and y[] are registers.
@@ -121,10 +153,8 @@ __device__ __forceinline__ void vm_outer(const float* __restrict__ M, float (&a)
 #pragma unroll
             for (int j = 0; j < NOUT; j += 4) {
                 const float4 w = *reinterpret_cast<const float4*>(Mc + i * LD + j);
-                y[j + 0] = fmaf(a[i], w.x, y[j + 0]);
-                y[j + 1] = fmaf(a[i], w.y, y[j + 1]);
-                y[j + 2] = fmaf(a[i], w.z, y[j + 2]);
-                y[j + 3] = fmaf(a[i], w.w, y[j + 3]);
+                fma2(y[j + 0], y[j + 1], a[i], w.x, w.y);
+                fma2(y[j + 2], y[j + 3], a[i], w.z, w.w);
             }
         }
         if (CH < NIN) rotate_regs<NIN, CH>(a);
@@ -143,10 +173,8 @@ __device__ __forceinline__ void vm_dot(const float* __restrict__ M, const float 
 #pragma unroll
             for (int i = 0; i < NIN; i += 4) {
                 const float4 w = *reinterpret_cast<const float4*>(Mc + j * LD + i);
-                acc0 = fmaf(a[i + 0], w.x, acc0);
-                acc1 = fmaf(a[i + 1], w.y, acc1);
-                acc0 = fmaf(a[i + 2], w.z, acc0);
-                acc1 = fmaf(a[i + 3], w.w, acc1);
+                fma2v(acc0, acc1, a[i + 0], a[i + 1], w.x, w.y);
+                fma2v(acc0, acc1, a[i + 2], a[i + 3], w.z, w.w);
             }
             y[j] += acc0 + acc1;
         }

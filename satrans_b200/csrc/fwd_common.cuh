@@ -69,10 +69,8 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
 #pragma unroll
                     for (int c = 0; c < DH; c += 4) {
                         const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                        o[c + 0] = fmaf(pj, vv.x, o[c + 0]);
-                        o[c + 1] = fmaf(pj, vv.y, o[c + 1]);
-                        o[c + 2] = fmaf(pj, vv.z, o[c + 2]);
-                        o[c + 3] = fmaf(pj, vv.w, o[c + 3]);
+                        fma2(o[c + 0], o[c + 1], pj, vv.x, vv.y);
+                        fma2(o[c + 2], o[c + 3], pj, vv.z, vv.w);
                     }
                 }
             }
