@@ -298,7 +298,8 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": phases['adam_sweep'],
                 "note": "6 x 128 B per untouched table row; timed with CUDA events on its own stream while "
                         "forward/backward run concurrently on the main stream" if args.overlap else
-                        "6 x 128 B per untouched table row; timed alone on the main stream"}
+                        "6 x 128 B per untouched table row; CUDA events around its launch on the main stream (the ~20 us "
+                        "touched-row and dense-parameter updates run beside it on a second stream)"}
 
     # ---- extra: stand-alone gather GB/s and eval-mode scoring ----------------------------------------------
     extra = {}

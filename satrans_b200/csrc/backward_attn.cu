@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
     const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
     const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+    const float sm_scale = inv_sqrt_dh;
     const bool stage = tid < tile_rows;                 // owns a row of the operand tiles (zeros past the last token)
 
     copy_to_smem(sWO, lay + OFF_WO, 1024, tid, BA_NT);
@@ -198,14 +199,15 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
 #pragma unroll
                         for (int j = j0; j < j0 + JC; ++j) {
                             const float* kr = sT2 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
-                            float acc = 0.f;
+                            float acc = 0.f, acc1 = 0.f;     // even / odd channels, same order as attention_fwd
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
                                 const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                                acc = fmaf(q[c + 0], kk.x, acc); acc = fmaf(q[c + 1], kk.y, acc);
-                                acc = fmaf(q[c + 2], kk.z, acc); acc = fmaf(q[c + 3], kk.w, acc);
+                                fma2v(acc, acc1, q[c + 0], q[c + 1], kk.x, kk.y);
+                                fma2v(acc, acc1, q[c + 2], q[c + 3], kk.z, kk.w);
                             }
-                            sc[j] = j < F ? acc * inv_sqrt_dh : -INFINITY;
+                            acc += acc1;
+                            sc[j] = j < F ? acc * sm_scale : -INFINITY;
                             mx = fmaxf(mx, sc[j]);
                         }
                     }
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                 for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
                     if (j0 < F) {
 #pragma unroll
-                        for (int j = j0; j < j0 + JC; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+                        for (int j = j0; j < j0 + JC; ++j) { sc[j] = softmax_exp(sc[j] - mx); sum += sc[j]; }
                     }
                 }
                 const float inv_sum = 1.f / sum;
@@ -231,13 +233,14 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                             const float pj = sc[j] * inv_sum;                  // exactly 0 for the padding keys
                             const float* vr = sT3 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
                             const float* kr = sT2 + (sbase + min(j, F - 1)) * KV_LD + h * DH;
-                            float dAd = 0.f;
+                            float dAd = 0.f, dAd1 = 0.f;
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
                                 const float4 vv = *reinterpret_cast<const float4*>(vr + c);
-                                dAd = fmaf(dr[c + 0], vv.x, dAd); dAd = fmaf(dr[c + 1], vv.y, dAd);
-                                dAd = fmaf(dr[c + 2], vv.z, dAd); dAd = fmaf(dr[c + 3], vv.w, dAd);
+                                fma2v(dAd, dAd1, dr[c + 0], dr[c + 1], vv.x, vv.y);
+                                fma2v(dAd, dAd1, dr[c + 2], dr[c + 3], vv.z, vv.w);
                             }
+                            dAd += dAd1;
                             const float dsc = pj * (dAd * fd[j - j0] - Dhh) * inv_sqrt_dh;
 #pragma unroll
                             for (int c = 0; c < DH; c += 4) {
@@ -302,10 +305,14 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                             qq[c] = q4.x; qq[c + 1] = q4.y; qq[c + 2] = q4.z; qq[c + 3] = q4.w;
                             dd[c] = d4.x; dd[c + 1] = d4.y; dd[c + 2] = d4.z; dd[c + 3] = d4.w;
                         }
-                        float acc = 0.f, dAd = 0.f;
+                        float acc = 0.f, acc1 = 0.f, dAd = 0.f, dAd1 = 0.f;
 #pragma unroll
-                        for (int c = 0; c < DH; ++c) { acc = fmaf(qq[c], kh[c], acc); dAd = fmaf(dd[c], vh[c], dAd); }
-                        const float pij = (i0 + ii < F) ? expf(acc * inv_sqrt_dh - st[h]) * st[8 + h] : 0.f;
+                        for (int c = 0; c < DH; c += 2) {
+                            fma2v(acc, acc1, qq[c], qq[c + 1], kh[c], kh[c + 1]);
+                            fma2v(dAd, dAd1, dd[c], dd[c + 1], vh[c], vh[c + 1]);
+                        }
+                        acc += acc1; dAd += dAd1;
+                        const float pij = (i0 + ii < F) ? softmax_exp(acc * sm_scale - st[h]) * st[8 + h] : 0.f;
                         dci.key = __float_as_uint(st[24]);
                         const float df = drop_factor(dci, e);
                         const float dsc = pij * (dAd * df - st[16 + h]) * inv_sqrt_dh;

@@ -31,23 +31,24 @@ __device__ __forceinline__ void layernorm_bwd32(float (&dy)[D], const float (&xh
     const float sb = warp_reduce_scatter32(t2, lane);
     atomicAdd(dgam + lane, sg);
     atomicAdd(dbet + lane, sb);
-    float m1 = 0.f, m2 = 0.f;
+    float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
 #pragma unroll
-    for (int i = 0; i < D; ++i) { dy[i] *= g[i]; m1 += dy[i]; m2 = fmaf(dy[i], xhat[i], m2); }
-    m1 *= (1.f / D); m2 *= (1.f / D);
+    for (int i = 0; i < D; i += 2) {
+        dy[i] *= g[i]; dy[i + 1] *= g[i + 1];
+        m1a += dy[i]; m1b += dy[i + 1];
+        m2a = fmaf(dy[i], xhat[i], m2a); m2b = fmaf(dy[i + 1], xhat[i + 1], m2b);
+    }
+    const float m1 = (m1a + m1b) * (1.f / D), m2 = (m2a + m2b) * (1.f / D);
 #pragma unroll
     for (int i = 0; i < D; ++i) dy[i] = rstd * (dy[i] - m1 - xhat[i] * m2);
 }
 
 // normalise in place, return rstd (no affine)
 __device__ __forceinline__ float normalize32(float (&v)[D]) {
-    float s = 0.f;
+    const float mean = sum32(v) * (1.f / D);
+    const float q = sumsq_dev32(v, mean);              // same reduction order as layernorm32 (the forward)
 #pragma unroll
-    for (int i = 0; i < D; ++i) s += v[i];
-    const float mean = s * (1.f / D);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    for (int i = 0; i < D; ++i) v[i] -= mean;
     const float rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
 #pragma unroll
     for (int i = 0; i < D; ++i) v[i] *= rstd;

@@ -88,6 +88,23 @@ __device__ __forceinline__ void drop_apply32(const DropCtx& c, float (&v)[SAT_D]
     }
 }
 
+// Softmax exponential of (score - row max) <= 0: one multiply by log2(e) and one MUFU.EX2 instead of expf's range reduction
+// (~7 instructions).  The difference is formed in the natural domain first, so the rounding of the log2(e) multiply is
+// relative to |score - max| (where exp is tiny when that is large) and not to |score|: scaling the scores themselves into the
+// log2 domain was measurably noisier in the K-side gradients.  y_pred error vs the reference's golden vectors stays 6e-8.
+#ifndef SAT_FAST_EXP2
+#define SAT_FAST_EXP2 1
+#endif
+__device__ __forceinline__ float softmax_exp(float x) {
+#if SAT_FAST_EXP2
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+#else
+    return expf(x);
+#endif
+}
+
 // Packed fp32 FMA (sm_100a FFMA2): c0 += a * g0, c1 += a * g1 in ONE instruction; each lane is an IEEE fp32 FMA, so the
 // results are bit-identical to two fmaf().  ptxas folds the packing moves: the scalar is read as a broadcast operand and
 // (g0, g1) / (c0, c1) as aligned register pairs.
@@ -189,15 +206,28 @@ __device__ __forceinline__ void zero(float (&v)[N]) {
 }
 
 // LayerNorm over the 32 channels a thread owns.  g/b in shared memory.  Returns mean / rstd for the backward.
+// sum / sum of squared deviations over the 32 channels with four interleaved partial sums (a single chain of 32 dependent
+// adds is 128 cycles of latency per reduction for a warp that has one or two neighbours to hide it)
+__device__ __forceinline__ float sum32(const float (&v)[D]) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float sumsq_dev32(const float (&v)[D], float mean) {
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; i += 4) {
+        const float t0 = v[i] - mean, t1 = v[i + 1] - mean, t2 = v[i + 2] - mean, t3 = v[i + 3] - mean;
+        q0 = fmaf(t0, t0, q0); q1 = fmaf(t1, t1, q1); q2 = fmaf(t2, t2, q2); q3 = fmaf(t3, t3, q3);
+    }
+    return (q0 + q1) + (q2 + q3);
+}
+
 __device__ __forceinline__ void layernorm32(float (&v)[D], const float* __restrict__ g, const float* __restrict__ b,
                                             float& mean, float& rstd) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) s += v[i];
-    mean = s * (1.f / D);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) { const float t = v[i] - mean; q = fmaf(t, t, q); }
+    mean = sum32(v) * (1.f / D);
+    const float q = sumsq_dev32(v, mean);
     rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
 #pragma unroll
     for (int i = 0; i < D; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);

@@ -16,7 +16,7 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
                                               const float* __restrict__ sV, int sbase, int F, const DropCtx& dc,
                                               float (&r)[D]) {
     constexpr int DH = D / H;
-    const float inv_sqrt_dh = 1.f / sqrtf((float)DH);   // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
+    const float sm_scale = 1.f / sqrtf((float)DH);       // scores * (1/sqrt(dh)); differs from the reference's division by <= 1 ulp
     // Keys are processed in chunks of JC inside ONE basic block (a per-key `if (j < F)` made every key its own block and
     // serialised the dot-product / hash / exp chains: "wait" was 41 % of the forward's stall samples).  Keys past F in the
     // last chunk read row F-1 and get score -inf: probability exactly 0, so the sums are unchanged bit for bit.
@@ -31,16 +31,15 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
 #pragma unroll
                 for (int j = j0; j < j0 + JC; ++j) {
                     const float* kr = sK + (sbase + min(j, F - 1)) * KV_LD + h * DH;
-                    float acc = 0.f;
+                    float acc = 0.f, acc1 = 0.f;             // even / odd channels (one FFMA2 per channel pair)
 #pragma unroll
                     for (int c = 0; c < DH; c += 4) {
                         const float4 kk = *reinterpret_cast<const float4*>(kr + c);
-                        acc = fmaf(q[c + 0], kk.x, acc);
-                        acc = fmaf(q[c + 1], kk.y, acc);
-                        acc = fmaf(q[c + 2], kk.z, acc);
-                        acc = fmaf(q[c + 3], kk.w, acc);
+                        fma2v(acc, acc1, q[c + 0], q[c + 1], kk.x, kk.y);
+                        fma2v(acc, acc1, q[c + 2], q[c + 3], kk.z, kk.w);
                     }
-                    sc[j] = j < F ? acc * inv_sqrt_dh : -INFINITY;     // inner_product /= dh ** 0.5   (satrans.py:85-86)
+                    acc += acc1;
+                    sc[j] = j < F ? acc * sm_scale : -INFINITY;     // inner_product /= dh ** 0.5   (satrans.py:85-86)
                     mx = fmaxf(mx, sc[j]);
                 }
             }
@@ -50,7 +49,7 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
         for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
             if (j0 < F) {
 #pragma unroll
-                for (int j = j0; j < j0 + JC; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+                for (int j = j0; j < j0 + JC; ++j) { sc[j] = softmax_exp(sc[j] - mx); sum += sc[j]; }
             }
         }
         float o[DH];

@@ -71,6 +71,7 @@ class Engine:
         self._work = {}
         self._adam = None
         self._sweep_stream = None
+        self.side_streams = True          # run the independent short launch chains of a step on a second stream
         self._ev_marked = None
         self._ev_swept = None
         self.step_count = 0
@@ -378,14 +379,27 @@ class Engine:
             self._sweep_stream = torch.cuda.Stream(device=self.device)
             self._ev_marked = torch.cuda.Event()
             self._ev_swept = torch.cuda.Event()
+            self._ev_fork = torch.cuda.Event()
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
         t = self._tic('prepare')
         if getattr(self, '_row_grad_dirty', False):
             w['row_grad'].zero_()
             self._row_grad_dirty = False
-        self._prepare(X, w, kind)
-        self._mark_rows(X, w, kind)
+        single = self.dist is None or self.dist.world == 1
+        if single and self.side_streams:
+            # the touched-row bitmap / ranks (ids only) are independent of bucketing + encoder + weight packing:
+            # two short launch chains side by side instead of one after the other
+            self._ev_fork.record(main)
+            self._sweep_stream.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._sweep_stream):
+                self._mark_rows(X, w, kind)
+            self._ev_marked.record(self._sweep_stream)
+            self._prepare(X, w, kind)
+            main.wait_event(self._ev_marked)
+        else:
+            self._prepare(X, w, kind)
+            self._mark_rows(X, w, kind)
         self._toc(t)
         sweep_on_side = bool(dense_mode and overlap)
         if sweep_on_side:
@@ -407,18 +421,34 @@ class Engine:
             t = self._tic('allreduce')
             self.dist.all_reduce_sum(w['dgrad'])            # dense grads; also orders the peers' row-gradient atomics
             self._toc(t)
-        t = self._tic('adam_rows')
-        check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, s), 'sat_tables_adam')
-        self._toc(t)
-        if dense_mode and not sweep_on_side:
+        tail_on_side = bool(dense_mode and not sweep_on_side and self.side_streams)
+        if tail_on_side:
+            # the short touched-row / dense-parameter updates run beside the HBM-bound sweep (disjoint rows)
+            self._ev_fork.record(main)
+            self._sweep_stream.wait_event(self._ev_fork)
+            t = self._tic('adam_rows+dense (side stream)', self._sweep_stream)
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, self._sweep_stream.cuda_stream),
+                  'sat_tables_adam')
+            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), self._sweep_stream.cuda_stream), 'sat_dense_adam')
+            self._toc(t)
+            self._ev_swept.record(self._sweep_stream)
             t = self._tic('adam_sweep')
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
             self._toc(t)
-        t = self._tic('adam_dense')
-        check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
-        self._toc(t)
-        if sweep_on_side:
             main.wait_event(self._ev_swept)
+        else:
+            t = self._tic('adam_rows')
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, s), 'sat_tables_adam')
+            self._toc(t)
+            if dense_mode and not sweep_on_side:
+                t = self._tic('adam_sweep')
+                check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
+                self._toc(t)
+            t = self._tic('adam_dense')
+            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
+            self._toc(t)
+            if sweep_on_side:
+                main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
         if self.dist is not None and self.dist.world > 1:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term

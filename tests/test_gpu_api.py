@@ -308,6 +308,7 @@ def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
     tg, _ = table_grads(model, w, 0.0)
     got.update(tg)
     checked = 0
+    gmax = max(v.abs().max().item() for v in grads.values())
     for k, r in grads.items():
         if k not in got:
             continue
@@ -317,6 +318,6 @@ def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
         if k.endswith('K_meta_mlp.ffn_layer_norm.bias'):
             assert err <= 1e-4 * max(v.abs().max().item() for kk, v in grads.items() if kk.endswith('Q_meta_mlp.ffn_layer_norm.bias')), k
         else:
-            assert err <= 2e-3 * scale + 1e-9, (k, err, scale)
+            assert err <= 2e-3 * scale + 1e-7 * gmax, (k, err, scale)     # (F = 1: d theta is analytically zero)
         checked += 1
     assert checked >= len(O.trainable_keys(cfg)) - 1
