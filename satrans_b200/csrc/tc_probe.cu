@@ -9,6 +9,66 @@
 #include "tc_common.cuh"
 
 namespace sat {
+
+// ---- probe-only helpers: SS-form MMAs and the K-major transposed staging of the (not shipped) tensor-core weight gradient ----
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M = 128 (both operands through shared-memory descriptors)
+__device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor with both operands MN-major (weight-gradient GEMMs: the reduction dimension K is the token index)
+__device__ __forceinline__ constexpr uint32_t make_idesc_mn(int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---- weight-gradient operand staging: [32 channels][128 tokens] fp32, K-major (K = token), SWIZZLE_NONE -----------------
+// (MN-major tf32 operands return zeros on this part -- tests/wgrad_probe.py -- so the token-major register rows are
+// transposed on the way into shared memory.)  Core matrix = 8 channels x 4 tokens (16 B per channel row, 128 B total).
+// Token chunks (4 tokens) are the OUTER index and the 4 channel groups the inner one:
+//     byte offset(ch, tok) = (tok/4)*528 + (ch/8)*128 + (ch%8)*16 + (tok%4)*4        LBO = 528 B, SBO = 128 B
+// 528 = 4*128 + 16: the 16 B skew makes the per-token scalar stores of a warp hit 32 distinct banks.  An M = 128 MMA reads
+// 16 channel groups (2 KB) per chunk: groups 4..15 alias the following chunks (finite don't-care rows of D).
+constexpr int WG_LBO = 528, WG_SBO = 128;
+constexpr int WG_TILE_FLOATS = (32 * WG_LBO + 2048) / 4;        // 32 chunks + overread room = 4736 floats
+__device__ __forceinline__ void wg_stage_row(float* __restrict__ tile_hi, float* __restrict__ tile_lo, int tok, const float (&v)[D]) {
+    const int base = (tok >> 2) * (WG_LBO / 4) + (tok & 3);      // floats
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const float h = tf32_hi(v[c]);
+        const int off = base + (c >> 3) * 32 + (c & 7) * 4;
+        tile_hi[off] = h;
+        tile_lo[off] = v[c] - h;
+    }
+}
+// first MMA of a chain (overwrites D) / accumulating MMA: compile-time predicate, no setp
+__device__ __forceinline__ void mma_ss_tf32_first(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma_ss_tf32_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+// D_w[128 x 32] = A^T G over the 128 tokens of the tile: 16 k-steps (8 tokens) x (hi*hi + lo*hi + hi*lo).
+// Fully unrolled; the descriptor of k-step ks is the base descriptor + ks * (2*LBO/16) in the start-address field.
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, const float* a_hi, const float* a_lo, const float* g_hi, const float* g_lo) {
+    const uint32_t idesc = make_idesc(32);
+    const uint64_t dah = make_b_desc(smem_u32(a_hi), WG_LBO, WG_SBO), dal = make_b_desc(smem_u32(a_lo), WG_LBO, WG_SBO);
+    const uint64_t dgh = make_b_desc(smem_u32(g_hi), WG_LBO, WG_SBO), dgl = make_b_desc(smem_u32(g_lo), WG_LBO, WG_SBO);
+    constexpr uint64_t STEP = (2 * WG_LBO) >> 4;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+        const uint64_t o = ks * STEP;
+        if (ks == 0) mma_ss_tf32_first(d_tmem, dah, dgh, idesc);
+        else mma_ss_tf32_acc(d_tmem, dah + o, dgh + o, idesc);
+        mma_ss_tf32_acc(d_tmem, dal + o, dgh + o, idesc);
+        mma_ss_tf32_acc(d_tmem, dah + o, dgl + o, idesc);
+    }
+}
+
+
 constexpr int TCB_W = 192;
 }
 
