@@ -346,7 +346,8 @@ class Trainer:
     train-mode forward (dropout from torch's RNG), BCE(sum) + dense L2, autograd backward (dense table
     gradients), torch.optim.Adam over every parameter.  Used as the timed CPU baseline."""
 
-    def __init__(self, st, cfg: OracleConfig, lr: float, optimizer: str = 'adam', loss: str = 'binary_crossentropy'):
+    def __init__(self, st, cfg: OracleConfig, lr: float, optimizer: str = 'adam', loss: str = 'binary_crossentropy',
+                 **opt_kwargs):
         self.cfg = cfg
         self.loss = loss
         self.state = dict(st)
@@ -354,7 +355,7 @@ class Trainer:
         self.state.update(self.params)
         cls = {'adam': torch.optim.Adam, 'sgd': torch.optim.SGD, 'adagrad': torch.optim.Adagrad,
                'rmsprop': torch.optim.RMSprop}[optimizer]                     # meta_basemodel.py:612-625
-        self.optim = cls(list(self.params.values()), lr=lr)
+        self.optim = cls(list(self.params.values()), lr=lr, **opt_kwargs)
 
     def step(self, X, y, train_mode=True):
         yp = forward(self.state, X, self.cfg, masks='rng' if train_mode else None).squeeze(-1)

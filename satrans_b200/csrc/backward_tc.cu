@@ -209,10 +209,11 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         float dv[D], res[D];                                     // requested now, used after the paired phase / at the end
         {
             float v[D];
-            if (valid) load_row(a.dqkv + tokpos, v); else zero(v);
+            // (written back by this thread at the end of each side: coherent loads, see load_row_cg)
+            if (valid) load_row_cg(a.dqkv + tokpos, v); else zero(v);
             if (stage) sts_row(sT0 + tid * KV_LD, v);
             tmem_st_operand<PASSES>(tlane + TCB_A, v);
-            if (valid) load_row(a.dqkv + a.act_stride + tokpos, v); else zero(v);
+            if (valid) load_row_cg(a.dqkv + a.act_stride + tokpos, v); else zero(v);
             if (stage) sts_row(sT1 + tid * KV_LD, v);
             tmem_st_operand<PASSES>(tlane + TCB_H, v);
             if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, v); else zero(v);

@@ -241,6 +241,15 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)
         v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
     }
 }
+// the same through L2 only (ld.global.cg): for a row this kernel has written earlier.  load_row's `const __restrict__` pointer
+// lets the compiler use the non-coherent path (LDG.CONSTANT), which may return the stale L1 copy of such a row.
+__device__ __forceinline__ void load_row_cg(const float* p, float (&v)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; i += 4) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(p + i));
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
 __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[D]) {
 #pragma unroll
     for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
