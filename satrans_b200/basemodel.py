@@ -275,6 +275,18 @@ class BaseModel(nn.Module):
             self._engine = Engine(self)
         return self._engine
 
+    @property
+    def precision(self):
+        """Arithmetic of the projection GEMMs: 'fp32' (default: CUDA-core FFMA, tightest parity with the reference), 'tf32x3'
+        (tcgen05 tensor cores, error-compensated 3xTF32: y_pred within 1e-7 of fp32, what bench.py times) or 'tf32'."""
+        return self.engine.precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ('fp32', 'tf32x3', 'tf32'):
+            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32', got %r" % (value,))
+        self.engine.precision = value
+
     def _as_device_matrix(self, X):
         if not torch.is_tensor(X):
             X = torch.as_tensor(np.ascontiguousarray(X))
