@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
             for (int h = 0; h < H; ++h) {
                 // keys in chunks of JC per basic block; keys past F read row F-1 with score -inf (see attention_fwd)
                 constexpr int JC = SAT_BWDA_JC;
+                static_assert(JC % 2 == 0 && SAT_MAXF % JC == 0, "keys are processed in pairs");
                 float sc[SAT_MAXF];
                 float mx = -INFINITY;
                 const float Dhh = sSt[tid * ST_LD + 16 + h];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                 for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
                     if (j0 < F) {
 #pragma unroll
-                        for (int j = j0; j < j0 + JC; ++j) { sc[j] = softmax_exp(sc[j] - mx); sum += sc[j]; }
+                        for (int j = j0; j < j0 + JC; j += 2) { softmax_exp_pair(sc[j], sc[j + 1], mx); sum += sc[j]; sum += sc[j + 1]; }
                     }
                 }
                 const float inv_sum = 1.f / sum;

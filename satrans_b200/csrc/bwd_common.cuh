@@ -48,10 +48,10 @@ __device__ __forceinline__ float normalize32(float (&v)[D]) {
     const float mean = sum32(v) * (1.f / D);
     const float q = sumsq_dev32(v, mean);              // same reduction order as layernorm32 (the forward)
 #pragma unroll
-    for (int i = 0; i < D; ++i) v[i] -= mean;
+    for (int i = 0; i < D; i += 2) add2(v[i], v[i + 1], v[i], v[i + 1], -mean, -mean);
     const float rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
 #pragma unroll
-    for (int i = 0; i < D; ++i) v[i] *= rstd;
+    for (int i = 0; i < D; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], rstd, rstd);
     return rstd;
 }
 

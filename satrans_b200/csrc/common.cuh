@@ -123,6 +123,29 @@ __device__ __forceinline__ void fma2(float& c0, float& c1, float a, float g0, fl
     c0 = fmaf(a, g0, c0); c1 = fmaf(a, g1, c1);
 #endif
 }
+// (c0, c1) = (a0 + b0, a1 + b1) and (a0 * b0, a1 * b1): FADD2 / FMUL2, each lane an IEEE fp32 operation
+__device__ __forceinline__ void add2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+#if SAT_FFMA2
+    unsigned long long A, B, R;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(R) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(R));
+#else
+    c0 = a0 + b0; c1 = a1 + b1;
+#endif
+}
+__device__ __forceinline__ void mul2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+#if SAT_FFMA2
+    unsigned long long A, B, R;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(R) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(R));
+#else
+    c0 = a0 * b0; c1 = a1 * b1;
+#endif
+}
 // c0 += a0 * g0, c1 += a1 * g1
 __device__ __forceinline__ void fma2v(float& c0, float& c1, float a0, float a1, float g0, float g1) {
 #if SAT_FFMA2
@@ -134,6 +157,19 @@ __device__ __forceinline__ void fma2v(float& c0, float& c1, float a0, float a1, 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(R));
 #else
     c0 = fmaf(a0, g0, c0); c1 = fmaf(a1, g1, c1);
+#endif
+}
+
+// two softmax exponentials: s = exp(s - mx), same arithmetic per lane as softmax_exp(s - mx)
+__device__ __forceinline__ void softmax_exp_pair(float& s0, float& s1, float mx) {
+#if SAT_FAST_EXP2
+    float t0, t1;
+    add2(t0, t1, s0, s1, -mx, -mx);
+    mul2(t0, t1, t0, t1, 1.4426950408889634f, 1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(t1));
+#else
+    s0 = expf(s0 - mx); s1 = expf(s1 - mx);
 #endif
 }
 
@@ -211,15 +247,16 @@ __device__ __forceinline__ void zero(float (&v)[N]) {
 __device__ __forceinline__ float sum32(const float (&v)[D]) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < D; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+    for (int i = 0; i < D; i += 4) { add2(s0, s1, s0, s1, v[i], v[i + 1]); add2(s2, s3, s2, s3, v[i + 2], v[i + 3]); }
     return (s0 + s1) + (s2 + s3);
 }
 __device__ __forceinline__ float sumsq_dev32(const float (&v)[D], float mean) {
     float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
     for (int i = 0; i < D; i += 4) {
-        const float t0 = v[i] - mean, t1 = v[i + 1] - mean, t2 = v[i + 2] - mean, t3 = v[i + 3] - mean;
-        q0 = fmaf(t0, t0, q0); q1 = fmaf(t1, t1, q1); q2 = fmaf(t2, t2, q2); q3 = fmaf(t3, t3, q3);
+        float t0, t1, t2, t3;
+        add2(t0, t1, v[i], v[i + 1], -mean, -mean); add2(t2, t3, v[i + 2], v[i + 3], -mean, -mean);
+        fma2v(q0, q1, t0, t1, t0, t1); fma2v(q2, q3, t2, t3, t2, t3);
     }
     return (q0 + q1) + (q2 + q3);
 }
@@ -230,7 +267,13 @@ __device__ __forceinline__ void layernorm32(float (&v)[D], const float* __restri
     const float q = sumsq_dev32(v, mean);
     rstd = 1.f / sqrtf(q * (1.f / D) + LN_EPS);
 #pragma unroll
-    for (int i = 0; i < D; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+    for (int i = 0; i < D; i += 2) {                     // v = fmaf((v - mean) * rstd, g, b), two channels per instruction
+        float t0, t1, o0 = b[i], o1 = b[i + 1];
+        add2(t0, t1, v[i], v[i + 1], -mean, -mean);
+        mul2(t0, t1, t0, t1, rstd, rstd);
+        fma2v(o0, o1, t0, t1, g[i], g[i + 1]);
+        v[i] = o0; v[i + 1] = o1;
+    }
 }
 
 // 128-byte row load/store helpers (global, 16 B aligned)

@@ -21,6 +21,7 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
     // serialised the dot-product / hash / exp chains: "wait" was 41 % of the forward's stall samples).  Keys past F in the
     // last chunk read row F-1 and get score -inf: probability exactly 0, so the sums are unchanged bit for bit.
     constexpr int JC = SAT_FWD_JC;
+    static_assert(JC % 2 == 0 && SAT_MAXF % JC == 0, "keys are processed in pairs");
 #pragma unroll 1
     for (int h = 0; h < H; ++h) {
         float sc[SAT_MAXF];
@@ -49,7 +50,7 @@ __device__ __forceinline__ void attention_fwd(float (&q)[D], const float* __rest
         for (int j0 = 0; j0 < SAT_MAXF; j0 += JC) {
             if (j0 < F) {
 #pragma unroll
-                for (int j = j0; j < j0 + JC; ++j) { sc[j] = softmax_exp(sc[j] - mx); sum += sc[j]; }
+                for (int j = j0; j < j0 + JC; j += 2) { softmax_exp_pair(sc[j], sc[j + 1], mx); sum += sc[j]; sum += sc[j + 1]; }
             }
         }
         float o[DH];

@@ -109,7 +109,10 @@ __device__ __forceinline__ void tmem_st_operand(uint32_t taddr, const float (&v)
     } else {
         float hi[D], lo[D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) { hi[i] = tf32_hi(v[i]); lo[i] = v[i] - hi[i]; }
+        for (int i = 0; i < D; i += 2) {
+            hi[i] = tf32_hi(v[i]); hi[i + 1] = tf32_hi(v[i + 1]);
+            add2(lo[i], lo[i + 1], v[i], v[i + 1], -hi[i], -hi[i + 1]);      // lo = v - hi (exact)
+        }
         tmem_st16(taddr, &hi[0]);
         tmem_st16(taddr + 16, &hi[16]);
         tmem_st16(taddr + 32, &lo[0]);
