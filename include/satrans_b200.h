@@ -249,6 +249,13 @@ int sat_selfatt_fwd(const float* x, float* out, const float* wq, const float* wk
                     const float* ln_g, const float* ln_b, int32_t B, int32_t F, int32_t H, int32_t use_res,
                     int32_t training, float dropout_p, uint64_t seed, void* stream);
 
+/* ---- per-batch training metrics of fit(verbose > 0) (reference meta_basemodel.py:330-337,352-356; metric table :655-671).
+ *      y_pred, y: device arrays; batch b covers [batch_off[b], batch_off[b+1]) (device int32, n_batches + 1 entries);
+ *      out[b][4] = { log_loss, roc_auc_score, mean_squared_error, accuracy(p > 0.5) } as sklearn computes them in float64
+ *      (NaN logloss / auc for a single-class batch).  One CTA per batch, max_batch <= 16384 samples. ---------------------- */
+int sat_batch_metrics(const float* y_pred, const float* y, const int32_t* batch_off, int32_t n_batches, int32_t max_batch,
+                      double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -468,7 +468,20 @@ class BaseModel(nn.Module):
             eng.check_errors(eng.workspace(1, True))
             lh = losses.double().cpu().numpy()
             epoch_logs["loss"] = float(lh.sum()) / sample_num                 # (bce + reg) summed / N (:353)
-            if want_metrics:
+            if want_metrics and getattr(self, 'device_metrics', True) and batch_size <= 16384:
+                # per-batch sklearn-equivalent metrics on the device (sat_batch_metrics): one CTA per training batch
+                from . import _lib
+                yo = (yd.index_select(0, order) if order is not None else yd).contiguous()
+                offs = torch.tensor(list(range(0, sample_num, batch_size)) + [sample_num], dtype=torch.int32, device=dev)
+                res = torch.empty((steps_per_epoch, 4), dtype=torch.float64, device=dev)
+                _lib.check(_lib.lib().sat_batch_metrics(preds.data_ptr(), yo.data_ptr(), offs.data_ptr(), steps_per_epoch,
+                                                        min(batch_size, sample_num), res.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream), 'sat_batch_metrics')
+                res = res.cpu().numpy()
+                col = {"binary_crossentropy": 0, "logloss": 0, "auc": 1, "mse": 2, "accuracy": 3, "acc": 3}
+                for name in self.metrics:
+                    epoch_logs[name] = np.sum(res[:, col[name]]) / steps_per_epoch
+            elif want_metrics:
                 ph = preds.cpu().numpy().astype("float64")
                 yh = (yd.index_select(0, order) if order is not None else yd).cpu().numpy()
                 train_result = {name: [] for name in self.metrics}

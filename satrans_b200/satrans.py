@@ -119,6 +119,7 @@ class SATrans(BaseModel):
         self.meta_dnn_hidden_units = units
         self.dropout_rate = 0.1             # attndrop_rate = drop_rate = 0.1 (reference satrans.py:27-28)
         self.dense_table_updates = True     # reference semantics: L2 + Adam on every table row every step
+        self.device_metrics = True          # fit(verbose>0): per-batch logloss/auc/mse/accuracy on the GPU (False: sklearn on the host)
 
         field_num = len(self.embedding_dict)
         if field_num > _lib.SAT_MAXF:

@@ -330,3 +330,52 @@ def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
             assert err <= 2e-3 * scale + 1e-7 * gmax, (k, err, scale)     # (F = 1: d theta is analytically zero)
         checked += 1
     assert checked >= len(O.trainable_keys(cfg)) - 1
+
+
+def test_batch_metrics_match_sklearn():
+    """sat_batch_metrics == sklearn's log_loss / roc_auc_score / mean_squared_error / accuracy per batch (the reference's
+    per-step metrics, meta_basemodel.py:330-337), including tied scores, saturated predictions, a ragged last batch and a
+    single-class batch (NaN like the host path); and fit(verbose=1) reports the same epoch metrics on both paths."""
+    from sklearn.metrics import log_loss, roc_auc_score
+    from satrans_b200 import _lib
+    rng = np.random.default_rng(5)
+    sizes = [4096, 4096, 1000, 37, 1, 8192, 333]
+    N = sum(sizes)
+    p = rng.random(N).astype(np.float32)
+    p[:3000] = np.round(p[:3000], 2)                  # many ties
+    p[3000:3010] = 0.0
+    p[3010:3020] = 1.0
+    y = (rng.random(N) < 0.2).astype(np.float32)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    y[offs[3]:offs[4]] = 0.0                           # single-class batch
+    pd, yd, od = torch.from_numpy(p).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(offs).cuda()
+    out = torch.empty((len(sizes), 4), dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib().sat_batch_metrics(pd.data_ptr(), yd.data_ptr(), od.data_ptr(), len(sizes), max(sizes), out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), 'sat_batch_metrics')
+    out = out.cpu().numpy()
+    for b, (a, e) in enumerate(zip(offs[:-1], offs[1:])):
+        yy, pp = y[a:e].astype(np.float64), p[a:e].astype(np.float64)
+        if len(np.unique(yy)) < 2:
+            assert np.isnan(out[b, 0]) and np.isnan(out[b, 1])
+        else:
+            assert abs(out[b, 0] - log_loss(yy, pp)) <= 1e-12 * max(1.0, abs(log_loss(yy, pp)))
+            assert abs(out[b, 1] - roc_auc_score(yy, pp)) <= 1e-12
+        assert abs(out[b, 2] - np.mean((yy - pp) ** 2)) <= 1e-13
+        assert abs(out[b, 3] - np.mean(yy == np.where(pp > 0.5, 1, 0))) <= 1e-15
+    with pytest.raises(_lib.SatError):
+        _lib.check(_lib.lib().sat_batch_metrics(pd.data_ptr(), yd.data_ptr(), od.data_ptr(), 1, 20000, pd.data_ptr(), None),
+                   'sat_batch_metrics')
+    # fit(verbose=1): device metrics == host (sklearn) metrics
+    schema, cfg, st = _small()
+    xs, ys = synth.make_inputs(schema, 1000, seed=11, ctr=0.3)
+    logs = {}
+    for dev_metrics in (True, False):
+        model = _model(cfg, st)
+        model.device_metrics = dev_metrics
+        model.dropout_rate = 0.0
+        model.compile(torch.optim.SGD(model.parameters(), lr=0.01), "binary_crossentropy",
+                      metrics=["binary_crossentropy", "auc", "mse", "acc"])
+        h = model.fit(x=xs, y=ys, batch_size=256, epochs=1, verbose=1, shuffle=True)
+        logs[dev_metrics] = {k: v[0] for k, v in h.history.items()}
+    for k in ("binary_crossentropy", "auc", "mse", "acc"):
+        assert abs(logs[True][k] - logs[False][k]) <= 2e-6, (k, logs)      # two training runs: float-atomic order noise in y_pred
