@@ -120,7 +120,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -366,14 +366,33 @@ def run_b200(args):
             "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "phases_ms": phases}
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Everything else that writes to fd 1 (NCCL prints "NCCL version ..." from C at communicator creation, libraries may
+    # warn) is sent to stderr, so that stdout carries exactly the JSON line.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
