@@ -174,3 +174,24 @@ def test_precision_knob():
     assert m.engine.precision == 'tf32x3'
     with pytest.raises(ValueError):
         m.precision = 'bf16'
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port of the reference's step on the host cores) prints exactly ONE JSON line on
+    stdout with the keys of the measurement contract; a tiny vocabulary / batch keeps this a seconds-long CPU test."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--vocab-scale', '0.001',
+                        '--batch', '128', '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'e2e', 'cpu_baseline', 'impl'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['metric'] == 'train_samples_per_sec' and d['unit'] == 'samples/s'
+    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and 'workload' in d['config']
