@@ -2,7 +2,8 @@
 
 Run in the build container only (needs /root/reference):
 
-    python oracle/make_golden.py            # writes tests/golden/{en_small,enp_small,q_small,relu_small_fwd}.npz
+    python oracle/make_golden.py            # writes tests/golden/{en_small,enp_small,q_small,relu_small_fwd,
+                                            #   selfatt_layer,compile_variants}.npz
 
 The reference modules `models/{satrans,meta_basemodel,submodules}.py` are imported as they lie
 under /root/reference, with `oracle/ref_shims` supplying the third-party names they import
@@ -222,8 +223,81 @@ def build_selfatt():
     return out
 
 
+VARIANTS = (('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae'))
+
+
+def build_compile_variants():
+    """compile(<optimizer string>, <loss string>) of the unmodified reference (meta_basemodel.py:598-640) on the q_small
+    model: two steps of its training-loop body (:311-328, eval-mode forward so that dropout is off) per variant.
+    Initial state, X and y are those of q_small.npz (same construction), so only losses and end states are stored."""
+    sys.path.insert(0, ROOT)
+    from satrans_b200 import synth
+    from oracle import satrans_oracle as O
+    SATrans, SparseFeat, DenseFeat = import_reference()
+    schema_name, scale, B, kw = CASES['q_small']
+    schema = synth.aliccp_schema(scale)
+    cols = [SparseFeat(f, vocabulary_size=schema.data_max[f] + 2, embedding_dim=32) for f in schema.fields]
+    cfg = O.OracleConfig(sparse_names=schema.fields, vocab_sizes=schema.vocab_sizes, dense_names=schema.dense,
+                         domain_col=schema.domain_col, num_domains=schema.num_domains, embedding_dim=32,
+                         layers=kw['domain_att_layer_num'], heads=kw['att_head_num'], meta_mode=kw['meta_mode'], flag=kw['flag'])
+    xs, ys = synth.make_inputs(schema, 3 * B, seed=1021, ctr=0.3)
+    Xall = synth.stack_columns(xs, schema.fields)
+    yall = ys.astype(np.float32)
+    base = np.load(os.path.join(ROOT, 'tests', 'golden', 'q_small.npz'))
+    out = {}
+    torch.set_num_threads(1)
+    for opt, loss in VARIANTS:
+        model = SATrans(linear_feature_columns=cols, dnn_feature_columns=cols, domain_column_list=[schema.domain_col],
+                        num_domains_list=[schema.num_domains], att_layer_num=0, use_linear=False, use_dnn=False, seed='1021',
+                        device='cpu', **kw)
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                if 'ffn_layer_norm' in k:
+                    v.add_(torch.randn(v.shape, generator=g) * 0.1)
+                if k == 'domain_map_dnn_Q.linears.0.weight':
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.05)
+                if k.startswith('embedding_dict.'):
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.3)
+        state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        for k in O.trainable_keys(cfg):
+            assert np.array_equal(state0[k].numpy(), base['state/' + k]), k      # same start as q_small.npz
+        model.compile(opt, loss)                                                 # the reference's own string tables
+        model.eval()
+        tr = O.Trainer({k: v.clone() for k, v in state0.items()}, cfg, lr=model.optim.param_groups[0]['lr'], optimizer=opt, loss=loss)
+        tag = '%s_%s' % (opt, loss)
+        for step in range(2):
+            Xk = torch.from_numpy(Xall[step * B:(step + 1) * B])
+            yk = torch.from_numpy(yall[step * B:(step + 1) * B])
+            y_pred = model(Xk).squeeze()
+            model.optim.zero_grad()
+            lv = model.loss_func(y_pred, yk.squeeze(), reduction='sum')           # meta_basemodel.py:317
+            reg = model.get_regularization_loss()
+            total = lv + reg + model.aux_loss
+            total.backward()
+            model.optim.step()
+            out['%s/loss%d' % (tag, step)] = np.float32(lv.item())
+            out['%s/reg%d' % (tag, step)] = np.float32(reg.item())
+            o_l, o_r = tr.step(Xk, yk, train_mode=False)
+            assert abs(o_l - lv.item()) <= 1e-5 * abs(lv.item()), (tag, step, o_l, lv.item())
+        sd = model.state_dict()
+        for k in O.trainable_keys(cfg):
+            sub = subsample(k)
+            out['%s/end/%s' % (tag, k)] = sd[k].detach().numpy()[sub].copy()
+            ref_p = sd[k].detach()
+            err = (tr.params[k].detach() - ref_p).abs().max().item()
+            assert err <= 2e-5 * max(ref_p.abs().max().item(), 1e-3) + 1e-7, (tag, k, err)   # pin: oracle == reference
+        out['%s/lr' % tag] = np.float32(model.optim.param_groups[0]['lr'])
+    return out
+
+
 def main():
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
+    if os.environ.get('SAT_GOLDEN_ONLY_VARIANTS'):
+        path = os.path.join(ROOT, 'tests', 'golden', 'compile_variants.npz')
+        np.savez_compressed(path, **build_compile_variants())
+        print('compile_variants ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+        return
     path = os.path.join(ROOT, 'tests', 'golden', 'selfatt_layer.npz')
     np.savez_compressed(path, **build_selfatt())
     print('selfatt_layer ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
@@ -234,6 +308,9 @@ def main():
         path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
         np.savez_compressed(path, **out)
         print(name, '->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+    path = os.path.join(ROOT, 'tests', 'golden', 'compile_variants.npz')
+    np.savez_compressed(path, **build_compile_variants())
+    print('compile_variants ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
 
 
 if __name__ == '__main__':

@@ -162,3 +162,32 @@ def test_tensor_core_forward_training_path(name, bwd):
         n_tight += int((err <= 1e-4 * scale + 1e-9).sum())
         n_all += err.numel()
     assert n_tight >= 0.99 * n_all, (n_tight, n_all)
+
+
+@pytest.mark.parametrize('opt,loss', [('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae')])
+def test_compile_string_variants_match_reference(opt, loss):
+    """compile('<optimizer>', '<loss>') (reference meta_basemodel.py:612-640) through the drop-in API: two train_on_batch steps on
+    the q_small golden model == the reference's own two steps (tests/golden/compile_variants.npz)."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from test_oracle_golden import assert_adam_close
+    g = Golden('q_small')
+    v = np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))
+    tag = '%s_%s' % (opt, loss)
+    lr = float(v[tag + '/lr'])
+    model = model_from_golden(g)
+    model.dropout_rate = 0.0
+    model.compile(opt, loss)
+    assert abs(model._opt_hparams['lr'] - lr) < 1e-12
+    for step in range(2):
+        l, r = model.train_on_batch(g.X(step).numpy(), g.y(step).numpy())
+        ref_l = float(v['%s/loss%d' % (tag, step)])
+        assert abs(l - ref_l) <= 2e-5 * abs(ref_l), (step, l, ref_l)
+    sd = {k: t.detach().cpu() for k, t in model.state_dict().items()}
+    for k in O.trainable_keys(g.cfg):
+        ref = torch.from_numpy(v['%s/end/%s' % (tag, k)])
+        got = sd[k][subsample(k)]
+        if opt == 'sgd':
+            assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
+        else:
+            assert_adam_close(got, ref, lr, 2, k)

@@ -96,3 +96,31 @@ def test_selfattention_layer_oracle_vs_reference():
         with torch.no_grad():
             y = O.self_attention_layer(torch.from_numpy(z[tag + '/x']), p, heads, res)
         assert torch.allclose(y, torch.from_numpy(z[tag + '/y']), atol=1e-6, rtol=0)
+
+
+VARIANTS = (('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae'))
+
+
+@pytest.mark.parametrize('opt,loss', VARIANTS)
+def test_compile_string_variants_match_reference(opt, loss):
+    """compile('<optimizer>', '<loss>') string tables of the reference (meta_basemodel.py:612-640): two steps of its loop on the
+    q_small model, dumped by oracle/make_golden.py; the oracle's Trainer must reproduce losses and end state."""
+    import numpy as np
+    import os
+    from golden_util import GOLDEN_DIR
+    g = Golden('q_small')
+    v = np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))
+    tag = '%s_%s' % (opt, loss)
+    lr = float(v[tag + '/lr'])
+    tr = O.Trainer(g.state(), g.cfg, lr=lr, optimizer=opt, loss=loss)
+    for step in range(2):
+        l, r = tr.step(g.X(step), g.y(step), train_mode=False)
+        assert abs(l - float(v['%s/loss%d' % (tag, step)])) <= 1e-5 * abs(float(v['%s/loss%d' % (tag, step)]))
+        assert abs(r - float(v['%s/reg%d' % (tag, step)])) <= 1e-3 * abs(float(v['%s/reg%d' % (tag, step)])) + 1e-6 * abs(l)
+    for k in O.trainable_keys(g.cfg):
+        ref = torch.from_numpy(v['%s/end/%s' % (tag, k)])
+        got = tr.params[k].detach()[subsample(k)]
+        if opt == 'sgd':
+            assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
+        else:       # normalised steps amplify round-off of near-zero gradient elements (thread-count dependent even on the CPU)
+            assert_adam_close(got, ref, lr, 2, k)
