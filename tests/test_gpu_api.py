@@ -378,4 +378,6 @@ def test_batch_metrics_match_sklearn():
         h = model.fit(x=xs, y=ys, batch_size=256, epochs=1, verbose=1, shuffle=True)
         logs[dev_metrics] = {k: v[0] for k, v in h.history.items()}
     for k in ("binary_crossentropy", "auc", "mse", "acc"):
-        assert abs(logs[True][k] - logs[False][k]) <= 2e-6, (k, logs)      # two training runs: float-atomic order noise in y_pred
+        # two separate training runs: float-atomic order noise in y_pred (1e-7) can swap neighbouring scores, and one swap
+        # moves a batch's AUC by 1 / (n_pos * n_neg) ~ 7e-5
+        assert abs(logs[True][k] - logs[False][k]) <= (2e-4 if k == "auc" else 2e-6), (k, logs)
