@@ -170,7 +170,7 @@ def test_compile_string_variants_match_reference(opt, loss):
     the q_small golden model == the reference's own two steps (tests/golden/compile_variants.npz)."""
     import os
     from golden_util import GOLDEN_DIR
-    from test_oracle_golden import assert_adam_close
+    from gpu_util import model_from_golden
     g = Golden('q_small')
     v = np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))
     tag = '%s_%s' % (opt, loss)
