@@ -178,7 +178,7 @@ def test_compile_string_variants_match_reference(opt, loss):
     model = model_from_golden(g)
     model.dropout_rate = 0.0
     model.compile(opt, loss)
-    assert abs(model._opt_hparams['lr'] - lr) < 1e-12
+    assert abs(model._opt_hparams['lr'] - lr) < 1e-8          # (the fixture stores lr as float32)
     for step in range(2):
         l, r = model.train_on_batch(g.X(step).numpy(), g.y(step).numpy())
         ref_l = float(v['%s/loss%d' % (tag, step)])
