@@ -190,4 +190,8 @@ def test_compile_string_variants_match_reference(opt, loss):
         if opt == 'sgd':
             assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
         else:
-            assert_adam_close(got, ref, lr, 2, k)
+            # Adagrad / RMSprop with their default eps (1e-10 / 1e-8) normalise the first steps to ~+-lr (RMSprop: +-10 lr), so
+            # the round-off of near-zero gradient elements decides their sign: most elements must agree to
+            # fp32 round-off, the step-1 loss above already pins the update as a whole
+            tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
+            assert ((got - ref).abs() <= tight).float().mean().item() >= 0.95, k
