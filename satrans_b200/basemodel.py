@@ -277,8 +277,8 @@ class BaseModel(nn.Module):
 
     @property
     def precision(self):
-        """Arithmetic of the projection GEMMs: 'fp32' (default: CUDA-core FFMA, tightest parity with the reference), 'tf32x3'
-        (tcgen05 tensor cores, error-compensated 3xTF32: y_pred within 1e-7 of fp32, what bench.py times) or 'tf32'."""
+        """Arithmetic of the projection GEMMs: 'tf32x3' (default: tcgen05 tensor cores, error-compensated 3xTF32, y_pred within
+        1e-7 of fp32; what bench.py times), 'fp32' (CUDA-core FFMA, tightest parity with the reference) or 'tf32' (plain TF32)."""
         return self.engine.precision
 
     @precision.setter

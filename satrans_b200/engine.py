@@ -78,9 +78,10 @@ class Engine:
         self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
         self.timing = None         # set to {} to collect CUDA-event pairs per phase: {name: [(start, end), ...]}
         self.dist = None           # satrans_b200.dist.DistContext when the tables are row-sharded over ranks
-        # forward precision: 'fp32' = CUDA-core FFMA kernels; 'tf32x3' = tcgen05 tensor cores with the error-
-        # compensated 3xTF32 split (fp32-level parity); 'tf32' = tcgen05 plain TF32 (fast mode)
-        self.precision = 'fp32'
+        # projection arithmetic: 'tf32x3' (default) = tcgen05 tensor cores with the error-compensated 3xTF32 split (fp32-level
+        # parity: y_pred within 1e-7 of the CUDA-core path); 'fp32' = CUDA-core FFMA kernels (bit-tight parity tests use it);
+        # 'tf32' = tcgen05 plain TF32 (fast mode)
+        self.precision = 'tf32x3'
         # backward of the MetaNet/QKV block: None = follow `precision`; 'fp32' forces the CUDA-core kernel
         self.backward_precision = None
         self._peer_tables = None

@@ -8,7 +8,7 @@ from oracle import satrans_oracle as O
 from satrans_b200 import DenseFeat, SATrans, SparseFeat
 
 
-def model_from_golden(g: Golden, device='cuda:0'):
+def model_from_golden(g: Golden, device='cuda:0', precision='fp32'):
     m = g.meta
     cols = ([SparseFeat(n, v, 32) for n, v in zip(m['sparse_names'], m['vocab_sizes'])] +
             [DenseFeat(n, 1) for n in m['dense_names']])
@@ -17,10 +17,11 @@ def model_from_golden(g: Golden, device='cuda:0'):
                     meta_mode=m['meta_mode'], seed='1021', device=device, flag=m['flag'])
     missing = model.load_state_dict(g.full_state_dict(), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
+    model.precision = precision        # CUDA-core kernels unless a test selects the tensor-core path (the package default)
     return model
 
 
-def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0'):
+def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0', precision='fp32'):
     cols = ([SparseFeat(n, v, cfg.embedding_dim) for n, v in zip(cfg.sparse_names, cfg.vocab_sizes)] +
             [DenseFeat(n, 1) for n in cfg.dense_names])
     model = SATrans(cols, cols, [cfg.domain_col], [cfg.num_domains], att_layer_num=0,
@@ -30,6 +31,7 @@ def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0'):
     with torch.no_grad():
         for k, v in state.items():
             sd[k].copy_(v)
+    model.precision = precision
     return model
 
 

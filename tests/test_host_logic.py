@@ -164,14 +164,14 @@ def test_synth_schemas():
 
 
 def test_precision_knob():
-    """model.precision selects the projection arithmetic of the engine ('fp32' default); unknown values raise."""
+    """model.precision selects the projection arithmetic of the engine ('tf32x3' default); unknown values raise."""
     s = synth.aliccp_schema(1e-4)
     cols = s.feature_columns(32)
     m = SATrans(cols, cols, ['301'], [3], att_layer_num=0, domain_att_layer_num=1, att_head_num=2, meta_mode='QK',
                 device='cpu', flag='sota')
-    assert m.precision == 'fp32'
-    m.precision = 'tf32x3'
-    assert m.engine.precision == 'tf32x3'
+    assert m.precision == 'tf32x3'
+    m.precision = 'fp32'
+    assert m.engine.precision == 'fp32'
     with pytest.raises(ValueError):
         m.precision = 'bf16'
 
