@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SAT_ABI_VERSION 1
+#define SAT_ABI_VERSION 2
 
 #define SAT_OK 0
 #define SAT_EINVAL (-1)      /* bad argument / unsupported shape            */
@@ -39,7 +39,11 @@ extern "C" {
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
-#define SAT_WORK_BUFFERS 22  /* pointer members of SatWork */
+#define SAT_WORK_BUFFERS 31  /* pointer members of SatWork */
+#define SAT_GRID_MAX (148 * 2) /* most CTAs any token kernel is launched with: rows of the per-CTA partial buffers */
+#define SAT_SORT_RADIX_BITS 9  /* digit width of the touched-row radix sort */
+#define SAT_SORT_TILE 2048     /* sorted entries per CTA and radix pass */
+#define SAT_ROWS_CHUNK 32      /* sorted entries one 8-lane group reduces */
 #define SAT_MAX_SHARDS 8     /* processes (GPUs) of one node sharing the row-sharded tables */
 #define SAT_ERR_BAD_ID 1     /* scalars[3] / counters[1] bit: a sparse id was outside its table     */
 #define SAT_ERR_BAD_DOMAIN 2 /* ... bit: a scenario id was outside [0, n_dom)                       */
@@ -108,6 +112,9 @@ typedef struct SatModel {
     uint32_t* shard_bitmap[SAT_MAX_SHARDS];     /* SatWork.bitmap of every shard            */
     int32_t* shard_word_rank[SAT_MAX_SHARDS];   /* SatWork.word_rank of every shard         */
     float* shard_row_grad[SAT_MAX_SHARDS];      /* SatWork.row_grad of every shard          */
+    float* shard_recv[SAT_MAX_SHARDS];          /* SatWork.recv of every shard              */
+    int32_t* shard_recv_idx[SAT_MAX_SHARDS];    /* SatWork.recv_idx of every shard          */
+    uint32_t* shard_flags[SAT_MAX_SHARDS];      /* SatWork.peer_flags of every shard        */
 } SatModel;
 
 /* Per-batch workspace, caller-allocated (sizes from sat_workspace_sizes).  */
@@ -137,6 +144,19 @@ typedef struct SatWork {
     float* scalars;       /* [8] device results: [0]=bce sum [1]=reg loss [2]=n_unique rows [3]=error flags */
     float* wpack;         /* [(L + n_keys)][8192] weights packed as tcgen05 B operands (hi | lo)         */
     int32_t* tiles2;      /* tile list of the tensor-core kernels (128 tokens per tile)                  */
+    /* deterministic gradient accumulation (no floating-point atomics anywhere): */
+    float* gpart;         /* per-CTA partial dense gradients, reduced in CTA order by sat_backward*:
+                             [L][SAT_GRID_MAX][1088] dW_out + d layer_norm | [L][SAT_GRID_MAX][3200] dW_q/k/v + d MetaNet-LN |
+                             [L][SAT_GRID_MAX][1 or 2][4096] d theta | [SAT_GRID_MAX][head_ld] d dnn_linear        */
+    uint32_t* sort_keys;  /* [2][cap_B*F] radix-sort ping-pong: key = (owner shard << slot_bits) | touched-row slot  */
+    int32_t* sort_vals;   /* [2][cap_B*F] ... value = token (sorted position * F + field)                           */
+    int32_t* sort_hist;   /* [2^SAT_SORT_RADIX_BITS][ceil(cap_B*F / SAT_SORT_TILE)] digit histogram / offsets       */
+    int32_t* chunk_info;  /* [ceil(cap_B*F / SAT_ROWS_CHUNK)][4] run bookkeeping of the segmented reduce            */
+    float* pieces;        /* [chunks][2][32] partial sums of runs that cross a chunk boundary                        */
+    /* row-sharded mode only (n_shards > 1): every source shard pushes ONE pre-reduced gradient per unique row */
+    float* recv;          /* [n_shards][cap_B*F][32] rows pushed by source shard s (filled by the peers)             */
+    int32_t* recv_idx;    /* [n_shards][touched rows cap] slot -> index into recv[s], -1 = nothing (filled by peers) */
+    uint32_t* peer_flags; /* [32] words: [0..8) epoch flags written by the peers, [8] own epoch, [16..24) push cursors */
 } SatWork;
 
 /* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */
@@ -160,6 +180,9 @@ typedef struct SatAdam {
 /* ---- library info ------------------------------------------------------------------------- */
 int sat_abi_version(void);
 const char* sat_last_error(void);
+/* sizes_host[0..2] = sizeof(SatModel), sizeof(SatWork), sizeof(SatAdam) as THIS library was compiled (a binding checks its
+ * struct mirrors against them). */
+int sat_struct_sizes(int64_t* sizes_host);
 /* bytes needed for each SatWork buffer, in the order of the struct's pointer members
  * (SAT_WORK_BUFFERS entries; 0 = not needed for inference-only use). */
 int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t training, int64_t* sizes_host, int32_t* max_tiles_host);
@@ -192,8 +215,10 @@ int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, c
                 SatWork* w, float* y_pred, int32_t training, float dropout_p, uint64_t seed, void* stream);
 
 /* ---- fused backward of the L layers + head; writes the dense-parameter gradient into w->dgrad,
- *      dtheta, and scatter-adds dLoss/dE0 into w->row_grad (rows ranked through the touched-row
- *      bitmap).  Replaces autograd over the graph of satrans.py:197-256. ------------------------ */
+ *      dtheta, and leaves dLoss/dE0 per token in w->dx (sat_rows_reduce sums it per touched table row).
+ *      Every reduction has a fixed order: CTAs write partial sums into w->gpart and one kernel adds
+ *      them in CTA order, so two runs give bit-identical gradients.  Replaces autograd over the graph
+ *      of satrans.py:197-256. ------------------------------------------------------------------- */
 int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
                  float dropout_p, uint64_t seed, void* stream);
 
@@ -205,18 +230,27 @@ int sat_rows_clear(const SatModel* m, SatWork* w, void* stream);
 int sat_rows_mark(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
 int sat_rows_rank(const SatModel* m, SatWork* w, void* stream);
 int sat_rows_mark_and_rank(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
+/* ---- sorted-index scatter-add of the table-row gradients (replaces embedding_dense_backward of the reference's
+ *      autograd, meta_basemodel.py:533-535 backward).  sat_rows_sort (after sat_bucket_by_domain and the touched-row
+ *      ranks; ids only, so it can run beside the forward) radix-sorts the batch's tokens by (owner shard, touched-row
+ *      slot), stable in the token index.  sat_rows_reduce (after sat_backward*) sums w->dx over each run of equal
+ *      keys in that order -- fixed chunks of SAT_ROWS_CHUNK sorted entries, chunk partials added in chunk order --
+ *      into w->row_grad[slot] (n_shards == 1) or pushes ONE row per unique (source shard, row) into the owner's
+ *      w->recv over NVLink; sat_rows_combine (row-sharded mode, after a cross-process barrier) adds the pushed rows
+ *      in source-shard order into w->row_grad.  No floating-point atomics: results do not depend on timing. ------- */
+int sat_rows_sort(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, void* stream);
+int sat_rows_reduce(const SatModel* m, SatWork* w, void* stream);
+int sat_rows_combine(const SatModel* m, SatWork* w, void* stream);
+/* Stream-ordered barrier across the n_shards processes through the peer-mapped w->peer_flags (one tiny kernel: bump the
+ * own epoch, store it into every peer's flag word with system scope, spin until every peer's epoch arrived).  Every
+ * process must call it the same number of times. */
+int sat_peer_barrier(const SatModel* m, SatWork* w, void* stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent). */
 int sat_enable_peer_access(int32_t peer_device);
 /* Map a peer process' allocation (64-byte cudaIpcMemHandle_t, host memory) into the CURRENT device's address
  * space with peer access over NVLink; *out_ptr_host receives the base pointer of the exporter's allocation. */
 int sat_ipc_open(const void* handle64_host, void** out_ptr_host);
 int sat_ipc_close(void* ptr);
-/* debugging aid: out[32][32] = A^T G (A, G: [128][32]) through the tensor-core weight-gradient path; raw: [128][32]. */
-int sat_debug_wgrad(const float* A, const float* G, float* out, float* raw, void* stream);
-/* debugging aid: raw[128][32] = P[128][128] Q[32][128]^T through SS tcgen05 MMAs with K-/MN-major staged operands. */
-int sat_debug_ss(const float* P, const float* Q, float* raw, int32_t a_mn, int32_t b_mn, int32_t swap, void* stream);
-/* debugging aid: one thread touches *p (mode 0 store, 1 atomicOr, 2 atomicAdd f32, 3 atomicAdd float4, 4 load -> *out). */
-int sat_debug_poke(void* p, int32_t mode, float* out, void* stream);
 
 /* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
  *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */

@@ -161,9 +161,12 @@ def _drop(x, p, masks, name):
     return x * masks[name].to(x.dtype) / (1.0 - p)
 
 
-def meta_net(x, mlp_params, units, ln_w, ln_b, masks=None, mname=None, p_drop=0.1):
+def meta_net(x, mlp_params, units, ln_w, ln_b, masks=None, mname=None, p_drop=0.1, relu_mask=None):
     """MetaNet.forward, submodules.py:77-103: per-sample 2-layer MLP whose weights are slices of
-    `mlp_params (B, P)`, no biases, ReLU between, dropout, residual, LayerNorm."""
+    `mlp_params (B, P)`, no biases, ReLU between, dropout, residual, LayerNorm.
+    `relu_mask` (B, F, hidden) bool: test hook -- use these ReLU decisions instead of the sign of the pre-activation (a
+    hidden unit within round-off of zero may be decided either way by two correct implementations; injecting the decisions
+    of the implementation under test makes both differentiate the same piecewise-linear function)."""
     off = 0
     ws = []
     for i in range(len(units) - 1):         # submodules.py:81-86 (row-major reshape)
@@ -174,7 +177,7 @@ def meta_net(x, mlp_params, units, ln_w, ln_b, masks=None, mname=None, p_drop=0.
     for i, w in enumerate(ws):              # submodules.py:94-97
         x = x @ w
         if i < len(ws) - 1:
-            x = F.relu(x)
+            x = F.relu(x) if relu_mask is None else x * relu_mask.to(x.dtype)
     x = _drop(x, p_drop, masks, mname)      # submodules.py:99
     x = x + res                             # submodules.py:100
     return _layer_norm(x, ln_w, ln_b)       # submodules.py:101-102
@@ -190,7 +193,8 @@ def gather_fields(st, X, cfg: OracleConfig):
 
 
 def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
-            masks: Optional[Dict[str, torch.Tensor]] = None, return_aux: bool = False):
+            masks: Optional[Dict[str, torch.Tensor]] = None, return_aux: bool = False,
+            relu_masks: Optional[Dict[str, torch.Tensor]] = None):
     """SATrans.forward (satrans.py:197-256) + Meta_Transformer_Layer.forward (satrans.py:50-100).
 
     `masks`: optional dict of dropout keep-masks keyed 'l{i}.q', 'l{i}.k' (B,F,d), 'l{i}.att'
@@ -227,9 +231,11 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
         qn = p + 'Q_meta_mlp.ffn_layer_norm.'
         kn = p + ('K_meta_mlp' if cfg.pos else 'Q_meta_mlp') + '.ffn_layer_norm.'
         if 'Q' in cfg.meta_mode:                                           # satrans.py:60-66 [K4]
-            q = meta_net(q, thetas[l][0][:, :P], cfg.units, st[qn + 'weight'], st[qn + 'bias'], masks, 'l%d.q' % l)
+            q = meta_net(q, thetas[l][0][:, :P], cfg.units, st[qn + 'weight'], st[qn + 'bias'], masks, 'l%d.q' % l,
+                         relu_mask=None if relu_masks is None else relu_masks['l%d.q' % l])
         if 'K' in cfg.meta_mode:                                           # satrans.py:67-73 [K4]
-            k = meta_net(k, thetas[l][1][:, :P], cfg.units, st[kn + 'weight'], st[kn + 'bias'], masks, 'l%d.k' % l)
+            k = meta_net(k, thetas[l][1][:, :P], cfg.units, st[kn + 'weight'], st[kn + 'bias'], masks, 'l%d.k' % l,
+                         relu_mask=None if relu_masks is None else relu_masks['l%d.k' % l])
         B_, F_ = q.shape[0], q.shape[1]
         qh = q.reshape(B_, F_, H, dh).permute(2, 0, 1, 3)                  # satrans.py:75-77 [K5]
         kh = k.reshape(B_, F_, H, dh).permute(2, 0, 1, 3)
@@ -291,14 +297,15 @@ def _loss(yp, y, kind='binary_crossentropy'):
     return fn(yp, y, reduction='sum')
 
 
-def loss_and_grads(st, X, y, cfg: OracleConfig, masks=None, with_reg: bool = True, loss: str = 'binary_crossentropy'):
+def loss_and_grads(st, X, y, cfg: OracleConfig, masks=None, with_reg: bool = True, loss: str = 'binary_crossentropy',
+                   relu_masks=None):
     """One forward + BCE(sum) + reg + backward (meta_basemodel.py:311-327) through torch autograd.
     Returns (y_pred (B,1), bce_sum, reg, {canonical key: grad})."""
     keys = trainable_keys(cfg)
     leaves = {k: st[k].detach().clone().requires_grad_(True) for k in keys}
     work = dict(st)
     work.update(leaves)
-    yp = forward(work, X, cfg, masks)
+    yp = forward(work, X, cfg, masks, relu_masks=relu_masks)
     bce = _loss(yp.squeeze(-1), y.to(yp.dtype).reshape(-1), loss)                               # :317
     reg = reg_loss(work, cfg) if with_reg else torch.zeros((), dtype=yp.dtype)
     total = bce + reg                                                                           # :320

@@ -13,7 +13,9 @@ CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 8 + 148 * 4
-SAT_WORK_BUFFERS = 22
+SAT_WORK_BUFFERS = 31
+SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
+SAT_ABI_VERSION = 2
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
@@ -35,12 +37,13 @@ class SatModel(C.Structure):
                 ('row_off', vp), ('sparse_cols', vp), ('dense_cols', vp), ('tables', vp), ('dense', vp),
                 ('n_shards', i32), ('shard_rank', i32), ('local_rows', i64),
                 ('shard_tables', vp * 8), ('shard_bitmap', vp * 8), ('shard_word_rank', vp * 8),
-                ('shard_row_grad', vp * 8)]
+                ('shard_row_grad', vp * 8), ('shard_recv', vp * 8), ('shard_recv_idx', vp * 8), ('shard_flags', vp * 8)]
 
 
 WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
                 'loss_part', 'dgrad', 'bitmap', 'word_rank', 'block_sums', 'uniq_rows', 'row_grad', 'reg_part',
-                'scalars', 'wpack', 'tiles2']
+                'scalars', 'wpack', 'tiles2', 'gpart', 'sort_keys', 'sort_vals', 'sort_hist', 'chunk_info', 'pieces',
+                'recv', 'recv_idx', 'peer_flags']
 assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
 
 
@@ -58,6 +61,7 @@ class SatAdam(C.Structure):
 PROTOTYPES = {
     'sat_abi_version': (C.c_int, []),
     'sat_last_error': (C.c_char_p, []),
+    'sat_struct_sizes': (C.c_int, [C.POINTER(i64)]),
     'sat_workspace_sizes': (C.c_int, [C.POINTER(SatModel), i32, i32, C.POINTER(i64), C.POINTER(i32)]),
     'sat_gather_fwd': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, i32, vp, vp, vp]),
     'sat_bucket_by_domain': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), i32, vp]),
@@ -71,9 +75,10 @@ PROTOTYPES = {
     'sat_rows_rank': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_rows_mark_and_rank': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
     'sat_enable_peer_access': (C.c_int, [i32]),
-    'sat_debug_wgrad': (C.c_int, [vp, vp, vp, vp, vp]),
-    'sat_debug_ss': (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
-    'sat_debug_poke': (C.c_int, [vp, i32, vp, vp]),
+    'sat_rows_sort': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
+    'sat_rows_reduce': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_rows_combine': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_peer_barrier': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_ipc_open': (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     'sat_ipc_close': (C.c_int, [vp]),
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
@@ -117,8 +122,12 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.sat_abi_version() != 1:
+        if l.sat_abi_version() != SAT_ABI_VERSION:
             raise SatError('libsatrans_b200.so ABI version mismatch')
+        sz = (i64 * 3)()
+        l.sat_struct_sizes(sz)
+        if list(sz) != [C.sizeof(SatModel), C.sizeof(SatWork), C.sizeof(SatAdam)]:
+            raise SatError('struct layout mismatch between _lib.py and libsatrans_b200.so: %s' % list(sz))
         _lib = l
     return _lib
 

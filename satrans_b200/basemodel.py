@@ -162,10 +162,14 @@ class BaseModel(nn.Module):
         total_rows = int(self._row_off[-1])
         n_local = (total_rows - self._shard[0] + self._shard[1] - 1) // self._shard[1]
         self._tables = torch.empty((n_local, d), dtype=torch.float32, device=device)
-        if not (flag and 'noembinit' in flag):                           # reference meta_basemodel.py:114-119
-            self._tables.normal_(mean=0.0, std=init_std)
-        else:
-            self._tables.normal_(mean=0.0, std=1.0)
+        # Row-sharded: every rank draws ITS rows from its own stream (seed folded with the rank); with one shared stream all
+        # ranks would draw the same values and global rows kR .. kR+R-1 would start identical instead of i.i.d.
+        gen = None
+        if self._shard[1] > 1:
+            gen = torch.Generator(device=self._tables.device)
+            gen.manual_seed((int(seed) * 1000003 + 7919 * (self._shard[0] + 1)) & (2 ** 63 - 1))
+        std = init_std if not (flag and 'noembinit' in flag) else 1.0    # reference meta_basemodel.py:114-119
+        self._tables.normal_(mean=0.0, std=std, generator=gen)
         self.embedding_dict = nn.ModuleDict()
         for i, f in enumerate(sparse):
             emb = nn.Embedding(f.vocabulary_size, d, device='meta')
@@ -289,9 +293,9 @@ class BaseModel(nn.Module):
 
     def _as_device_matrix(self, X):
         if not torch.is_tensor(X):
-            X = torch.as_tensor(np.ascontiguousarray(X))
+            X = torch.as_tensor(np.ascontiguousarray(self._normalise_matrix(X)))
         if X.dtype not in (torch.float32, torch.int32, torch.int64):
-            X = X.float()
+            X = X.long() if not X.dtype.is_floating_point else X.float()
         return X.to(self._tables.device, non_blocking=True).contiguous()
 
     # ---- compile -----------------------------------------------------------------------------------------
@@ -300,6 +304,8 @@ class BaseModel(nn.Module):
         torch.optim instance built over `model.parameters()`; its hyper-parameters are read and the update
         itself runs inside the fused kernels (Adam: tables + dense parameters)."""
         self.metrics_names = ["loss"]
+        if getattr(self, '_engine', None) is not None:
+            self._engine.reset_optimizer()          # a new optimiser starts from fresh state, like a new torch.optim instance
         self.optim = self._get_optim(optimizer)
         self.loss_func = self._get_loss_func(loss)
         self.metrics = self._get_metrics(metrics)
@@ -340,6 +346,21 @@ class BaseModel(nn.Module):
                                       "torch.optim instance (reference meta_basemodel.py:612-625)")
         return optimizer
 
+    def _hparams(self):
+        """Hyper-parameters of the next fused update.  With a torch.optim instance the learning rate (and betas / eps) are
+        read from its live param_groups[0], so lr schedulers and manual edits take effect like in the reference's loop."""
+        hp = dict(self._opt_hparams)
+        g = self.optim.param_groups[0] if hasattr(self.optim, 'param_groups') else None
+        if g is not None:
+            hp['lr'] = g['lr']
+            if 'eps' in g and hp['kind'] != 1:
+                hp['eps'] = g['eps']
+            if 'betas' in g:
+                hp['betas'] = tuple(g['betas'])
+            elif 'alpha' in g:
+                hp['betas'] = (0.0, g['alpha'])
+        return hp
+
     def _get_loss_func(self, loss):
         """'binary_crossentropy' | 'mse' | 'mae' (reference meta_basemodel.py:627-640), fused into the forward
         kernel's logit head; custom callables are not supported."""
@@ -368,14 +389,32 @@ class BaseModel(nn.Module):
         return metrics_
 
     # ---- data staging ------------------------------------------------------------------------------------
+    def _n_cols(self):
+        return max(end for (_start, end) in self.feature_index.values())
+
+    @staticmethod
+    def _normalise_matrix(X):
+        """(N, n_cols) array in any numeric dtype -> float32 (the reference's `.float()`), int32 or int64.  Integer matrices
+        stay integer (exact ids); anything else becomes float32, refusing ids the float32 route cannot represent."""
+        X = np.asarray(X)
+        if X.dtype in (np.float32, np.int32, np.int64):
+            return X
+        if np.issubdtype(X.dtype, np.integer) or X.dtype == np.bool_:
+            return X.astype(np.int64)
+        if X.size and np.abs(X).max() >= 2 ** 24 and np.all(X == np.round(X)):
+            raise ValueError("ids >= 2**24 cannot travel through the reference's float32 input matrix; pass an integer matrix")
+        return X.astype(np.float32)
+
     def _stack_inputs(self, x):
-        """dict / list of 1-D columns -> (N, n_cols) matrix in feature_index order (reference
-        meta_basemodel.py:221-222,257-264).  float32 exactly like the reference when any column is
-        non-integer; int32 otherwise (exact for ids >= 2**24, which the fp32 route cannot represent)."""
-        if isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] == len(self.feature_index):
-            return x if x.dtype in (np.float32, np.int32) else x.astype(np.float32)      # already stacked
+        """dict / list of 1-D columns (or an already stacked matrix / tensor) -> (N, n_cols) matrix in feature_index order
+        (reference meta_basemodel.py:221-222,257-264).  float32 exactly like the reference when any column is non-integer;
+        int32 otherwise (exact for ids >= 2**24, which the fp32 route cannot represent)."""
         if torch.is_tensor(x):
-            return x.detach().cpu().numpy()
+            x = x.detach().cpu().numpy()
+        if isinstance(x, np.ndarray) and x.ndim == 2:
+            if x.shape[1] != self._n_cols():
+                raise ValueError('expected an (N, %d) input matrix, got %s' % (self._n_cols(), x.shape))
+            return self._normalise_matrix(x)
         if isinstance(x, dict):
             x = [x[feature] for feature in self.feature_index]
         cols = [np.asarray(c) for c in x]
@@ -418,7 +457,6 @@ class BaseModel(nn.Module):
         self.train()
         eng = self.engine
         dev = self._tables.device
-        hp = self._opt_hparams
         sample_num = len(X)
         steps_per_epoch = (sample_num - 1) // batch_size + 1
         steps_to_valid = steps_per_epoch // valid_cnt_per_epoch + 1
@@ -435,8 +473,10 @@ class BaseModel(nn.Module):
         if verbose > 0:
             print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(
                 sample_num, len(val_y), steps_per_epoch))
-        gen = torch.Generator(device='cpu')
-        gen.manual_seed(torch.initial_seed() & (2 ** 63 - 1))
+        if getattr(self, '_shuffle_gen', None) is None:        # one stream per model: repeated fit() calls keep drawing from it
+            self._shuffle_gen = torch.Generator(device='cpu')
+            self._shuffle_gen.manual_seed(torch.initial_seed() & (2 ** 63 - 1))
+        gen = self._shuffle_gen
         for epoch in range(initial_epoch, epochs):
             callbacks.on_epoch_begin(epoch)
             epoch_logs = {}
@@ -452,6 +492,7 @@ class BaseModel(nn.Module):
                     xb, yb = Xd.index_select(0, idx).contiguous(), yd.index_select(0, idx).contiguous()
                 else:
                     xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
+                hp = self._hparams()
                 y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                            l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                            training=True, dropout_p=self.dropout_rate,
@@ -520,11 +561,14 @@ class BaseModel(nn.Module):
         """One optimiser step on one batch given as HOST data (dict / list of columns or an (B, n_cols) array)
         and labels; returns (bce_sum, reg_loss) as Python floats — the per-step body of `fit`
         (reference meta_basemodel.py:311-328, incl. its `.item()` synchronisation)."""
-        X = x if (isinstance(x, np.ndarray) and x.ndim == 2) or torch.is_tensor(x) else self._stack_inputs(x)
+        if torch.is_tensor(x) and x.dtype in (torch.float32, torch.int32, torch.int64):
+            X = x                                           # (pinned) host or device tensor in a kernel-ready dtype: no host pass
+        else:
+            X = self._stack_inputs(x)
         dev = self._tables.device
         Xd = torch.as_tensor(X).to(dev, non_blocking=True)
         yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)
-        hp = self._opt_hparams
+        hp = self._hparams()
         eng = self.engine
         self.train()
         _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],

@@ -51,6 +51,7 @@ struct BwdArgs {
     const uint32_t* bitmap;
     const int32_t* word_rank;
     float* row_grad;
+    float* gpart;              // per-CTA partial gradient buffers (layout: gpart_layout in bwd_common.cuh)
     int layer;
     float p_drop;
     unsigned long long seed;

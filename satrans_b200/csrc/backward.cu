@@ -7,7 +7,8 @@
 // Data gradients are thread-local GEMVs against weights in shared memory (as in the forward).  Weight
 // gradients are reductions over tokens: the two operands are staged as [token][36] shared tiles and every
 // thread owns a 4x4 block of the 32x32 product (64 blocks x 3 token groups = 192 threads), accumulated
-// into shared-memory accumulators that are flushed to HBM with one atomicAdd per element per CTA.
+// into shared-memory accumulators.  No floating-point atomics: every CTA stores its accumulators into its own
+// row of SatWork.gpart and k_dense_reduce adds the rows in CTA order, so the gradients are bit-reproducible.
 // Attention uses the FlashAttention identity  sum_j P_ij dP_ij = dR_i . R_i  so no (F x F) tensor is
 // stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
 #include "bwd_common.cuh"
@@ -67,22 +68,21 @@ __global__ void __launch_bounds__(NT) k_bwd_head(const BwdArgs a) {
             }
         }
     }
+    // this CTA's row of the head partial buffer: [F*32 weights | n_dense weights | bias]
+    const GPart gp = gpart_layout(m);
+    float* part = a.gpart + gp.head + (long long)blockIdx.x * gp.head_ld;
     for (int pass = 0; pass < 2; ++pass) {
         const int ff = (tid >> 3) + pass * (NT / 8), ch = (tid & 7) * 4;
-        if (ff < F) {
-            float* d = a.dgrad + m.off_headw + ff * D + ch;
-            atomicAdd(d + 0, accw[pass].x); atomicAdd(d + 1, accw[pass].y);
-            atomicAdd(d + 2, accw[pass].z); atomicAdd(d + 3, accw[pass].w);
-        }
+        if (ff < F) *reinterpret_cast<float4*>(part + ff * D + ch) = accw[pass];
     }
-    if (tid == 0) atomicAdd(a.dgrad + m.off_headb, accb);
-    if (tid >= 32 && tid < 32 + m.n_dense) atomicAdd(a.dgrad + m.off_headw + F * D + (tid - 32), accd);
+    if (tid == 0) part[F * D + m.n_dense] = accb;
+    if (tid >= 32 && tid < 32 + m.n_dense) part[F * D + (tid - 32)] = accd;
 }
 
 // =====================================================================================================
 // kernel B: MetaNet LayerNorm bwd + MetaNet bwd + QKV projection bwd; layer 0 scatters dE0 to table rows.
 // =====================================================================================================
-constexpr int BWDB_SMEM_FLOATS = 3072 /*WQ WK WV*/ + 3072 /*dWQ dWK dWV*/ + 192 /*LN params*/ + 128 /*dLN q,k*/ +
+constexpr int BWDB_SMEM_FLOATS = 3072 /*WQ WK WV*/ + 3072 /*dWQ dWK dWV*/ + 192 /*LN params*/ + (NT / 32) * 128 /*dLN q,k per warp*/ +
                                  2 * PSZ /*theta q,k*/ + 2 * PSZ /*dtheta q,k*/ + 2 * NT * KV_LD;
 
 // One MetaNet side (Q or K).  On entry dqp holds dLoss/dQ' (post-LN); on exit dLoss/d(x @ W) .
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     float* sW = smem;                    // WQ WK WV
     float* sdW = sW + 3072;
     float* sLN = sdW + 3072;             // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
-    float* sdLN = sLN + 192;             // dQLN_G dQLN_B dKLN_G dKLN_B
-    float* sThQ = sdLN + 128;
+    float* sdLN = sLN + 192;             // per warp: dQLN_G dQLN_B dKLN_G dKLN_B
+    float* sThQ = sdLN + (NT / 32) * 128;
     float* sThK = sThQ + PSZ;
     float* sdThQ = sThK + PSZ;
     float* sdThK = sdThQ + PSZ;
@@ -190,9 +190,10 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
-    const int n_tiles = a.counters[CNT_NTILES];
     const int s = tid / F, f = tid - s * F;
-    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    // every CTA stays inside ONE scenario (one set of generated-weight gradients per CTA, see scenario_partition)
+    int t0, t1, g_cta, c0_, c1_;
+    scenario_partition(a.counters + CNT_HIST, m.n_dom, NT / F, gridDim.x, blockIdx.x, -1, t0, t1, g_cta, c0_, c1_);
     const float* lay = m.dense + m.off_layers + (long long)l * LAYER_FLOATS;
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
 
@@ -200,9 +201,10 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, NT);
     for (int i = tid; i < 3072; i += NT) sdW[i] = 0.f;
     for (int i = tid; i < 2 * PSZ; i += NT) sdThQ[i] = 0.f;      // sdThQ and sdThK are contiguous
-    if (tid < 128) sdLN[tid] = 0.f;
+    for (int i = tid; i < (NT / 32) * 128; i += NT) sdLN[i] = 0.f;
     int cur_q = -1, cur_k = -1;
-    float* sdLNk = pos ? sdLN + 64 : sdLN;                     // without 'pos' K shares Q's MetaNet LayerNorm
+    float* sdLNq = sdLN + (tid >> 5) * 128;                    // this warp's slots
+    float* sdLNk = pos ? sdLNq + 64 : sdLNq;                   // without 'pos' K shares Q's MetaNet LayerNorm
     const float* klng = pos ? sLN + 128 : sLN + 64;
     float* sdThKuse = pos ? sdThK : sdThQ;                     // ... and Q's generated weights
 
@@ -217,16 +219,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
         const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
         const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
         __syncthreads();
-        if (kq != cur_q) {
-            if (cur_q >= 0) flush_add(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
-            copy_to_smem(sThQ, a.theta + (long long)kq * PSZ, PSZ, tid, NT);
-            cur_q = kq;
-        }
-        if (pos && kk != cur_k) {
-            if (cur_k >= 0) flush_add(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
-            copy_to_smem(sThK, a.theta + (long long)kk * PSZ, PSZ, tid, NT);
-            cur_k = kk;
-        }
+        if (kq != cur_q) { copy_to_smem(sThQ, a.theta + (long long)kq * PSZ, PSZ, tid, NT); cur_q = kq; }       // (once per CTA)
+        if (pos && kk != cur_k) { copy_to_smem(sThK, a.theta + (long long)kk * PSZ, PSZ, tid, NT); cur_k = kk; }
         __syncthreads();
         const float* thK = pos ? sThK : sThQ;
 
@@ -235,7 +229,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
         {   // ---- Q side ---------------------------------------------------------------------------------
             float dqp[D];
             if (valid) load_row(a.dqkv + 0 * a.act_stride + tokpos, dqp); else zero(dqp);
-            metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLN, sdW + OFF_WQ, sA,
+            metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLNq, sdW + OFF_WQ, sA,
                              sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride,
                              relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 0, tokpos / D), tokpos,
                              make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, true), dqp);
@@ -264,35 +258,97 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
             __syncthreads();
             if (valid) vm_dot<D, D, D>(sW + OFF_WV, dv, dxa);
         }
-        if (valid) {
-            if (l > 0) {
-                store_row(a.dx + tokpos, dxa);
-            } else {
-                // layer 0: dLoss/dE0 -> accumulated per unique touched table row (rank through the bitmap)
-                long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
-                const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
-                if (id < 0 || id >= hi - lo) id = 0;
-                const long long row = lo + id;
-                const int owner = (int)(row % m.n_shards);
-                const long long lrow = row / m.n_shards;
-                // volatile loads: the owner's bitmap / ranks may live in a peer GPU's memory
-                const uint32_t wbits = *reinterpret_cast<const volatile uint32_t*>(m.shard_bitmap[owner] + (lrow >> 5));
-                const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
-                                 __popc(wbits & ((1u << (lrow & 31)) - 1u));
-                float* dst = m.shard_row_grad[owner] + (long long)slot * D;
-                // 16-byte vector reductions, local or over NVLink peer memory (verified: tests/p2p_probe.py mode 3)
-#pragma unroll
-                for (int i = 0; i < D; i += 4)
-                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
-            }
-        }
+        // layer 0: this is dLoss/dE0 of the token; sat_rows_reduce sums it per touched table row in sorted (row, token) order
+        if (valid) store_row(a.dx + tokpos, dxa);
     }
     __syncthreads();
-    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
-    flush_add(dlay, sdW, 3072, tid);
-    flush_add(dlay + OFF_QLN_G, sdLN, 128, tid);
-    if (cur_q >= 0) flush_add(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
-    if (pos && cur_k >= 0) flush_add(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+    const GPart gp = gpart_layout(m);
+    float* part = a.gpart + gp.meta + ((long long)l * SAT_GRID_MAX + blockIdx.x) * GP_META;
+    store_partial(part, sdW, 3072, tid);
+    store_partial_warps(part + 3072, sdLN, 128, tid);
+    float* tpart = a.gpart + gp.theta + ((long long)l * SAT_GRID_MAX + blockIdx.x) * gp.nside * PSZ;
+    store_partial(tpart, sdThQ, gp.nside * PSZ, tid);          // sdThQ | sdThK are contiguous
+}
+
+// =====================================================================================================
+// Fixed-order reduction of the per-CTA partial buffers into the flat dense gradient and d theta.
+// One thread per output element x RED_SPLIT CTA groups; the groups' sums are combined in group order.
+// =====================================================================================================
+constexpr int RED_SPLIT = 4;
+struct RedArgs {
+    SatModel m;
+    const float* gpart;
+    const int32_t* counters;
+    float* dgrad;
+    float* dtheta;
+    int g_attn, g_meta, g_head;   // CTAs that wrote partials
+    int spt_meta;                 // samples per tile of the tile set the MetaNet backward walked
+};
+
+__device__ __forceinline__ float sum_rows(const float* __restrict__ base, long long stride, int c0, int c1, int grp) {
+    // rows [c0, c1) split into RED_SPLIT contiguous groups; this thread adds group `grp` in row order
+    const int n = c1 - c0, per = (n + RED_SPLIT - 1) / RED_SPLIT;
+    const int a0 = c0 + grp * per, a1 = min(c1, a0 + per);
+    float acc = 0.f;
+    int c = a0;
+    for (; c + 4 <= a1; c += 4) {
+        const float v0 = base[(long long)c * stride], v1 = base[(long long)(c + 1) * stride];
+        const float v2 = base[(long long)(c + 2) * stride], v3 = base[(long long)(c + 3) * stride];
+        acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; c < a1; ++c) acc += base[(long long)c * stride];
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) k_dense_reduce(const RedArgs a) {
+    __shared__ float s_part[RED_SPLIT][64];
+    const SatModel& m = a.m;
+    const GPart gp = gpart_layout(m);
+    const int L = m.L;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    const int n_keys = pos ? m.n_dom * L * 2 : m.n_dom;
+    const long long n_lay = (long long)L * LAYER_FLOATS, n_head = m.F * D + m.n_dense + 1, n_theta = (long long)n_keys * PSZ;
+    const long long total = n_lay + n_head + n_theta;
+    const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    for (long long e0 = (long long)blockIdx.x * 64; e0 < total; e0 += (long long)gridDim.x * 64) {
+        const long long e = e0 + el;
+        float v = 0.f;
+        float* out = nullptr;
+        if (e < n_lay) {
+            const int l = (int)(e / LAYER_FLOATS), i = (int)(e - (long long)l * LAYER_FLOATS);
+            out = a.dgrad + m.off_layers + e;
+            if (i < OFF_WO)             // dW_Q, dW_K, dW_V
+                v = sum_rows(a.gpart + gp.meta + (long long)l * SAT_GRID_MAX * GP_META + i, GP_META, 0, a.g_meta, grp);
+            else if (i < OFF_QLN_G)     // dW_out, d layer_norm
+                v = sum_rows(a.gpart + gp.attn + (long long)l * SAT_GRID_MAX * GP_ATTN + (i - OFF_WO), GP_ATTN, 0, a.g_attn, grp);
+            else                        // d MetaNet LayerNorms
+                v = sum_rows(a.gpart + gp.meta + (long long)l * SAT_GRID_MAX * GP_META + 3072 + (i - OFF_QLN_G), GP_META, 0, a.g_meta, grp);
+        } else if (e < n_lay + n_head) {
+            const int i = (int)(e - n_lay);
+            out = a.dgrad + m.off_headw + i;            // off_headb == off_headw + F*32 + n_dense
+            v = sum_rows(a.gpart + gp.head + i, gp.head_ld, 0, a.g_head, grp);
+        } else if (e < total) {
+            const long long j = e - n_lay - n_head;
+            const int key = (int)(j / PSZ), i = (int)(j - (long long)key * PSZ);
+            out = a.dtheta + j;
+            int g, t0, t1, g_of, c0, c1;
+            if (pos) {                  // key = (g * L + l) * 2 + side: one layer, one side
+                const int side = key & 1, l = (key >> 1) % L;
+                g = (key >> 1) / L;
+                scenario_partition(a.counters + CNT_HIST, m.n_dom, a.spt_meta, a.g_meta, -1, g, t0, t1, g_of, c0, c1);
+                v = sum_rows(a.gpart + gp.theta + ((long long)l * SAT_GRID_MAX * 2 + side) * PSZ + i, 2 * PSZ, c0, c1, grp);
+            } else {                    // key = g: the Q and K sides of all L layers share theta; layers added last to first
+                g = key;
+                scenario_partition(a.counters + CNT_HIST, m.n_dom, a.spt_meta, a.g_meta, -1, g, t0, t1, g_of, c0, c1);
+                for (int l = L - 1; l >= 0; --l)
+                    v += sum_rows(a.gpart + gp.theta + (long long)l * SAT_GRID_MAX * PSZ + i, PSZ, c0, c1, grp);
+            }
+        }
+        s_part[grp][el] = v;
+        __syncthreads();
+        if (grp == 0 && out) *out = (s_part[0][el] + s_part[1][el]) + (s_part[2][el] + s_part[3][el]);
+        __syncthreads();
+    }
 }
 
 }  // namespace sat
@@ -304,19 +360,19 @@ int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys
 // passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
 static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
                          uint64_t seed, int passes, void* stream) {
-    if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->row_grad || !w->tiles2)
+    if (!m || !x || !w || !w->acts || !w->dx || !w->dqkv || !w->dgrad || !w->dtheta || !w->gpart || !w->tiles2)
         return sat_host::fail(SAT_EINVAL, "sat_backward: null argument / workspace not sized for training");
     if (w->B == 0) return SAT_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int n_keys = (m->flags & SAT_FLAG_POS) ? m->n_dom * m->L * 2 : m->n_dom;
-    if (cudaMemsetAsync(w->dgrad, 0, (size_t)m->n_dense_params * sizeof(float), s) != cudaSuccess ||
-        cudaMemsetAsync(w->dtheta, 0, (size_t)n_keys * PSZ * sizeof(float), s) != cudaSuccess)
+    // (k_dense_reduce writes every layer / head / d theta element; the encoder backward accumulates into the rest)
+    if (cudaMemsetAsync(w->dgrad, 0, (size_t)m->n_dense_params * sizeof(float), s) != cudaSuccess)
         return sat_host::fail(SAT_ECUDA, "sat_backward: memset failed");
     BwdArgs a;
     a.m = *m; a.x = x; a.id_kind = id_kind; a.ld = ld; a.perm = w->perm; a.tiles = w->tiles; a.counters = w->counters;
     a.theta = w->theta; a.dtheta = w->dtheta; a.acts = w->acts; a.act_stride = (long long)w->cap_B * m->F * D;
     a.dz = w->dz; a.dx = w->dx; a.dqkv = w->dqkv; a.dgrad = w->dgrad; a.bitmap = w->bitmap; a.word_rank = w->word_rank;
-    a.row_grad = w->row_grad; a.layer = 0; a.p_drop = dropout_p; a.seed = seed;
+    a.row_grad = w->row_grad; a.layer = 0; a.p_drop = dropout_p; a.seed = seed; a.gpart = w->gpart;
     const int spt = NT / m->F;
     const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
     const int grid2 = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
@@ -353,8 +409,19 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
         } else {
             BwdArgs a2 = a;
             a2.tiles = w->tiles2;
-            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2, passes, s);
+            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, grid_a, passes, s);
         }
+        if (rc) return rc;
+    }
+    RedArgs ra;
+    ra.m = *m; ra.gpart = w->gpart; ra.counters = w->counters; ra.dgrad = w->dgrad; ra.dtheta = w->dtheta;
+    ra.g_attn = grid_a; ra.g_meta = passes == 0 ? grid1 : grid_a; ra.g_head = grid2; ra.spt_meta = passes == 0 ? spt : spt2;
+    {
+        const long long total = (long long)m->L * LAYER_FLOATS + m->F * D + m->n_dense + 1 + (long long)n_keys * PSZ;
+        long long blocks = (total + 63) / 64;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_dense_reduce<<<(int)blocks, 256, 0, s>>>(ra);
+        rc = sat_host::check_launch("k_dense_reduce");
         if (rc) return rc;
     }
     return sat_encoder_bwd(m, w, stream);

@@ -28,7 +28,7 @@ constexpr int BA_NT = NT2;             // threads per CTA
 
 static size_t bwda_smem_bytes(int F) {
     const int rows = ((BA_NT / F) * F + 3) & ~3;
-    return (size_t)(1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + 64 /*dgamma,dbeta*/ + 2048 /*dWO partial blocks*/ +
+    return (size_t)(1024 /*WO*/ + 1024 /*dWO*/ + 192 /*LN params*/ + (BA_NT / 32) * 64 /*dgamma,dbeta per warp*/ + 2048 /*dWO partial blocks*/ +
                     4 * rows * KV_LD /*tiles*/ + BA_NT * ST_LD /*mx,sum,Dh per head + dropout key*/) * sizeof(float);
 }
 
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
     float* sWO = smem;
     float* sdWO = sWO + 1024;
     float* sLN = sdWO + 1024;           // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
-    float* sdLN = sLN + 192;            // dgamma[32] dbeta[32] of the layer's output LayerNorm
-    float* sPart = sdLN + 64;           // [2][64][16] partial dW_out blocks of the two token halves
+    float* sdLN = sLN + 192;            // per warp: dgamma[32] dbeta[32] of the layer's output LayerNorm
+    float* sPart = sdLN + (BA_NT / 32) * 64;   // [2][64][16] partial dW_out blocks of the two token halves
     float* sT0 = sPart + 2048;          // [rows][36]  r  -> Q'
     float* sT1 = sT0 + tile_rows * KV_LD;      //      dO -> dR
     float* sT2 = sT1 + tile_rows * KV_LD;      //      K'
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
     copy_to_smem(sWO, lay + OFF_WO, 1024, tid, BA_NT);
     copy_to_smem(sLN, lay + OFF_LN_G, 192, tid, BA_NT);
     for (int i = tid; i < 1024; i += BA_NT) sdWO[i] = 0.f;
-    if (tid < 64) sdLN[tid] = 0.f;
+    for (int i = tid; i < (BA_NT / 32) * 64; i += BA_NT) sdLN[i] = 0.f;
     const float* qln = sLN + 64;
     const float* kln = pos ? sLN + 128 : sLN + 64;
 
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
             } else {
                 zero(dy);
             }
-            layernorm_bwd32(dy, o, rstd, sLN, sdLN, sdLN + 32, lane, valid);     // dy := dLoss/dy
+            layernorm_bwd32(dy, o, rstd, sLN, sdLN + (tid >> 5) * 64, sdLN + (tid >> 5) * 64 + 32, lane, valid);   // this warp's slots; dy := dLoss/dy
             if (valid) {
                 if (use_res) store_row(a.dx + tokpos, dy);                  // residual branch of dX
                 else { float zr[D]; zero(zr); store_row(a.dx + tokpos, zr); }
@@ -334,10 +334,11 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
         }
     }
     __syncthreads();
-    // flush: dWO and the output-LayerNorm parameter gradients
-    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
-    flush_add<BA_NT>(dlay + OFF_WO, sdWO, 1024, tid);
-    flush_add<BA_NT>(dlay + OFF_LN_G, sdLN, 64, tid);
+    // this CTA's row of the partial buffer: dWO and the output-LayerNorm parameter gradients (k_dense_reduce adds the rows)
+    const GPart gp = gpart_layout(m);
+    float* part = a.gpart + gp.attn + ((long long)l * SAT_GRID_MAX + blockIdx.x) * GP_ATTN;
+    store_partial<BA_NT>(part, sdWO, 1024, tid);
+    store_partial_warps<BA_NT>(part + 1024, sdLN, 64, tid);
 }
 
 }  // namespace sat

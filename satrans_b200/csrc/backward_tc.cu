@@ -18,10 +18,10 @@ constexpr int TCB_SB = 4096;                                             // floa
 // Shared memory (floats): B staging | three [tile_rows][36] weight-gradient operand tiles | LN params | dW_Q/K/V | dLN | d theta
 // (one key block, two with per-position keys).  tile_rows = (128 / F) * F rounded up to 4: the threads past a tile's last
 // token store zero rows, so the weight-gradient loops run over whole groups of 4 tokens.
-// F = 19: 96.4 KB (EN) / 112.9 KB (ENP) -> 2 CTAs per SM either way.
+// F = 19: 97.9 KB (EN) / 114.4 KB (ENP) -> 2 CTAs per SM either way.
 static size_t tcb_smem_bytes(int F, bool pos) {
     const int rows = ((TC_NT / F) * F + 3) & ~3;
-    return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);
+    return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + (TC_NT / 32) * 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);
 }
 
 // copy n floats of packed operand into sB (all threads); the round macro issues the generic->async proxy fence
@@ -44,15 +44,16 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     float* sT2 = sT1 + tile_rows * KV_LD;
     float* sLN = sT2 + tile_rows * KV_LD;     // LN_G LN_B QLN_G QLN_B KLN_G KLN_B
     float* sdW = sLN + 192;                   // dWQ dWK dWV
-    float* sdLN = sdW + 3072;                 // dQLN_G dQLN_B dKLN_G dKLN_B
-    float* sdThQ = sdLN + 128;
+    float* sdLN = sdW + 3072;                 // per warp: dQLN_G dQLN_B dKLN_G dKLN_B
+    float* sdThQ = sdLN + (TC_NT / 32) * 128;
     float* sdThK = sdThQ + PSZ;               // only with per-position keys
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThQ + (pos ? 2 : 1) * PSZ);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
 
-    const int n_tiles = a.counters[CNT_NTILES2];
     const int s = tid / F, f = tid - s * F;
-    const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    // every CTA stays inside ONE scenario: one set of generated-weight gradients per CTA, reduced over CTAs in a fixed order
+    int t0, t1, g_cta, c0_, c1_;
+    scenario_partition(a.counters + CNT_HIST, m.n_dom, TC_NT / F, gridDim.x, blockIdx.x, -1, t0, t1, g_cta, c0_, c1_);
     const float* act_l = a.acts + (long long)l * ACT_PER_LAYER * a.act_stride;
     const int nblk = L + n_keys;
     const float* pk_lf = wpack + (long long)l * PACK_FLOATS;                    // forward layer block
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     copy_to_smem(sLN, m.dense + m.off_layers + (long long)l * LAYER_FLOATS + OFF_LN_G, 192, tid, TC_NT);
     for (int i = tid; i < 3072; i += TC_NT) sdW[i] = 0.f;
     for (int i = tid; i < (pos ? 2 : 1) * PSZ; i += TC_NT) sdThQ[i] = 0.f;
-    if (tid < 128) sdLN[tid] = 0.f;
+    for (int i = tid; i < (TC_NT / 32) * 128; i += TC_NT) sdLN[i] = 0.f;
     if (warp == 0) tmem_alloc(s_tmem, TC_COLS);
     if (tid == 0) mbar_init(mbar, 1);
     tc_fence_before();
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     const uint32_t tbase = *s_tmem;
     const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
-    int cur_q = -1, cur_k = -1;
+    float* const sdLNw = sdLN + warp * 128;   // this warp's LayerNorm-gradient slots
     float* const sTh = hsel ? sT1 : sT0;      // this 64-thread half's tile in the paired weight-gradient phases
 
 #define SAT_TC_ROUND(ISSUE)                                  \
@@ -101,14 +102,6 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
         const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
         __syncthreads();                       // previous tile's weight-gradient phases are done with the tiles / accumulators
-        if (kq != cur_q) {
-            if (cur_q >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
-            cur_q = kq;
-        }
-        if (pos && kk != cur_k) {
-            if (cur_k >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
-            cur_k = kk;
-        }
 
         // Rolled over the Q / K sides (half the code of an unrolled body: the kernel was instruction-fetch bound).  The
         // side's d(x W) goes back to its dqkv slot in place and is re-read for the projection phase below.
@@ -122,7 +115,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             const float* pk_kb = wpack + (long long)(nblk + L + key) * PACK_FLOATS;      // backward key block
             float* sdTh = (side && pos) ? sdThK : sdThQ;
             const float* lng = (side && pos) ? sLN + 128 : sLN + 64;
-            float* sdLNs = (side && pos) ? sdLN + 64 : sdLN;
+            float* sdLNs = (side && pos) ? sdLNw + 64 : sdLNw;
 
             float du[D], zh[D];
             if (valid) {
@@ -257,32 +250,20 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
         if (valid) {
 #pragma unroll
             for (int i = 0; i < D; ++i) dxa[i] += res[i];
-            if (l > 0) {
-                store_row(a.dx + tokpos, dxa);
-            } else {
-                long long id = load_id(a.x, a.id_kind, (long long)b * a.ld + __ldg(m.sparse_cols + f));
-                const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
-                if (id < 0 || id >= hi - lo) id = 0;
-                const long long row = lo + id;
-                const int owner = (int)(row % m.n_shards);
-                const long long lrow = row / m.n_shards;
-                const uint32_t wbits = *reinterpret_cast<const volatile uint32_t*>(m.shard_bitmap[owner] + (lrow >> 5));
-                const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
-                                 __popc(wbits & ((1u << (lrow & 31)) - 1u));
-                float* dst = m.shard_row_grad[owner] + (long long)slot * D;
-#pragma unroll
-                for (int i = 0; i < D; i += 4)
-                    atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(dxa[i], dxa[i + 1], dxa[i + 2], dxa[i + 3]));
-            }
+            // layer 0: this is dLoss/dE0 of the token; sat_rows_reduce sums it per touched table row in sorted (row, token) order
+            store_row(a.dx + tokpos, dxa);
         }
     }
 #undef SAT_TC_ROUND
     __syncthreads();
-    float* dlay = a.dgrad + m.off_layers + (long long)l * LAYER_FLOATS;
-    flush_add<TC_NT>(dlay, sdW, 3072, tid);
-    flush_add<TC_NT>(dlay + OFF_QLN_G, sdLN, 128, tid);
-    if (cur_q >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_q * PSZ, sdThQ, PSZ, tid);
-    if (pos && cur_k >= 0) flush_add<TC_NT>(a.dtheta + (long long)cur_k * PSZ, sdThK, PSZ, tid);
+    {   // this CTA's rows of the partial buffers (k_dense_reduce adds the rows in CTA order)
+        const GPart gp = gpart_layout(m);
+        float* part = a.gpart + gp.meta + ((long long)l * SAT_GRID_MAX + blockIdx.x) * GP_META;
+        store_partial<TC_NT>(part, sdW, 3072, tid);
+        store_partial_warps<TC_NT>(part + 3072, sdLN, 128, tid);
+        float* tpart = a.gpart + gp.theta + ((long long)l * SAT_GRID_MAX + blockIdx.x) * gp.nside * PSZ;
+        store_partial<TC_NT>(tpart, sdThQ, gp.nside * PSZ, tid);          // sdThQ | sdThK are contiguous
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, TC_COLS);

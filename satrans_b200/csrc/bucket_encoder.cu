@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encoder_fwd(SatModel m, int n_k
 }
 
 // Encoder backward, part 1: dW[o][i] = sum_k dtheta[k][o] u[k][i], db[o] = sum_k dtheta[k][o] (each o owned
-// by one thread -> plain stores), and du[k][i] += sum_o dtheta[k][o] W[o][i] (block reduce + atomics).
+// by one thread -> plain stores), and du[k][i] = sum_o dtheta[k][o] W[o][i]: every block reduces its 256 outputs in a fixed
+// order and stores the partial into du_part[block][k][64]; k_encoder_bwd_emb adds the blocks in order (no atomics).
 __global__ void __launch_bounds__(ENC_THREADS)
 k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* __restrict__ dgrad,
               float* __restrict__ du) {
@@ -192,7 +193,7 @@ k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* _
                 float t = 0.f;
 #pragma unroll
                 for (int w2 = 0; w2 < ENC_THREADS / 32; ++w2) t += s_red[w2][threadIdx.x];
-                atomicAdd(du + (long long)(k0 + k) * 2 * D + threadIdx.x, t);
+                du[((long long)blockIdx.x * n_keys + (k0 + k)) * 2 * D + threadIdx.x] = t;
             }
             __syncthreads();
         }
@@ -204,7 +205,8 @@ k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* _
 }
 
 // Encoder backward, part 2: through the ReLUs into the domain / layer-id / qkv-id embedding gradients.
-__global__ void k_encoder_bwd_emb(SatModel m, int n_keys, const float* __restrict__ du, float* __restrict__ dgrad) {
+__global__ void k_encoder_bwd_emb(SatModel m, int n_keys, const float* __restrict__ du_part, int n_part,
+                                  float* __restrict__ dgrad) {
     const bool pos = m.flags & SAT_FLAG_POS;
     const int i = threadIdx.x;          // 0 .. enc_in-1
     if (i >= m.enc_in) return;
@@ -213,7 +215,9 @@ __global__ void k_encoder_bwd_emb(SatModel m, int n_keys, const float* __restric
         key_decode(key, m.L, pos, g, l, q);
         float pre;
         enc_input(m.dense, m, key, i, &pre);
-        const float d = pre > 0.f ? du[(long long)key * 2 * D + i] : 0.f;
+        float du = 0.f;
+        for (int pb = 0; pb < n_part; ++pb) du += du_part[((long long)pb * n_keys + key) * 2 * D + i];
+        const float d = pre > 0.f ? du : 0.f;
         if (i < D) {
             dgrad[m.off_dom + (long long)g * D + i] += d;          // thread i owns column i: no race
         } else {
@@ -263,9 +267,7 @@ extern "C" int sat_encoder_bwd(const SatModel* m, SatWork* w, void* stream) {
     if (!m || !w || !w->dtheta || !w->dgrad || !w->enc_du) return sat_host::fail(SAT_EINVAL, "sat_encoder_bwd: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = n_keys_of(m);
-    if (cudaMemsetAsync(w->enc_du, 0, (size_t)nk * 2 * D * sizeof(float), s) != cudaSuccess)
-        return sat_host::fail(SAT_ECUDA, "sat_encoder_bwd: memset failed");
     k_encoder_bwd<<<PSZ / ENC_THREADS, ENC_THREADS, 0, s>>>(*m, nk, w->dtheta, w->dgrad, w->enc_du);
-    k_encoder_bwd_emb<<<1, 64, 0, s>>>(*m, nk, w->enc_du, w->dgrad);
+    k_encoder_bwd_emb<<<1, 64, 0, s>>>(*m, nk, w->enc_du, PSZ / ENC_THREADS, w->dgrad);
     return sat_host::check_launch("k_encoder_bwd");
 }

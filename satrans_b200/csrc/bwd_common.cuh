@@ -20,7 +20,9 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[D], int lane) 
 }
 
 // LayerNorm backward for one token.  xhat = normalised input, g = gamma (smem).  dy is overwritten by dx.
-// dgam/dbet (smem, 32 floats each) receive the token-summed parameter gradients.
+// dgam/dbet (smem, 32 floats each, PRIVATE TO THE CALLING WARP) receive the token-summed parameter gradients: lane L owns
+// element L, so the update is a plain read-modify-write and the summation order (tiles in order, then warps in order at the
+// flush) does not depend on timing.
 __device__ __forceinline__ void layernorm_bwd32(float (&dy)[D], const float (&xhat)[D], float rstd,
                                                 const float* __restrict__ g, float* __restrict__ dgam,
                                                 float* __restrict__ dbet, int lane, bool valid) {
@@ -29,8 +31,8 @@ __device__ __forceinline__ void layernorm_bwd32(float (&dy)[D], const float (&xh
     for (int i = 0; i < D; ++i) { t1[i] = valid ? dy[i] * xhat[i] : 0.f; t2[i] = valid ? dy[i] : 0.f; }
     const float sg = warp_reduce_scatter32(t1, lane);
     const float sb = warp_reduce_scatter32(t2, lane);
-    atomicAdd(dgam + lane, sg);
-    atomicAdd(dbet + lane, sb);
+    dgam[lane] += sg;
+    dbet[lane] += sb;
     float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
 #pragma unroll
     for (int i = 0; i < D; i += 2) {
@@ -75,10 +77,20 @@ __device__ __forceinline__ void wgrad32(const float* __restrict__ A, const float
         c[2][0] = fmaf(a.z, g.x, c[2][0]); c[2][1] = fmaf(a.z, g.y, c[2][1]); c[2][2] = fmaf(a.z, g.z, c[2][2]); c[2][3] = fmaf(a.z, g.w, c[2][3]);
         c[3][0] = fmaf(a.w, g.x, c[3][0]); c[3][1] = fmaf(a.w, g.y, c[3][1]); c[3][2] = fmaf(a.w, g.z, c[3][2]); c[3][3] = fmaf(a.w, g.w, c[3][3]);
     }
+    // the NTHREADS / 64 token groups add their blocks one after the other (fixed order, no atomics); every thread of the
+    // CTA calls wgrad32, so the barriers are uniform
+    for (int gsel = 0; gsel < NTHREADS / 64; ++gsel) {
+        if (grp == gsel) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) atomicAdd(acc + (ia + r) * ldacc + jg + cc, c[r][cc]);
+            for (int r = 0; r < 4; ++r) {
+                float4* p = reinterpret_cast<float4*>(acc + (ia + r) * ldacc + jg);
+                float4 v = *p;
+                v.x += c[r][0]; v.y += c[r][1]; v.z += c[r][2]; v.w += c[r][3];
+                *p = v;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ void fma_block(float (&c)[4][4], const float4& a, const float4& g) {
@@ -148,12 +160,71 @@ __device__ __forceinline__ void wgrad_half(const float* __restrict__ A, const fl
     wgrad_store(acc, ldacc, tid, c);
 }
 
+// This CTA's partial sums -> its row of a per-CTA partial buffer (plain stores; k_dense_reduce adds the rows in CTA order).
 template <int NTHREADS = NT>
-__device__ __forceinline__ void flush_add(float* __restrict__ dst, float* __restrict__ sacc, int n, int tid) {
+__device__ __forceinline__ void store_partial(float* __restrict__ dst, const float* __restrict__ sacc, int n, int tid) {
+    for (int i = tid * 4; i < n; i += NTHREADS * 4)
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(sacc + i);
+}
+// the same for the per-warp LayerNorm slots [NW][n]: warps added in order
+template <int NTHREADS = NT>
+__device__ __forceinline__ void store_partial_warps(float* __restrict__ dst, const float* __restrict__ sacc, int n, int tid) {
     for (int i = tid; i < n; i += NTHREADS) {
-        const float v = sacc[i];
-        if (v != 0.f) atomicAdd(dst + i, v);
-        sacc[i] = 0.f;
+        float v = sacc[i];
+#pragma unroll
+        for (int w = 1; w < NTHREADS / 32; ++w) v += sacc[w * n + i];
+        dst[i] = v;
+    }
+}
+
+// ---- per-CTA partial gradient buffers (SatWork.gpart) ---------------------------------------------------------------------
+constexpr int GP_ATTN = 1088;      // dW_out [1024] | d layer_norm gamma, beta [64]
+constexpr int GP_META = 3200;      // dW_Q, dW_K, dW_V [3072] | d MetaNet-LN (Q gamma, beta, K gamma, beta) [128]
+struct GPart {
+    long long attn, meta, theta, head, total;   // float offsets
+    int nside, head_ld;
+};
+__host__ __device__ __forceinline__ GPart gpart_layout(const SatModel& m) {
+    GPart g;
+    g.nside = (m.flags & SAT_FLAG_POS) ? 2 : 1;
+    g.head_ld = (m.F * D + m.n_dense + 1 + 3) & ~3;
+    g.attn = 0;
+    g.meta = g.attn + (long long)m.L * SAT_GRID_MAX * GP_ATTN;
+    g.theta = g.meta + (long long)m.L * SAT_GRID_MAX * GP_META;
+    g.head = g.theta + (long long)m.L * SAT_GRID_MAX * g.nside * PSZ;
+    g.total = g.head + (long long)SAT_GRID_MAX * g.head_ld;
+    return g;
+}
+
+// ---- CTA -> tile range with every CTA inside ONE scenario ------------------------------------------------------------------
+// The MetaNet backward accumulates d theta of one scenario per CTA, and the reduction over CTAs must not depend on timing, so
+// the CTAs are dealt to the scenarios in proportion to their tile counts (every non-empty scenario gets at least one) and a
+// scenario's tiles are split evenly over its CTAs.  hist = samples per scenario (counters[CNT_HIST..]), spt = samples per
+// tile.  c_sel >= 0 asks for the range of that CTA; g_sel >= 0 asks for the CTA range [c0, c1) of that scenario.
+__device__ __forceinline__ void scenario_partition(const int32_t* __restrict__ hist, int n_dom, int spt, int G, int c_sel,
+                                                   int g_sel, int& t0, int& t1, int& g_of, int& c0, int& c1) {
+    long long T = 0;
+    int K = 0;
+    for (int g = 0; g < n_dom; ++g) {
+        const int nt = (hist[g] + spt - 1) / spt;
+        T += nt; K += nt > 0;
+    }
+    const int extra = G - K;
+    int cbase = 0, tbase = 0;
+    t0 = t1 = 0; g_of = -1; c0 = c1 = 0;
+    for (int g = 0; g < n_dom; ++g) {
+        const int nt = (hist[g] + spt - 1) / spt;
+        if (nt == 0) continue;
+        int c = 1 + (int)((long long)extra * nt / T);
+        if (c > nt) c = nt;
+        if (c_sel >= cbase && c_sel < cbase + c) {
+            const int j = c_sel - cbase;
+            t0 = tbase + (int)((long long)nt * j / c);
+            t1 = tbase + (int)((long long)nt * (j + 1) / c);
+            g_of = g;
+        }
+        if (g == g_sel) { c0 = cbase; c1 = cbase + c; }
+        cbase += c; tbase += nt;
     }
 }
 

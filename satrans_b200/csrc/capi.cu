@@ -3,7 +3,10 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "bwd_common.cuh"
+
+long long sat_touched_cap(const SatModel* m, long long cap_tok);      // rows.cu
+long long sat_idx_stride(const SatModel* m, long long cap_tok);
 
 namespace sat_host {
 
@@ -27,6 +30,11 @@ int check_launch(const char* what) {
 
 extern "C" int sat_abi_version(void) { return SAT_ABI_VERSION; }
 extern "C" const char* sat_last_error(void) { return sat_host::g_err; }
+extern "C" int sat_struct_sizes(int64_t* sz) {
+    if (!sz) return sat_host::fail(SAT_EINVAL, "sat_struct_sizes: null argument");
+    sz[0] = sizeof(SatModel); sz[1] = sizeof(SatWork); sz[2] = sizeof(SatAdam);
+    return SAT_OK;
+}
 
 extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t training, int64_t* sz, int32_t* max_tiles_host) {
     if (!m || !sz || cap_B <= 0 || m->F <= 0 || m->F > SAT_MAXF || m->n_shards < 1 || m->n_shards > SAT_MAX_SHARDS)
@@ -38,8 +46,10 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     const int64_t n_keys = (m->flags & SAT_FLAG_POS) ? (int64_t)m->n_dom * m->L * 2 : m->n_dom;
     const int64_t tok = (int64_t)cap_B * m->F;
     const int64_t words = (m->local_rows + 31) / 32;
-    int64_t touched_cap = tok * (m->n_shards > 0 ? m->n_shards : 1);      // rows of this shard any process may touch
-    if (touched_cap > m->local_rows) touched_cap = m->local_rows;
+    const int64_t touched_cap = sat_touched_cap(m, tok);                  // rows of this shard any process may touch
+    const int64_t n_chunks = (tok + SAT_ROWS_CHUNK - 1) / SAT_ROWS_CHUNK;
+    const int64_t sort_blocks = (tok + SAT_SORT_TILE - 1) / SAT_SORT_TILE;
+    const bool sharded = m->n_shards > 1;
     int i = 0;
     sz[i++] = cap_B * 4;                                   // perm
     sz[i++] = cap_B * 4;                                   // dom
@@ -47,7 +57,7 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = 64 * 4;                                      // counters
     sz[i++] = n_keys * SAT_P * 4;                          // theta
     sz[i++] = training ? n_keys * SAT_P * 4 : 0;           // dtheta
-    sz[i++] = training ? n_keys * 64 * 4 : 0;              // enc_du
+    sz[i++] = training ? 16 * n_keys * 64 * 4 : 0;         // enc_du: one partial per block of k_encoder_bwd (4096 / 256)
     sz[i++] = training ? ((int64_t)m->L * 5 + 1) * tok * SAT_D * 4 + (int64_t)m->L * 2 * tok * 2 * 4 : 0;   // acts + ReLU masks
     sz[i++] = cap_B * 4;                                   // dz
     sz[i++] = training ? tok * SAT_D * 4 : 0;              // dx
@@ -63,13 +73,20 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = 8 * 4;                                       // scalars
     sz[i++] = 2 * ((int64_t)m->L + n_keys) * 8192 * 4;     // wpack (tensor-core B operands: forward + backward blocks)
     sz[i++] = max_tiles2 * 16;                             // tiles2
+    sz[i++] = training ? sat::gpart_layout(*m).total * 4 : 0;          // gpart
+    sz[i++] = training ? 2 * tok * 4 : 0;                  // sort_keys
+    sz[i++] = training ? 2 * tok * 4 : 0;                  // sort_vals
+    sz[i++] = training ? (int64_t)(1 << SAT_SORT_RADIX_BITS) * sort_blocks * 4 : 0;   // sort_hist
+    sz[i++] = training ? n_chunks * 16 : 0;                // chunk_info
+    sz[i++] = training ? n_chunks * 2 * SAT_D * 4 : 0;     // pieces
+    sz[i++] = training && sharded ? (int64_t)m->n_shards * tok * SAT_D * 4 : 0;               // recv
+    sz[i++] = training && sharded ? (int64_t)m->n_shards * sat_idx_stride(m, tok) * 4 : 0;    // recv_idx (the caller fills it with -1)
+    sz[i++] = training ? 32 * 4 : 0;                       // peer_flags
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
     return SAT_OK;
 }
 
 // ---- sat_forward: argument marshalling + dispatch on the head count ---------------------------------
-#include "args.cuh"
-
 extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
                            float* y_pred, int32_t training, float dropout_p, uint64_t seed, void* stream) {
     using namespace sat;
@@ -97,19 +114,6 @@ extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, in
         case 8: return sat_launch_forward_h8(a, grid, training, s);
         default: return sat_host::fail(SAT_EINVAL, "sat_forward: heads=%d not in {1,2,4,8}", m->H);
     }
-}
-
-// ---- debugging aid: touch one word of (possibly peer-mapped) memory in a given way -----------------------
-__global__ void k_debug_poke(void* p, int mode, float* out) {
-    if (mode == 0) *reinterpret_cast<volatile uint32_t*>(p) = 0x12345678u;
-    else if (mode == 1) atomicOr(reinterpret_cast<uint32_t*>(p), 0xF0u);
-    else if (mode == 2) atomicAdd(reinterpret_cast<float*>(p), 1.0f);
-    else if (mode == 3) atomicAdd(reinterpret_cast<float4*>(p), make_float4(1.f, 2.f, 3.f, 4.f));
-    else if (mode == 4) *out = *reinterpret_cast<volatile float*>(p);
-}
-extern "C" int sat_debug_poke(void* p, int32_t mode, float* out, void* stream) {
-    k_debug_poke<<<1, 1, 0, (cudaStream_t)stream>>>(p, mode, out);
-    return sat_host::check_launch("k_debug_poke");
 }
 
 // ---- CUDA IPC: map a peer process' allocation into THIS device's address space (NVLink P2P) ---------------

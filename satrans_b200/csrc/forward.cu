@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
     float* sK = sThK + PSZ;              // [NT][36]
     float* sV = sK + NT * KV_LD;         // [NT][36]
     float* sRed = sV + NT * KV_LD;       // [NT]
-    __shared__ double s_loss;
+    __shared__ double s_lossv[NT];      // per-sample loss terms of the tile, added in sample order (no atomics)
 
     const SatModel& m = a.m;
     const int tid = threadIdx.x;
@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
             if (id < 0 || id >= hi - lo) { atomicOr(&a.counters[CNT_ERR], 1); id = 0; }
             load_row(table_row(m, lo + id), x);
         }
-        if (tid == 0) s_loss = 0.0;
 
         for (int l = 0; l < L; ++l) {
             __syncthreads();
@@ -194,28 +193,34 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
             z += __ldg(m.dense + m.off_headb);
             const float yp = 1.f / (1.f + expf(-z));
             a.y_pred[b] = yp;
+            double lossv = 0.0;
             if (a.y) {
                 const float yt = __ldg(a.y + b);
                 const float pq = (1.f - yp) * yp;            // d sigmoid / d logit
                 if (m.flags & SAT_FLAG_LOSS_MSE) {           // F.mse_loss(reduction='sum')
                     const float d = yp - yt;
-                    atomicAdd(&s_loss, (double)(d * d));
+                    lossv = (double)(d * d);
                     a.dz[p] = 2.f * d * pq;
                 } else if (m.flags & SAT_FLAG_LOSS_MAE) {    // F.l1_loss(reduction='sum')
                     const float d = yp - yt;
-                    atomicAdd(&s_loss, (double)fabsf(d));
+                    lossv = (double)fabsf(d);
                     a.dz[p] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * pq;
                 } else {
                     // F.binary_cross_entropy(reduction='sum'): logs clamped at -100; autograd of BCE then sigmoid:
                     // (p - y) / max((1-p) p, 1e-12) * (1-p) p
                     const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
-                    atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
+                    lossv = (double)(-(yt * lp + (1.f - yt) * l1p));
                     a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
                 }
             }
+            s_lossv[s] = lossv;
         }
         __syncthreads();
-        if (tid == 0 && a.loss_part) a.loss_part[t] = s_loss;
+        if (tid == 0 && a.loss_part) {
+            double acc = 0.0;
+            for (int ss = 0; ss < cnt; ++ss) acc += s_lossv[ss];
+            a.loss_part[t] = acc;
+        }
     }
 }
 

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
     float* sRed = sLN + 192;                      // [128]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sRed + TC_NT);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
-    __shared__ double s_loss;
+    __shared__ double s_lossv[TC_NT];      // per-sample loss terms of the tile, added in sample order (no atomics)
 
     const SatModel& m = a.m;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
             if (id < 0 || id >= hi - lo) { atomicOr(&a.counters[CNT_ERR], 1); id = 0; }
             load_row(table_row(m, lo + id), x);
         }
-        if (tid == 0) s_loss = 0.0;
 
         for (int l = 0; l < L; ++l) {
             __syncthreads();                      // previous users of sBL / sBT / sK / sV are done
@@ -279,28 +278,34 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
             z += __ldg(m.dense + m.off_headb);
             const float yp = 1.f / (1.f + expf(-z));
             a.y_pred[b] = yp;
+            double lossv = 0.0;
             if (a.y) {
                 const float yt = __ldg(a.y + b);
                 const float pq = (1.f - yp) * yp;            // d sigmoid / d logit
                 if (m.flags & SAT_FLAG_LOSS_MSE) {           // F.mse_loss(reduction='sum')
                     const float d = yp - yt;
-                    atomicAdd(&s_loss, (double)(d * d));
+                    lossv = (double)(d * d);
                     a.dz[p] = 2.f * d * pq;
                 } else if (m.flags & SAT_FLAG_LOSS_MAE) {    // F.l1_loss(reduction='sum')
                     const float d = yp - yt;
-                    atomicAdd(&s_loss, (double)fabsf(d));
+                    lossv = (double)fabsf(d);
                     a.dz[p] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * pq;
                 } else {
                     // F.binary_cross_entropy(reduction='sum'): logs clamped at -100; autograd of BCE then sigmoid:
                     // (p - y) / max((1-p) p, 1e-12) * (1-p) p
                     const float lp = fmaxf(logf(yp), -100.f), l1p = fmaxf(logf(1.f - yp), -100.f);
-                    atomicAdd(&s_loss, (double)(-(yt * lp + (1.f - yt) * l1p)));
+                    lossv = (double)(-(yt * lp + (1.f - yt) * l1p));
                     a.dz[p] = (yp - yt) / fmaxf(pq, 1e-12f) * pq;
                 }
             }
+            s_lossv[s] = lossv;
         }
         __syncthreads();
-        if (tid == 0 && a.loss_part) a.loss_part[t] = s_loss;
+        if (tid == 0 && a.loss_part) {
+            double acc = 0.0;
+            for (int ss = 0; ss < cnt; ++ss) acc += s_lossv[ss];
+            a.loss_part[t] = acc;
+        }
     }
 #undef SAT_TC_ROUND
     tc_fence_before();

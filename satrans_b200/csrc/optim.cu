@@ -219,6 +219,12 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
         int rc = sat_host::check_launch("k_adam_rows");
         if (rc) return rc;
     }
+    if ((which & SAT_ADAM_UNTOUCHED) && !a->dense_mode) {
+        // lazy mode: no sweep runs, so its slice of the sum-of-squares partials must not keep an earlier step's values; the
+        // regulariser term reported by sat_finalize_loss then covers the touched rows only
+        if (cudaMemsetAsync(w->reg_part, 0, SWEEP_BLOCKS * sizeof(double), s) != cudaSuccess)
+            return sat_host::fail(SAT_ECUDA, "sat_tables_adam: memset failed");
+    }
     if ((which & SAT_ADAM_UNTOUCHED) && a->dense_mode) {
         k_adam_sweep<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),

@@ -12,8 +12,8 @@ single-process nn.DataParallel of meta_basemodel.py:272-275, which replicates th
     gradients add without re-weighting and R ranks x B samples == one step on the R*B global batch.
   * L2 + Adam over untouched rows: local to each shard (no communication).
 
-Cross-rank ordering inside a step uses stream-ordered NCCL all-reduces of one element as barriers
-(no host synchronisation).
+Cross-rank ordering inside a step: `sat_peer_barrier`, one tiny kernel that exchanges epoch flags through the
+peer-mapped workspaces (stream-ordered, no host synchronisation, no NCCL call).
 """
 import torch
 import torch.distributed as dist
@@ -37,6 +37,10 @@ class DistContext:
         if self._flag is None:
             self._flag = torch.zeros(1, dtype=torch.float32, device=device)
         dist.all_reduce(self._flag, group=self.group)
+
+    def host_barrier(self):
+        """Blocking barrier of the processes (set-up time only; steps use Engine._barrier = sat_peer_barrier)."""
+        dist.barrier(group=self.group)
 
     def all_reduce_sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

@@ -4,12 +4,13 @@ stream choreography.  PyTorch is used only for device memory, streams and events
 One training step (reference meta_basemodel.py:311-328: forward, BCE(sum), dense L2, backward,
 dense Adam) becomes, on two streams:
 
-    main : bucket-by-scenario -> encoder -> mark+rank touched rows --E1--> fused forward(+BCE, dLogit)
-           -> head bwd -> L x (attention bwd, MetaNet/QKV bwd [layer 0 scatters dE0 to touched rows])
-           -> encoder bwd -> Adam on touched rows -> Adam on the flat dense buffer --(join E2)--> finalize
-    sweep: wait E1 -> L2 + Adam over every UNTOUCHED table row (HBM-bound, 6 x table bytes) --E2-->
+    main : bucket-by-scenario -> encoder -> pack weights -> fused forward(+BCE, dLogit) -> head bwd
+           -> L x (attention bwd, MetaNet/QKV bwd) -> fixed-order reduce of the per-CTA partial gradients -> encoder bwd
+           --(join)--> sorted segmented reduce of dE0 per touched row -> L2 + Adam sweep over the untouched rows -> finalize
+    side : mark + rank the touched rows -> radix sort of the tokens by touched-row slot (ids only: runs beside the
+           forward) ... later: Adam on the touched rows + Adam on the flat dense buffer (beside the HBM-bound sweep)
 
-The sweep never touches a row the batch reads, so it overlaps the compute-bound forward/backward.
+No floating-point atomics anywhere: every sum has a fixed order, so two runs of a step are bit-identical.
 """
 import ctypes as C
 
@@ -21,7 +22,9 @@ from ._lib import SatAdam, SatModel, SatWork, check, lib
 
 _BUF_DTYPES = {'perm': torch.int32, 'dom': torch.int32, 'tiles': torch.int32, 'counters': torch.int32,
                'loss_part': torch.float64, 'reg_part': torch.float64, 'bitmap': torch.int32,
-               'word_rank': torch.int32, 'block_sums': torch.int32, 'uniq_rows': torch.int32}
+               'word_rank': torch.int32, 'block_sums': torch.int32, 'uniq_rows': torch.int32,
+               'sort_keys': torch.int32, 'sort_vals': torch.int32, 'sort_hist': torch.int32, 'chunk_info': torch.int32,
+               'recv_idx': torch.int32, 'peer_flags': torch.int32}
 
 
 def _id_kind(X):
@@ -55,6 +58,8 @@ class Workspace:
             dt = _BUF_DTYPES.get(name, torch.float32)
             n = (nbytes + dt.itemsize - 1) // dt.itemsize
             t = torch.zeros(n, dtype=dt, device=dev)
+            if name == 'recv_idx':
+                t.fill_(-1)            # "no row pushed" (sat_rows_combine re-arms the entries it consumes)
             self.bufs[name] = t
             setattr(self.c, name, t.data_ptr())
 
@@ -119,9 +124,12 @@ class Engine:
             d.shard_word_rank[r] = w['word_rank'].data_ptr()
             d.shard_row_grad[r] = w['row_grad'].data_ptr()
             return
-        for name, field in (('bitmap', d.shard_bitmap), ('word_rank', d.shard_word_rank), ('row_grad', d.shard_row_grad)):
+        for name, field in (('bitmap', d.shard_bitmap), ('word_rank', d.shard_word_rank), ('row_grad', d.shard_row_grad),
+                            ('recv', d.shard_recv), ('recv_idx', d.shard_recv_idx), ('peer_flags', d.shard_flags)):
             for k, ptr in enumerate(self.dist.exchange_pointers(w[name])):
                 field[k] = ptr
+        torch.cuda.synchronize()
+        self.dist.host_barrier()        # every peer's buffers are initialised before anybody's kernels touch them
 
     def _tic(self, name, stream=None):
         if self.timing is None:
@@ -181,6 +189,9 @@ class Engine:
             d.shard_bitmap[k] = None
             d.shard_word_rank[k] = None
             d.shard_row_grad[k] = None
+            d.shard_recv[k] = None
+            d.shard_recv_idx[k] = None
+            d.shard_flags[k] = None
         if world == 1:
             d.shard_tables[0] = ptrs[0]
         else:
@@ -191,7 +202,13 @@ class Engine:
                 d.shard_tables[k] = ptr
         self._bound_ptrs = ptrs
         self._work = {}
-        self._adam = None
+        if self._adam is not None and self._adam['tab_v'] is not None and \
+                (self._adam['tab_v'].device != self.device or self._adam['tab_v'].shape != m._tables.shape):
+            # the parameters moved (model.cpu() / .cuda() around a checkpoint, as reference main.py does): the optimiser
+            # state follows them, like torch.optim's state tensors follow param.data only if re-created -- here it is kept
+            for k in ('tab_m', 'tab_v', 'dense_m', 'dense_v'):
+                if self._adam[k] is not None:
+                    self._adam[k] = self._adam[k].to(self.device)
 
     def workspace(self, B, training):
         key = bool(training)
@@ -269,18 +286,36 @@ class Engine:
             check(l.sat_backward_tc(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), float(p), seed, passes, s),
                   'sat_backward_tc')
 
+    def _barrier(self, w, stream=None):
+        """Stream-ordered cross-process barrier through the peer-mapped flags (one tiny kernel, no NCCL call)."""
+        check(lib().sat_peer_barrier(C.byref(self.desc), C.byref(w.c), self._stream() if stream is None else stream),
+              'sat_peer_barrier')
+
     def _mark_rows(self, X, w, kind):
-        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomics) | barrier | rank | barrier."""
+        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomicOr) | barrier | rank | barrier."""
         l, s, d = lib(), self._stream(), C.byref(self.desc)
         if self.dist is None or self.dist.world == 1:
             check(l.sat_rows_mark_and_rank(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark_and_rank')
             return
         check(l.sat_rows_clear(d, C.byref(w.c), s), 'sat_rows_clear')
-        self.dist.barrier(self.device)
+        self._barrier(w)
         check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
-        self.dist.barrier(self.device)
+        self._barrier(w)
         check(l.sat_rows_rank(d, C.byref(w.c), s), 'sat_rows_rank')
-        self.dist.barrier(self.device)
+        self._barrier(w)
+
+    def _sort_rows(self, X, w, kind):
+        """Tokens sorted by (owner shard, touched-row slot): needs the scenario permutation and the ranks."""
+        check(lib().sat_rows_sort(C.byref(self.desc), X.data_ptr(), kind, X.shape[1], C.byref(w.c), self._stream()),
+              'sat_rows_sort')
+
+    def _reduce_rows(self, w):
+        """dE0 per token (w['dx']) -> w['row_grad'][slot]: sorted segmented reduce; sharded: push + barrier + combine."""
+        l, s, d = lib(), self._stream(), C.byref(self.desc)
+        check(l.sat_rows_reduce(d, C.byref(w.c), s), 'sat_rows_reduce')
+        if self.dist is not None and self.dist.world > 1:
+            self._barrier(w)
+            check(l.sat_rows_combine(d, C.byref(w.c), s), 'sat_rows_combine')
 
     def forward(self, X, y=None, training=False, dropout_p=0.1, seed=0):
         """y_pred (B,) in sample order.  With y: also leaves BCE partials / dLogit in the workspace."""
@@ -319,17 +354,15 @@ class Engine:
         l, s, d = lib(), self._stream(), C.byref(self.desc)
         self._prepare(X, w, kind)
         self._mark_rows(X, w, kind)
+        self._sort_rows(X, w, kind)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
-        w['row_grad'].zero_()
-        self._row_grad_dirty = True          # left populated for the caller; train_step clears it before reuse
-        if self.dist is not None and self.dist.world > 1:
-            self.dist.barrier(self.device)
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, float(dropout_p if training else 0.0),
                            int(seed) & (2 ** 64 - 1), s)
         self._backward_call(X, kind, w, float(dropout_p if training else 0.0), int(seed) & (2 ** 64 - 1), s)
-        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2)
+        self._reduce_rows(w)
+        self.launches += self._launch_count(False)
         if self.dist is not None and self.dist.world > 1:
-            self.dist.all_reduce_sum(w['dgrad'])            # also orders the peers' row-gradient atomics
+            self.dist.all_reduce_sum(w['dgrad'])
         if with_reg:
             check(l.sat_tables_sumsq(d, C.byref(w.c), s), 'sat_tables_sumsq')
             self.launches += 1
@@ -353,6 +386,24 @@ class Engine:
                 'dense_v': torch.zeros_like(m._dense) if need_v else None,
             }
         return self._adam
+
+    def _launch_count(self, with_update, dense_mode=True):
+        """Kernels of THIS library launched by one loss_and_grads / train_step (memsets and NCCL calls not counted)."""
+        L, tc = self.desc.L, self.precision != 'fp32'
+        sharded = self.dist is not None and self.dist.world > 1
+        cap = self._work[True].cap_B * self.desc.F if True in self._work else 1
+        idx = min(cap * self.desc.n_shards, -(-self.desc.total_rows // self.desc.n_shards))
+        key_bits = max(idx, 1).bit_length() + (self.desc.n_shards - 1).bit_length()
+        passes = -(-key_bits // _lib.SAT_SORT_RADIX_BITS)
+        n = 2 + (1 if tc else 0)              # bucket, encoder, pack
+        n += 3 + (3 if sharded else 0)        # mark, rank x2 (+ barriers)
+        n += 1 + 3 * passes                   # sort keys + radix passes
+        n += 1                                # forward
+        n += 1 + 2 * L + 1 + 2                # head bwd, per layer attn + meta, dense reduce, encoder bwd x2
+        n += 2 + (2 if sharded else 0)        # rows reduce + fixup (+ barrier + combine)
+        if with_update:
+            n += 1 + (1 if dense_mode else 0) + 1      # adam rows, sweep, dense adam
+        return n
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
                    dropout_p=0.1, seed=0, overlap=False, opt_kind=0):
@@ -381,36 +432,40 @@ class Engine:
             self._ev_marked = torch.cuda.Event()
             self._ev_swept = torch.cuda.Event()
             self._ev_fork = torch.cuda.Event()
+            self._ev_bucket = torch.cuda.Event()
+        side = self._sweep_stream
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
-        t = self._tic('prepare')
-        if getattr(self, '_row_grad_dirty', False):
-            w['row_grad'].zero_()
-            self._row_grad_dirty = False
         single = self.dist is None or self.dist.world == 1
-        if single and self.side_streams:
-            # the touched-row bitmap / ranks (ids only) are independent of bucketing + encoder + weight packing:
-            # two short launch chains side by side instead of one after the other
+        use_side = bool(single and self.side_streams)
+        t = self._tic('prepare')
+        if use_side:
+            # the touched-row bitmap / ranks and the token sort depend on the ids only: they run on the second stream beside
+            # bucketing + encoder + weight packing + the forward, and are joined before the row-gradient reduce
             self._ev_fork.record(main)
-            self._sweep_stream.wait_event(self._ev_fork)
-            with torch.cuda.stream(self._sweep_stream):
+            side.wait_event(self._ev_fork)
+            with torch.cuda.stream(side):
                 self._mark_rows(X, w, kind)
-            self._ev_marked.record(self._sweep_stream)
             self._prepare(X, w, kind)
-            main.wait_event(self._ev_marked)
+            self._ev_bucket.record(main)
+            side.wait_event(self._ev_bucket)           # the sort reads the scenario permutation
+            with torch.cuda.stream(side):
+                self._sort_rows(X, w, kind)
+            self._ev_marked.record(side)
         else:
             self._prepare(X, w, kind)
             self._mark_rows(X, w, kind)
+            self._sort_rows(X, w, kind)
         self._toc(t)
-        sweep_on_side = bool(dense_mode and overlap)
+        sweep_on_side = bool(dense_mode and overlap and single)
         if sweep_on_side:
-            self._ev_marked.record(main)
-            self._sweep_stream.wait_event(self._ev_marked)
-            t = self._tic('adam_sweep', self._sweep_stream)
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, self._sweep_stream.cuda_stream),
-                  'sat_tables_adam')
+            if not use_side:
+                self._ev_marked.record(main)
+            side.wait_event(self._ev_marked)
+            t = self._tic('adam_sweep', side)
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, side.cuda_stream), 'sat_tables_adam')
             self._toc(t)
-            self._ev_swept.record(self._sweep_stream)
+            self._ev_swept.record(side)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
         t = self._tic('forward')
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
@@ -418,28 +473,34 @@ class Engine:
         t = self._tic('backward')
         self._backward_call(X, kind, w, p, sd, s)
         self._toc(t)
-        if self.dist is not None and self.dist.world > 1:
+        if use_side:
+            main.wait_event(self._ev_marked)           # sorted order + touched-row ranks are ready
+        t = self._tic('rows_reduce')
+        self._reduce_rows(w)
+        self._toc(t)
+        if not single:
             t = self._tic('allreduce')
-            self.dist.all_reduce_sum(w['dgrad'])            # dense grads; also orders the peers' row-gradient atomics
+            self.dist.all_reduce_sum(w['dgrad'])
             self._toc(t)
         tail_on_side = bool(dense_mode and not sweep_on_side and self.side_streams)
         if tail_on_side:
             # the short touched-row / dense-parameter updates run beside the HBM-bound sweep (disjoint rows)
             self._ev_fork.record(main)
-            self._sweep_stream.wait_event(self._ev_fork)
-            t = self._tic('adam_rows+dense (side stream)', self._sweep_stream)
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, self._sweep_stream.cuda_stream),
-                  'sat_tables_adam')
-            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), self._sweep_stream.cuda_stream), 'sat_dense_adam')
+            side.wait_event(self._ev_fork)
+            t = self._tic('adam_rows+dense (side stream)', side)
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, side.cuda_stream), 'sat_tables_adam')
+            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_dense_adam')
             self._toc(t)
-            self._ev_swept.record(self._sweep_stream)
+            self._ev_swept.record(side)
             t = self._tic('adam_sweep')
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
             self._toc(t)
             main.wait_event(self._ev_swept)
         else:
             t = self._tic('adam_rows')
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, s), 'sat_tables_adam')
+            # (lazy mode: ADAM_UNTOUCHED only clears the sweep's slice of the sum-of-squares partials)
+            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a),
+                                    _lib.ADAM_TOUCHED | (0 if dense_mode else _lib.ADAM_UNTOUCHED), s), 'sat_tables_adam')
             self._toc(t)
             if dense_mode and not sweep_on_side:
                 t = self._tic('adam_sweep')
@@ -451,17 +512,15 @@ class Engine:
             if sweep_on_side:
                 main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
-        if self.dist is not None and self.dist.world > 1:
+        if not single:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
-        # own kernels per step: bucket 1, encoder 1, mark+rank 3, forward 1, head bwd 1, 2 per layer, encoder bwd 2,
-        # adam rows 1, sweep 0/1, dense adam 1, finalize 1
-        self.launches += 2 + 3 + 1 + (1 + 2 * self.desc.L + 2) + 1 + (1 if dense_mode else 0) + 1 + 1 + \
-            (1 if self.precision != 'fp32' else 0)
+        self.launches += self._launch_count(True, dense_mode) + 1
         return y_pred, w
 
     def adam_state(self):
         return self._adam_state(self._adam['kind'] if self._adam else 0)
 
     def reset_optimizer(self):
+        """Fresh optimiser state (moments and step counter), as a new torch.optim instance would have."""
         self._adam = None
         self.step_count = 0

@@ -144,7 +144,7 @@ class SATrans(BaseModel):
         # ---- flat dense-parameter buffer ------------------------------------------------------------------
         L, pos = domain_att_layer_num, 'pos' in flag
         n_dom = num_domains_list[0] + 1
-        lay = dict(F=field_num, L=L, H=att_head_num, n_dom=n_dom, n_dense=n_dense, n_cols=len(self.feature_index),
+        lay = dict(F=field_num, L=L, H=att_head_num, n_dom=n_dom, n_dense=n_dense, n_cols=self._n_cols(),
                    enc_in=self.domain_embedding_dim)
         lay['flags'] = ((_lib.FLAG_POS if pos else 0) | (_lib.FLAG_META_Q if 'Q' in meta_mode else 0) |
                         (_lib.FLAG_META_K if 'K' in meta_mode else 0) | (_lib.FLAG_RELU if 'relu' in flag else 0) |

@@ -8,7 +8,7 @@ from oracle import satrans_oracle as O
 from satrans_b200 import DenseFeat, SATrans, SparseFeat
 
 
-def model_from_golden(g: Golden, device='cuda:0', precision='fp32'):
+def model_from_golden(g: Golden, device='cuda:0', precision=None):
     m = g.meta
     cols = ([SparseFeat(n, v, 32) for n, v in zip(m['sparse_names'], m['vocab_sizes'])] +
             [DenseFeat(n, 1) for n in m['dense_names']])
@@ -17,11 +17,12 @@ def model_from_golden(g: Golden, device='cuda:0', precision='fp32'):
                     meta_mode=m['meta_mode'], seed='1021', device=device, flag=m['flag'])
     missing = model.load_state_dict(g.full_state_dict(), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
-    model.precision = precision        # CUDA-core kernels unless a test selects the tensor-core path (the package default)
+    if precision is not None:          # None: the package default (tcgen05 3xTF32, what bench.py times)
+        model.precision = precision
     return model
 
 
-def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0', precision='fp32'):
+def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0', precision=None):
     cols = ([SparseFeat(n, v, cfg.embedding_dim) for n, v in zip(cfg.sparse_names, cfg.vocab_sizes)] +
             [DenseFeat(n, 1) for n in cfg.dense_names])
     model = SATrans(cols, cols, [cfg.domain_col], [cfg.num_domains], att_layer_num=0,
@@ -31,8 +32,55 @@ def model_from_cfg(cfg: O.OracleConfig, state, device='cuda:0', precision='fp32'
     with torch.no_grad():
         for k, v in state.items():
             sd[k].copy_(v)
-    model.precision = precision
+    if precision is not None:
+        model.precision = precision
     return model
+
+
+def relu_masks(model, w, B):
+    """The MetaNet ReLU decisions the forward kernel took, as {'l{i}.q' | 'l{i}.k': bool (B, F, 64)} in sample order
+    (saved behind the activations: uint32 [L][2 sides][cap_B*F][2], indexed by sorted position * F + field)."""
+    lay = model._layout
+    L, F = lay['L'], lay['F']
+    cap_tok = w.cap_B * F
+    raw = w['acts'].view(torch.int32)[(L * 5 + 1) * cap_tok * 32:(L * 5 + 1) * cap_tok * 32 + L * 2 * cap_tok * 2]
+    raw = raw.view(L, 2, cap_tok, 2)[:, :, :B * F].reshape(L, 2, B, F, 2).cpu()
+    perm = w['perm'][:B].long().cpu()
+    bits = torch.arange(32, dtype=torch.int64)
+    out = {}
+    for l in range(L):
+        for side, name in ((0, 'q'), (1, 'k')):
+            words = raw[l, side].long() & 0xFFFFFFFF                       # (B sorted, F, 2)
+            m = ((words.unsqueeze(-1) >> bits) & 1).bool().reshape(B, F, 64)
+            full = torch.zeros_like(m)
+            full[perm] = m                                                 # sorted position p holds sample perm[p]
+            out['l%d.%s' % (l, name)] = full
+    return out
+
+
+def compact_vocab(cfg: O.OracleConfig, state, X):
+    """(cfg', state', X') with every table cut down to the rows this batch touches (ids renumbered): the same function of the
+    same rows, small enough for an fp64 autograd pass at full-vocabulary configurations.  Also returns per field the original
+    ids of the kept rows."""
+    import copy
+    X = X.clone()
+    st = dict(state)
+    kept = {}
+    sizes = []
+    for f, n in enumerate(cfg.sparse_names):
+        c = cfg.col_of(n)
+        ids = X[:, c].long()
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        if n == cfg.domain_col:                                            # the scenario id also indexes domain_embeddings: keep as is
+            uniq = torch.arange(cfg.vocab_sizes[f])
+            inv = ids
+        st['embedding_dict.%s.weight' % n] = state['embedding_dict.%s.weight' % n][uniq]
+        X[:, c] = inv.to(X.dtype)
+        kept[n] = uniq
+        sizes.append(int(uniq.numel()))
+    cfg2 = copy.copy(cfg)
+    cfg2.vocab_sizes = sizes
+    return cfg2, st, X, kept
 
 
 def dense_grads(model, w):

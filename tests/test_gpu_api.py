@@ -25,29 +25,32 @@ def _small(scale=2e-4, flag='sota', mode='QK', heads=4, layers=2, alimama=False,
     return schema, cfg, st
 
 
-def _model(cfg, st):
+def _model(cfg, st, precision=None):
+    """precision=None: the package default (tcgen05 3xTF32, the benchmarked path)."""
     from gpu_util import model_from_cfg
-    return model_from_cfg(cfg, {k: v.clone() for k, v in st.items()})
+    return model_from_cfg(cfg, {k: v.clone() for k, v in st.items()}, precision=precision)
 
 
-def test_fit_matches_oracle_training_loop():
+@pytest.mark.parametrize('precision', ['tf32x3', 'fp32'])
+@pytest.mark.parametrize('eps', [1e-8, 1e-4])
+def test_fit_matches_oracle_training_loop(precision, eps):
     """fit(shuffle=False, dropout off) == the reference's loop (meta_basemodel.py:311-328) on successive batches,
-    including a ragged last batch; History carries the epoch loss = sum(bce + reg) / N.
+    including a ragged last batch; History carries the epoch loss = sum(bce + reg) / N.  Both arithmetic paths.
 
-    Adam runs with eps = 1e-4 here.  With the default 1e-8 the normalised step lr*m/(sqrt(v)+eps) turns the fp32 round-off of
-    gradient elements below ~1e-7 (a few per cent of W_Key in this random model) into +-lr moves whose sign depends on the
-    order of the floating-point atomics; four steps later the whole trajectory has drifted by per cents of lr*steps in some
-    runs and not in others.  That sensitivity belongs to Adam (the reference on two devices shows it too), not to the loop
-    under test; default-eps Adam is pinned against the reference's own 1- and 3-step golden vectors in test_gpu_parity.py."""
+    eps = 1e-8 is torch.optim.Adam's default: the normalised step lr*m/(sqrt(v)+eps) turns the fp32 round-off of gradient
+    elements below ~1e-7 into +-lr moves, so two correct fp32 implementations agree only statistically on those elements --
+    the bar is the one the CPU oracle itself is held to against the reference's golden vectors (assert_adam_close).  The
+    kernels have no floating-point atomics, so this comparison gives the same result on every run.
+    eps = 1e-4 conditions the division: every parameter must then track the oracle to fp32 round-off through all steps."""
     schema, cfg, st = _small()
     n, bs, lr = 1000, 256, 0.005                       # 4 steps, last batch 232 samples
     xs, ys = synth.make_inputs(schema, n, seed=11, ctr=0.3)
-    model = _model(cfg, st)
+    model = _model(cfg, st, precision)
     model.dropout_rate = 0.0
-    model.compile(torch.optim.Adam(model.parameters(), lr=lr, eps=1e-4), "binary_crossentropy",
+    model.compile(torch.optim.Adam(model.parameters(), lr=lr, eps=eps), "binary_crossentropy",
                   metrics=["binary_crossentropy", "auc"])
     hist = model.fit(x=xs, y=ys, batch_size=bs, epochs=1, verbose=0, shuffle=False)
-    tr = O.Trainer({k: v.clone() for k, v in st.items()}, cfg, lr=lr, eps=1e-4)
+    tr = O.Trainer({k: v.clone() for k, v in st.items()}, cfg, lr=lr, eps=eps)
     X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense))
     y = torch.from_numpy(ys.astype(np.float32))
     tot = 0.0
@@ -57,7 +60,12 @@ def test_fit_matches_oracle_training_loop():
     assert abs(hist.history['loss'][0] - tot / n) <= 1e-5 * abs(tot / n)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     for k in O.trainable_keys(cfg):
-        assert_adam_close(sd[k], tr.params[k].detach(), lr, 4, k)
+        ref = tr.params[k].detach()
+        if eps == 1e-4:
+            tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
+            assert (sd[k] - ref).abs().max().item() <= tight, (k, (sd[k] - ref).abs().max().item(), tight)
+        else:
+            assert_adam_close(sd[k], ref, lr, 4, k)
 
 
 def test_fit_verbose_metrics_and_validation(capsys):
@@ -167,8 +175,8 @@ def test_train_on_batch_host_api_and_lazy_mode():
     n_u = int(w['scalars'][2].item())
     rows = w['uniq_rows'][:n_u].long()
     t0 = torch.cat([st['embedding_dict.%s.weight' % f] for f in cfg.sparse_names]).cuda()
-    # (the row-gradient accumulation uses float atomics: summation order may differ between two runs)
-    assert torch.allclose(dense._tables[rows], lazy._tables[rows], atol=1e-6, rtol=0)
+    # (no float atomics: the touched rows get bit-identical updates in both modes)
+    assert torch.equal(dense._tables[rows], lazy._tables[rows])
     untouched = torch.ones(t0.shape[0], dtype=torch.bool, device='cuda')
     untouched[rows] = False
     assert torch.equal(lazy._tables[untouched], t0[untouched])
@@ -215,12 +223,14 @@ def test_gather_full_vocab_properties():
     assert yp.shape == (8192, 1) and torch.isfinite(yp).all() and (yp > 0).all() and (yp < 1).all()
 
 
+@pytest.mark.parametrize('conditioned', [False, True])
 @pytest.mark.parametrize('opt,lr', [('sgd', 0.01), ('adagrad', 0.01), ('rmsprop', 0.001)])
-def test_other_optimizers_match_torch(opt, lr):
-    """compile('sgd' | 'adagrad' | 'rmsprop') (reference meta_basemodel.py:612-625): 3 fused steps == torch.optim.
-    (eps = 1e-4 for the normalising optimisers: see test_fit_matches_oracle_training_loop.)"""
+def test_other_optimizers_match_torch(opt, lr, conditioned):
+    """compile('sgd' | 'adagrad' | 'rmsprop') (reference meta_basemodel.py:612-625): 3 fused steps == torch.optim, on the
+    default (tcgen05 3xTF32) path.  conditioned: eps = 1e-4 for the normalising optimisers -> every element to fp32 round-off;
+    otherwise torch's default eps with the statistical bar of assert_adam_close (see test_fit_matches_oracle_training_loop)."""
     schema, cfg, st = _small(layers=1)
-    kw = {} if opt == 'sgd' else {'eps': 1e-4}
+    kw = {} if (opt == 'sgd' or not conditioned) else {'eps': 1e-4}
     xs, ys = synth.make_inputs(schema, 3 * 128, seed=21, ctr=0.3)
     X = synth.stack_columns(xs, schema.fields)
     y = ys.astype(np.float32)
@@ -236,9 +246,11 @@ def test_other_optimizers_match_torch(opt, lr):
     for k in O.trainable_keys(cfg):
         ref = tr.params[k].detach()
         err = (sd[k] - ref).abs()
-        tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
-        assert (err <= tight).float().mean().item() >= 0.995, (k, opt)
-        assert err.max().item() <= 0.05 * max(lr, 1e-3) * 3 * (10 if opt != 'sgd' else 1), (k, opt, err.max().item())
+        if opt == 'sgd' or conditioned:
+            tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
+            assert err.max().item() <= tight, (k, opt, err.max().item(), tight)
+        else:
+            assert_adam_close(sd[k], ref, lr * (10 if opt == 'rmsprop' else 1), 3, k)
 
 
 @pytest.mark.parametrize('loss', ['mse', 'mae'])
@@ -287,10 +299,11 @@ def test_selfattention_layer_matches_reference():
 def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
     """Field counts other than the two benchmark schemas (F = 32 = SAT_MAXF and F = 16 fill all 128 rows of the operand tiles,
     F = 5 leaves a 3-row remainder, F = 1 is the scenario column alone) at batch sizes that give every CTA several tiles and
-    scenario changes inside a CTA: prediction, loss and every gradient against the oracle's autograd.
-    Gradient bar: max-norm relative 2e-3 (sums over up to 10^5 tokens of random-label gradients cancel heavily; the CUDA-core path
-    measures <= 2e-4 here, the 3xTF32 path <= 8e-4); the analytically-zero K-LayerNorm-bias gradient is compared absolutely."""
-    from gpu_util import dense_grads, table_grads
+    scenario changes inside a CTA: prediction, loss and every gradient against the fp64 oracle's autograd with the kernel's own
+    MetaNet ReLU decisions injected (test_gpu_parity.py explains why).  Gradient bar: max-norm relative 1e-4, the stated fp32
+    tolerance; gradients that are analytically zero (K-LayerNorm bias; d theta for F = 1) are compared against 1e-7 of the
+    largest gradient of the model."""
+    from gpu_util import dense_grads, relu_masks, table_grads
     fields = ['f%d' % i for i in range(F - 1)] + ['dom']
     data_max = {f: 40 + 13 * i for i, f in enumerate(fields)}
     data_max['dom'] = 4
@@ -309,9 +322,12 @@ def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
     model = _model(cfg, st)
     model.engine.precision = precision
     model.eval()
-    yp_ref, bce_ref, _, grads = O.loss_and_grads(st, X, y, cfg, with_reg=False)
     yp, w = model.engine.loss_and_grads(X.cuda(), y.cuda(), training=False)
-    np.testing.assert_allclose(yp.cpu().numpy().reshape(-1), yp_ref.detach().numpy().reshape(-1), atol=3e-6)
+    torch.cuda.synchronize()
+    rm = relu_masks(model, w, B)
+    st64 = {k: v.double() for k, v in st.items()}
+    yp_ref, bce_ref, _, grads = O.loss_and_grads(st64, X.double(), y.double(), cfg, with_reg=False, relu_masks=rm)
+    np.testing.assert_allclose(yp.cpu().numpy().reshape(-1), yp_ref.detach().float().numpy().reshape(-1), atol=3e-6)
     assert abs(float(w['scalars'][0].item()) - float(bce_ref)) <= 2e-5 * abs(float(bce_ref))
     got = dense_grads(model, w)
     tg, _ = table_grads(model, w, 0.0)
@@ -321,13 +337,10 @@ def test_field_counts_and_many_tiles_per_cta(F, flag, heads, B, precision):
     for k, r in grads.items():
         if k not in got:
             continue
-        r = r.detach()
+        r = r.detach().float()
         err = (got[k] - r).abs().max().item()
         scale = r.abs().max().item()
-        if k.endswith('K_meta_mlp.ffn_layer_norm.bias'):
-            assert err <= 1e-4 * max(v.abs().max().item() for kk, v in grads.items() if kk.endswith('Q_meta_mlp.ffn_layer_norm.bias')), k
-        else:
-            assert err <= 2e-3 * scale + 1e-7 * gmax, (k, err, scale)     # (F = 1: d theta is analytically zero)
+        assert err <= 1e-4 * scale + 1e-7 * gmax, (k, err, scale, gmax)
         checked += 1
     assert checked >= len(O.trainable_keys(cfg)) - 1
 
@@ -378,6 +391,66 @@ def test_batch_metrics_match_sklearn():
         h = model.fit(x=xs, y=ys, batch_size=256, epochs=1, verbose=1, shuffle=True)
         logs[dev_metrics] = {k: v[0] for k, v in h.history.items()}
     for k in ("binary_crossentropy", "auc", "mse", "acc"):
-        # two separate training runs: float-atomic order noise in y_pred (1e-7) can swap neighbouring scores, and one swap
-        # moves a batch's AUC by 1 / (n_pos * n_neg) ~ 7e-5
-        assert abs(logs[True][k] - logs[False][k]) <= (2e-4 if k == "auc" else 2e-6), (k, logs)
+        # two separate training runs give bit-identical predictions (no float atomics); the device metrics equal sklearn's
+        assert abs(logs[True][k] - logs[False][k]) <= 1e-9, (k, logs)
+
+
+@pytest.mark.parametrize('init', ['default', 'scaled'])
+def test_config2_full_size_parity(init):
+    """BASELINE config 2 exactly -- full Ali-CCP vocabulary (6,571,961 rows), B = 8192, F = 19, L = 3, H = 4, meta_mode QK,
+    flag 'sota' -- on the package-default tcgen05 3xTF32 path: y_pred, BCE and EVERY gradient against the fp64 oracle.
+
+    The oracle runs on the batch's touched rows only (tables cut down to the touched rows, ids renumbered: the same function
+    of the same rows; gather bit-exactness at full vocabulary is test_gather_full_vocab_properties) with the kernel's own
+    MetaNet ReLU decisions injected, so fp32-oracle noise and knife-edge ReLU flips are not charged to the kernel.
+    'default' = the constructor's initialisation (what bench.py trains from); 'scaled' = O(0.3) embeddings and O(0.05)
+    encoder weights, which exercises every term of the backward at full magnitude.
+    Bars: y_pred atol 2e-6, BCE rtol 1e-5, gradients max-norm rtol 1e-4 (meta_basemodel.py:311-327 semantics)."""
+    from gpu_util import compact_vocab, dense_grads, relu_masks, table_grads
+    from satrans_b200 import SATrans
+    schema = synth.aliccp_schema()
+    cols = schema.feature_columns(32)
+    model = SATrans(cols, cols, ['301'], [3], att_layer_num=0, domain_att_layer_num=3, att_head_num=4, meta_mode='QK',
+                    seed=1021, device='cuda:0', flag='sota')
+    assert model.precision == 'tf32x3'
+    if init == 'scaled':
+        g = torch.Generator(device='cuda').manual_seed(5)
+        with torch.no_grad():
+            model._tables.normal_(0.0, 0.3, generator=g)
+            model.domain_map_dnn_Q.linears[0].weight.normal_(0.0, 0.05, generator=g)
+    B = 8192
+    xs, ys = synth.make_inputs(schema, B, seed=1021, ctr=0.04)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    y = torch.from_numpy(ys.astype(np.float32))
+    cfg = O.OracleConfig(sparse_names=schema.fields, vocab_sizes=schema.vocab_sizes, domain_col='301', num_domains=3,
+                         layers=3, heads=4, meta_mode='QK', flag='sota')
+    yp, w = model.engine.loss_and_grads(X.cuda(), y.cuda(), training=False, l2_emb=0.0, with_reg=False)
+    torch.cuda.synchronize()
+    # oracle state: dense parameters as they are; tables = the touched rows
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    state = {k: sd[k] for k in O.trainable_keys(cfg)}
+    cfg_c, st_c, X_c, kept = compact_vocab(cfg, state, X)
+    st64 = {k: v.double() for k, v in st_c.items()}
+    rm = relu_masks(model, w, B)
+    yp64, bce64, _, og = O.loss_and_grads(st64, X_c.double(), y.double(), cfg_c, with_reg=False, relu_masks=rm)
+    assert (yp.cpu() - yp64[:, 0].float()).abs().max().item() <= 2e-6
+    assert abs(float(w['scalars'][0]) - bce64.item()) <= 1e-5 * abs(bce64.item())
+    grads = dense_grads(model, w)
+    tg, _ = table_grads(model, w, 0.0)
+    worst = {}
+    for k in O.trainable_keys(cfg):
+        ref = og[k].float()
+        if k.startswith('embedding_dict.'):
+            name = k[len('embedding_dict.'):-len('.weight')]
+            full = tg[k]
+            got = full[kept[name]]
+            mask = torch.ones(full.shape[0], dtype=torch.bool)
+            mask[kept[name]] = False
+            assert torch.count_nonzero(full[mask]) == 0, k             # untouched rows carry no gradient
+        else:
+            got = grads[k]
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        worst[k] = err / max(scale, 1e-30)
+        assert err <= 1e-4 * scale + 1e-9, (k, err, scale)
+    print('config 2 (%s init): worst max-norm relative gradient error %.2e' % (init, max(worst.values())))

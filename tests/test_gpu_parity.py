@@ -1,7 +1,10 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the golden vectors dumped from the unmodified
 reference and against the CPU oracle on the same seeded inputs.  Tolerances (SURVEY.md §8c, fp32 noise floor
 of the reference itself): gathered rows bit-exact; y_pred atol 2e-6; BCE / reg rtol 1e-5; gradients
-max-norm rtol 1e-4 (+1e-9 abs); post-Adam parameters per `assert_adam_close`."""
+max-norm rtol 1e-4 (+1e-9 abs); post-Adam parameters per `assert_adam_close`.
+
+Every training-path test runs on BOTH arithmetic paths: 'tf32x3' (tcgen05 tensor cores, error-compensated 3xTF32: the
+package default and what bench.py times) and 'fp32' (CUDA-core FFMA kernels)."""
 import numpy as np
 import pytest
 import torch
@@ -48,11 +51,19 @@ def test_forward_eval_matches_reference(name):
     assert np.allclose(pred, g.z['predict'], atol=2e-6, rtol=0)
 
 
+PRECISIONS = ['tf32x3', 'fp32']
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
 @pytest.mark.parametrize('name', CASES)
-def test_loss_and_gradients_match_reference(name):
-    from gpu_util import dense_grads, model_from_golden, table_grads
+def test_loss_and_gradients_match_reference(name, precision):
+    """Loss and every gradient against the reference's golden vectors at the stated bar (max-norm rtol 1e-4) on both paths.
+    A hidden unit of a MetaNet that the reference evaluated within round-off of zero may be decided the other way by the
+    3xTF32 products; if any golden-vector comparison misses the bar, the gradient must then meet it against the fp64 oracle
+    differentiating with the kernel's own ReLU decisions injected (same piecewise-linear function) -- never a looser bar."""
+    from gpu_util import dense_grads, model_from_golden, relu_masks, table_grads
     g = Golden(name)
-    model = model_from_golden(g)
+    model = model_from_golden(g, precision=precision)
     l2 = g.cfg.l2_reg_embedding
     yp, w = model.engine.loss_and_grads(_dev(g.X()), _dev(g.y()), training=False, l2_emb=l2)
     torch.cuda.synchronize()
@@ -62,19 +73,30 @@ def test_loss_and_gradients_match_reference(name):
     grads = dense_grads(model, w)
     tg, _ = table_grads(model, w, l2)
     grads.update(tg)
+    missed = []
     for k in O.trainable_keys(g.cfg):
         ref = g.arr('grad/' + k)
         got = grads[k][subsample(k)]
         tol = 1e-4 * ref.abs().max().item() + 1e-9
         err = (got - ref).abs().max().item()
-        assert err <= tol, (k, err, tol)
+        if err > tol:
+            missed.append((k, err, tol))
+    if missed:
+        assert precision != 'fp32', missed            # the CUDA-core path takes the reference's own ReLU decisions
+        rm = relu_masks(model, w, g.B)
+        _, _, _, og = O.loss_and_grads(g.state(torch.float64), g.X().double(), g.y().double(), g.cfg, relu_masks=rm)
+        for k in O.trainable_keys(g.cfg):
+            ref = og[k].float()
+            err = (grads[k] - ref).abs().max().item()
+            assert err <= 1e-4 * ref.abs().max().item() + 1e-9, (k, err, 'vs fp64 oracle with the kernel ReLU decisions', missed)
 
 
+@pytest.mark.parametrize('precision', PRECISIONS)
 @pytest.mark.parametrize('name', CASES)
-def test_dense_adam_steps_match_reference(name):
+def test_dense_adam_steps_match_reference(name, precision):
     from gpu_util import model_from_golden
     g = Golden(name)
-    model = model_from_golden(g)
+    model = model_from_golden(g, precision=precision)
     lr = float(g.z['lr'])
     eng = model.engine
     for step in range(1, 4):
@@ -106,10 +128,11 @@ def test_dense_adam_steps_match_reference(name):
         assert (tv[int(a):int(b)] - v_ref).abs().max().item() <= 1e-4 * v_ref.abs().max().item() + 1e-12, k
 
 
-def test_reg_and_loss_reported_by_train_step():
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_reg_and_loss_reported_by_train_step(precision):
     from gpu_util import model_from_golden
     g = Golden('en_small')
-    model = model_from_golden(g)
+    model = model_from_golden(g, precision=precision)
     _, w = model.engine.train_step(_dev(g.X()), _dev(g.y()), lr=1e-3, l2_emb=g.cfg.l2_reg_embedding, training=False)
     torch.cuda.synchronize()
     assert abs(float(w['scalars'][0]) - float(g.z['bce'])) <= 1e-5 * abs(float(g.z['bce']))
@@ -133,18 +156,15 @@ def test_tensor_core_forward_matches_reference(name, precision, atol):
 
 @pytest.mark.parametrize('bwd', ['fp32', None])
 @pytest.mark.parametrize('name', CASES)
-def test_tensor_core_forward_training_path(name, bwd):
-    """3xTF32 tensor-core forward feeding the (CUDA-core) backward.  y_pred / loss keep the fp32 bars.  Gradients:
-    3xTF32 perturbs pre-activations by ~1e-7, which can flip the ReLU decision of a MetaNet hidden unit that the
-    reference evaluated within ~1e-7 of zero (about one of the 5e5 units of a fixture; measured on enp_small) — both
-    sub-gradients are valid, but that unit's contribution (up to ~1e-3 of the max-norm of a small, cancellation-
-    dominated gradient) differs from the golden vector.  Bar: 99 % of all gradient entries within the fp32 bar
-    (rtol 1e-4 max-norm), every entry within 2e-3."""
-    from gpu_util import dense_grads, model_from_golden, table_grads
+def test_tensor_core_gradients_with_injected_relu_decisions(name, bwd):
+    """3xTF32 tensor-core forward feeding the CUDA-core ('fp32') or the tensor-core (None) backward: with the forward's own
+    ReLU decisions injected into the fp64 oracle, 100 % of the gradient entries meet the fp32 bar (max-norm rtol 1e-4) -- the
+    only thing the 3xTF32 rounding can change beyond that bar is which side of zero a hidden pre-activation within ~1e-7 of
+    it falls (that claim is what this test pins: no entry is excused)."""
+    from gpu_util import dense_grads, model_from_golden, relu_masks, table_grads
     g = Golden(name)
-    model = model_from_golden(g)
-    model.engine.precision = 'tf32x3'
-    model.engine.backward_precision = bwd          # 'fp32': CUDA-core k_bwd_meta; None: tensor-core k_bwd_meta_tc
+    model = model_from_golden(g, precision='tf32x3')
+    model.engine.backward_precision = bwd
     l2 = g.cfg.l2_reg_embedding
     yp, w = model.engine.loss_and_grads(_dev(g.X()), _dev(g.y()), training=False, l2_emb=l2)
     torch.cuda.synchronize()
@@ -152,16 +172,39 @@ def test_tensor_core_forward_training_path(name, bwd):
     grads = dense_grads(model, w)
     tg, _ = table_grads(model, w, l2)
     grads.update(tg)
-    n_tight = n_all = 0
+    rm = relu_masks(model, w, g.B)
+    # the injected decisions differ from the sign of the fp64 pre-activations in at most a handful of units
+    yp64, _, _, og = O.loss_and_grads(g.state(torch.float64), g.X().double(), g.y().double(), g.cfg, relu_masks=rm)
+    assert (yp.cpu() - yp64[:, 0].float()).abs().max().item() <= 2e-6
     for k in O.trainable_keys(g.cfg):
-        ref = g.arr('grad/' + k)
-        got = grads[k][subsample(k)]
-        err = (got - ref).abs()
-        scale = ref.abs().max().item()
-        assert err.max().item() <= 2e-3 * scale + 1e-9, k
-        n_tight += int((err <= 1e-4 * scale + 1e-9).sum())
-        n_all += err.numel()
-    assert n_tight >= 0.99 * n_all, (n_tight, n_all)
+        ref = og[k].float()
+        err = (grads[k] - ref).abs().max().item()
+        assert err <= 1e-4 * ref.abs().max().item() + 1e-9, (k, err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_two_runs_are_bit_identical(precision):
+    """No floating-point atomics: two runs of three train-mode (dropout on) default-eps Adam steps from the same state give
+    bit-identical parameters, Adam moments, predictions and losses."""
+    from gpu_util import model_from_golden
+    g = Golden('enp_small')
+    outs = []
+    for run in range(2):
+        model = model_from_golden(g, precision=precision)
+        eng = model.engine
+        rec = []
+        for step in range(3):
+            yp, w = eng.train_step(_dev(g.X(step)), _dev(g.y(step)), lr=float(g.z['lr']), l2_emb=g.cfg.l2_reg_embedding,
+                                   dense_mode=True, training=True, dropout_p=0.1, seed=77 + step)
+            rec.append(yp.clone())
+            rec.append(w['scalars'][0:2].clone())
+        torch.cuda.synchronize()
+        st = eng.adam_state()
+        outs.append([t.cpu() for t in rec] + [model._tables.detach().cpu().clone(), model._dense.detach().cpu().clone(),
+                                              st['tab_m'].cpu().clone(), st['tab_v'].cpu().clone(),
+                                              st['dense_m'].cpu().clone(), st['dense_v'].cpu().clone()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize('opt,loss', [('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae')])
@@ -175,7 +218,7 @@ def test_compile_string_variants_match_reference(opt, loss):
     v = np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))
     tag = '%s_%s' % (opt, loss)
     lr = float(v[tag + '/lr'])
-    model = model_from_golden(g)
+    model = model_from_golden(g)                      # package default: tcgen05 3xTF32
     model.dropout_rate = 0.0
     model.compile(opt, loss)
     assert abs(model._opt_hparams['lr'] - lr) < 1e-8          # (the fixture stores lr as float32)
@@ -191,7 +234,6 @@ def test_compile_string_variants_match_reference(opt, loss):
             assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
         else:
             # Adagrad / RMSprop with their default eps (1e-10 / 1e-8) normalise the first steps to ~+-lr (RMSprop: +-10 lr), so
-            # the round-off of near-zero gradient elements decides their sign: most elements must agree to
-            # fp32 round-off, the step-1 loss above already pins the update as a whole
-            tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
-            assert ((got - ref).abs() <= tight).float().mean().item() >= 0.95, k
+            # the round-off of near-zero gradient elements decides their sign: the same bar as the CPU
+            # oracle itself is held to against these vectors (tests/test_oracle_golden.py)
+            assert_adam_close(got, ref, lr, 2, k)
