@@ -39,7 +39,7 @@ extern "C" {
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
-#define SAT_WORK_BUFFERS 31  /* pointer members of SatWork */
+#define SAT_WORK_BUFFERS 32  /* pointer members of SatWork */
 #define SAT_GRID_MAX (148 * 2) /* most CTAs any token kernel is launched with: rows of the per-CTA partial buffers */
 #define SAT_SORT_RADIX_BITS 9  /* digit width of the touched-row radix sort */
 #define SAT_SORT_TILE 2048     /* sorted entries per CTA and radix pass */
@@ -121,6 +121,11 @@ typedef struct SatModel {
 typedef struct SatWork {
     int32_t B;            /* samples in this batch                                          */
     int32_t cap_B;        /* capacity the buffers were sized for                            */
+    int32_t device_step;  /* != 0: the dropout seed and the optimiser's step-dependent constants come from step_state
+                             (advanced on the device by sat_step_begin) instead of the by-value arguments, so that a
+                             whole training step can be captured ONCE in a CUDA graph and replayed            */
+    int32_t head_bwd_done; /* set by sat_forward_tc when it also ran the logit head's backward (training, labels given); read by
+                             the next sat_backward*, which then skips its own head kernel; cleared by sat_forward      */
     int32_t* perm;        /* [cap_B] sorted position -> sample index (bucketed by scenario) */
     int32_t* dom;         /* [cap_B] scenario id per sorted position                        */
     int32_t* tiles;       /* [max_tiles][4] (key/domain, start, count, pad)                 */
@@ -157,6 +162,8 @@ typedef struct SatWork {
     float* recv;          /* [n_shards][cap_B*F][32] rows pushed by source shard s (filled by the peers)             */
     int32_t* recv_idx;    /* [n_shards][touched rows cap] slot -> index into recv[s], -1 = nothing (filled by peers) */
     uint32_t* peer_flags; /* [32] words: [0..8) epoch flags written by the peers, [8] own epoch, [16..24) push cursors */
+    float* step_state;    /* [32] words, see sat_step_begin: [0..1] u64 seed, [2] i32 step, [4..7] f32 lr, beta1, beta2, eps (the
+                             caller copies them in, e.g. from pinned memory inside the graph), [8..15] derived constants  */
 } SatWork;
 
 /* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */
@@ -251,6 +258,13 @@ int sat_enable_peer_access(int32_t peer_device);
  * space with peer access over NVLink; *out_ptr_host receives the base pointer of the exporter's allocation. */
 int sat_ipc_open(const void* handle64_host, void** out_ptr_host);
 int sat_ipc_close(void* ptr);
+
+/* ---- device-side step state (CUDA-graph replay).  One 1-thread kernel: step += 1; seed = seed_base + step; the optimiser
+ *      constants of THIS step (bias corrections in double precision, like torch.optim.Adam) are derived from the
+ *      hyper-parameters lr, beta1, beta2, eps found in w->step_state[4..7].  Kernels launched with w->device_step != 0 read
+ *      them from there.  sat_step_set writes the step counter and the hyper-parameters from the host (stream-ordered). ---- */
+int sat_step_begin(SatWork* w, uint64_t seed_base, void* stream);
+int sat_step_set(SatWork* w, int32_t step, float lr, float beta1, float beta2, float eps, void* stream);
 
 /* ---- optimiser: replaces get_regularization_loss (reference meta_basemodel.py:577-593), the dense
  *      embedding_dense_backward and torch.optim.Adam.step (main.py:343, meta_basemodel.py:328). ---- */

@@ -197,14 +197,17 @@ def build_case(name):
 
 
 def build_selfatt():
-    """SelfAttention_Layer of the unmodified reference (submodules.py:178-238): eval-mode forward goldens."""
+    """SelfAttention_Layer of the unmodified reference (submodules.py:178-238): eval-mode forward goldens and the gradients of
+    sum(y * cot) w.r.t. the input and every parameter (torch autograd through the reference module).  Seeded: the module's
+    constructor draws from torch's global stream."""
     sys.path.insert(0, ROOT)
     from oracle import satrans_oracle as O
     import_reference()
     from models.submodules import SelfAttention_Layer
     out = {}
     g = torch.Generator().manual_seed(3)
-    for heads, Fn, res in ((4, 19, True), (2, 15, True), (4, 7, False)):
+    for idx, (heads, Fn, res) in enumerate(((4, 19, True), (2, 15, True), (4, 7, False))):
+        torch.manual_seed(1021 + idx)
         layer = SelfAttention_Layer(32, heads, use_res=res).eval()
         with torch.no_grad():
             layer.layer_norm.weight.add_(1.0)          # N(0, .05) gamma would squash the output to ~0
@@ -220,6 +223,16 @@ def build_selfatt():
         with torch.no_grad():
             o = O.self_attention_layer(x, sd, heads, res)
         assert torch.allclose(o, y, atol=1e-6, rtol=0), (o - y).abs().max()
+        # backward goldens
+        cot = torch.randn((24, Fn, 32), generator=g)
+        xg = x.clone().requires_grad_(True)
+        layer.zero_grad()
+        (layer(xg) * cot).sum().backward()
+        out[tag + '/cot'] = cot.numpy()
+        out[tag + '/grad/x'] = xg.grad.numpy()
+        for k, p_ in layer.named_parameters():
+            if p_.grad is not None:
+                out[tag + '/grad/' + k] = p_.grad.detach().numpy()
     return out
 
 

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 8 + 148 * 4
-SAT_WORK_BUFFERS = 31
+SAT_WORK_BUFFERS = 32
 SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
 SAT_ABI_VERSION = 2
 SAT_MAX_SHARDS = 8
@@ -43,12 +43,12 @@ class SatModel(C.Structure):
 WORK_BUFFERS = ['perm', 'dom', 'tiles', 'counters', 'theta', 'dtheta', 'enc_du', 'acts', 'dz', 'dx', 'dqkv',
                 'loss_part', 'dgrad', 'bitmap', 'word_rank', 'block_sums', 'uniq_rows', 'row_grad', 'reg_part',
                 'scalars', 'wpack', 'tiles2', 'gpart', 'sort_keys', 'sort_vals', 'sort_hist', 'chunk_info', 'pieces',
-                'recv', 'recv_idx', 'peer_flags']
+                'recv', 'recv_idx', 'peer_flags', 'step_state']
 assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
 
 
 class SatWork(C.Structure):
-    _fields_ = [('B', i32), ('cap_B', i32)] + [(n, vp) for n in WORK_BUFFERS]
+    _fields_ = [('B', i32), ('cap_B', i32), ('device_step', i32), ('head_bwd_done', i32)] + [(n, vp) for n in WORK_BUFFERS]
 
 
 class SatAdam(C.Structure):
@@ -81,6 +81,8 @@ PROTOTYPES = {
     'sat_peer_barrier': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_ipc_open': (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     'sat_ipc_close': (C.c_int, [vp]),
+    'sat_step_begin': (C.c_int, [C.POINTER(SatWork), C.c_uint64, vp]),
+    'sat_step_set': (C.c_int, [C.POINTER(SatWork), i32, f32, f32, f32, f32, vp]),
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),

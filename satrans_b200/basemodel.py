@@ -566,15 +566,26 @@ class BaseModel(nn.Module):
         else:
             X = self._stack_inputs(x)
         dev = self._tables.device
-        Xd = torch.as_tensor(X).to(dev, non_blocking=True)
-        yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)
         hp = self._hparams()
         eng = self.engine
         self.train()
-        _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
-                              opt_kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates, training=True,
-                              dropout_p=self.dropout_rate,
-                              seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
+        seed0 = int(torch.initial_seed()) & (2 ** 63 - 1)
+        host_batch = not (torch.is_tensor(X) and X.is_cuda)
+        gkey = (tuple(X.shape), str(X.dtype), hp['kind'])
+        seen = eng._graph_seen.get(gkey, 0)
+        eng._graph_seen[gkey] = seen + 1
+        if host_batch and eng.use_cuda_graph and eng.dist is None and seen >= 2:
+            # third and later batches of this shape: the step (H2D copies included) is ONE CUDA-graph launch
+            w = eng.graph_train_step(X, np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y.float(),
+                                     lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
+                                     l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                     dropout_p=self.dropout_rate, seed0=seed0)
+        else:
+            Xd = torch.as_tensor(X).to(dev, non_blocking=True)
+            yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)
+            _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
+                                  opt_kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                  training=True, dropout_p=self.dropout_rate, seed=(seed0 + eng.step_count) & (2 ** 63 - 1))
         sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()
         if sc[3] != 0:
             eng.check_errors(w)

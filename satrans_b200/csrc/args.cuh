@@ -21,6 +21,9 @@ struct FwdArgs {
     float* y_pred;
     float p_drop;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;   // != NULL: the seed lives in SatWork.step_state (CUDA-graph replay)
+    float* dx;                 // tensor-core forward with labels: receives dLoss/dX_L (the logit head's backward is folded in)
+    float* gpart;              // ... and the head's parameter-gradient partials (gpart_layout in bwd_common.cuh)
 };
 
 enum { ACT_X = 0, ACT_ZQ = 1, ACT_ZK = 2, ACT_V = 3, ACT_R = 4, ACT_PER_LAYER = 5 };
@@ -55,6 +58,7 @@ struct BwdArgs {
     int layer;
     float p_drop;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;   // != NULL: the seed lives in SatWork.step_state (CUDA-graph replay)
 };
 
 }  // namespace sat

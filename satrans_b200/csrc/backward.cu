@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     float* sG = sA + NT * KV_LD;
 
     const SatModel& m = a.m;
+    const uint32_t seed32 = step_seed32(a.seed, a.seed_ptr);
     const int tid = threadIdx.x, lane = tid & 31, F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
             metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLNq, sdW + OFF_WQ, sA,
                              sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride,
                              relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 0, tokpos / D), tokpos,
-                             make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, true), dqp);
+                             make_drop(seed32, token_gid, l, SITE_Q, a.p_drop, true), dqp);
             if (valid) vm_dot<D, D, D>(sW + OFF_WQ, dqp, dxa);          // dX[i] += sum_j dqp[j] WQ[i][j]
         }
         {   // ---- K side ---------------------------------------------------------------------------------
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
             metanet_side_bwd(a, meta_k, valid, ntok, tid, lane, sW + OFF_WK, thK, sdThKuse, klng, sdLNk, sdW + OFF_WK, sA,
                              sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZK * a.act_stride,
                              relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 1, tokpos / D), tokpos,
-                             make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, true), dkp);
+                             make_drop(seed32, token_gid, l, SITE_K, a.p_drop, true), dkp);
             if (valid) vm_dot<D, D, D>(sW + OFF_WK, dkp, dxa);
         }
         {   // ---- V side ---------------------------------------------------------------------------------
@@ -373,6 +374,7 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
     a.theta = w->theta; a.dtheta = w->dtheta; a.acts = w->acts; a.act_stride = (long long)w->cap_B * m->F * D;
     a.dz = w->dz; a.dx = w->dx; a.dqkv = w->dqkv; a.dgrad = w->dgrad; a.bitmap = w->bitmap; a.word_rank = w->word_rank;
     a.row_grad = w->row_grad; a.layer = 0; a.p_drop = dropout_p; a.seed = seed; a.gpart = w->gpart;
+    a.seed_ptr = w->device_step ? reinterpret_cast<const unsigned long long*>(w->step_state) : nullptr;
     const int spt = NT / m->F;
     const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
     const int grid2 = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
@@ -384,9 +386,13 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
             return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem_b);
         configured_b = true;
     }
-    k_bwd_head<<<grid2, NT, 0, s>>>(a);
-    int rc = sat_host::check_launch("k_bwd_head");
-    if (rc) return rc;
+    int rc = SAT_OK;
+    const bool head_done = w->head_bwd_done != 0;      // sat_forward_tc already ran the logit head's backward in its epilogue
+    if (!head_done) {
+        k_bwd_head<<<grid2, NT, 0, s>>>(a);
+        rc = sat_host::check_launch("k_bwd_head");
+        if (rc) return rc;
+    }
     const int spt2 = NT2 / m->F;
     const int max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
     BwdArgs aa = a;                           // k_bwd_attn walks the 128-token tile set
@@ -415,7 +421,7 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
     }
     RedArgs ra;
     ra.m = *m; ra.gpart = w->gpart; ra.counters = w->counters; ra.dgrad = w->dgrad; ra.dtheta = w->dtheta;
-    ra.g_attn = grid_a; ra.g_meta = passes == 0 ? grid1 : grid_a; ra.g_head = grid2; ra.spt_meta = passes == 0 ? spt : spt2;
+    ra.g_attn = grid_a; ra.g_meta = passes == 0 ? grid1 : grid_a; ra.g_head = head_done ? grid_a : grid2; ra.spt_meta = passes == 0 ? spt : spt2;
     {
         const long long total = (long long)m->L * LAYER_FLOATS + m->F * D + m->n_dense + 1 + (long long)n_keys * PSZ;
         long long blocks = (total + 63) / 64;

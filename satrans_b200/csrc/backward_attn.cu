@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
     constexpr int DH = D / H;
     extern __shared__ __align__(16) float smem[];
     const SatModel& m = a.m;
+    const uint32_t seed32 = step_seed32(a.seed, a.seed_ptr);
     const int tid = threadIdx.x, lane = tid & 31, hsel = tid >> 6, F = m.F, l = a.layer;
     const int tile_rows = ((BA_NT / F) * F + 3) & ~3;
     float* sWO = smem;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                 cp_async_wait_all();                       // own rows of T0 / T2 / T3 have landed
                 lds_row(sT0 + tid * KV_LD, r);
                 vm_dot<D, D, D>(sWO, r, o);
-                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
+                const DropCtx dco = make_drop(seed32, token_gid, l, SITE_OUT, a.p_drop, true);
 #pragma unroll
                 for (int i = 0; i < D; i += 2) {
                     float fk[2];
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
             if (valid) {
                 if (use_res) store_row(a.dx + tokpos, dy);                  // residual branch of dX
                 else { float zr[D]; zero(zr); store_row(a.dx + tokpos, zr); }
-                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, true);
+                const DropCtx dco = make_drop(seed32, token_gid, l, SITE_OUT, a.p_drop, true);
 #pragma unroll
                 for (int i = 0; i < D; i += 2) {                                                  // dy := dO
                     float f0, f1;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
         if (valid) {
             float dq[D];
             zero(dq);
-            const DropCtx dca = make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, true);
+            const DropCtx dca = make_drop(seed32, token_gid, l, SITE_ATT, a.p_drop, true);
             const int sbase = s * F;
             sSt[tid * ST_LD + 24] = __uint_as_float(dca.key);          // read back by the key-role pass of the other tokens
             // rolled over heads: q / dr / dq are rotated by DH per head (compact code, see common.cuh)
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
             const int sbase = s * F;
             float* dk_out = a.dqkv + 1 * a.act_stride + tokpos;
             float* dv_out = a.dqkv + 2 * a.act_stride + tokpos;
-            DropCtx dci = make_drop(a.seed, 0u, l, SITE_ATT, a.p_drop, true);     // .key is replaced per query below
+            DropCtx dci = make_drop(seed32, 0u, l, SITE_ATT, a.p_drop, true);     // .key is replaced per query below
 #pragma unroll 1
             for (int h = 0; h < H; ++h) {
                 float kh[DH], vh[DH], dk[DH], dv[DH];

@@ -21,18 +21,36 @@ constexpr int TCB_SB = 4096;                                             // floa
 // F = 19: 97.9 KB (EN) / 114.4 KB (ENP) -> 2 CTAs per SM either way.
 static size_t tcb_smem_bytes(int F, bool pos) {
     const int rows = ((TC_NT / F) * F + 3) & ~3;
-    return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + (TC_NT / 32) * 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);
+    return (size_t)(TCB_SB + 3 * rows * KV_LD + 192 + 3072 + (TC_NT / 32) * 128 + (pos ? 2 : 1) * PSZ + 8) * sizeof(float);   // (+8: two mbarriers, TMEM address)
 }
 
-// copy n floats of packed operand into sB (all threads); the round macro issues the generic->async proxy fence
-__device__ __forceinline__ void load_b(float* __restrict__ sB, const float* __restrict__ src, int n, int tid) {
-    copy_to_smem(sB, src, n, tid, TC_NT);
+// B operands of the next round: n floats of packed weights -> sB by TMA (cp.async.bulk, SASS UBLKCP), issued by the MMA-issuing
+// thread; it waits for the bytes (mbarrier transaction count) right before issuing the round's MMAs, so the copy rides under
+// the CUDA-core work in between.  Callers make sure every MMA / thread that read the destination has finished (a round has
+// been waited for, or a __syncthreads); the proxy fence orders earlier generic-proxy accesses of sB before the async write.
+__device__ __forceinline__ void load_b(float* __restrict__ sB, const float* __restrict__ src, int n, int tid, uint64_t* bar) {
+    if (tid == 0) {
+        fence_async_smem();
+        mbar_expect_tx(bar, (uint32_t)n * 4u);
+        tma_load_1d(sB, src, (uint32_t)n * 4u, bar);
+    }
+}
+// two pieces, one transaction
+__device__ __forceinline__ void load_b2(float* __restrict__ d0, const float* __restrict__ s0, float* __restrict__ d1,
+                                        const float* __restrict__ s1, int n, int tid, uint64_t* bar) {
+    if (tid == 0) {
+        fence_async_smem();
+        mbar_expect_tx(bar, 2u * (uint32_t)n * 4u);
+        tma_load_1d(d0, s0, (uint32_t)n * 4u, bar);
+        tma_load_1d(d1, s1, (uint32_t)n * 4u, bar);
+    }
 }
 
 template <int PASSES>
 __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const float* __restrict__ wpack, int n_keys) {
     extern __shared__ __align__(128) float smem[];
     const SatModel& m = a.m;
+    const uint32_t seed32 = step_seed32(a.seed, a.seed_ptr);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, hsel = tid >> 6;
     const int F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
@@ -47,8 +65,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     float* sdLN = sdW + 3072;                 // per warp: dQLN_G dQLN_B dKLN_G dKLN_B
     float* sdThQ = sdLN + (TC_NT / 32) * 128;
     float* sdThK = sdThQ + PSZ;               // only with per-position keys
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThQ + (pos ? 2 : 1) * PSZ);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 1);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sdThQ + (pos ? 2 : 1) * PSZ);   // [0] MMA completion, [1] B operands landed (TMA)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar + 2);
 
     const int s = tid / F, f = tid - s * F;
     // every CTA stays inside ONE scenario: one set of generated-weight gradients per CTA, reduced over CTAs in a fixed order
@@ -64,27 +82,28 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
     for (int i = tid; i < (pos ? 2 : 1) * PSZ; i += TC_NT) sdThQ[i] = 0.f;
     for (int i = tid; i < (TC_NT / 32) * 128; i += TC_NT) sdLN[i] = 0.f;
     if (warp == 0) tmem_alloc(s_tmem, TC_COLS);
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *s_tmem;
     const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase = 0;
+    uint32_t phase = 0, bphase = 0;           // bphase: parity of the B-operand barrier (every round waits for exactly one load)
     float* const sdLNw = sdLN + warp * 128;   // this warp's LayerNorm-gradient slots
     float* const sTh = hsel ? sT1 : sT0;      // this 64-thread half's tile in the paired weight-gradient phases
 
 #define SAT_TC_ROUND(ISSUE)                                  \
     do {                                                     \
-        fence_async_smem();                                  \
         tc_wait_st();                                        \
         tc_fence_before();                                   \
         __syncthreads();                                     \
         if (tid == 0) {                                      \
+            mbar_wait(mbar + 1, bphase);                     \
             tc_fence_after();                                \
             ISSUE;                                           \
             mma_commit(mbar);                                \
         }                                                    \
+        bphase ^= 1u;                                        \
         mbar_wait(mbar, phase);                              \
         phase ^= 1u;                                         \
         tc_fence_after();                                    \
@@ -126,8 +145,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             {
                 float xin[D];
                 if (valid) load_row(act_l + ACT_X * a.act_stride + tokpos, xin); else zero(xin);
-                load_b(sB, pk_lf + PK_QKV_HI + side * 1024, 1024, tid);
-                load_b(sB + 1024, pk_lf + PK_QKV_LO + side * 1024, 1024, tid);
+                load_b2(sB, pk_lf + PK_QKV_HI + side * 1024, sB + 1024, pk_lf + PK_QKV_LO + side * 1024, 1024, tid, mbar + 1);
                 tmem_st_operand<PASSES>(tlane + TCB_A, xin);
                 SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB, sB + 1024, 32, false));
                 tmem_ld32(tlane + TCB_D, u);
@@ -138,7 +156,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
                 float rstd = 0.f;
                 if (valid) rstd = normalize32(zh);
                 layernorm_bwd32(du, zh, rstd, lng, sdLNs, sdLNs + 32, lane, valid);         // du := dLoss/dz
-                const DropCtx dc = make_drop(a.seed, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
+                const DropCtx dc = make_drop(seed32, token_gid, l, side ? SITE_K : SITE_Q, a.p_drop, true);
 #pragma unroll
                 for (int i = 0; i < D; i += 2) {
                     float f0, f1;
@@ -150,7 +168,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             if (valid) mk = *reinterpret_cast<const uint2*>(relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, side, tokpos / D));
 
             // ---- pre = u @ W1 (N = 64): hidden activations; dW2[half*32 + c][j] += h[c] dm[j], both halves at once ------------
-            load_b(sB, pk_kf + PK_W1_HI, 4096, tid);
+            load_b(sB, pk_kf + PK_W1_HI, 4096, tid, mbar + 1);
             tmem_st_operand<PASSES>(tlane + TCB_A, u);
             SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PK_W1_HI, sB + PK_W1_LO, 64, false));
             if (stage) sts_row(sT2 + tid * KV_LD, dm);
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             __syncthreads();
             wgrad_half(sTh, sT2, ntok4, sdTh + D * HID + hsel * D * D, D, tid);
             // ---- dh = dm @ W2^T (N = 64), masked; dW1[i][half*32 + c] += u[i] dh[c]; du += dh @ W1^T ---------------------------
-            load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid);
+            load_b(sB, pk_kb + PKB_W2T_HI, 4096, tid, mbar + 1);
             tmem_st_operand<PASSES>(tlane + TCB_A, dm);
             SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_W2T_HI, sB + PKB_W2T_LO, 64, false));
             if (stage) sts_row(sT2 + tid * KV_LD, u);            // (the round's barrier: dW2 phase is done with the tiles)
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             }
             __syncthreads();
             wgrad_half(sT2, sTh, ntok4, sdTh + hsel * D, HID, tid);
-            load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid);
+            load_b(sB, pk_kb + PKB_W1N0_HI, 4096, tid, mbar + 1);
             SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB, sB + 1024, 32, false),
                           issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB + 2048, sB + 3072, 32, true)));
             {
@@ -214,14 +232,14 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
             if (valid) { load_row(a.dqkv + 2 * a.act_stride + tokpos, dv); load_row(a.dx + tokpos, res); }
             else { zero(dv); zero(res); }
         }
-        load_b(sB, pk_lb + PKB_WQN_HI, 4096, tid);
+        load_b(sB, pk_lb + PKB_WQN_HI, 4096, tid, mbar + 1);
         __syncthreads();
         wgrad_half(sT2, sTh, ntok4, sdW + (hsel ? OFF_WK : OFF_WQ), D, tid);
         SAT_TC_ROUND((issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_A, sB + PKB_WQN_HI, sB + PKB_WQN_LO, 32, false),
                       issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H, sB + PKB_WKN_HI, sB + PKB_WKN_LO, 32, true)));
         if (stage) sts_row(sT0 + tid * KV_LD, dv);               // (the round's barrier: paired phase is done with sT0)
         tmem_st_operand<PASSES>(tlane + TCB_H2, dv);
-        load_b(sB, pk_lb + PKB_WVN_HI, 2048, tid);
+        load_b(sB, pk_lb + PKB_WVN_HI, 2048, tid, mbar + 1);
         __syncthreads();
         // dW_V: one product for 128 threads -> each half takes half of the token groups; the upper half parks its partial
         // block in the free part of sB and the lower half adds both to the accumulator after the round's barrier

@@ -82,6 +82,7 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = training && sharded ? (int64_t)m->n_shards * tok * SAT_D * 4 : 0;               // recv
     sz[i++] = training && sharded ? (int64_t)m->n_shards * sat_idx_stride(m, tok) * 4 : 0;    // recv_idx (the caller fills it with -1)
     sz[i++] = training ? 32 * 4 : 0;                       // peer_flags
+    sz[i++] = 32 * 4;                                      // step_state
     if (max_tiles_host) *max_tiles_host = (int32_t)max_tiles;
     return SAT_OK;
 }
@@ -103,6 +104,9 @@ extern "C" int sat_forward(const SatModel* m, const void* x, int32_t id_kind, in
     a.counters = w->counters; a.theta = w->theta; a.acts = w->acts;
     a.act_stride = (long long)w->cap_B * m->F * D;
     a.dz = w->dz; a.loss_part = w->loss_part; a.y_pred = y_pred; a.p_drop = dropout_p; a.seed = seed;
+    a.seed_ptr = w->device_step ? reinterpret_cast<const unsigned long long*>(w->step_state) : nullptr;
+    a.dx = nullptr; a.gpart = nullptr;
+    w->head_bwd_done = 0;
     const int spt = NT / m->F;
     const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
     const int grid = max_tiles < 148 * 2 ? max_tiles : 148 * 2;
@@ -159,6 +163,11 @@ extern "C" int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind,
     a.counters = w->counters; a.theta = w->theta; a.acts = w->acts;
     a.act_stride = (long long)w->cap_B * m->F * D;
     a.dz = w->dz; a.loss_part = w->loss_part; a.y_pred = y_pred; a.p_drop = dropout_p; a.seed = seed;
+    a.seed_ptr = w->device_step ? reinterpret_cast<const unsigned long long*>(w->step_state) : nullptr;
+    // training with labels: the logit head's backward runs in this kernel's epilogue (dLoss/dX_L -> w->dx, head partials)
+    const bool fold = training && y && w->dx && w->gpart;
+    a.dx = fold ? w->dx : nullptr; a.gpart = fold ? w->gpart : nullptr;
+    w->head_bwd_done = fold ? 1 : 0;
     const int spt = 128 / m->F;
     const int max_tiles = (w->B + spt - 1) / spt + m->n_dom;
     const int grid = max_tiles < 148 * 2 ? max_tiles : 148 * 2;

@@ -54,14 +54,21 @@ struct DropCtx {
     float scale;      // 1/(1-p)
     bool on;
 };
-__device__ __forceinline__ DropCtx make_drop(uint64_t seed, uint32_t token_gid, uint32_t layer, uint32_t site,
+// 64-bit step seed -> the 32 bits the per-token keys are derived from (once per kernel)
+__device__ __forceinline__ uint32_t fold_seed(uint64_t seed) { return (uint32_t)seed ^ (uint32_t)(seed >> 32) * 0x9E3779B1U; }
+// words of SatWork.step_state (device-side step state, see sat_step_begin)
+constexpr int SS_SEED = 0, SS_STEP = 2, SS_HYPER = 4, SS_CONST = 8;
+// the step's seed: by value, or from the device-side step state when the step is replayed from a CUDA graph
+__device__ __forceinline__ uint32_t step_seed32(uint64_t seed, const unsigned long long* __restrict__ seed_ptr) {
+    return fold_seed(seed_ptr ? *seed_ptr : seed);
+}
+__device__ __forceinline__ DropCtx make_drop(uint32_t seed32, uint32_t token_gid, uint32_t layer, uint32_t site,
                                              float p, bool training) {
     DropCtx c;
     c.on = training && p > 0.f;
     c.thr = (uint32_t)(p * 65536.f + 0.5f);
     c.scale = 1.f / (1.f - p);
-    uint32_t s = (uint32_t)seed ^ (uint32_t)(seed >> 32) * 0x9E3779B1U;
-    c.key = mix32(s + token_gid * 0x9E3779B1U) ^ ((layer * 4u + site + 1u) * 0x85EBCA77U);
+    c.key = mix32(seed32 + token_gid * 0x9E3779B1U) ^ ((layer * 4u + site + 1u) * 0x85EBCA77U);
     return c;
 }
 // keep-mask factor (0 or 1/(1-p)) of element e

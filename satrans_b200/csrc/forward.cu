@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
     __shared__ double s_lossv[NT];      // per-sample loss terms of the tile, added in sample order (no atomics)
 
     const SatModel& m = a.m;
+    const uint32_t seed32 = step_seed32(a.seed, a.seed_ptr);
     const int tid = threadIdx.x;
     const int F = m.F, L = m.L;
     const bool pos = m.flags & SAT_FLAG_POS;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                     if (meta_k) {
                         float z[D];
                         uint32_t mk[2];
-                        metanet_fwd(kp, thK, make_drop(a.seed, token_gid, l, SITE_K, a.p_drop, TRAIN), z, mk);
+                        metanet_fwd(kp, thK, make_drop(seed32, token_gid, l, SITE_K, a.p_drop, TRAIN), z, mk);
                         if (TRAIN) {
                             store_row(act_l + ACT_ZK * a.act_stride + tokpos, z);
                             *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, 1, tokpos / D)) = make_uint2(mk[0], mk[1]);
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                     vm_outer<D, D, D>(sW + OFF_WQ, x, qp);
                     if (meta_q) {
                         uint32_t mq[2];
-                        metanet_fwd(qp, sThQ, make_drop(a.seed, token_gid, l, SITE_Q, a.p_drop, TRAIN), q, mq);
+                        metanet_fwd(qp, sThQ, make_drop(seed32, token_gid, l, SITE_Q, a.p_drop, TRAIN), q, mq);
                         if (TRAIN) {
                             store_row(act_l + ACT_ZQ * a.act_stride + tokpos, q);
                             *reinterpret_cast<uint2*>(relu_mask_ptr(a.acts, a.act_stride, L, l, 0, tokpos / D)) = make_uint2(mq[0], mq[1]);
@@ -147,13 +148,13 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
             __syncthreads();
             if (valid) {
                 float r[D];
-                attention_fwd<H>(q, sK, sV, s * F, F, make_drop(a.seed, token_gid, l, SITE_ATT, a.p_drop, TRAIN), r);
+                attention_fwd<H>(q, sK, sV, s * F, F, make_drop(seed32, token_gid, l, SITE_ATT, a.p_drop, TRAIN), r);
                 if (TRAIN) store_row(act_l + ACT_R * a.act_stride + tokpos, r);
                 // O = dropout(act(R @ W_out^T)); x = LN(O + x)   (satrans.py:91-99)
                 float o[D];
                 zero(o);
                 vm_dot<D, D, D>(sW + OFF_WO, r, o);
-                const DropCtx dco = make_drop(a.seed, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
+                const DropCtx dco = make_drop(seed32, token_gid, l, SITE_OUT, a.p_drop, TRAIN);
 #pragma unroll
                 for (int i = 0; i < D; i += 2) {
                     float fk[2];

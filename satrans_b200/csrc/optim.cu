@@ -20,9 +20,18 @@
 namespace sat {
 
 struct AdamConst {
-    float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, two_l2, lr;
+    float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, lr, two_l2;
     int kind;
 };
+// with a device-side step state (CUDA-graph replay) the first seven constants come from SatWork.step_state[SS_CONST..]
+__device__ __forceinline__ AdamConst resolve_const(const AdamConst& by_value, const float* __restrict__ dev) {
+    AdamConst c = by_value;
+    if (dev) {
+        c.one_minus_b1 = dev[0]; c.b2 = dev[1]; c.one_minus_b2 = dev[2]; c.step_size = dev[3]; c.bc2_sqrt = dev[4];
+        c.eps = dev[5]; c.lr = dev[6];
+    }
+    return c;
+}
 
 // one parameter element; follows the op order of torch.optim's single-tensor implementations
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, const AdamConst& c) {
@@ -70,7 +79,9 @@ constexpr int SWEEP_BLOCKS = 148 * 8;     // SAT_REG_PARTS = SWEEP_BLOCKS + ROWS
 // read once and written once.  reg_part[blockIdx] receives sum(p_old^2) over the rows this block swept.
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_adam_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const uint32_t* __restrict__ bitmap,
-             long long n_vec /* total_rows * 8 */, AdamConst c, double* __restrict__ reg_part) {
+             long long n_vec /* total_rows * 8 */, const AdamConst c_in, const float* __restrict__ dev_const,
+             double* __restrict__ reg_part) {
+    const AdamConst c = resolve_const(c_in, dev_const);
     float sq = 0.f;
     const long long stride = (long long)gridDim.x * SWEEP_THREADS;
     for (long long i0 = (long long)blockIdx.x * SWEEP_THREADS + threadIdx.x; i0 < n_vec; i0 += stride * SWEEP_UNROLL) {
@@ -113,8 +124,9 @@ constexpr int ROWS_BLOCKS = 148 * 4;
 // Touched rows: g = accumulated dE + 2*l2*p, Adam, clear the accumulator for the next step.
 __global__ void __launch_bounds__(ROWS_THREADS)
 k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const int32_t* __restrict__ uniq_rows,
-            float4* __restrict__ row_grad, const int32_t* __restrict__ counters, AdamConst c,
-            double* __restrict__ reg_part) {
+            float4* __restrict__ row_grad, const int32_t* __restrict__ counters, const AdamConst c_in,
+            const float* __restrict__ dev_const, double* __restrict__ reg_part) {
+    const AdamConst c = resolve_const(c_in, dev_const);
     const long long n_vec = (long long)counters[CNT_NUNIQ] * 8;
     float sq = 0.f;
     for (long long i = (long long)blockIdx.x * ROWS_THREADS + threadIdx.x; i < n_vec;
@@ -124,8 +136,7 @@ k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__
         float4 p = P[e], m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
         if (c.kind == SAT_OPT_ADAM) m = M[e];
         if (c.kind != SAT_OPT_SGD) v = V[e];
-        float4 g = row_grad[i];
-        row_grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = row_grad[i];                  // (fully rewritten by sat_rows_reduce / sat_rows_combine every step)
         sq = fmaf(p.x, p.x, sq); sq = fmaf(p.y, p.y, sq); sq = fmaf(p.z, p.z, sq); sq = fmaf(p.w, p.w, sq);
         g.x = fmaf(c.two_l2, p.x, g.x); g.y = fmaf(c.two_l2, p.y, g.y);
         g.z = fmaf(c.two_l2, p.z, g.z); g.w = fmaf(c.two_l2, p.w, g.w);
@@ -140,7 +151,8 @@ k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__
 // Flat dense-parameter buffer (148 k floats in the EN configuration).
 __global__ void __launch_bounds__(256)
 k_adam_dense(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V, const float* __restrict__ G, long long n,
-             AdamConst c) {
+             const AdamConst c_in, const float* __restrict__ dev_const) {
+    const AdamConst c = resolve_const(c_in, dev_const);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         float p = P[i], m = 0.f, v = 0.f;
         if (c.kind == SAT_OPT_ADAM) m = M[i];
@@ -210,12 +222,13 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
         return sat_host::fail(SAT_EINVAL, "sat_tables_adam: null argument / bad optimiser kind");
     if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_tables_adam: step must be >= 1");
     const AdamConst c = make_const(a, true);
+    const float* dev_const = w->device_step ? w->step_state + SS_CONST : nullptr;
     const long long n_vec = m->local_rows * 8;
     cudaStream_t s = (cudaStream_t)stream;
     if (which & SAT_ADAM_TOUCHED) {
         k_adam_rows<<<ROWS_BLOCKS, ROWS_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
-            w->uniq_rows, reinterpret_cast<float4*>(w->row_grad), w->counters, c, w->reg_part + SWEEP_BLOCKS);
+            w->uniq_rows, reinterpret_cast<float4*>(w->row_grad), w->counters, c, dev_const, w->reg_part + SWEEP_BLOCKS);
         int rc = sat_host::check_launch("k_adam_rows");
         if (rc) return rc;
     }
@@ -228,7 +241,7 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
     if ((which & SAT_ADAM_UNTOUCHED) && a->dense_mode) {
         k_adam_sweep<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
-            w->bitmap, n_vec, c, w->reg_part);
+            w->bitmap, n_vec, c, dev_const, w->reg_part);
         int rc = sat_host::check_launch("k_adam_sweep");
         if (rc) return rc;
     }
@@ -251,8 +264,36 @@ extern "C" int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, v
     const AdamConst c = make_const(a, false);
     int blocks = (int)((m->n_dense_params + 255) / 256);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    k_adam_dense<<<blocks, 256, 0, (cudaStream_t)stream>>>(m->dense, a->dense_m, a->dense_v, w->dgrad, m->n_dense_params, c);
+    const float* dev_const = w->device_step ? w->step_state + SS_CONST : nullptr;
+    k_adam_dense<<<blocks, 256, 0, (cudaStream_t)stream>>>(m->dense, a->dense_m, a->dense_v, w->dgrad, m->n_dense_params, c, dev_const);
     return sat_host::check_launch("k_adam_dense");
+}
+
+// ---- device-side step state -------------------------------------------------------------------------------------------
+__global__ void k_step_begin(float* __restrict__ st, unsigned long long seed_base) {
+    int* sti = reinterpret_cast<int*>(st);
+    const int step = sti[SS_STEP] + 1;
+    sti[SS_STEP] = step;
+    *reinterpret_cast<unsigned long long*>(st + SS_SEED) = seed_base + (unsigned long long)step;
+    const float lr = st[SS_HYPER + 0], b1 = st[SS_HYPER + 1], b2 = st[SS_HYPER + 2], eps = st[SS_HYPER + 3];
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    float* c = st + SS_CONST;
+    c[0] = (float)(1.0 - (double)b1); c[1] = b2; c[2] = (float)(1.0 - (double)b2);
+    c[3] = (float)((double)lr / bc1); c[4] = (float)sqrt(bc2); c[5] = eps; c[6] = lr;
+}
+__global__ void k_step_set(float* __restrict__ st, int step, float lr, float b1, float b2, float eps) {
+    reinterpret_cast<int*>(st)[SS_STEP] = step;
+    st[SS_HYPER + 0] = lr; st[SS_HYPER + 1] = b1; st[SS_HYPER + 2] = b2; st[SS_HYPER + 3] = eps;
+}
+extern "C" int sat_step_begin(SatWork* w, uint64_t seed_base, void* stream) {
+    if (!w || !w->step_state) return sat_host::fail(SAT_EINVAL, "sat_step_begin: null argument");
+    k_step_begin<<<1, 1, 0, (cudaStream_t)stream>>>(w->step_state, seed_base);
+    return sat_host::check_launch("k_step_begin");
+}
+extern "C" int sat_step_set(SatWork* w, int32_t step, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!w || !w->step_state || step < 0) return sat_host::fail(SAT_EINVAL, "sat_step_set: bad argument");
+    k_step_set<<<1, 1, 0, (cudaStream_t)stream>>>(w->step_state, step, lr, beta1, beta2, eps);
+    return sat_host::check_launch("k_step_set");
 }
 
 extern "C" int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, int32_t tile_set, void* stream) {

@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(NT, 2) k_selfatt_fwd(const SelfAttArgs a) {
         __syncthreads();
         if (valid) {
             float r[D];
-            attention_fwd<H>(q, sK, sV, s * F, F, make_drop(a.seed, token_gid, 0, SITE_ATT, a.p_drop, a.training), r);
-            const DropCtx dc = make_drop(a.seed, token_gid, 0, SITE_OUT, a.p_drop, a.training);
+            attention_fwd<H>(q, sK, sV, s * F, F, make_drop(fold_seed(a.seed), token_gid, 0, SITE_ATT, a.p_drop, a.training), r);
+            const DropCtx dc = make_drop(fold_seed(a.seed), token_gid, 0, SITE_OUT, a.p_drop, a.training);
 #pragma unroll
             drop_apply32(dc, r);                                               // result = self.dropout(result)
             if (a.use_res) vm_outer<D, D, D>(sW + 3072, x, r);                  // result += inputs @ W_Res

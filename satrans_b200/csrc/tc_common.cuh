@@ -1,5 +1,7 @@
 // tcgen05 / TMEM / mbarrier PTX wrappers and the packed-weight (UMMA B operand) layout shared by the tensor-core kernels.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace sat {
@@ -57,6 +59,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     } while (!ok);
 }
+// ---- TMA: bulk asynchronous copies global -> shared, completion counted in bytes on an mbarrier -------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one box of the 2-D tensor map (cp.async.bulk.tensor -> SASS UTMALDG): x = element column, y = row of the box's first element
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+// contiguous bytes (multiple of 16, both sides 16 B aligned) without a tensor map (cp.async.bulk -> SASS UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// the packed weights as a 2-D tensor [blocks * 32 rows][256 floats]; one box = TMA_BOX_ROWS rows = 8 KB
+constexpr int TMA_ROW_FLOATS = 256, TMA_BOX_ROWS = 8, TMA_BOX_FLOATS = TMA_ROW_FLOATS * TMA_BOX_ROWS;
+constexpr int PACK_ROWS = PACK_FLOATS / TMA_ROW_FLOATS;      // 32 rows per packed block
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

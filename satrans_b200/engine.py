@@ -83,6 +83,9 @@ class Engine:
         self.launches = 0          # kernels launched by this engine (counted per C-ABI call)
         self.timing = None         # set to {} to collect CUDA-event pairs per phase: {name: [(start, end), ...]}
         self.dist = None           # satrans_b200.dist.DistContext when the tables are row-sharded over ranks
+        self.use_cuda_graph = True # train_on_batch: replay the step from a CUDA graph once a batch shape has been seen twice
+        self._graphs = {}          # key -> captured step (see graph_train_step)
+        self._graph_seen = {}
         # projection arithmetic: 'tf32x3' (default) = tcgen05 tensor cores with the error-compensated 3xTF32 split (fp32-level
         # parity: y_pred within 1e-7 of the CUDA-core path); 'fp32' = CUDA-core FFMA kernels (bit-tight parity tests use it);
         # 'tf32' = tcgen05 plain TF32 (fast mode)
@@ -202,6 +205,7 @@ class Engine:
                 d.shard_tables[k] = ptr
         self._bound_ptrs = ptrs
         self._work = {}
+        self._graphs, self._graph_seen = {}, {}      # captured steps hold the old pointers
         if self._adam is not None and self._adam['tab_v'] is not None and \
                 (self._adam['tab_v'].device != self.device or self._adam['tab_v'].shape != m._tables.shape):
             # the parameters moved (model.cpu() / .cuda() around a checkpoint, as reference main.py does): the optimiser
@@ -377,6 +381,7 @@ class Engine:
         """Optimiser state buffers: Adam m+v, Adagrad / RMSprop v only, SGD none."""
         if self._adam is None or self._adam.get('kind') != kind:
             m = self.model
+            self._graphs, self._graph_seen = {}, {}
             need_m, need_v = kind == _lib.OPT_ADAM, kind != _lib.OPT_SGD
             self._adam = {
                 'kind': kind,
@@ -406,7 +411,7 @@ class Engine:
         return n
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0):
+                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0, _capturing=False):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
         finalize kernel (read them with .item() only when needed: that synchronises)."""
@@ -415,11 +420,12 @@ class Engine:
         B = X.shape[0]
         w = self.workspace(B, True)
         st = self._adam_state(opt_kind)
-        self.step_count += 1
+        if not _capturing:                       # (a captured step takes its step index from the device-side state)
+            self.step_count += 1
         a = SatAdam()
         a.kind = int(opt_kind)
         a.lr, a.beta1, a.beta2, a.eps, a.l2_emb = float(lr), float(betas[0]), float(betas[1]), float(eps), float(l2_emb)
-        a.step, a.dense_mode = self.step_count, int(bool(dense_mode))
+        a.step, a.dense_mode = max(self.step_count, 1), int(bool(dense_mode))
         a.tab_m = st['tab_m'].data_ptr() if st['tab_m'] is not None else None
         a.tab_v = st['tab_v'].data_ptr() if st['tab_v'] is not None else None
         a.dense_m = st['dense_m'].data_ptr() if st['dense_m'] is not None else None
@@ -514,8 +520,71 @@ class Engine:
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
         if not single:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
-        self.launches += self._launch_count(True, dense_mode) + 1
+        if not _capturing:
+            self.launches += self._launch_count(True, dense_mode) + 1
         return y_pred, w
+
+    # ------------------------------------------------------------------------------------------
+    def graph_train_step(self, Xh, yh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
+        """One optimiser step on a HOST batch, replayed from a CUDA graph (single-GPU mode).
+
+        The whole step -- H2D copies of the batch and of the four hyper-parameters from pinned staging buffers,
+        sat_step_begin (step counter, dropout seed = seed0 + step - 1 and Adam's bias corrections advance ON THE DEVICE) and
+        every kernel of train_step on its two streams -- is captured once per (batch shape, dtype, l2, mode, dropout,
+        optimiser kind, precision) and then costs one cudaGraphLaunch per step instead of ~45 launches and their host-side
+        marshalling.  lr / betas / eps are data (a scheduler can change them every step without re-capturing).
+        Returns the workspace; w['scalars'] holds (bce, reg, n_unique, error flags) once the replay has finished."""
+        Xh = torch.as_tensor(Xh)
+        yh = torch.as_tensor(yh).reshape(-1)
+        key = (tuple(Xh.shape), Xh.dtype, float(l2_emb), bool(dense_mode), float(dropout_p), int(opt_kind), self.precision)
+        G = self._graphs.get(key)
+        if G is None:
+            G = self._capture_step(key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0)
+        G['x_pin'].copy_(Xh)
+        G['y_pin'].copy_(yh)
+        hp = G['hyper_pin']
+        hp[0], hp[1], hp[2], hp[3] = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        G['graph'].replay()
+        self.step_count += 1
+        self.launches += G['launches']
+        return G['w']
+
+    def _capture_step(self, key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
+        self.bind()
+        B = Xh.shape[0]
+        w = self.workspace(B, True)
+        self._adam_state(opt_kind)
+        G = {'w': w,
+             'x_pin': torch.empty(tuple(Xh.shape), dtype=Xh.dtype).pin_memory(),
+             'y_pin': torch.empty(B, dtype=torch.float32).pin_memory(),
+             'hyper_pin': torch.zeros(4, dtype=torch.float32).pin_memory(),
+             'Xs': torch.empty(tuple(Xh.shape), dtype=Xh.dtype, device=self.device),
+             'ys': torch.empty(B, dtype=torch.float32, device=self.device)}
+        l = lib()
+        # the device-side step counter continues from the host's
+        check(l.sat_step_set(C.byref(w.c), int(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                             self._stream()), 'sat_step_set')
+        torch.cuda.synchronize()
+        timing, self.timing = self.timing, None
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=self.device)
+        w.c.device_step = 1
+        try:
+            with torch.cuda.graph(graph, stream=cap):
+                G['Xs'].copy_(G['x_pin'], non_blocking=True)
+                G['ys'].copy_(G['y_pin'], non_blocking=True)
+                w['step_state'][4:8].copy_(G['hyper_pin'], non_blocking=True)
+                check(l.sat_step_begin(C.byref(w.c), (int(seed0) - 1) & (2 ** 64 - 1), self._stream()), 'sat_step_begin')
+                G['y_pred'], _ = self.train_step(G['Xs'], G['ys'], lr=lr, betas=betas, eps=eps, l2_emb=l2_emb,
+                                                 dense_mode=dense_mode, training=True, dropout_p=dropout_p, seed=0,
+                                                 opt_kind=opt_kind, _capturing=True)
+        finally:
+            w.c.device_step = 0
+            self.timing = timing
+        G['graph'] = graph
+        G['launches'] = self._launch_count(True, dense_mode) + 2
+        self._graphs[key] = G
+        return G
 
     def adam_state(self):
         return self._adam_state(self._adam['kind'] if self._adam else 0)
@@ -524,3 +593,4 @@ class Engine:
         """Fresh optimiser state (moments and step counter), as a new torch.optim instance would have."""
         self._adam = None
         self.step_count = 0
+        self._graphs, self._graph_seen = {}, {}      # captured steps hold the old state pointers

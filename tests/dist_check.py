@@ -35,7 +35,7 @@ def build(g, rank, world, dev):
     model.load_state_dict(dense_sd, strict=False)
     table = torch.cat([full['embedding_dict.%s.weight' % n] for n in m['sparse_names']], dim=0)
     model.load_full_tables(table)
-    model.precision = os.environ.get('SAT_PRECISION', 'fp32')      # bit-tight bars below: CUDA-core kernels unless overridden
+    model.precision = os.environ.get('SAT_PRECISION', 'tf32x3')    # package default unless overridden
     return model, table
 
 

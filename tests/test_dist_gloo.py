@@ -34,6 +34,9 @@ def _worker(rank, world, port, q):
         model = SATrans(cols, cols, ['301'], [3], att_head_num=2, seed=7, device='cpu', flag='sota',
                         table_shard=(rank, world))
         assert model._tables.shape[0] == local_rows(22, rank, world)
+        # every rank draws its rows from its own stream: global rows kR .. kR+R-1 are i.i.d., not copies of each other
+        fresh = model.gather_tables()
+        assert all(not torch.equal(fresh[i], fresh[i + 1]) for i in range(21))
         full = torch.arange(22 * 32, dtype=torch.float32).view(22, 32)
         model.load_full_tables(full)
         assert torch.equal(model._tables, full[rank::world])

@@ -183,6 +183,35 @@ def test_train_on_batch_host_api_and_lazy_mode():
     assert not torch.equal(dense._tables[untouched], t0[untouched])
 
 
+def test_cuda_graph_step_equals_eager_step():
+    """train_on_batch replays the step from a CUDA graph from the third batch of a shape on (device-side step counter, dropout
+    seed and Adam bias corrections; H2D copies inside the graph): same losses and parameters as the eager launches, with
+    dropout on and a learning rate that changes every step (lr is data of the graph, not a captured constant)."""
+    schema, cfg, st = _small()
+    xs, ys = synth.make_inputs(schema, 6 * 256, seed=10, ctr=0.3)
+    X = synth.stack_columns(xs, schema.fields)
+    y = ys.astype(np.float32)
+    res = {}
+    for use_graph in (False, True):
+        torch.manual_seed(1234)
+        m = _model(cfg, st)
+        m.engine.use_cuda_graph = use_graph
+        opt = torch.optim.Adam(m.parameters(), lr=0.005)
+        m.compile(opt, "binary_crossentropy")
+        losses = []
+        for k in range(6):
+            opt.param_groups[0]['lr'] = 0.005 * (0.8 ** k)
+            losses.append(m.train_on_batch(X[k * 256:(k + 1) * 256], y[k * 256:(k + 1) * 256]))
+        assert (len(m.engine._graphs) == 1) == use_graph
+        assert m.engine.step_count == 6
+        res[use_graph] = (losses, m._tables.detach().cpu().clone(), m._dense.detach().cpu().clone())
+    for (b0, r0), (b1, r1) in zip(res[False][0], res[True][0]):
+        assert abs(b0 - b1) <= 1e-6 * abs(b0) and abs(r0 - r1) <= 1e-6 * abs(r0)
+    # (the bias corrections are computed by pow() on the host in one mode and on the device in the other: <= 1 ulp apart)
+    assert torch.allclose(res[False][1], res[True][1], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(res[False][2], res[True][2], rtol=1e-6, atol=1e-9)
+
+
 def test_dropout_is_seeded_and_unbiased():
     schema, cfg, st = _small(layers=1)
     xs, _ = synth.make_inputs(schema, 2048, seed=12)
