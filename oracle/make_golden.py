@@ -236,6 +236,72 @@ def build_selfatt():
     return out
 
 
+def build_star_trans():
+    """MDR_InteractingLayer (star_trans.py:146-242) and the Star_Trans model (star_trans.py:674-775) of the unmodified reference:
+    eval-mode forward goldens (+ gradients of sum(y * cot) for the layer), the oracle restatement asserted against them."""
+    sys.path.insert(0, ROOT)
+    from oracle import satrans_oracle as O
+    import_reference()
+    from models.star_trans import MDR_InteractingLayer, Star_Trans
+    from deepctr_torch.inputs import SparseFeat
+    from satrans_b200 import synth
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for idx, (heads, Fn, nd, merge, res) in enumerate(((4, 18, 3, 'no', True), (2, 14, 4, 'sum', True), (4, 6, 3, 'dot', False))):
+        torch.manual_seed(2021 + idx)
+        layer = MDR_InteractingLayer(32, nd, heads, merge, res).eval()
+        with torch.no_grad():
+            for ln in layer.domain_layer_norms:
+                ln.weight.add_(1.0)                     # N(0, .05) gamma would squash the output to ~0
+        B = 40
+        x = torch.randn((B, Fn, 32), generator=g) * 0.5
+        dom = torch.randint(0, nd + 1, (B,), generator=g)          # 0 = a scenario outside 1..nd: the layer leaves zeros
+        with torch.no_grad():
+            y = layer(x, dom)
+        tag = 'mdr_h%d_f%d_d%d_%s_r%d' % (heads, Fn, nd, merge, int(res))
+        out[tag + '/x'], out[tag + '/dom'], out[tag + '/y'] = x.numpy(), dom.numpy(), y.numpy()
+        sd = {k: v.detach().clone() for k, v in layer.state_dict().items()}
+        for k, v in sd.items():
+            out[tag + '/state/' + k] = v.numpy()
+        with torch.no_grad():
+            o = O.mdr_interacting_layer(x, dom, sd, heads, nd, merge, res)
+        assert torch.allclose(o, y, atol=1e-6, rtol=0), (o - y).abs().max()
+        cot = torch.randn((B, Fn, 32), generator=g)
+        xg = x.clone().requires_grad_(True)
+        layer.zero_grad()
+        (layer(xg, dom) * cot).sum().backward()
+        out[tag + '/cot'], out[tag + '/grad/x'] = cot.numpy(), xg.grad.numpy()
+        for k, p_ in layer.named_parameters():
+            if p_.grad is not None:
+                out[tag + '/grad/' + k] = p_.grad.detach().numpy()
+    # the whole Star_Trans model on an Ali-CCP-shaped schema (main.py's configuration: scenario column filtered out of the fields)
+    schema = synth.aliccp_schema(1e-4)
+    cols = [SparseFeat(f, vocabulary_size=schema.data_max[f] + 2, embedding_dim=32) for f in schema.fields]
+    torch.manual_seed(2030)
+    model = Star_Trans(cols, cols, schema.domain_col, schema.num_domains, att_layer_num=2, domain_att_layer_num=1, att_head_num=4,
+                       merge='no', use_linear=False, seed=1021, device='cpu').eval()
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            if k.startswith('embedding_dict.'):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.3)
+            if 'layer_norm' in k and k.endswith('weight'):
+                v.add_(1.0)
+    xs, _ = synth.make_inputs(schema, 64, seed=1021)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    with torch.no_grad():
+        yp = model(X)
+    st = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    o = O.star_trans_forward(st, X, schema.fields, schema.domain_col, schema.num_domains, 4, 2, 1)
+    assert torch.allclose(o, yp, atol=1e-6, rtol=0), (o - yp).abs().max()
+    out['model/X'], out['model/y_pred'] = X.numpy(), yp.numpy()
+    out['model/fields'] = np.frombuffer(json.dumps(dict(fields=schema.fields, vocab=schema.vocab_sizes, domain_col=schema.domain_col,
+                                                        num_domains=schema.num_domains)).encode(), dtype=np.uint8)
+    for k, v in st.items():
+        if not k.startswith('linear_model.'):
+            out['model/state/' + k] = v.numpy()
+    return out
+
+
 VARIANTS = (('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae'))
 
 
@@ -311,11 +377,19 @@ def main():
         np.savez_compressed(path, **build_compile_variants())
         print('compile_variants ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
         return
+    if os.environ.get('SAT_GOLDEN_ONLY_STAR'):
+        path = os.path.join(ROOT, 'tests', 'golden', 'star_trans.npz')
+        np.savez_compressed(path, **build_star_trans())
+        print('star_trans ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+        return
     path = os.path.join(ROOT, 'tests', 'golden', 'selfatt_layer.npz')
     np.savez_compressed(path, **build_selfatt())
     print('selfatt_layer ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
     if os.environ.get('SAT_GOLDEN_ONLY_SELFATT'):
         return
+    path = os.path.join(ROOT, 'tests', 'golden', 'star_trans.npz')
+    np.savez_compressed(path, **build_star_trans())
+    print('star_trans ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
     for name in CASES:
         out = build_case(name)
         path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')

@@ -281,6 +281,84 @@ def self_attention_layer(x, p, heads: int, use_res: bool = True, masks=None):
     return _layer_norm(F.relu(r), p['layer_norm.weight'], p['layer_norm.bias'])     # :234-235
 
 
+def interacting_layer(x, p, heads: int, use_res: bool = True, scaling: bool = False):
+    """deepctr-torch 0.2.9 `InteractingLayer.forward` (the AutoInt layer; call sites autoint.py:75-76,104-105).  PARITY UNPINNED:
+    the source lives in the un-vendored third-party package (pin: readme.md:37), so this restates its published algorithm --
+    Q,K,V = x W_{Query,key,Value}; per-head softmax(Q K^T [/ sqrt(dh) only if scaling]) V; + x W_Res; ReLU -- no dropout, no
+    LayerNorm.  p: dict with W_Query, W_key, W_Value (and W_Res)."""
+    B_, F_, d = x.shape
+    dh = d // heads
+    q, k, v = x @ p['W_Query'], x @ p['W_key'], x @ p['W_Value']
+    qh = q.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    kh = k.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    vh = v.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    s = torch.matmul(qh, kh.transpose(-1, -2))
+    if scaling:
+        s = s / (dh ** 0.5)
+    r = torch.matmul(F.softmax(s, dim=-1), vh).permute(1, 2, 0, 3).reshape(B_, F_, d)
+    if use_res:
+        r = r + x @ p['W_Res']
+    return F.relu(r)
+
+
+def mdr_interacting_layer(x, domain_ids, p, heads: int, num_domains: int, merge: str = 'no', use_res: bool = True, masks=None):
+    """MDR_InteractingLayer.forward, star_trans.py:197-242: shared W_key / W_Value / W_Res, one W_Query and one LayerNorm per
+    scenario (merge 'no' | 'sum' | 'dot' with the shared W_Query, :209-217); samples whose scenario id is outside 1..num_domains
+    keep a zero result (:208,239).  p: dict keyed like the module's state dict."""
+    B_, F_, d = x.shape
+    dh = d // heads
+    k, v = x @ p['W_key'], x @ p['W_Value']                                          # :204-205
+    kh = k.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    vh = v.reshape(B_, F_, heads, dh).permute(2, 0, 1, 3)
+    out = torch.zeros_like(x)
+    for i in range(num_domains):
+        wq = p['domain_W_Queries.%d' % i]
+        if merge == 'sum':
+            wq = wq + p['W_Query']
+        elif merge == 'dot':
+            wq = wq * p['W_Query']
+        elif merge != 'no':
+            raise NotImplementedError('not implemented parameters merge')
+        m = domain_ids == (i + 1)                                                    # :218
+        if not bool(m.any()):
+            continue
+        sx = x[m]
+        qh = (sx @ wq).reshape(-1, F_, heads, dh).permute(2, 0, 1, 3)
+        a = F.softmax(torch.matmul(qh, kh[:, m].transpose(-1, -2)) / (dh ** 0.5), dim=-1)      # :225-228
+        a = _drop(a, 0.1, None if masks is None else {'att': masks['att'][:, m]}, 'att')
+        r = torch.matmul(a, vh[:, m]).permute(1, 2, 0, 3).reshape(-1, F_, d)
+        r = _drop(r, 0.1, None if masks is None else {'out': masks['out'][m]}, 'out')          # :233
+        if use_res:
+            r = r + sx @ p['W_Res']                                                  # :234-235
+        r = _layer_norm(F.relu(r), p['domain_layer_norms.%d.weight' % i], p['domain_layer_norms.%d.bias' % i])   # :236-237
+        out[m] = r
+    return out
+
+
+def star_trans_forward(st, X, sparse_names, domain_col, num_domains, heads, att_layer_num, domain_att_layer_num, merge='no',
+                       use_res=True, dense_names=()):
+    """Star_Trans.forward (star_trans.py:744-775) with use_linear=False, domain_id_as_feature=False, att_layer_type='deepctr',
+    use_domain_dnn_linear=False (main.py's call): gather of every field except the scenario column, SelfAttention_Layer x
+    att_layer_num, MDR_InteractingLayer x domain_att_layer_num, flatten (+ dense), dnn_linear, sigmoid."""
+    names = list(sparse_names) + list(dense_names)
+    fields = [n for n in sparse_names if n != domain_col]                            # filter_feature_columns, :702-704
+    x = torch.stack([st['embedding_dict.%s.weight' % n][X[:, names.index(n)].long()] for n in fields], dim=1)
+    dom = X[:, names.index(domain_col)].long()
+    for i in range(att_layer_num):
+        pre = 'int_layers.%d.' % i
+        p = {k[len(pre):]: v for k, v in st.items() if k.startswith(pre)}
+        p['W_Key'] = p['W_key']                                                      # star_trans.py's own class spells it W_key
+        x = self_attention_layer(x, p, heads, use_res)
+    for i in range(domain_att_layer_num):
+        pre = 'domain_int_layers.%d.' % i
+        p = {k[len(pre):]: v for k, v in st.items() if k.startswith(pre)}
+        x = mdr_interacting_layer(x, dom, p, heads, num_domains, merge, use_res)
+    out = torch.flatten(x, start_dim=1)
+    if dense_names:
+        out = torch.cat([out, torch.stack([X[:, names.index(n)] for n in dense_names], dim=1).to(out.dtype)], dim=1)
+    return torch.sigmoid(out @ st['dnn_linear.weight'].t() + st['dnn_linear.bias'])
+
+
 def reg_loss(st, cfg: OracleConfig):
     """get_regularization_loss, meta_basemodel.py:577-593: l2 * sum(square(w)) over the embedding
     tables only (linear_model is registered with l2=0, satrans.py:120)."""

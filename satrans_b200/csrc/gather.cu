@@ -6,15 +6,19 @@
 // Layout: all tables back to back in one [total_rows][32] fp32 buffer; row_off[f] is the first row of
 // field f.  A row is 128 B = one L2 line = 8 lanes x float4, so a warp moves 4 rows per instruction and
 // every request is a full-line transaction; each thread keeps GATHER_UNROLL independent rows in flight.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace sat {
 
 constexpr int GATHER_THREADS = 256;
-constexpr int GATHER_UNROLL = 4;
+#ifndef SAT_GATHER_DEFAULT
+#define SAT_GATHER_DEFAULT 0
+#endif
 
-template <int KIND>
-__global__ void __launch_bounds__(GATHER_THREADS)
+template <int KIND, int GATHER_UNROLL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(GATHER_THREADS, MIN_BLOCKS)
 k_gather(const SatModel m, const void* __restrict__ x, int ld, int B, float* __restrict__ out, int32_t* __restrict__ err) {
     const int64_t* __restrict__ row_off = m.row_off;
     const int32_t* __restrict__ cols = m.sparse_cols;
@@ -47,6 +51,71 @@ k_gather(const SatModel m, const void* __restrict__ x, int ld, int B, float* __r
         for (int u = 0; u < GATHER_UNROLL; ++u)
             if (src[u]) __stcs(reinterpret_cast<float4*>(out + item[u] * D + lane8 * 4), v[u]);
     }
+    if (bad && err) atomicOr(err, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// TMA variant: every row travels table -> shared memory as ONE 128-byte bulk asynchronous copy (cp.async.bulk, no registers
+// held while it is in flight), and a chunk of GB_ROWS consecutive output rows leaves as ONE bulk store shared -> global.
+// GB_STAGES chunks per CTA circulate: GB_STAGES - 2 chunks of row fetches are in flight while the oldest is being stored.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int GB_ROWS = 128, GB_STAGES = 6, GB_LAG = GB_STAGES - 2;
+constexpr int GB_SMEM_BYTES = GB_STAGES * GB_ROWS * D * 4 + GB_STAGES * 8;
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <int KIND>
+__global__ void __launch_bounds__(GB_ROWS)
+k_gather_tma(const SatModel m, const void* __restrict__ x, int ld, int B, float* __restrict__ out, int32_t* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char gsm[];
+    float* stage = reinterpret_cast<float*>(gsm);
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + GB_STAGES * GB_ROWS * D * 4);
+    const int tid = threadIdx.x, F = m.F;
+    const long long n_items = (long long)B * F;
+    const long long n_chunks = (n_items + GB_ROWS - 1) / GB_ROWS;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GB_STAGES; ++s) mbar_init(full + s, 1);
+    }
+    __syncthreads();
+    bool bad = false;
+    // this CTA's chunks: c = blockIdx.x + i * gridDim.x
+    const long long my_n = n_chunks > (long long)blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (long long i = 0; i < my_n + GB_LAG; ++i) {
+        if (i < my_n) {
+            const int s = (int)(i % GB_STAGES);
+            // the store that last read this stage (chunk i - GB_STAGES, committed at iteration i - 2) must have read it
+            if (tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+            const long long c = blockIdx.x + i * gridDim.x;
+            const long long item0 = c * GB_ROWS;
+            const int rows = (int)min((long long)GB_ROWS, n_items - item0);
+            if (tid == 0) mbar_expect_tx(full + s, (uint32_t)rows * D * 4);
+            if (tid < rows) {
+                const long long item = item0 + tid;
+                const int b = (int)(item / F), f = (int)(item - (long long)b * F);
+                long long id = load_id(x, KIND, (long long)b * ld + __ldg(m.sparse_cols + f));
+                const long long lo = __ldg(m.row_off + f), hi = __ldg(m.row_off + f + 1);
+                if (id < 0 || id >= hi - lo) { bad = true; id = 0; }
+                tma_load_1d(stage + ((long long)s * GB_ROWS + tid) * D, table_row(m, lo + id), D * 4, full + s);
+            }
+        }
+        const long long j = i - GB_LAG;                        // the chunk whose rows should have landed by now
+        if (j >= 0 && tid == 0) {
+            const int s = (int)(j % GB_STAGES);
+            mbar_wait(full + s, (uint32_t)((j / GB_STAGES) & 1));
+            const long long c = blockIdx.x + j * gridDim.x;
+            const long long item0 = c * GB_ROWS;
+            const int rows = (int)min((long long)GB_ROWS, n_items - item0);
+            bulk_store(out + item0 * D, stage + (long long)s * GB_ROWS * D, (uint32_t)rows * D * 4);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (bad && err) atomicOr(err, 1);
 }
 
@@ -159,23 +228,42 @@ extern "C" int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind,
     if (!m || !x || !out || B < 0 || m->F <= 0) return sat_host::fail(SAT_EINVAL, "sat_gather_fwd: bad argument");
     if (B == 0) return SAT_OK;
     const long long items = (long long)B * m->F;
-    const long long per_block = (GATHER_THREADS / 8) * GATHER_UNROLL;
-    long long blocks = (items + per_block - 1) / per_block;
-    if (blocks > 148 * 16) blocks = 148 * 16;
     cudaStream_t s = (cudaStream_t)stream;
+    // SAT_GATHER_VARIANT (tuning aid): 0 = 4 rows in flight per thread, 1 = 8 rows, 2 = 4 rows at full occupancy (<= 32 registers),
+    // 3 = 8 rows at 6 CTAs per SM, 4 = TMA bulk row fetch + bulk store
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("SAT_GATHER_VARIANT"); variant = e ? atoi(e) : SAT_GATHER_DEFAULT; }
+#define SAT_GATHER_LAUNCH(KIND)                                                                                              \
+    do {                                                                                                                     \
+        if (variant == 4 && m->n_shards == 1) {                                                                              \
+            static bool cfg = false;                                                                                         \
+            if (!cfg) {                                                                                                      \
+                if (cudaFuncSetAttribute(k_gather_tma<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_BYTES) != cudaSuccess) \
+                    return sat_host::fail(SAT_ECUDA, "sat_gather_fwd: cannot raise dynamic shared memory");                  \
+                cfg = true;                                                                                                  \
+            }                                                                                                                \
+            long long chunks = (items + GB_ROWS - 1) / GB_ROWS;                                                              \
+            const int grid = (int)(chunks < 148 * 2 ? chunks : 148 * 2);                                                     \
+            k_gather_tma<KIND><<<grid, GB_ROWS, GB_SMEM_BYTES, s>>>(*m, x, ld, B, out, err_flag);                            \
+        } else {                                                                                                             \
+            const int unroll = (variant == 1 || variant == 3) ? 8 : 4;                                                       \
+            const long long per_block = (GATHER_THREADS / 8) * unroll;                                                       \
+            long long blocks = (items + per_block - 1) / per_block;                                                          \
+            if (blocks > 148 * 16) blocks = 148 * 16;                                                                        \
+            if (variant == 1) k_gather<KIND, 8, 1><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);      \
+            else if (variant == 2) k_gather<KIND, 4, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
+            else if (variant == 3) k_gather<KIND, 8, 6><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
+            else k_gather<KIND, 4, 1><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);                   \
+        }                                                                                                                    \
+    } while (0)
     switch (id_kind) {
-        case SAT_IDS_F32:
-            k_gather<SAT_IDS_F32><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
-            break;
-        case SAT_IDS_I32:
-            k_gather<SAT_IDS_I32><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
-            break;
-        case SAT_IDS_I64:
-            k_gather<SAT_IDS_I64><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);
-            break;
+        case SAT_IDS_F32: SAT_GATHER_LAUNCH(SAT_IDS_F32); break;
+        case SAT_IDS_I32: SAT_GATHER_LAUNCH(SAT_IDS_I32); break;
+        case SAT_IDS_I64: SAT_GATHER_LAUNCH(SAT_IDS_I64); break;
         default:
             return sat_host::fail(SAT_EINVAL, "sat_gather_fwd: id_kind %d", id_kind);
     }
+#undef SAT_GATHER_LAUNCH
     return sat_host::check_launch("k_gather");
 }
 

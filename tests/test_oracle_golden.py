@@ -124,3 +124,68 @@ def test_compile_string_variants_match_reference(opt, loss):
             assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
         else:       # normalised steps amplify round-off of near-zero gradient elements (thread-count dependent even on the CPU)
             assert_adam_close(got, ref, lr, 2, k)
+
+
+def _star_golden():
+    import numpy as np
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'star_trans.npz'))
+
+
+MDR_TAGS = (('mdr_h4_f18_d3_no_r1', 4, 3, 'no', True), ('mdr_h2_f14_d4_sum_r1', 2, 4, 'sum', True),
+            ('mdr_h4_f6_d3_dot_r0', 4, 3, 'dot', False))
+
+
+@pytest.mark.parametrize('tag,heads,nd,merge,res', MDR_TAGS)
+def test_mdr_interacting_layer_oracle_vs_reference(tag, heads, nd, merge, res):
+    """'next' row 3: MDR_InteractingLayer restatement (star_trans.py:146-242) against vectors from the reference's own module,
+    forward and (autograd through the restatement) every gradient."""
+    z = _star_golden()
+    p = {k[len(tag) + 7:]: torch.from_numpy(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith(tag + '/state/')}
+    x = torch.from_numpy(z[tag + '/x']).clone().requires_grad_(True)
+    dom = torch.from_numpy(z[tag + '/dom'])
+    y = O.mdr_interacting_layer(x, dom, p, heads, nd, merge, res)
+    assert torch.allclose(y.detach(), torch.from_numpy(z[tag + '/y']), atol=1e-6, rtol=0)
+    assert torch.count_nonzero(y.detach()[dom == 0]) == 0            # scenario ids outside 1..nd keep zeros
+    (y * torch.from_numpy(z[tag + '/cot'])).sum().backward()
+    ref = torch.from_numpy(z[tag + '/grad/x'])
+    assert (x.grad - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9
+    for k, v in p.items():
+        gk = tag + '/grad/' + k
+        if gk in z.files:
+            ref = torch.from_numpy(z[gk])
+            assert (v.grad - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, k
+
+
+def test_star_trans_model_oracle_vs_reference():
+    import json
+    z = _star_golden()
+    meta = json.loads(bytes(z['model/fields']).decode())
+    st = {k[len('model/state/'):]: torch.from_numpy(z[k]) for k in z.files if k.startswith('model/state/')}
+    with torch.no_grad():
+        yp = O.star_trans_forward(st, torch.from_numpy(z['model/X']), meta['fields'], meta['domain_col'], meta['num_domains'], 4, 2, 1)
+    assert torch.allclose(yp, torch.from_numpy(z['model/y_pred']), atol=1e-6, rtol=0)
+
+
+def test_interacting_layer_restatement_properties():
+    """deepctr-torch's InteractingLayer is not vendored (parity unpinned): the restatement is checked against an independent
+    einsum formulation and against SelfAttention_Layer's shared sub-graph (same Q/K/V/Res projections, softmax, ReLU)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((5, 7, 32), generator=g)
+    p = {k: torch.randn((32, 32), generator=g) * 0.2 for k in ('W_Query', 'W_key', 'W_Value', 'W_Res')}
+    for heads in (1, 2, 4):
+        for scaling in (False, True):
+            y = O.interacting_layer(x, p, heads, True, scaling)
+            dh = 32 // heads
+            q = (x @ p['W_Query']).view(5, 7, heads, dh)
+            k = (x @ p['W_key']).view(5, 7, heads, dh)
+            v = (x @ p['W_Value']).view(5, 7, heads, dh)
+            s = torch.einsum('bihd,bjhd->bhij', q, k) / ((dh ** 0.5) if scaling else 1.0)
+            r = torch.einsum('bhij,bjhd->bihd', torch.softmax(s, -1), v).reshape(5, 7, 32) + x @ p['W_Res']
+            assert torch.allclose(y, torch.relu(r), atol=1e-5) and (y >= 0).all()
+    # with scaling, it is SelfAttention_Layer without its LayerNorm
+    p2 = dict(p, W_Key=p['W_key'])
+    p2['layer_norm.weight'], p2['layer_norm.bias'] = torch.ones(32), torch.zeros(32)
+    a = O.interacting_layer(x, p, 4, True, True)
+    b = O.self_attention_layer(x, p2, 4, True)
+    assert torch.allclose(torch.nn.functional.layer_norm(a, (32,), eps=1e-6), b, atol=1e-5)
