@@ -297,6 +297,19 @@ int sat_selfatt_fwd(const float* x, float* out, const float* wq, const float* wk
                     const float* ln_g, const float* ln_b, int32_t B, int32_t F, int32_t H, int32_t use_res,
                     int32_t training, float dropout_p, uint64_t seed, void* stream);
 
+/* ---- the general form: SelfAttention_Layer (n_wq = 1, ln given, scaling = 1), MDR_InteractingLayer (reference
+ *      star_trans.py:146-242: wq / ln_g / ln_b hold n_wq <= 8 scenario-specific sets, dom[b] in 1..n_wq selects set dom-1, any
+ *      other id leaves a zero output; the 'sum' / 'dot' merge with the shared W_Query is done by the caller) and deepctr-torch's
+ *      InteractingLayer (AutoInt: ln_g = ln_b = NULL, scaling = 0, dropout_p = 0).  Forward only. ---------------------------- */
+int sat_field_attention_fwd(const float* x, float* out, const float* wq, int32_t n_wq, const float* wk, const float* wv,
+                            const float* wres, const float* ln_g, const float* ln_b, const int32_t* dom, int32_t B, int32_t F,
+                            int32_t H, int32_t use_res, int32_t scaling, int32_t training, float dropout_p, uint64_t seed,
+                            void* stream);
+/* ---- logit head of the baselines (reference star_trans.py:762-775, autoint.py:107-121): y[b] = sigmoid(bias + feat[b] . w[0:n]
+ *      + dense[b] . w[n:n+n_dense]); feat: [B][n], dense: [B][ld_dense] or NULL, bias may be NULL, apply_sigmoid = 0 -> logit. */
+int sat_head_fwd(const float* feat, int32_t n, const float* dense, int32_t n_dense, int32_t ld_dense, const float* w,
+                 const float* bias, int32_t B, float* y, int32_t apply_sigmoid, void* stream);
+
 /* ---- per-batch training metrics of fit(verbose > 0) (reference meta_basemodel.py:330-337,352-356; metric table :655-671).
  *      y_pred, y: device arrays; batch b covers [batch_off[b], batch_off[b+1]) (device int32, n_batches + 1 entries);
  *      out[b][4] = { log_loss, roc_auc_score, mean_squared_error, accuracy(p > 0.5) } as sklearn computes them in float64

@@ -359,6 +359,28 @@ def star_trans_forward(st, X, sparse_names, domain_col, num_domains, heads, att_
     return torch.sigmoid(out @ st['dnn_linear.weight'].t() + st['dnn_linear.bias'])
 
 
+def autoint_forward(st, X, sparse_names, heads, att_layer_num, use_res=True, dense_names=()):
+    """AutoInt.forward (autoint.py:82-123, flag without 'usemetatrans'): gather, InteractingLayer x att_layer_num, the deepctr DNN
+    tower on the flattened embeddings (+ dense), dnn_linear (no bias) on [att_out | deep_out], PredictionLayer (bias + sigmoid).
+    PARITY UNPINNED (InteractingLayer / DNN / PredictionLayer are deepctr-torch 0.2.9 code, not vendored)."""
+    names = list(sparse_names) + list(dense_names)
+    x = torch.stack([st['embedding_dict.%s.weight' % n][X[:, names.index(n)].long()] for n in sparse_names], dim=1)
+    flat = torch.flatten(x, start_dim=1)
+    if dense_names:
+        flat = torch.cat([flat, torch.stack([X[:, names.index(n)] for n in dense_names], dim=1).to(flat.dtype)], dim=1)
+    att = x
+    for i in range(att_layer_num):
+        pre = 'int_layers.%d.' % i
+        att = interacting_layer(att, {k[len(pre):]: v for k, v in st.items() if k.startswith(pre)}, heads, use_res)
+    deep = flat
+    i = 0
+    while 'dnn.linears.%d.weight' % i in st:                                   # DNN: Linear -> relu for every layer
+        deep = F.relu(deep @ st['dnn.linears.%d.weight' % i].t() + st['dnn.linears.%d.bias' % i])
+        i += 1
+    stack = torch.cat([torch.flatten(att, start_dim=1), deep], dim=1)          # autoint.py:107-110
+    return torch.sigmoid(stack @ st['dnn_linear.weight'].t() + st['out.bias'])
+
+
 def reg_loss(st, cfg: OracleConfig):
     """get_regularization_loss, meta_basemodel.py:577-593: l2 * sum(square(w)) over the embedding
     tables only (linear_model is registered with l2=0, satrans.py:120)."""

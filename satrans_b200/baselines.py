@@ -1,0 +1,186 @@
+"""Scoring (inference) path of the attention baselines of BASELINE config 5 through this framework's kernels: multi-field
+embedding gather -> field-attention layers -> logit head.  Same constructors, state-dict keys and predict() contract as the
+reference classes; TRAINING IS NOT BUILT for them (fit / train_on_batch raise) -- SATrans is the trained model of this package.
+
+    Star_Trans   reference models/star_trans.py:674-775 (SelfAttention_Layer x att_layer_num, MDR_InteractingLayer x
+                 domain_att_layer_num, dnn_linear), pinned by tests/golden/star_trans.npz
+    AutoInt      reference models/autoint.py:39-123 on deepctr-torch's InteractingLayer / DNN -- PARITY UNPINNED (the layers live in
+                 an un-vendored third-party package); its plain DNN tower runs as torch.nn.Linear (library GEMM)
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .basemodel import BaseModel
+from .inputs import DenseFeat, SparseFeat
+from .selfatt import InteractingLayer, MDR_InteractingLayer, SelfAttention_Layer
+
+
+class _ScoringModel(BaseModel):
+    """Shared plumbing: gather through the engine's kernel, scoring-only contract."""
+
+    def _init_layout(self, device):
+        sparse = self._sparse_feats
+        self._layout = dict(F=len(sparse), L=0, H=1, n_dom=1, n_dense=0, n_cols=self._n_cols(), enc_in=32, flags=0,
+                            off_dom=0, off_lid=0, off_qkv=0, off_encw=0, off_encb=0, off_layers=0, off_headw=0, off_headb=0,
+                            n_dense_params=4, total_rows=int(self._row_off[-1]), row_off=[int(v) for v in self._row_off],
+                            sparse_cols=[self.feature_index[f.name][0] for f in sparse], dense_cols=[], dom_col=0)
+        self._dense = torch.zeros(4, dtype=torch.float32, device=device)
+
+    def _ensure_flat(self):
+        dev = self.dnn_linear.weight.device
+        if self._tables.device != dev:
+            tables = self._tables.to(dev)
+            for f, a, b in zip(self._sparse_feats, self._row_off[:-1], self._row_off[1:]):
+                self.embedding_dict[f.embedding_name].weight.data = tables[int(a):int(b)]
+            self._tables = tables
+        if self._dense.device != dev:
+            self._dense = self._dense.to(dev)
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        if hasattr(self, '_layout'):
+            self._ensure_flat()
+            self.device = str(self.dnn_linear.weight.device)
+        return out
+
+    def _gather_fields(self, X, keep):
+        Xd = self._as_device_matrix(X)
+        E = self.engine.gather(Xd)                                   # (B, all sparse fields, 32): one launch
+        if len(keep) != E.shape[1]:
+            E = E[:, keep, :].contiguous()
+        return Xd, E
+
+    def _head(self, feat, dense, w, bias, sigmoid=True):
+        B, n = feat.shape
+        y = torch.empty(B, dtype=torch.float32, device=feat.device)
+        nd = 0 if dense is None else dense.shape[1]
+        _lib.check(_lib.lib().sat_head_fwd(feat.data_ptr(), n, dense.data_ptr() if nd else None, nd, nd,
+                                           w.detach().contiguous().data_ptr(), bias.detach().data_ptr() if bias is not None else None,
+                                           B, y.data_ptr(), int(sigmoid), torch.cuda.current_stream().cuda_stream), 'sat_head_fwd')
+        return y.unsqueeze(1)
+
+    def fit(self, *a, **k):
+        raise NotImplementedError("%s is a scoring-only baseline here (BASELINE config 5): training is not built" % type(self).__name__)
+
+    train_on_batch = fit
+
+    def predict(self, x, batch_size=256, y=None, domain_ids=None):
+        self.eval()
+        X = self._stack_inputs(x)
+        n = len(X)
+        out = torch.empty(n, dtype=torch.float32, device=self._tables.device)
+        Xd = torch.as_tensor(np.ascontiguousarray(X)).to(self._tables.device)
+        for s0 in range(0, n, batch_size):
+            s1 = min(s0 + batch_size, n)
+            out[s0:s1] = self.forward(Xd[s0:s1].contiguous())[:, 0]
+        if n:
+            self.engine.check_errors(self.engine.workspace(1, False))
+        return out.cpu().numpy().astype("float64").reshape(-1, 1)
+
+
+class Star_Trans(_ScoringModel):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, domain_column, num_domains, domain_id_as_feature=False,
+                 att_layer_num=2, domain_att_layer_num=1, att_head_num=2, merge='no', att_layer_type='deepctr',
+                 use_domain_dnn_linear=False, att_res=True, use_linear=True, use_dnn=False, dnn_hidden_units=(256, 128),
+                 dnn_activation='relu', l2_reg_dnn=0, l2_reg_embedding=1e-5, dnn_use_bn=False, dnn_dropout=0, init_std=0.0001,
+                 seed=1024, task='binary', device='cpu', gpus=None):
+        super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=0, l2_reg_embedding=l2_reg_embedding,
+                         init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
+        if att_layer_type != 'deepctr':
+            raise NotImplementedError("att_layer_type='%s' (Transformer_Layer, reference star_trans.py:449-509) is not built" % att_layer_type)
+        if use_linear:
+            raise NotImplementedError("use_linear=True (the dim-1 linear tables) is not built; main.py's Star_Trans call passes False")
+        if use_domain_dnn_linear:
+            raise NotImplementedError("use_domain_dnn_linear=True is not built")
+        self.use_linear, self.use_dnn, self.num_domains = use_linear, use_dnn, num_domains
+        self.use_domain_dnn_linear, self.domain_column = use_domain_dnn_linear, domain_column
+        d = self.embedding_size
+        names = [f.name for f in self._sparse_feats]
+        if domain_id_as_feature:
+            self._keep = list(range(len(names)))
+        else:                                                            # reference star_trans.py:702-704
+            self._keep = [i for i, n in enumerate(names) if n != domain_column]
+        field_num = len(self._keep)
+        dense = [f for f in linear_feature_columns if isinstance(f, DenseFeat)]
+        self._dense_cols = [c for f in dense for c in range(*self.feature_index[f.name])]
+        self.att_layer_num, self.dnn_hidden_units = att_layer_num, dnn_hidden_units
+        self.int_layers = nn.ModuleList([SelfAttention_Layer(d, att_head_num, att_res, device='cpu', key_name='W_key')
+                                         for _ in range(att_layer_num)])
+        self.domain_int_layers = nn.ModuleList([MDR_InteractingLayer(d, num_domains, att_head_num, merge, att_res, device='cpu')
+                                                for _ in range(domain_att_layer_num)])
+        self.dnn_linear = nn.Linear(field_num * d + len(self._dense_cols), 1)
+        self._init_layout(device)
+        self.to(device)
+
+    def forward(self, X):
+        Xd, x = self._gather_fields(X, self._keep)
+        dom = Xd[:, self.feature_index[self.domain_column][0]].to(torch.int32)      # .long() of the reference: truncation
+        for layer in self.int_layers:
+            x = layer(x)
+        for layer in self.domain_int_layers:
+            x = layer(x, dom)
+        dense = Xd[:, self._dense_cols].float().contiguous() if self._dense_cols else None
+        return self._head(x.reshape(x.shape[0], -1), dense, self.dnn_linear.weight, self.dnn_linear.bias)
+
+
+class _DNN(nn.Module):
+    """deepctr-torch DNN with its state-dict keys (`linears.i.*`): Linear -> activation (-> dropout) for EVERY layer."""
+
+    def __init__(self, inputs_dim, hidden_units, init_std=0.0001):
+        super().__init__()
+        units = [inputs_dim] + list(hidden_units)
+        self.linears = nn.ModuleList([nn.Linear(units[i], units[i + 1]) for i in range(len(units) - 1)])
+        for name, t in self.linears.named_parameters():
+            if 'weight' in name:
+                nn.init.normal_(t, mean=0, std=init_std)
+
+    def forward(self, x):
+        for lin in self.linears:
+            x = torch.relu(lin(x))
+        return x
+
+
+class AutoInt(_ScoringModel):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, att_layer_num=3, att_head_num=2, att_res=True,
+                 dnn_hidden_units=(256, 128), dnn_activation='relu', l2_reg_dnn=0, l2_reg_embedding=1e-5, dnn_use_bn=False,
+                 dnn_dropout=0, init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None, flag=None,
+                 domain_column=None, num_domains=None, meta_dnn_hidden_units=(32, 64, 32)):
+        if flag and 'usemetatrans' in flag:
+            raise NotImplementedError("'usemetatrans' (BaseModel.meta_transformation, reference basemodel.py:191-199) is not built")
+        super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=0, l2_reg_embedding=l2_reg_embedding,
+                         init_std=init_std, seed=seed, task=task, device=device, gpus=gpus, flag=flag)
+        if len(dnn_hidden_units) <= 0 and att_layer_num <= 0:
+            raise ValueError("Either hidden_layer or att_layer_num must > 0")
+        if dnn_activation != 'relu' or dnn_use_bn:
+            raise NotImplementedError("AutoInt tower: relu without batch norm (reference main.py:235-241 defaults)")
+        d = self.embedding_size
+        field_num = len(self._sparse_feats)
+        dense = [f for f in dnn_feature_columns if isinstance(f, DenseFeat)]
+        self._dense_cols = [c for f in dense for c in range(*self.feature_index[f.name])]
+        self.use_dnn = len(dnn_feature_columns) > 0 and len(dnn_hidden_units) > 0
+        self.dnn_hidden_units, self.att_layer_num = dnn_hidden_units, att_layer_num
+        n_in = (dnn_hidden_units[-1] if len(dnn_hidden_units) else 0) + (field_num * d if att_layer_num > 0 else 0)
+        self.dnn_linear = nn.Linear(n_in, 1, bias=False)
+        if self.use_dnn:
+            self.dnn = _DNN(field_num * d + len(self._dense_cols), dnn_hidden_units, init_std)
+        self.int_layers = nn.ModuleList([InteractingLayer(d, att_head_num, att_res, device='cpu') for _ in range(att_layer_num)])
+        self._init_layout(device)
+        self.to(device)
+
+    def forward(self, X):
+        Xd, x = self._gather_fields(X, list(range(len(self._sparse_feats))))
+        flat = x.reshape(x.shape[0], -1)
+        att = x
+        for layer in self.int_layers:
+            att = layer(att)
+        parts = []
+        if self.att_layer_num > 0:
+            parts.append(att.reshape(att.shape[0], -1))
+        if len(self.dnn_hidden_units) > 0:
+            dnn_in = flat if not self._dense_cols else torch.cat([flat, Xd[:, self._dense_cols].float()], dim=1)
+            with torch.no_grad():
+                parts.append(self.dnn(dnn_in))
+        stack = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1).contiguous()
+        return self._head(stack, None, self.dnn_linear.weight, self.out.bias)       # y = sigmoid(dnn_linear(stack) + out.bias)

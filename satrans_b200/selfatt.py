@@ -1,30 +1,63 @@
-"""SelfAttention_Layer — drop-in for `models/submodules.py:178-238` of the reference ("next" row 1 of SURVEY.md
-§8f: the attention front-end of the AutoInt / STAR / MMOE 'usetrans' baselines), run through the same per-sample
-field-attention kernel code as SATrans.  Same constructor, same state-dict keys (W_Query, W_Key, W_Value, W_Out,
-W_Res, layer_norm.*).  Forward only (inference, and train-mode dropout with the counter-based RNG); the backward of
-this layer is not built."""
+"""Field self-attention layers of the baselines that share SATrans' attention front end ("next" rows of SURVEY.md section 8f, the
+AutoInt / STAR-Trans scoring of BASELINE config 5), run through the same per-sample field-attention kernel code as SATrans
+(`sat_field_attention_fwd`).  Same constructors and state-dict keys as the reference classes.  FORWARD ONLY (inference, and
+train-mode dropout with the counter-based RNG): the backward of these layers is not built, training them raises.
+
+    SelfAttention_Layer    reference submodules.py:178-238 (key `W_Key`) and star_trans.py:335-396 (key `W_key`)
+    MDR_InteractingLayer   reference star_trans.py:146-242: one W_Query and one LayerNorm per scenario
+    InteractingLayer       deepctr-torch 0.2.9 (AutoInt); the package is not vendored in the reference tree, so this follows its
+                           published algorithm -- PARITY UNPINNED (checked against oracle.interacting_layer only)
+"""
 import torch
 import torch.nn as nn
 
 from . import _lib
 
 
+def _ptr(t):
+    return t.detach().contiguous().data_ptr()
+
+
+def _check_shape(embedding_size, head_num):
+    if head_num <= 0:
+        raise ValueError('head_num must be a int > 0')
+    if embedding_size % head_num != 0:
+        raise ValueError('embedding_size is not an integer multiple of head_num!')
+    if embedding_size != _lib.SAT_D or head_num not in (1, 2, 4, 8):
+        raise NotImplementedError("kernels are built for embedding_size=32 and head_num in {1,2,4,8}")
+
+
+def _run(layer, inputs, wq, n_wq, wk, ln_g, ln_b, dom, scaling, p_drop):
+    if len(inputs.shape) != 3:
+        raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
+    if not inputs.is_cuda:
+        raise _lib.SatError('%s needs CUDA tensors; there is no CPU fallback' % type(layer).__name__)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters()) and layer.training and inputs.requires_grad:
+        raise NotImplementedError("the backward of %s is not built (forward / scoring only)" % type(layer).__name__)
+    x = inputs.detach().contiguous().float()
+    B, F, _ = x.shape
+    out = torch.empty_like(x)
+    layer._calls += 1
+    _lib.check(_lib.lib().sat_field_attention_fwd(
+        x.data_ptr(), out.data_ptr(), wq, n_wq, wk, _ptr(layer.W_Value), _ptr(layer.W_Res) if layer.use_res else None,
+        ln_g, ln_b, dom, B, F, layer.head_num, int(layer.use_res), int(scaling), int(layer.training), float(p_drop),
+        (int(torch.initial_seed()) + layer._calls) & (2 ** 64 - 1), torch.cuda.current_stream().cuda_stream),
+        'sat_field_attention_fwd')
+    return out
+
+
 class SelfAttention_Layer(nn.Module):
-    def __init__(self, embedding_size, head_num=2, use_res=True, scaling=True, seed=1024, device='cpu'):
+    def __init__(self, embedding_size, head_num=2, use_res=True, scaling=True, seed=1024, device='cpu', key_name='W_Key'):
+        """key_name: 'W_Key' (models/submodules.py) or 'W_key' (the copy of the class inside models/star_trans.py)."""
         super().__init__()
-        if head_num <= 0:
-            raise ValueError('head_num must be a int > 0')
-        if embedding_size % head_num != 0:
-            raise ValueError('embedding_size is not an integer multiple of head_num!')
-        if embedding_size != _lib.SAT_D or head_num not in (1, 2, 4, 8):
-            raise NotImplementedError("kernels are built for embedding_size=32 and head_num in {1,2,4,8}")
-        if not scaling:
-            raise NotImplementedError("scaling=False is not built (every call site of the reference uses the default)")
+        _check_shape(embedding_size, head_num)
+        if key_name not in ('W_Key', 'W_key'):
+            raise ValueError("key_name must be 'W_Key' or 'W_key'")
         self.att_embedding_size = embedding_size // head_num
-        self.head_num, self.use_res, self.scaling, self.seed = head_num, use_res, scaling, seed
+        self.head_num, self.use_res, self.scaling, self.seed, self._key_name = head_num, use_res, scaling, seed, key_name
         d = embedding_size
         self.W_Query = nn.Parameter(torch.empty(d, d))
-        self.W_Key = nn.Parameter(torch.empty(d, d))
+        setattr(self, key_name, nn.Parameter(torch.empty(d, d)))
         self.W_Value = nn.Parameter(torch.empty(d, d))
         self.W_Out = nn.Parameter(torch.empty(d, d))          # declared, never used (reference submodules.py:195)
         self.layer_norm = nn.LayerNorm(d, eps=1e-6)
@@ -37,19 +70,72 @@ class SelfAttention_Layer(nn.Module):
         self.to(device)
 
     def forward(self, inputs):
-        if len(inputs.shape) != 3:
-            raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
-        if not inputs.is_cuda:
-            raise _lib.SatError('SelfAttention_Layer needs CUDA tensors; there is no CPU fallback')
-        x = inputs.detach().contiguous().float()
-        B, F, d = x.shape
-        out = torch.empty_like(x)
-        self._calls += 1
-        ptr = lambda t: t.detach().contiguous().data_ptr()
-        _lib.check(_lib.lib().sat_selfatt_fwd(
-            x.data_ptr(), out.data_ptr(), ptr(self.W_Query), ptr(self.W_Key), ptr(self.W_Value),
-            ptr(self.W_Res) if self.use_res else None, ptr(self.layer_norm.weight), ptr(self.layer_norm.bias),
-            B, F, self.head_num, int(self.use_res), int(self.training), float(self.dropout_rate),
-            (int(torch.initial_seed()) + self._calls) & (2 ** 64 - 1), torch.cuda.current_stream().cuda_stream),
-            'sat_selfatt_fwd')
-        return out
+        return _run(self, inputs, _ptr(self.W_Query), 1, _ptr(getattr(self, self._key_name)), _ptr(self.layer_norm.weight),
+                    _ptr(self.layer_norm.bias), None, self.scaling, self.dropout_rate)
+
+
+class InteractingLayer(nn.Module):
+    """deepctr-torch 0.2.9 InteractingLayer (AutoInt): relu(softmax(Q K^T [/ sqrt(dh) if scaling]) V + X W_Res)."""
+
+    def __init__(self, embedding_size, head_num=2, use_res=True, scaling=False, seed=1024, device='cpu'):
+        super().__init__()
+        _check_shape(embedding_size, head_num)
+        self.att_embedding_size = embedding_size // head_num
+        self.head_num, self.use_res, self.scaling, self.seed = head_num, use_res, scaling, seed
+        d = embedding_size
+        self.W_Query = nn.Parameter(torch.empty(d, d))
+        self.W_key = nn.Parameter(torch.empty(d, d))
+        self.W_Value = nn.Parameter(torch.empty(d, d))
+        if use_res:
+            self.W_Res = nn.Parameter(torch.empty(d, d))
+        for t in self.parameters():
+            nn.init.normal_(t, mean=0.0, std=0.05)
+        self._calls = 0
+        self.to(device)
+
+    def forward(self, inputs):
+        return _run(self, inputs, _ptr(self.W_Query), 1, _ptr(self.W_key), None, None, None, self.scaling, 0.0)
+
+
+class MDR_InteractingLayer(nn.Module):
+    MAX_DOMAINS = 8
+
+    def __init__(self, embedding_size, num_domains, head_num=2, merge='no', use_res=True, scaling=True, seed=1024, device='cpu'):
+        super().__init__()
+        _check_shape(embedding_size, head_num)
+        if merge not in ('no', 'sum', 'dot'):
+            raise NotImplementedError('not implemented parameters merge')
+        if not 1 <= num_domains <= self.MAX_DOMAINS:
+            raise NotImplementedError("1 <= num_domains <= %d" % self.MAX_DOMAINS)
+        self.att_embedding_size = embedding_size // head_num
+        self.head_num, self.use_res, self.scaling, self.seed = head_num, use_res, scaling, seed
+        self.merge, self.embedding_size, self.num_domains = merge, embedding_size, num_domains
+        d = embedding_size
+        self.W_Query = nn.Parameter(torch.empty(d, d))
+        self.domain_W_Queries = nn.ParameterList([nn.Parameter(torch.empty(d, d)) for _ in range(num_domains)])
+        self.W_key = nn.Parameter(torch.empty(d, d))
+        self.W_Value = nn.Parameter(torch.empty(d, d))
+        self.domain_layer_norms = nn.ModuleList([nn.LayerNorm(d, eps=1e-6) for _ in range(num_domains)])
+        if use_res:
+            self.W_Res = nn.Parameter(torch.empty(d, d))
+        for t in self.parameters():                            # reference star_trans.py:192-193
+            nn.init.normal_(t, mean=0.0, std=0.05)
+        self.dropout_rate = 0.1
+        self._calls = 0
+        self.to(device)
+
+    def forward(self, inputs, domain_ids):
+        with torch.no_grad():
+            wq = torch.stack([w.detach() for w in self.domain_W_Queries])              # (n, 32, 32)
+            if self.merge == 'sum':                                                     # reference star_trans.py:209-217
+                wq = wq + self.W_Query.detach()
+            elif self.merge == 'dot':
+                wq = wq * self.W_Query.detach()
+            wq = wq.contiguous().float()
+            ln_g = torch.stack([ln.weight.detach() for ln in self.domain_layer_norms]).contiguous().float()
+            ln_b = torch.stack([ln.bias.detach() for ln in self.domain_layer_norms]).contiguous().float()
+            dom = domain_ids.detach().to(device=inputs.device, dtype=torch.int32).contiguous()
+        if dom.numel() != inputs.shape[0]:
+            raise ValueError('domain_ids must hold one id per sample')
+        return _run(self, inputs, wq.data_ptr(), self.num_domains, _ptr(self.W_key), ln_g.data_ptr(), ln_b.data_ptr(),
+                    dom.data_ptr(), self.scaling, self.dropout_rate)

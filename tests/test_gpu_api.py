@@ -312,6 +312,7 @@ def test_selfattention_layer_matches_reference():
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'selfatt_layer.npz'))
     for tag, heads, res in (('h4_f19_r1', 4, True), ('h2_f15_r1', 2, True), ('h4_f7_r0', 4, False)):
         layer = SelfAttention_Layer(32, heads, use_res=res, device='cuda:0').eval()
+        assert 'W_Key' in layer.state_dict()
         sd = {k[len(tag) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + '/state/')}
         assert set(sd) == set(layer.state_dict())
         layer.load_state_dict(sd)
@@ -320,6 +321,65 @@ def test_selfattention_layer_matches_reference():
         layer.train()
         yt = layer(torch.from_numpy(z[tag + '/x']).cuda())
         assert torch.isfinite(yt).all() and not torch.equal(yt, y)
+
+
+def test_mdr_interacting_layer_and_star_trans_match_reference():
+    """'next' row 3: MDR_InteractingLayer and the Star_Trans scoring path through the field-attention / gather / head
+    kernels against vectors dumped from the reference's own classes (star_trans.py:146-242,674-775)."""
+    import json
+    import os
+    from satrans_b200 import MDR_InteractingLayer, SparseFeat, Star_Trans
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'star_trans.npz'))
+    for tag, heads, nd, merge, res in (('mdr_h4_f18_d3_no_r1', 4, 3, 'no', True), ('mdr_h2_f14_d4_sum_r1', 2, 4, 'sum', True),
+                                       ('mdr_h4_f6_d3_dot_r0', 4, 3, 'dot', False)):
+        layer = MDR_InteractingLayer(32, nd, heads, merge, res, device='cuda:0').eval()
+        sd = {k[len(tag) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + '/state/')}
+        assert set(sd) == set(layer.state_dict())
+        layer.load_state_dict(sd)
+        y = layer(torch.from_numpy(z[tag + '/x']).cuda(), torch.from_numpy(z[tag + '/dom']).cuda())
+        assert torch.allclose(y.cpu(), torch.from_numpy(z[tag + '/y']), atol=2e-6, rtol=0), tag
+    meta = json.loads(bytes(z['model/fields']).decode())
+    cols = [SparseFeat(f, v, 32) for f, v in zip(meta['fields'], meta['vocab'])]
+    model = Star_Trans(cols, cols, meta['domain_col'], meta['num_domains'], att_layer_num=2, domain_att_layer_num=1, att_head_num=4,
+                       merge='no', use_linear=False, seed=1021, device='cuda:0')
+    sd = {k[len('model/state/'):]: torch.from_numpy(z[k]) for k in z.files if k.startswith('model/state/')}
+    r = model.load_state_dict(sd, strict=False)
+    assert not r.unexpected_keys and all(k.startswith('linear_model.') for k in r.missing_keys)
+    X = z['model/X']
+    yp = model.eval()(torch.from_numpy(X).cuda())
+    assert torch.allclose(yp.cpu(), torch.from_numpy(z['model/y_pred']), atol=2e-6, rtol=0)
+    pred = model.predict({f: X[:, i].astype(np.int64) for i, f in enumerate(meta['fields'])}, batch_size=17)
+    assert pred.dtype == np.float64 and np.allclose(pred, z['model/y_pred'], atol=2e-6, rtol=0)
+    with pytest.raises(NotImplementedError):
+        model.fit({}, [])
+
+
+def test_interacting_layer_and_autoint_match_the_oracle():
+    """'next' row 2: deepctr-torch's InteractingLayer and the AutoInt scoring path.  PARITY UNPINNED -- the layers live in an
+    un-vendored third-party package; the kernels are checked against the oracle's restatement of the published algorithm."""
+    from satrans_b200 import AutoInt, InteractingLayer
+    g = torch.Generator().manual_seed(4)
+    for heads, Fn, res, scaling in ((2, 19, True, False), (4, 7, False, False), (1, 32, True, True)):
+        layer = InteractingLayer(32, heads, res, scaling, device='cuda:0').eval()
+        x = torch.randn((50, Fn, 32), generator=g) * 0.7
+        p = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+        ref = O.interacting_layer(x, p, heads, res, scaling)
+        assert torch.allclose(layer(x.cuda()).cpu(), ref, atol=2e-6, rtol=0), (heads, Fn)
+    schema, cfg, st = _small()
+    cols = schema.feature_columns(32)
+    model = AutoInt(cols, cols, att_layer_num=3, att_head_num=2, device='cuda:0', seed=7).eval()
+    with torch.no_grad():
+        model._tables.normal_(0.0, 0.3)
+        for lin in model.dnn.linears:
+            lin.weight.normal_(0.0, 0.05)
+    xs, _ = synth.make_inputs(schema, 300, seed=4)
+    X = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = O.autoint_forward(sd, X, schema.fields, 2, 3)
+    # (the DNN tower is a library GEMM: TF32 is off by default in torch, so the fp32 tolerance holds)
+    assert torch.allclose(model(X.cuda()).cpu(), ref, atol=3e-6, rtol=0)
+    assert np.allclose(model.predict(xs, 64), ref.numpy(), atol=3e-6, rtol=0)
 
 
 @pytest.mark.parametrize('F,flag,heads,B,precision', [(32, 'sota', 4, 2600, 'tf32x3'), (32, 'sota', 4, 2600, 'fp32'),
