@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_bwd_meta_tc(const BwdArgs a, const
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
                     *reinterpret_cast<float4*>(sB + 2048 + (tid & 63) * 16 + r * 4) = make_float4(cv[r][0], cv[r][1], cv[r][2], cv[r][3]);
+                fence_async_smem();        // these generic-proxy stores are ordered before the next TMA write of this part of sB
             }
         }
         SAT_TC_ROUND(issue_gemm_k32<PASSES>(tbase + TCB_D, tbase + TCB_H2, sB, sB + 1024, 32, true));

@@ -206,8 +206,9 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
             const int kq = theta_key(g, l, 0, L, pos), kk = theta_key(g, l, 1, L, pos);
             const bool has_next = !(last_tile && l == L - 1);         // another (tile, layer) follows in this CTA
             const int l_next = l + 1 < L ? l + 1 : 0;
-            // K side first: its generated weights go into sBT now, the Q side's (ENP) are swapped in later
-            if (kk != cur_key) { if (tid == 0) fetch_key(kk); cur_key = kk; }
+            // K side first: its generated weights go into sBT now, the Q side's (ENP) are swapped in later.  A key block is only
+            // fetched for a side that has a MetaNet, so that every fetch is waited for (by that side's W1 round) before the next
+            if (meta_k && kk != cur_key) { if (tid == 0) fetch_key(kk); cur_key = kk; }
             float* act_l = TRAIN ? a.acts + (long long)l * ACT_PER_LAYER * a.act_stride : nullptr;
             if (TRAIN && valid) store_row(act_l + ACT_X * a.act_stride + tokpos, x);
 
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
             for (int side = 1; side >= 0; --side) {
                 float (&u)[D] = side ? k : q;
                 const bool has_meta = side ? meta_k : meta_q;
-                if (side == 0 && pos && kq != cur_key) {          // ENP: swap in the Q side's generated weights (the K side's
-                    if (tid == 0) fetch_key(kq);                  // MMAs have all completed)
+                if (side == 0 && meta_q && kq != cur_key) {       // ENP (or no K-side MetaNet): the Q side's generated weights
+                    if (tid == 0) fetch_key(kq);                  // (every MMA that read sBT has completed)
                     cur_key = kq;
                 }
                 if (has_meta) {

@@ -47,6 +47,7 @@ class Workspace:
         check(lib().sat_workspace_sizes(C.byref(engine.desc), self.cap_B, int(training), sizes, C.byref(mt)),
               'sat_workspace_sizes')
         self.max_tiles = mt.value
+        self.dev_step = None       # value of the device-side step counter (step_state), None = unknown
         self.bufs = {}
         self.c = SatWork()
         self.c.B, self.c.cap_B = 0, self.cap_B
@@ -544,8 +545,13 @@ class Engine:
         G['y_pin'].copy_(yh)
         hp = G['hyper_pin']
         hp[0], hp[1], hp[2], hp[3] = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        w = G['w']
+        if w.dev_step != self.step_count:          # eager steps ran in between: the device-side counter continues from the host's
+            check(lib().sat_step_set(C.byref(w.c), int(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                     self._stream()), 'sat_step_set')
         G['graph'].replay()
         self.step_count += 1
+        w.dev_step = self.step_count
         self.launches += G['launches']
         return G['w']
 
@@ -561,10 +567,8 @@ class Engine:
              'Xs': torch.empty(tuple(Xh.shape), dtype=Xh.dtype, device=self.device),
              'ys': torch.empty(B, dtype=torch.float32, device=self.device)}
         l = lib()
-        # the device-side step counter continues from the host's
-        check(l.sat_step_set(C.byref(w.c), int(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                             self._stream()), 'sat_step_set')
         torch.cuda.synchronize()
+        w.dev_step = None                        # (graph_train_step writes the counter before the first replay)
         timing, self.timing = self.timing, None
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=self.device)

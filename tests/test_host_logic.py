@@ -197,3 +197,63 @@ def test_bench_reference_arm_contract():
     have_ref = os.path.exists(os.path.join(root, 'oracle', '_ref', 'models', 'satrans.py'))
     assert d['value'] > 0 and d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and 'workload' in d['config']
+
+
+def test_constructor_error_contract():
+    """What the drop-in constructor accepts and what it refuses: same ValueErrors as the reference
+    (satrans.py:16-19, meta_basemodel.py:685), NotImplementedError -- never a silent fallback -- for configurations whose
+    kernels are not built."""
+    import pytest
+    from satrans_b200 import SATrans, SparseFeat
+
+    def cols(d=32, n=3):
+        return [SparseFeat('f%d' % i, 7 + i, d) for i in range(n - 1)] + [SparseFeat('dom', 5, d)]
+
+    def make(c=None, **kw):
+        c = c or cols()
+        args = dict(att_layer_num=0, domain_att_layer_num=2, att_head_num=4, meta_mode='QK', seed=3, device='cpu', flag='sota')
+        args.update(kw)
+        return SATrans(c, c, ['dom'], [3], **args)
+
+    make()                                                     # the supported configuration builds on the CPU (parameters only)
+    make(flag='sota-pos', meta_mode='Q', att_head_num=8, att_res=False, seed='1021')
+    for bad_heads in (0, -1):
+        with pytest.raises(ValueError):
+            make(att_head_num=bad_heads)
+    with pytest.raises(ValueError):
+        make(att_head_num=3)                                   # 32 % 3 != 0
+    with pytest.raises(ValueError):                            # unequal embedding dims (meta_basemodel.py:677-686)
+        c = cols()
+        c[0] = SparseFeat('f0', 7, 16)
+        make(c)
+    for d in (16, 64):
+        with pytest.raises(NotImplementedError, match='embedding_dim=32'):
+            make(cols(d))
+    with pytest.raises(NotImplementedError, match='meta_dnn_hidden_units'):
+        make(meta_dnn_hidden_units=(32, 32))
+    with pytest.raises(NotImplementedError, match='att_head_num'):
+        make(att_head_num=16)
+    for flag in ('sota-gate', 'sota-bilinear', 'sota-onlyemb'):
+        with pytest.raises(NotImplementedError, match="flag variant"):
+            make(flag=flag)
+    with pytest.raises(NotImplementedError, match='multi-column'):
+        c = cols()
+        SATrans(c, c, ['dom', 'f0'], [3, 7], att_layer_num=0, domain_att_layer_num=2, att_head_num=4, device='cpu', flag='sota')
+    with pytest.raises(NotImplementedError):
+        make(cols(n=40))                                       # more than SAT_MAXF = 32 sparse fields
+    with pytest.raises(TypeError):
+        make(flag=None)                                        # the reference substring-tests the flag: it must be a str
+    m = make()
+    with pytest.raises(NotImplementedError):
+        m.compile('adamw')                                     # unknown optimizer string (meta_basemodel.py:623)
+    with pytest.raises(NotImplementedError):
+        m.compile('adam', loss='hinge')                        # unknown loss string (meta_basemodel.py:637)
+    with pytest.raises(NotImplementedError):
+        m.compile('adam', loss=lambda p, y, reduction='sum': (p - y).abs().sum())      # custom loss callables are not fused
+    import torch
+    with pytest.raises(NotImplementedError):
+        m.compile(torch.optim.Adam(m.parameters(), lr=0.01, amsgrad=True), 'binary_crossentropy')
+    from satrans_b200 import _lib
+    m.compile('adam', 'binary_crossentropy')
+    with pytest.raises(_lib.SatError, match='no CPU fallback'):
+        m.engine.bind()                                        # the kernels need the model on a CUDA device
