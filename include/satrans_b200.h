@@ -305,6 +305,15 @@ int sat_field_attention_fwd(const float* x, float* out, const float* wq, int32_t
                             const float* wres, const float* ln_g, const float* ln_b, const int32_t* dom, int32_t B, int32_t F,
                             int32_t H, int32_t use_res, int32_t scaling, int32_t training, float dropout_p, uint64_t seed,
                             void* stream);
+/* ---- backward of the same layer for n_wq = 1, dom = NULL (SelfAttention_Layer: ln_g given, scaling = 1; InteractingLayer: ln_g =
+ *      NULL): replaces torch autograd over reference submodules.py:208-238.  Only x is needed from the forward (it is recomputed
+ *      per tile with the same seed, so the dropout masks are the forward's).  dx and the parameter gradients are OVERWRITTEN
+ *      (not accumulated); every sum has a fixed order.  scratch: sat_field_attention_bwd_scratch(B, F) bytes. ---------------- */
+int64_t sat_field_attention_bwd_scratch(int32_t B, int32_t F);
+int sat_field_attention_bwd(const float* x, const float* dy, float* dx, const float* wq, const float* wk, const float* wv,
+                            const float* wres, const float* ln_g, int32_t B, int32_t F, int32_t H, int32_t use_res, int32_t scaling,
+                            int32_t training, float dropout_p, uint64_t seed, float* dwq, float* dwk, float* dwv, float* dwres,
+                            float* dln_g, float* dln_b, float* scratch, void* stream);
 /* ---- logit head of the baselines (reference star_trans.py:762-775, autoint.py:107-121): y[b] = sigmoid(bias + feat[b] . w[0:n]
  *      + dense[b] . w[n:n+n_dense]); feat: [B][n], dense: [B][ld_dense] or NULL, bias may be NULL, apply_sigmoid = 0 -> logit. */
 int sat_head_fwd(const float* feat, int32_t n, const float* dense, int32_t n_dense, int32_t ld_dense, const float* w,

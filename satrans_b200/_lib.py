@@ -89,6 +89,9 @@ PROTOTYPES = {
     'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, i32, vp]),
     'sat_selfatt_fwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, C.c_uint64, vp]),
     'sat_field_attention_fwd': (C.c_int, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64, vp]),
+    'sat_field_attention_bwd_scratch': (C.c_int64, [i32, i32]),
+    'sat_field_attention_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64,
+                                          vp, vp, vp, vp, vp, vp, vp, vp]),
     'sat_head_fwd': (C.c_int, [vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, vp]),
     'sat_pack_weights': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_batch_metrics': (C.c_int, [vp, vp, vp, i32, i32, vp, vp]),

@@ -1,7 +1,9 @@
 """Field self-attention layers of the baselines that share SATrans' attention front end ("next" rows of SURVEY.md section 8f, the
 AutoInt / STAR-Trans scoring of BASELINE config 5), run through the same per-sample field-attention kernel code as SATrans
-(`sat_field_attention_fwd`).  Same constructors and state-dict keys as the reference classes.  FORWARD ONLY (inference, and
-train-mode dropout with the counter-based RNG): the backward of these layers is not built, training them raises.
+(`sat_field_attention_fwd` / `sat_field_attention_bwd`).  Same constructors and state-dict keys as the reference classes.
+SelfAttention_Layer and InteractingLayer are differentiable (a torch.autograd.Function around the two kernels: gradients w.r.t. the
+input and every parameter, dropout masks of the backward = the forward's through the shared counter-based seed);
+MDR_InteractingLayer is forward only (scoring), using it under autograd raises.
 
     SelfAttention_Layer    reference submodules.py:178-238 (key `W_Key`) and star_trans.py:335-396 (key `W_key`)
     MDR_InteractingLayer   reference star_trans.py:146-242: one W_Query and one LayerNorm per scenario
@@ -27,13 +29,54 @@ def _check_shape(embedding_size, head_num):
         raise NotImplementedError("kernels are built for embedding_size=32 and head_num in {1,2,4,8}")
 
 
+class _FieldAttention(torch.autograd.Function):
+    """y = layer(x) for the single-W_Query layers; backward = sat_field_attention_bwd (recomputes the forward from x)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, wres, ln_g, ln_b, heads, scaling, training, p_drop, seed):
+        x = x.contiguous().float()
+        B, F, _ = x.shape
+        out = torch.empty_like(x)
+        c = lambda t: None if t is None else t.detach().contiguous()
+        wq_, wk_, wv_, wres_, g_, b_ = c(wq), c(wk), c(wv), c(wres), c(ln_g), c(ln_b)
+        p = lambda t: None if t is None else t.data_ptr()
+        _lib.check(_lib.lib().sat_field_attention_fwd(
+            x.data_ptr(), out.data_ptr(), p(wq_), 1, p(wk_), p(wv_), p(wres_), p(g_), p(b_), None, B, F, heads,
+            int(wres is not None), int(scaling), int(training), float(p_drop), seed, torch.cuda.current_stream().cuda_stream),
+            'sat_field_attention_fwd')
+        ctx.save_for_backward(x, wq_, wk_, wv_, wres_, g_)
+        ctx.cfg = (heads, scaling, training, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wq, wk, wv, wres, g = ctx.saved_tensors
+        heads, scaling, training, p_drop, seed = ctx.cfg
+        B, F, _ = x.shape
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        dwq, dwk, dwv = torch.empty_like(wq), torch.empty_like(wk), torch.empty_like(wv)
+        dwres = torch.empty_like(wres) if wres is not None else None
+        dg = torch.empty_like(g) if g is not None else None
+        db = torch.empty_like(g) if g is not None else None
+        l = _lib.lib()
+        scratch = torch.empty(max(1, l.sat_field_attention_bwd_scratch(B, F) // 4), dtype=torch.float32, device=x.device)
+        p = lambda t: None if t is None else t.data_ptr()
+        _lib.check(l.sat_field_attention_bwd(
+            x.data_ptr(), dy.data_ptr(), dx.data_ptr(), p(wq), p(wk), p(wv), p(wres), p(g), B, F, heads, int(wres is not None),
+            int(scaling), int(training), float(p_drop), seed, p(dwq), p(dwk), p(dwv), p(dwres), p(dg), p(db), scratch.data_ptr(),
+            torch.cuda.current_stream().cuda_stream), 'sat_field_attention_bwd')
+        return dx, dwq, dwk, dwv, dwres, dg, db, None, None, None, None, None
+
+
 def _run(layer, inputs, wq, n_wq, wk, ln_g, ln_b, dom, scaling, p_drop):
     if len(inputs.shape) != 3:
         raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
     if not inputs.is_cuda:
         raise _lib.SatError('%s needs CUDA tensors; there is no CPU fallback' % type(layer).__name__)
-    if torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters()) and layer.training and inputs.requires_grad:
-        raise NotImplementedError("the backward of %s is not built (forward / scoring only)" % type(layer).__name__)
+    if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in layer.parameters())) and dom is not None:
+        if inputs.requires_grad:
+            raise NotImplementedError("the backward of %s is not built (forward / scoring only)" % type(layer).__name__)
     x = inputs.detach().contiguous().float()
     B, F, _ = x.shape
     out = torch.empty_like(x)
@@ -44,6 +87,17 @@ def _run(layer, inputs, wq, n_wq, wk, ln_g, ln_b, dom, scaling, p_drop):
         (int(torch.initial_seed()) + layer._calls) & (2 ** 64 - 1), torch.cuda.current_stream().cuda_stream),
         'sat_field_attention_fwd')
     return out
+
+
+def _differentiable(layer, inputs, wk, ln_g, ln_b, scaling, p_drop):
+    if len(inputs.shape) != 3:
+        raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
+    if not inputs.is_cuda:
+        raise _lib.SatError('%s needs CUDA tensors; there is no CPU fallback' % type(layer).__name__)
+    layer._calls += 1
+    seed = (int(torch.initial_seed()) + layer._calls) & (2 ** 64 - 1)
+    return _FieldAttention.apply(inputs, layer.W_Query, wk, layer.W_Value, layer.W_Res if layer.use_res else None, ln_g, ln_b,
+                                 layer.head_num, bool(scaling), bool(layer.training), float(p_drop), seed)
 
 
 class SelfAttention_Layer(nn.Module):
@@ -70,6 +124,9 @@ class SelfAttention_Layer(nn.Module):
         self.to(device)
 
     def forward(self, inputs):
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.W_Query.requires_grad):
+            return _differentiable(self, inputs, getattr(self, self._key_name), self.layer_norm.weight, self.layer_norm.bias,
+                                   self.scaling, self.dropout_rate)
         return _run(self, inputs, _ptr(self.W_Query), 1, _ptr(getattr(self, self._key_name)), _ptr(self.layer_norm.weight),
                     _ptr(self.layer_norm.bias), None, self.scaling, self.dropout_rate)
 
@@ -94,6 +151,8 @@ class InteractingLayer(nn.Module):
         self.to(device)
 
     def forward(self, inputs):
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.W_Query.requires_grad):
+            return _differentiable(self, inputs, self.W_key, None, None, self.scaling, 0.0)
         return _run(self, inputs, _ptr(self.W_Query), 1, _ptr(self.W_key), None, None, None, self.scaling, 0.0)
 
 

@@ -323,6 +323,66 @@ def test_selfattention_layer_matches_reference():
         assert torch.isfinite(yt).all() and not torch.equal(yt, y)
 
 
+def test_selfattention_layer_backward_matches_reference():
+    """'next' row 1: gradients of sum(y * cot) w.r.t. the input and every parameter of SelfAttention_Layer through the backward
+    kernel (torch.autograd.Function around sat_field_attention_fwd / _bwd) against torch autograd through the reference's own
+    module (tests/golden/selfatt_layer.npz); and the same for deepctr's InteractingLayer against autograd through the oracle's
+    restatement (parity unpinned).  Bar: max-norm rtol 1e-4.  Two backward calls give bit-identical gradients."""
+    import os
+    from satrans_b200 import InteractingLayer, SelfAttention_Layer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'selfatt_layer.npz'))
+    for tag, heads, res in (('h4_f19_r1', 4, True), ('h2_f15_r1', 2, True), ('h4_f7_r0', 4, False)):
+        layer = SelfAttention_Layer(32, heads, use_res=res, device='cuda:0').eval()
+        layer.load_state_dict({k[len(tag) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + '/state/')})
+        runs = []
+        for _ in range(2):
+            x = torch.from_numpy(z[tag + '/x']).cuda().requires_grad_(True)
+            layer.zero_grad()
+            y = layer(x)
+            assert torch.allclose(y.detach().cpu(), torch.from_numpy(z[tag + '/y']), atol=2e-6, rtol=0)
+            (y * torch.from_numpy(z[tag + '/cot']).cuda()).sum().backward()
+            got = {'x': x.grad.cpu()}
+            got.update({k: p.grad.cpu() for k, p in layer.named_parameters() if p.grad is not None})
+            runs.append(got)
+        assert all(torch.equal(runs[0][k], runs[1][k]) for k in runs[0])
+        for k in [f[len(tag) + 6:] for f in z.files if f.startswith(tag + '/grad/')]:
+            ref = torch.from_numpy(z[tag + '/grad/' + k])
+            err = (runs[0][k] - ref).abs().max().item()
+            assert err <= 1e-4 * ref.abs().max().item() + 1e-9, (tag, k, err)
+        assert 'W_Out' not in runs[0]                                   # declared by the reference, never used: no gradient
+    # train mode: the backward re-creates the forward's dropout masks (finite-difference check of one directional derivative)
+    layer = SelfAttention_Layer(32, 4, device='cuda:0').train()
+    g = torch.Generator().manual_seed(2)
+    x0 = (torch.randn((16, 9, 32), generator=g) * 0.5).cuda()
+    v = torch.randn((16, 9, 32), generator=g).cuda()
+    cot = torch.randn((16, 9, 32), generator=g).cuda()
+    torch.manual_seed(99)
+    calls = layer._calls
+    x = x0.clone().requires_grad_(True)
+    (layer(x) * cot).sum().backward()
+    analytic = (x.grad * v).sum().item()
+    vals = []
+    for eps in (1e-2, -1e-2):
+        layer._calls = calls                                            # same seed -> same masks
+        with torch.no_grad():
+            vals.append((layer(x0 + eps * v) * cot).sum().item())
+    numeric = (vals[0] - vals[1]) / 2e-2
+    assert abs(analytic - numeric) <= 2e-2 * max(abs(numeric), 1.0), (analytic, numeric)
+    # InteractingLayer (no LayerNorm / dropout / scaling)
+    for heads, Fn, res, scaling in ((2, 19, True, False), (4, 6, False, True)):
+        layer = InteractingLayer(32, heads, res, scaling, device='cuda:0')
+        xh = torch.randn((30, Fn, 32), generator=g) * 0.7
+        ch = torch.randn((30, Fn, 32), generator=g)
+        x = xh.cuda().requires_grad_(True)
+        (layer(x) * ch.cuda()).sum().backward()
+        p = {k: t.detach().cpu().clone().requires_grad_(True) for k, t in layer.state_dict().items()}
+        xr = xh.clone().requires_grad_(True)
+        (O.interacting_layer(xr, p, heads, res, scaling) * ch).sum().backward()
+        assert (x.grad.cpu() - xr.grad).abs().max().item() <= 1e-4 * xr.grad.abs().max().item() + 1e-9
+        for k, t in layer.named_parameters():
+            assert (t.grad.cpu() - p[k].grad).abs().max().item() <= 1e-4 * p[k].grad.abs().max().item() + 1e-9, k
+
+
 def test_mdr_interacting_layer_and_star_trans_match_reference():
     """'next' row 3: MDR_InteractingLayer and the Star_Trans scoring path through the field-attention / gather / head
     kernels against vectors dumped from the reference's own classes (star_trans.py:146-242,674-775)."""

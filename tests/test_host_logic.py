@@ -25,7 +25,7 @@ def _model(g, device='cpu'):
 
 def test_header_symbols_exported_and_bound():
     hdr = open(os.path.join(ROOT, 'include', 'satrans_b200.h')).read()
-    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(sat_\w+)\s*\(', hdr, flags=re.M))
+    declared = set(re.findall(r'^\s*(?:int|int64_t|const char\*)\s+(sat_\w+)\s*\(', hdr, flags=re.M))
     assert declared, 'no declarations parsed'
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     if not os.path.exists(_lib.LIB_PATH):
