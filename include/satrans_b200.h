@@ -283,8 +283,9 @@ int sat_finalize_loss(const SatModel* m, SatWork* w, float l2_emb, int32_t tile_
 
 /* ---- tensor-core forward (tcgen05 / TMEM): same contract as sat_forward.  sat_pack_weights (after
  *      sat_encoder_fwd) packs the layer weights and the generated MetaNet weights as UMMA B operands;
- *      passes = 3: error-compensated 3xTF32 (fp32-level parity), passes = 1: plain TF32. -------------------- */
-int sat_pack_weights(const SatModel* m, SatWork* w, void* stream);
+ *      passes = 3: error-compensated 3xTF32 (fp32-level parity), passes = 1: plain TF32, passes = 2: bf16 operands with fp32
+ *      accumulation (kind::f16; the packing must have been done with the same value). ---------------------------- */
+int sat_pack_weights(const SatModel* m, SatWork* w, int32_t passes, void* stream);
 int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,
                    float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream);
 /* sat_backward with the MetaNet / QKV data-gradient projections on the tensor cores (same contract, same outputs). */

@@ -93,7 +93,7 @@ PROTOTYPES = {
     'sat_field_attention_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64,
                                           vp, vp, vp, vp, vp, vp, vp, vp]),
     'sat_head_fwd': (C.c_int, [vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, vp]),
-    'sat_pack_weights': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
+    'sat_pack_weights': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), i32, vp]),
     'sat_batch_metrics': (C.c_int, [vp, vp, vp, i32, i32, vp, vp]),
     'sat_forward_tc': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, i32, vp]),
 }

@@ -287,8 +287,8 @@ class BaseModel(nn.Module):
 
     @precision.setter
     def precision(self, value):
-        if value not in ('fp32', 'tf32x3', 'tf32'):
-            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32', got %r" % (value,))
+        if value not in ('fp32', 'tf32x3', 'tf32', 'bf16'):
+            raise ValueError("precision must be 'fp32', 'tf32x3', 'tf32' or 'bf16', got %r" % (value,))
         self.engine.precision = value
 
     def _as_device_matrix(self, X):

@@ -73,4 +73,4 @@ SAT_DECL_H(2)
 SAT_DECL_H(4)
 SAT_DECL_H(8)
 #undef SAT_DECL_H
-int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, cudaStream_t s);
+int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, int bf16, cudaStream_t s);

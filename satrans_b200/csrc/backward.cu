@@ -440,7 +440,7 @@ extern "C" int sat_backward(const SatModel* m, const void* x, int32_t id_kind, i
 
 extern "C" int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
                                uint64_t seed, int32_t passes, void* stream) {
-    if (passes != 1 && passes != 3) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: passes must be 1 or 3, got %d", passes);
+    if (passes < 1 || passes > 3) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: passes must be 1, 2 or 3, got %d", passes);
     if (!w || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: workspace has no packed weights");
     return backward_impl(m, x, id_kind, ld, w, dropout_p, seed, passes, stream);
 }

@@ -297,11 +297,13 @@ int sat_launch_bwd_meta_tc(const BwdArgs& a, const float* wpack, int n_keys, int
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k_bwd_meta_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_bwd_meta_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(k_bwd_meta_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return sat_host::fail(SAT_ECUDA, "sat_backward: cannot raise dynamic shared memory to %zu", smem);
         configured = smem;
     }
     if (passes == 3) k_bwd_meta_tc<3><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
+    else if (passes == 2) k_bwd_meta_tc<2><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
     else k_bwd_meta_tc<1><<<grid, TC_NT, smem, s>>>(a, wpack, n_keys);
     return sat_host::check_launch("k_bwd_meta_tc");
 }

@@ -141,10 +141,11 @@ extern "C" int sat_ipc_close(void* ptr) {
 }
 
 // ---- tensor-core forward: pack the B operands, then the tcgen05 kernel ---------------------------------------
-extern "C" int sat_pack_weights(const SatModel* m, SatWork* w, void* stream) {
+extern "C" int sat_pack_weights(const SatModel* m, SatWork* w, int32_t passes, void* stream) {
     if (!m || !w || !w->theta || !w->wpack) return sat_host::fail(SAT_EINVAL, "sat_pack_weights: null argument");
+    if (passes < 1 || passes > 3) return sat_host::fail(SAT_EINVAL, "sat_pack_weights: passes must be 1, 2 or 3, got %d", passes);
     const int n_keys = (m->flags & SAT_FLAG_POS) ? m->n_dom * m->L * 2 : m->n_dom;
-    return sat_launch_pack_weights(m, n_keys, w->theta, w->wpack, (cudaStream_t)stream);
+    return sat_launch_pack_weights(m, n_keys, w->theta, w->wpack, passes == 2, (cudaStream_t)stream);
 }
 
 extern "C" int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, const float* y, SatWork* w,

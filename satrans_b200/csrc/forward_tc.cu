@@ -17,6 +17,8 @@
 // Precision: PASSES = 3 is the error-compensated 3xTF32 scheme (x = hi + lo, D = A_hi B_hi + A_lo B_hi + A_hi B_lo),
 // which keeps fp32-level parity with the reference; PASSES = 1 is plain TF32 (fast mode, reported separately).
 // Attention over the F <= 32 tokens of a sample (9 % of the FLOPs, F x F x 8 per head) stays on the CUDA cores.
+#include <cuda_bf16.h>
+
 #include "fwd_common.cuh"
 #include "bwd_common.cuh"
 #include "tc_common.cuh"
@@ -29,63 +31,65 @@ namespace sat {
 // ---------------------------------------------------------------------------------------------------------
 #if SAT_INST_H == 4      // one copy of the packing kernel (this file is compiled once per head count)
 __global__ void __launch_bounds__(256) k_pack_weights(const SatModel m, int n_keys, const float* __restrict__ theta,
-                                                      float* __restrict__ wpack) {
+                                                      float* __restrict__ wpack, int bf16) {
     const int nblk = m.L + n_keys;
     const int total = 2 * nblk * 4096;
     for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         const int blk = e >> 12, i = e & 4095;
         float v;
-        int off_hi, off_lo;
+        int base_hi, base_lo, pn, pk_;
         if (blk < m.L) {
             const float* lay = m.dense + m.off_layers + (long long)blk * LAYER_FLOATS;
             if (i < 3072) {                      // B[n][k] = W_{Q|K|V}[k][n']   (x @ W)
                 const int n = i >> 5, k = i & 31;
                 v = lay[(n >> 5) * 1024 + k * 32 + (n & 31)];
-                off_hi = PK_QKV_HI + b_off32(n, k); off_lo = PK_QKV_LO + b_off32(n, k);
+                base_hi = PK_QKV_HI; base_lo = PK_QKV_LO; pn = n; pk_ = k;
             } else {                             // B[n][k] = Out_linear.weight[n][k]   (r @ W^T)
                 const int j = i - 3072, n = j >> 5, k = j & 31;
                 v = lay[OFF_WO + n * 32 + k];
-                off_hi = PK_WO_HI + b_off32(n, k); off_lo = PK_WO_LO + b_off32(n, k);
+                base_hi = PK_WO_HI; base_lo = PK_WO_LO; pn = n; pk_ = k;
             }
         } else if (blk < nblk) {
             const float* th = theta + (long long)(blk - m.L) * PSZ;
             if (i < 2048) {                      // W1: B[n][k] = theta[k*64 + n], N = 64
                 const int n = i >> 5, k = i & 31;
                 v = th[k * HID + n];
-                off_hi = PK_W1_HI + b_off32(n, k); off_lo = PK_W1_LO + b_off32(n, k);
+                base_hi = PK_W1_HI; base_lo = PK_W1_LO; pn = n; pk_ = k;
             } else {                             // W2 halves: B[n][k] = theta[2048 + (half*32 + k)*32 + n], N = 32
                 const int j = i - 2048, half = j >> 10, jj = j & 1023, n = jj >> 5, k = jj & 31;
                 v = th[D * HID + (half * 32 + k) * D + n];
-                off_hi = (half ? PK_W2B_HI : PK_W2A_HI) + b_off32(n, k);
-                off_lo = (half ? PK_W2B_LO : PK_W2A_LO) + b_off32(n, k);
+                base_hi = (half ? PK_W2B_HI : PK_W2A_HI); base_lo = (half ? PK_W2B_LO : PK_W2A_LO); pn = n; pk_ = k;
             }
         } else if (blk < nblk + m.L) {           // backward layer block
             const float* lay = m.dense + m.off_layers + (long long)(blk - nblk) * LAYER_FLOATS;
             const int which = i >> 10, j = i & 1023, n = j >> 5, k = j & 31;
             if (which < 3) {                     // B[n=i][k=j] = W[i][j]
                 v = lay[which * 1024 + n * 32 + k];
-                off_hi = which * 2048 + b_off32(n, k); off_lo = which * 2048 + 1024 + b_off32(n, k);
+                base_hi = which * 2048; base_lo = which * 2048 + 1024; pn = n; pk_ = k;
             } else {                             // B[n=i][k=j] = W_out[j][i]
                 v = lay[OFF_WO + k * 32 + n];
-                off_hi = PKB_WOT_HI + b_off32(n, k); off_lo = PKB_WOT_LO + b_off32(n, k);
+                base_hi = PKB_WOT_HI; base_lo = PKB_WOT_LO; pn = n; pk_ = k;
             }
         } else {                                 // backward key block
             const float* th = theta + (long long)(blk - nblk - m.L) * PSZ;
             if (i < 2048) {                      // W2T: B[n=c][k=j] = W2[c][j], N = 64
                 const int n = i >> 5, k = i & 31;
                 v = th[D * HID + n * D + k];
-                off_hi = PKB_W2T_HI + b_off32(n, k); off_lo = PKB_W2T_LO + b_off32(n, k);
+                base_hi = PKB_W2T_HI; base_lo = PKB_W2T_LO; pn = n; pk_ = k;
             } else {                             // W1N halves: B[n=i][k=c] = W1[i][half*32 + c]
                 const int j = i - 2048, half = j >> 10, jj = j & 1023, n = jj >> 5, k = jj & 31;
                 v = th[n * HID + half * 32 + k];
-                off_hi = (half ? PKB_W1N1_HI : PKB_W1N0_HI) + b_off32(n, k);
-                off_lo = (half ? PKB_W1N1_LO : PKB_W1N0_LO) + b_off32(n, k);
+                base_hi = (half ? PKB_W1N1_HI : PKB_W1N0_HI); base_lo = (half ? PKB_W1N1_LO : PKB_W1N0_LO); pn = n; pk_ = k;
             }
         }
         float* dst = wpack + (long long)blk * PACK_FLOATS;
-        const float hi = tf32_hi(v);
-        dst[off_hi] = hi;
-        dst[off_lo] = v - hi;
+        if (bf16) {                 // bf16: groups of 32 rows, group g in the first half of floats [1024 g, 1024 g + 1024) of the "hi" region
+            reinterpret_cast<__nv_bfloat16*>(dst + base_hi + (pn >> 5) * 1024)[b_off16(pn & 31, pk_)] = __float2bfloat16_rn(v);
+        } else {
+            const float hi = tf32_hi(v);
+            dst[base_hi + b_off32(pn, pk_)] = hi;
+            dst[base_lo + b_off32(pn, pk_)] = v - hi;
+        }
     }
 }
 #endif
@@ -473,14 +477,15 @@ int SAT_CAT(sat_launch_forward_tc_h, SAT_INST_H)(const FwdArgs& a, const float* 
     if (rc) return rc;
     if (passes == 3) return training ? launch_tc<true, 3>(a, tmap, grid, s) : launch_tc<false, 3>(a, tmap, grid, s);
     if (passes == 1) return training ? launch_tc<true, 1>(a, tmap, grid, s) : launch_tc<false, 1>(a, tmap, grid, s);
-    return sat_host::fail(SAT_EINVAL, "sat_forward_tc: passes must be 1 (tf32) or 3 (3xtf32), got %d", passes);
+    if (passes == 2) return training ? launch_tc<true, 2>(a, tmap, grid, s) : launch_tc<false, 2>(a, tmap, grid, s);
+    return sat_host::fail(SAT_EINVAL, "sat_forward_tc: passes must be 1 (tf32), 2 (bf16) or 3 (3xtf32), got %d", passes);
 }
 
 #if SAT_INST_H == 4
 // one copy of the packing entry point (any H translation unit would do)
-int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, cudaStream_t s) {
+int sat_launch_pack_weights(const SatModel* m, int n_keys, const float* theta, float* wpack, int bf16, cudaStream_t s) {
     const int total = 2 * (m->L + n_keys) * 4096;
-    k_pack_weights<<<(total + 255) / 256, 256, 0, s>>>(*m, n_keys, theta, wpack);
+    k_pack_weights<<<(total + 255) / 256, 256, 0, s>>>(*m, n_keys, theta, wpack, bf16);
     return sat_host::check_launch("k_pack_weights");
 }
 #endif

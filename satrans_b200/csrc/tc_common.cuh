@@ -27,6 +27,9 @@ constexpr int PKB_W2T_HI = 0, PKB_W2T_LO = 2048, PKB_W1N0_HI = 4096, PKB_W1N0_LO
 // core matrix = 8 rows (n) x 16 B (4 k); core matrices contiguous along k (LBO = 128 B), 8-row groups SBO = 1024 B apart
 __host__ __device__ __forceinline__ int b_off32(int n, int k) { return (n >> 3) * 256 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
 
+// the same for K = 32 bf16 elements (kind::f16): core matrix = 8 rows x 16 B (8 k); LBO = 128 B, SBO = 512 B; offset in ELEMENTS
+__host__ __device__ __forceinline__ int b_off16(int n, int k) { return (n >> 3) * 256 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7); }
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -91,6 +94,13 @@ __device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16 (bf16 operands, fp32 accumulate), M = 128
+__device__ __forceinline__ void mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -99,6 +109,11 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128
 __device__ __forceinline__ constexpr uint32_t make_idesc(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t make_idesc_bf16(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -123,10 +138,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[D]) {
     tmem_ld16(taddr, &v[0]);
     tmem_ld16(taddr + 16, &v[16]);
 }
-// write a 32-vector as A operand: hi at col, lo at col + 32 (PASSES == 3) or as is (PASSES == 1)
+// PASSES selects the arithmetic of the projections: 1 = TF32, 3 = error-compensated 3xTF32 (default, fp32-level parity),
+// 2 = bf16 operands with fp32 accumulation (kind::f16; reported separately, never the headline).
+// write a 32-vector as A operand: hi at col, lo at col + 32 (PASSES == 3), as is (PASSES == 1), or as 16 columns of packed bf16
+// pairs (PASSES == 2: element 2c in the low half of column c)
 template <int PASSES>
 __device__ __forceinline__ void tmem_st_operand(uint32_t taddr, const float (&v)[D]) {
-    if (PASSES == 1) {
+    if (PASSES == 2) {
+        float pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            uint32_t w;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(v[2 * i + 1]), "f"(v[2 * i]));      // {hi half, lo half}
+            pk[i] = __uint_as_float(w);
+        }
+        tmem_st16(taddr, &pk[0]);
+    } else if (PASSES == 1) {
         tmem_st16(taddr, &v[0]);
         tmem_st16(taddr + 16, &v[16]);
     } else {
@@ -147,9 +174,21 @@ __device__ __forceinline__ void tmem_st_operand(uint32_t taddr, const float (&v)
 template <int PASSES>
 __device__ __forceinline__ void issue_gemm_k32(uint32_t d_tmem, uint32_t a_tmem, const float* b_hi, const float* b_lo, int N,
                                                bool accumulate) {
-    const uint32_t idesc = make_idesc(N);
     const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
     uint32_t acc = accumulate ? 1u : 0u;
+    if (PASSES == 2) {
+        // bf16: the operand is stored as independent groups of 32 rows, group g at float offset 1024 g of the "hi" region (so
+        // that the 32-row slices the backward fetches sit where the fp32 layout has them); per group two k-steps of K = 16
+        const uint32_t idesc16 = make_idesc_bf16(32);
+        for (int g = 0; g < (N >> 5); ++g) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+                mma_ts_bf16(d_tmem + 32 * g, a_tmem + kk * 8, make_b_desc(bh + g * 4096 + kk * 256, 128, 512), idesc16,
+                            (kk > 0 || accumulate) ? 1u : 0u);
+        }
+        return;
+    }
+    const uint32_t idesc = make_idesc(N);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         const uint64_t dh = make_b_desc(bh + kk * 256, 128, 1024);

@@ -261,13 +261,13 @@ class Engine:
               'sat_bucket_by_domain')
         check(l.sat_encoder_fwd(C.byref(self.desc), C.byref(w.c), s), 'sat_encoder_fwd')
         if self.precision != 'fp32':
-            check(l.sat_pack_weights(C.byref(self.desc), C.byref(w.c), s), 'sat_pack_weights')
+            check(l.sat_pack_weights(C.byref(self.desc), C.byref(w.c), self._passes(), s), 'sat_pack_weights')
 
     def _passes(self):
         try:
-            return {'fp32': 0, 'tf32x3': 3, 'tf32': 1}[self.precision]
+            return {'fp32': 0, 'tf32x3': 3, 'tf32': 1, 'bf16': 2}[self.precision]
         except KeyError:
-            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32', got %r" % (self.precision,))
+            raise ValueError("precision must be 'fp32', 'tf32x3', 'tf32' or 'bf16', got %r" % (self.precision,))
 
     def _forward_call(self, X, kind, y_ptr, w, y_pred, training, p, seed, s):
         l, d = lib(), C.byref(self.desc)
@@ -282,7 +282,9 @@ class Engine:
     def _backward_call(self, X, kind, w, p, seed, s):
         l, d = lib(), C.byref(self.desc)
         bp = self.backward_precision or self.precision
-        passes = {'fp32': 0, 'tf32x3': 3, 'tf32': 1}[bp]
+        passes = {'fp32': 0, 'tf32x3': 3, 'tf32': 1, 'bf16': 2}[bp]
+        if passes and passes != self._passes() and self.precision != 'fp32':
+            raise ValueError("the tensor-core backward reads the weights packed for the forward: same precision required")
         if passes and self.precision == 'fp32':
             raise ValueError("a tensor-core backward needs the packed weights of a tensor-core forward precision")
         if passes == 0:
