@@ -172,8 +172,10 @@ def test_precision_knob():
     assert m.precision == 'tf32x3'
     m.precision = 'fp32'
     assert m.engine.precision == 'fp32'
+    m.precision = 'bf16'            # the kind::f16 variant (reported separately)
+    assert m.engine.precision == 'bf16'
     with pytest.raises(ValueError):
-        m.precision = 'bf16'
+        m.precision = 'fp8'
 
 
 def test_bench_reference_arm_contract():
