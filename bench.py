@@ -482,6 +482,26 @@ def run_b200(args):
     except Exception as e:  # the headline number must survive a failure of the extras
         extra["extra_error"] = repr(e)
 
+    # ---- the bf16 variant (kind::f16 MMAs on bf16 operands, fp32 accumulation): reported separately, never the headline ------
+    if world == 1:
+        try:
+            eng.precision = 'bf16'
+            model.train()
+            for i in range(3):
+                step(i)
+            bms = _time_loop(lambda i: step(1000 + i), min(K, 20), torch)
+            model.eval()
+            for _ in range(3):
+                eng.forward(Xd[:B], training=False)
+            bi = _time_loop(lambda i: eng.forward(Xd[:B], training=False), 10, torch)
+            extra["bf16"] = {"train_samples_per_sec": B / (bms * 1e-3), "ms_per_step": bms, "infer_samples_per_sec": B / (bi * 1e-3),
+                             "note": "projection GEMMs as tcgen05 kind::f16 on bf16 operands, fp32 accumulate; tolerance vs the reference: "
+                                     "y_pred atol 2e-2, loss rtol 2e-2, gradient cosine >= 0.98 (tests/test_gpu_parity.py)"}
+        except Exception as e:
+            extra["bf16"] = {"error": repr(e)}
+        eng.precision = args.precision
+        model.train()
+
     cpu = None
     eager = None
     if world == 1 and args.config == 2:
