@@ -220,7 +220,7 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
                 u = F.relu(torch.cat([e, pos_emb.expand(e.shape[0], -1)], dim=1))
                 per.append(u @ We.t() + be)
             thetas.append(tuple(per))
-    aux['ids'], aux['E0'], aux['layer_in'] = ids, x, []
+    aux['ids'], aux['E0'], aux['layer_in'], aux['att'] = ids, x, [], []
     for l in range(L):
         p = 'domain_int_layers.%d.' % l
         aux['layer_in'].append(x)
@@ -243,6 +243,7 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
         s = torch.matmul(qh, kh.transpose(-1, -2)) / (dh ** 0.5)           # satrans.py:84-86 [K6]
         a = F.softmax(s, dim=-1)
         a = _drop(a, 0.1, masks, 'l%d.att' % l)                            # satrans.py:87
+        aux['att'].append(a)                                               # = layer.normalized_att_scores (H, B, F, F)
         r = torch.matmul(a, vh)                                            # satrans.py:88 [K7]
         r = r.permute(1, 2, 0, 3).reshape(B_, F_, d)                       # satrans.py:89-90
         o = r @ st[p + 'Out_linear.weight'].t()                            # satrans.py:91-94 [K8]

@@ -120,6 +120,11 @@ class SATrans(BaseModel):
         self.dropout_rate = 0.1             # attndrop_rate = drop_rate = 0.1 (reference satrans.py:27-28)
         self.dense_table_updates = True     # reference semantics: L2 + Adam on every table row every step
         self.device_metrics = True          # fit(verbose>0): per-batch logloss/auc/mse/accuracy on the GPU (False: sklearn on the host)
+        # Debug switch: the reference stores softmax(QK^T/sqrt(dh)) of every layer in
+        # `domain_int_layers[i].normalized_att_scores` (H, B, F, F) as a side effect of forward (satrans.py:87), read only by its
+        # 'showattn' / 'instattn' analysis dumps.  The fused kernels never materialise it; with this switch on, forward() saves
+        # the layer activations and rebuilds the scores from them (plain torch ops, analysis path, not the hot path).
+        self.debug_att_scores = False
 
         field_num = len(self.embedding_dict)
         if field_num > _lib.SAT_MAXF:
@@ -241,6 +246,33 @@ class SATrans(BaseModel):
         int32/int64 ids when there are no dense features) -> y_pred (B, 1) float32.  Inference-only entry
         point (no autograd graph): training goes through `fit` / `Engine.train_step`."""
         Xd = self._as_device_matrix(X)
+        if self.debug_att_scores:
+            return self._forward_with_att_scores(Xd)
         y = self.engine.forward(Xd, training=self.training, dropout_p=self.dropout_rate,
                                 seed=int(torch.initial_seed()) + self.engine.launches)
+        return y.unsqueeze(1)
+
+    def _forward_with_att_scores(self, Xd):
+        """forward() that also fills `domain_int_layers[i].normalized_att_scores` (H, B, F, F), eval-mode semantics (dropout off):
+        the kernels save the pre-LayerNorm q / k of every layer (training workspace), the scores are rebuilt from them."""
+        import torch.nn.functional as Fn
+        eng = self.engine
+        y = eng.forward(Xd, training=True, dropout_p=0.0, seed=0)
+        w = eng.workspace(Xd.shape[0], True)
+        lay = self._layout
+        B, F, L, H, d = Xd.shape[0], lay['F'], lay['L'], lay['H'], _lib.SAT_D
+        cap_tok = w.cap_B * F
+        acts = w['acts'][:(L * 5 + 1) * cap_tok * d].view(L * 5 + 1, cap_tok, d)
+        perm = w['perm'][:B].long()
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(B, device=perm.device)
+        for l, layer in enumerate(self.domain_int_layers):
+            zq = acts[l * 5 + 1, :B * F].view(B, F, d)[inv]              # ACT_ZQ / ACT_ZK, sorted position -> sample order
+            zk = acts[l * 5 + 2, :B * F].view(B, F, d)[inv]
+            qn, kn = layer.Q_meta_mlp.ffn_layer_norm, layer.K_meta_mlp.ffn_layer_norm
+            q = Fn.layer_norm(zq, (d,), qn.weight, qn.bias, 1e-6) if 'Q' in self.meta_mode else zq
+            k = Fn.layer_norm(zk, (d,), kn.weight, kn.bias, 1e-6) if 'K' in self.meta_mode else zk
+            qh = q.view(B, F, H, d // H).permute(2, 0, 1, 3)
+            kh = k.view(B, F, H, d // H).permute(2, 0, 1, 3)
+            layer.normalized_att_scores = torch.softmax(torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(d // H), dim=-1).detach()
         return y.unsqueeze(1)

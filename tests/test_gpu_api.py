@@ -212,6 +212,27 @@ def test_cuda_graph_step_equals_eager_step():
     assert torch.allclose(res[False][2], res[True][2], rtol=1e-6, atol=1e-9)
 
 
+def test_debug_att_scores_switch():
+    """`domain_int_layers[i].normalized_att_scores` (H, B, F, F), the reference's analysis side channel (satrans.py:87): None by
+    default, filled by forward() when `model.debug_att_scores` is on; equal to the oracle's attention probabilities."""
+    for flag in ('sota', 'sota-pos'):
+        schema, cfg, st = _small(flag=flag, alimama=(flag == 'sota-pos'))
+        xs, _ = synth.make_inputs(schema, 70, seed=3)
+        X = torch.from_numpy(synth.stack_columns(xs, schema.fields + schema.dense))
+        model = _model(cfg, st).eval()
+        y0 = model(X.cuda())
+        assert all(l.normalized_att_scores is None for l in model.domain_int_layers)
+        model.debug_att_scores = True
+        y1 = model(X.cuda())
+        assert torch.allclose(y0, y1, atol=1e-6)
+        with torch.no_grad():
+            _, aux = O.forward(st, X, cfg, return_aux=True)
+        for l, layer in enumerate(model.domain_int_layers):
+            a = layer.normalized_att_scores
+            assert a.shape == (cfg.heads, 70, len(cfg.sparse_names), len(cfg.sparse_names))
+            assert torch.allclose(a.cpu(), aux['att'][l], atol=2e-6, rtol=0), (flag, l)
+
+
 def test_dropout_is_seeded_and_unbiased():
     schema, cfg, st = _small(layers=1)
     xs, _ = synth.make_inputs(schema, 2048, seed=12)
