@@ -259,3 +259,22 @@ def test_constructor_error_contract():
     m.compile('adam', 'binary_crossentropy')
     with pytest.raises(_lib.SatError, match='no CPU fallback'):
         m.engine.bind()                                        # the kernels need the model on a CUDA device
+
+
+def test_no_floating_point_atomics_in_the_library():
+    """Determinism by construction: the SASS of libsatrans_b200.so contains no floating-point atomic / reduction instruction
+    (every gradient sum has a fixed order; the remaining ATOM* / RED* are integer counters, bitmap ORs and mbarrier-style
+    shared-memory bit operations).  Also: the tcgen05 / TMA instructions the design rests on are present."""
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    atomics = set(re.findall(r'\b((?:ATOMS|ATOMG|ATOM|REDG|RED)\.[A-Z0-9_.]+)', sass))
+    assert atomics, 'no atomics parsed: cuobjdump output changed?'
+    bad = [a for a in atomics if re.search(r'F32|F16|F64|BF16|FADD|\.F\b', a)]
+    assert not bad, bad
+    for op in ('UTCHMMA', 'UTMALDG', 'UBLKCP', 'LDTM', 'STTM'):
+        assert op in sass, op
