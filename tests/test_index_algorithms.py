@@ -1,0 +1,171 @@
+"""CPU models of the three index algorithms behind the deterministic gradient path, restated line by line from
+satrans_b200/csrc/rows.cu and bwd_common.cuh and checked on random inputs (the CUDA kernels themselves are checked on the GPU
+by the bit-identical-runs and gradient-parity tests):
+  * the chunked segmented reduce over the sorted (slot, token) order with boundary pieces and the fix-up pass,
+  * the CTA -> tile partition with every CTA inside one scenario,
+  * one pass of the stable LSD radix sort (tile histograms, digit-major scan, warp-match ranking)."""
+import numpy as np
+
+RCH = 32
+CI_HEAD, CI_TAIL, CI_SINGLE = 1, 2, 4
+
+def emulate(keys, vals, dx):
+    N = len(keys); n_chunks = (N + RCH - 1)//RCH
+    out = {}
+    pieces = np.zeros((n_chunks, 2, dx.shape[1])); info = np.zeros((n_chunks, 2), dtype=np.int64)
+    def rows_out(k, acc):
+        assert k not in out, 'double emit %d' % k
+        out[k] = acc.copy()
+    for g in range(n_chunks):
+        i0 = g*RCH; i1 = min(N, i0+RCH)
+        cur = keys[i0]; head_cont = i0 > 0 and keys[i0-1] == cur; first_run = True
+        acc = np.zeros(dx.shape[1])
+        for i in range(i0, i1):
+            kk = keys[i]
+            if kk != cur:
+                if first_run and head_cont: pieces[g,0] = acc
+                else: rows_out(cur, acc)
+                acc = np.zeros(dx.shape[1]); cur = kk; first_run = False
+            acc = acc + dx[vals[i]]
+        tail_cont = i1 < N and keys[i1] == cur
+        if first_run and head_cont: pieces[g,0] = acc
+        elif tail_cont: pieces[g,1] = acc
+        else: rows_out(cur, acc)
+        info[g] = ((CI_HEAD if head_cont else 0) | (CI_TAIL if tail_cont else 0) | (CI_SINGLE if first_run else 0), cur)
+    for g in range(n_chunks):
+        fl, key = info[g]
+        owns = (fl & CI_TAIL) and not ((fl & CI_SINGLE) and (fl & CI_HEAD))
+        if not owns: continue
+        acc = pieces[g,1].copy(); done = False; j = g+1
+        while not done:
+            for u in range(8):
+                jj = min(j+u, n_chunks-1)
+                if not done:
+                    acc = acc + pieces[jj,0]
+                    goes_on = (info[jj,0] & CI_SINGLE) and (info[jj,0] & CI_TAIL) and (j+u < n_chunks-1)
+                    if not goes_on: done = True
+            j += 8
+        rows_out(key, acc)
+    return out
+
+
+
+def test_segmented_reduce_over_sorted_order():
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        N = int(rng.integers(1, 600))
+        nkeys = int(rng.integers(1, 40))
+        p = rng.random(nkeys) ** 4
+        p /= p.sum()
+        _, keys = np.unique(np.sort(rng.choice(nkeys, size=N, p=p)), return_inverse=True)      # every slot present, hot slots
+        vals = rng.permutation(N)
+        dx = rng.integers(-5, 6, size=(N, 4)).astype(np.float64)
+        out = emulate(keys, vals, dx)
+        ref = np.zeros((keys.max() + 1, 4))
+        np.add.at(ref, keys, dx[vals])
+        assert set(out) == set(range(keys.max() + 1))
+        assert all(np.array_equal(v, ref[k]) for k, v in out.items())
+
+
+def scenario_partition(hist, spt, G, c_sel=-1, g_sel=-1):
+    T = 0; K = 0
+    for h in hist:
+        nt = (h + spt - 1)//spt; T += nt; K += nt > 0
+    extra = G - K
+    cbase = tbase = 0; t0 = t1 = 0; g_of = -1; c0 = c1 = 0
+    for g, h in enumerate(hist):
+        nt = (h + spt - 1)//spt
+        if nt == 0: continue
+        c = 1 + (extra*nt)//T
+        if c > nt: c = nt
+        if cbase <= c_sel < cbase + c:
+            j = c_sel - cbase; t0 = tbase + nt*j//c; t1 = tbase + nt*(j+1)//c; g_of = g
+        if g == g_sel: c0, c1 = cbase, cbase + c
+        cbase += c; tbase += nt
+    return t0, t1, g_of, c0, c1
+
+
+
+def test_scenario_partition_covers_every_tile_once():
+    rng = np.random.default_rng(1)
+    for trial in range(200):
+        n_dom = int(rng.integers(1, 9))
+        hist = [int(x) for x in rng.integers(0, 5000, size=n_dom) * (rng.random(n_dom) < 0.8)]
+        B = sum(hist)
+        if B == 0:
+            continue
+        spt = int(rng.integers(4, 129))
+        G = min((B + spt - 1) // spt + n_dom, 296)
+        tiles_key = []
+        for g, h in enumerate(hist):
+            tiles_key += [g] * ((h + spt - 1) // spt)
+        covered = np.zeros(len(tiles_key), dtype=int)
+        for c in range(G):
+            t0, t1, g_of, _, _ = scenario_partition(hist, spt, G, c_sel=c)
+            for t in range(t0, t1):
+                covered[t] += 1
+                assert tiles_key[t] == g_of
+            if t1 > t0:
+                _, _, _, c0, c1 = scenario_partition(hist, spt, G, g_sel=g_of)
+                assert c0 <= c < c1
+        assert (covered == 1).all()
+
+
+RB, RADIX, TILE, THREADS, WARPS = 9, 512, 2048, 256, 8
+def radix_pass(keys, vals, shift):
+    N = len(keys); nblk = (N + TILE - 1)//TILE
+    hist = np.zeros((RADIX, nblk), dtype=np.int64)
+    for b in range(nblk):
+        seg = keys[b*TILE:(b+1)*TILE]
+        d = (seg >> shift) & (RADIX-1)
+        np.add.at(hist[:, b], d, 1)
+    flat = hist.reshape(-1)  # digit-major, block-minor
+    # scan emul: 1024 threads, per = ceil(n/1024)
+    n = flat.size; per = (n + 1023)//1024
+    sums = np.array([flat[min(n, t*per):min(n, t*per+per)].sum() for t in range(1024)])
+    excl = np.concatenate([[0], np.cumsum(sums)[:-1]])
+    out = np.zeros_like(flat)
+    for t in range(1024):
+        a0 = min(n, t*per); a1 = min(n, a0+per); run = excl[t]
+        for i in range(a0, a1):
+            out[i] = run; run += flat[i]
+    scanned = out.reshape(RADIX, nblk)
+    ko = np.zeros_like(keys); vo = np.zeros_like(vals)
+    for b in range(nblk):
+        base = scanned[:, b].copy()
+        cnt = np.zeros((WARPS, RADIX), dtype=np.int64)
+        for j in range(0, TILE, THREADS):
+            idx = b*TILE + j + np.arange(THREADS)
+            valid = idx < N
+            d = np.where(valid, (keys[np.minimum(idx, N-1)] >> shift) & (RADIX-1), -1)
+            rank = np.zeros(THREADS, dtype=np.int64)
+            for w in range(WARPS):
+                lanes = slice(w*32, w*32+32)
+                dd = d[lanes]
+                for l in range(32):
+                    rank[w*32+l] = np.sum(dd[:l] == dd[l])
+                    if valid[w*32+l] and rank[w*32+l] == 0:
+                        cnt[w, dd[l]] = np.sum(dd == dd[l])
+            for t in range(THREADS):
+                if valid[t]:
+                    w = t//32
+                    before = cnt[:w, d[t]].sum()
+                    pos = base[d[t]] + before + rank[t]
+                    ko[pos] = keys[idx[t]]; vo[pos] = vals[idx[t]]
+            base += cnt.sum(axis=0); cnt[:] = 0
+    return ko, vo
+
+
+def test_radix_sort_is_stable():
+    rng = np.random.default_rng(2)
+    for trial in range(3):
+        N = int(rng.integers(1, 5000))
+        bits = int(rng.integers(1, 24))
+        keys = rng.integers(0, 2 ** bits, size=N).astype(np.int64)
+        if trial == 0:
+            keys[:] = 5
+        k, v = keys, np.arange(N)
+        for p in range((bits + RB - 1) // RB):
+            k, v = radix_pass(k, v, p * RB)
+        order = np.argsort(keys, kind='stable')
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, order)
