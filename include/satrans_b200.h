@@ -161,7 +161,8 @@ typedef struct SatWork {
     /* row-sharded mode only (n_shards > 1): every source shard pushes ONE pre-reduced gradient per unique row */
     float* recv;          /* [n_shards][cap_B*F][32] rows pushed by source shard s (filled by the peers)             */
     int32_t* recv_idx;    /* [n_shards][touched rows cap] slot -> index into recv[s], -1 = nothing (filled by peers) */
-    uint32_t* peer_flags; /* [32] words: [0..8) epoch flags written by the peers, [8] own epoch, [16..24) push cursors */
+    uint32_t* peer_flags; /* [32] words: [0..8) epoch flags written by the peers, [8] own epoch, [9] != 0: sat_peer_barrier gave
+                             up waiting for peer [9]-1 after 20 s, [16..24) push cursors                                  */
     float* step_state;    /* [32] words, see sat_step_begin: [0..1] u64 seed, [2] i32 step, [4..7] f32 lr, beta1, beta2, eps (the
                              caller copies them in, e.g. from pinned memory inside the graph), [8..15] derived constants  */
 } SatWork;

@@ -19,7 +19,7 @@ constexpr int RB = SAT_SORT_RADIX_BITS, RADIX = 1 << RB;
 constexpr int SORT_THREADS = 256, SORT_WARPS = SORT_THREADS / 32, SORT_TILE = SAT_SORT_TILE;
 constexpr int RCH = SAT_ROWS_CHUNK;
 constexpr int CI_HEAD = 1, CI_TAIL = 2, CI_SINGLE = 4;     // chunk_info flags
-constexpr int PF_EPOCH = 8, PF_CURSOR = 16;                // words of SatWork.peer_flags
+constexpr int PF_EPOCH = 8, PF_TIMEOUT = 9, PF_CURSOR = 16;   // words of SatWork.peer_flags
 
 // ---------------------------------------------------------------------------------------------------------------------
 // keys
@@ -304,9 +304,18 @@ __global__ void k_peer_barrier(const SatModel m, uint32_t* __restrict__ my_flags
     if (r < m.n_shards) {
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.shard_flags[r] + m.shard_rank), "r"(e) : "memory");
         uint32_t seen;
+        unsigned long long t_start, t_now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + r) : "memory");
-            if ((int32_t)(seen - e) < 0) __nanosleep(200);
+            if ((int32_t)(seen - e) < 0) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                if (t_now - t_start > 20000000000ull) {       // 20 s: a peer never arrived -- give up instead of hanging the GPU
+                    my_flags[PF_TIMEOUT] = 1u + (uint32_t)r;    // (the host raises on it: Engine.check_errors)
+                    break;
+                }
+            }
         } while ((int32_t)(seen - e) < 0);
     }
     __syncthreads();

@@ -341,6 +341,11 @@ class Engine:
 
     def check_errors(self, w):
         """Raise like the reference's nn.Embedding would for ids outside their table (device->host sync)."""
+        if self.dist is not None and self.dist.world > 1 and 'peer_flags' in w.bufs:
+            stuck = int(w['peer_flags'][9].item())
+            if stuck:
+                raise _lib.SatError('cross-process barrier timed out waiting for rank %d: the ranks no longer run the same '
+                                    'sequence of steps' % (stuck - 1))
         flags = int(w['counters'][1].item())
         if flags:
             w['counters'][1] = 0
