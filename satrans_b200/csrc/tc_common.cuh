@@ -54,12 +54,20 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Spin on the barrier's phase.  A wait that has not completed after ~4 s of SM clock (a lost TMA transaction / MMA commit: a bug)
+// traps, so that the launch fails loudly instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
+    uint32_t ok, spins = 0;
+    long long t0 = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && (++spins & 0x3FFu) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) __trap();
+        }
     } while (!ok);
 }
 // ---- TMA: bulk asynchronous copies global -> shared, completion counted in bytes on an mbarrier -------------------------------
