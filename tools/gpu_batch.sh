@@ -1,0 +1,23 @@
+#!/bin/bash
+# Everything one GPU lease should produce, each step under its own timeout (run ON the box from the repo root):
+#   tools/gpu_batch.sh <tag> [steps...]     steps: test smoke bench gather profile (default: all)
+TAG=${1:-r2}; shift
+STEPS=${@:-test smoke bench gather profile}
+OUT=gpurun_out; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+for S in $STEPS; do
+  case $S in
+    test)   timeout 1200 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x --timeout 600 > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log ;;
+    testall) timeout 1500 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider --timeout 600 > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log ;;
+    smoke)  timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/${TAG}_smoke.log ;;
+    bench)  timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?" >> $OUT/${TAG}_bench.err ;;
+    benchlong) timeout 600 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err ;;
+    gather) timeout 600 python tools/gather_sweep.py > $OUT/${TAG}_gather.jsonl 2>&1 ;;
+    profile) timeout 1500 tools/profile_r2.sh $TAG > $OUT/${TAG}_profile.log 2>&1 ;;
+    configs) timeout 900 python bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err ;;
+  esac
+done
+echo "== pytest"; tail -15 $OUT/${TAG}_pytest.log 2>/dev/null
+echo "== smoke"; tail -3 $OUT/${TAG}_smoke.log 2>/dev/null
+echo "== bench"; cut -c1-1500 $OUT/${TAG}_bench.json 2>/dev/null; tail -5 $OUT/${TAG}_bench.err 2>/dev/null
+echo "== gather"; cat $OUT/${TAG}_gather.jsonl 2>/dev/null | cut -c1-200
