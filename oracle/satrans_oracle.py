@@ -465,8 +465,8 @@ class Trainer:
                'rmsprop': torch.optim.RMSprop}[optimizer]                     # meta_basemodel.py:612-625
         self.optim = cls(list(self.params.values()), lr=lr, **opt_kwargs)
 
-    def step(self, X, y, train_mode=True):
-        yp = forward(self.state, X, self.cfg, masks='rng' if train_mode else None).squeeze(-1)
+    def step(self, X, y, train_mode=True, relu_masks=None):
+        yp = forward(self.state, X, self.cfg, masks='rng' if train_mode else None, relu_masks=relu_masks).squeeze(-1)
         self.optim.zero_grad()
         loss = _loss(yp, y.reshape(-1), self.loss)
         reg = reg_loss(self.state, self.cfg)

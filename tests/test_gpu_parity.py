@@ -261,13 +261,22 @@ def test_compile_string_variants_match_reference(opt, loss):
         ref_l = float(v['%s/loss%d' % (tag, step)])
         assert abs(l - ref_l) <= 2e-5 * abs(ref_l), (step, l, ref_l)
     sd = {k: t.detach().cpu() for k, t in model.state_dict().items()}
+    # Adagrad / RMSprop start from a zero accumulator, so their normalised steps lr * g / (sqrt(v) + eps) amplify the fp32 round-off
+    # of small gradient elements (RMSprop's first step is +-10 lr whatever |g| is).  The yardstick for "as close to the reference as
+    # a correct implementation can be" is the reference's own conditioning: the SAME two steps evaluated by the oracle in fp64 differ
+    # from the reference's fp32 end state by e64 per tensor; the kernels must stay within 3 x that (+ fp32 round-off), and match
+    # at least as large a fraction of the elements to fp32 round-off (- 2 %).
+    tr64 = O.Trainer({k: t.double() for k, t in g.state().items()}, g.cfg, lr=lr, optimizer=opt, loss=loss)
+    for step in range(2):
+        tr64.step(g.X(step).double(), g.y(step).double(), train_mode=False)
     for k in O.trainable_keys(g.cfg):
         ref = torch.from_numpy(v['%s/end/%s' % (tag, k)])
         got = sd[k][subsample(k)]
+        err = (got - ref).abs()
+        tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
         if opt == 'sgd':
-            assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7, k
+            assert err.max().item() <= tight, k
         else:
-            # Adagrad / RMSprop with their default eps (1e-10 / 1e-8) normalise the first steps to ~+-lr (RMSprop: +-10 lr), so
-            # the round-off of near-zero gradient elements decides their sign: the same bar as the CPU
-            # oracle itself is held to against these vectors (tests/test_oracle_golden.py)
-            assert_adam_close(got, ref, lr, 2, k)
+            e64 = (tr64.params[k].detach().float()[subsample(k)] - ref).abs()
+            assert err.max().item() <= 3 * e64.max().item() + tight, (k, err.max().item(), e64.max().item(), tight)
+            assert (err <= tight).float().mean().item() >= (e64 <= tight).float().mean().item() - 0.02, k
