@@ -294,6 +294,30 @@ def _time_loop(fn, n, torch):
     return e0.elapsed_time(e1) / n
 
 
+def _time_graph(fn, n, torch):
+    """ms per call of n calls captured in ONE CUDA graph (kernels back to back on the device: for launches shorter than the host
+    needs to enqueue them)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(2):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -448,7 +472,7 @@ def run_b200(args):
             slices = [Xg[i * Bg:(i + 1) * Bg] for i in range(n_slices)]
             for i in range(3):
                 eng.gather(slices[i % n_slices])
-            gms = _time_loop(lambda i: eng.gather(slices[i % n_slices]), reps, torch)
+            gms = _time_graph(lambda i: eng.gather(slices[i % n_slices]), reps, torch)
             gb = Bg * per_sample / (gms * 1e-3) / 1e9
             others.append({"kernel": "k_gather", "bound": "hbm", "batch": Bg, "achieved": gb, "peak": hbm_peak, "unit": "GB/s",
                            "frac": gb / hbm_peak, "traffic": traffic_of('k_gather_B%d' % Bg), "ms_per_launch": gms,

@@ -576,10 +576,15 @@ class BaseModel(nn.Module):
         eng._graph_seen[gkey] = seen + 1
         if host_batch and eng.use_cuda_graph and eng.dist is None and seen >= 2:
             # third and later batches of this shape: the step (H2D copies included) is ONE CUDA-graph launch
-            w = eng.graph_train_step(X, np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y.float(),
-                                     lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
-                                     l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
-                                     dropout_p=self.dropout_rate, seed0=seed0)
+            w, sc_pin = eng.graph_train_step(X, np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y,
+                                             lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
+                                             l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                             dropout_p=self.dropout_rate, seed0=seed0)
+            torch.cuda.current_stream().synchronize()     # like the reference's .item(): the step is done, the scalars are on the host
+            sc = sc_pin.tolist()
+            if sc[3] != 0:
+                eng.check_errors(w)
+            return sc[0], sc[1]
         else:
             Xd = torch.as_tensor(X).to(dev, non_blocking=True)
             yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)

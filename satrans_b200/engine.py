@@ -541,15 +541,26 @@ class Engine:
         every kernel of train_step on its two streams -- is captured once per (batch shape, dtype, l2, mode, dropout,
         optimiser kind, precision) and then costs one cudaGraphLaunch per step instead of ~45 launches and their host-side
         marshalling.  lr / betas / eps are data (a scheduler can change them every step without re-capturing).
-        Returns the workspace; w['scalars'] holds (bce, reg, n_unique, error flags) once the replay has finished."""
+        Returns (workspace, pinned host tensor): the last node of the graph copies w['scalars'][0:4] = (bce, reg, n_unique, error
+        flags) into the pinned tensor; it is valid after a synchronisation of the current stream."""
         Xh = torch.as_tensor(Xh)
         yh = torch.as_tensor(yh).reshape(-1)
         key = (tuple(Xh.shape), Xh.dtype, float(l2_emb), bool(dense_mode), float(dropout_p), int(opt_kind), self.precision)
         G = self._graphs.get(key)
         if G is None:
             G = self._capture_step(key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0)
-        G['x_pin'].copy_(Xh)
-        G['y_pin'].copy_(yh)
+        # H2D copies of the batch: stream-ordered in front of the replay, straight from the caller's buffers when they are pinned
+        # (no host-side staging pass), through the pinned staging buffers otherwise
+        if Xh.is_pinned():
+            G['Xs'].copy_(Xh, non_blocking=True)
+        else:
+            G['x_pin'].copy_(Xh)
+            G['Xs'].copy_(G['x_pin'], non_blocking=True)
+        if yh.dtype == torch.float32 and yh.is_pinned():
+            G['ys'].copy_(yh, non_blocking=True)
+        else:
+            G['y_pin'].copy_(yh)
+            G['ys'].copy_(G['y_pin'], non_blocking=True)
         hp = G['hyper_pin']
         hp[0], hp[1], hp[2], hp[3] = float(lr), float(betas[0]), float(betas[1]), float(eps)
         w = G['w']
@@ -560,7 +571,7 @@ class Engine:
         self.step_count += 1
         w.dev_step = self.step_count
         self.launches += G['launches']
-        return G['w']
+        return G['w'], G['sc_pin']
 
     def _capture_step(self, key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
         self.bind()
@@ -571,6 +582,7 @@ class Engine:
              'x_pin': torch.empty(tuple(Xh.shape), dtype=Xh.dtype).pin_memory(),
              'y_pin': torch.empty(B, dtype=torch.float32).pin_memory(),
              'hyper_pin': torch.zeros(4, dtype=torch.float32).pin_memory(),
+             'sc_pin': torch.zeros(4, dtype=torch.float32).pin_memory(),
              'Xs': torch.empty(tuple(Xh.shape), dtype=Xh.dtype, device=self.device),
              'ys': torch.empty(B, dtype=torch.float32, device=self.device)}
         l = lib()
@@ -582,13 +594,12 @@ class Engine:
         w.c.device_step = 1
         try:
             with torch.cuda.graph(graph, stream=cap):
-                G['Xs'].copy_(G['x_pin'], non_blocking=True)
-                G['ys'].copy_(G['y_pin'], non_blocking=True)
                 w['step_state'][4:8].copy_(G['hyper_pin'], non_blocking=True)
                 check(l.sat_step_begin(C.byref(w.c), (int(seed0) - 1) & (2 ** 64 - 1), self._stream()), 'sat_step_begin')
                 G['y_pred'], _ = self.train_step(G['Xs'], G['ys'], lr=lr, betas=betas, eps=eps, l2_emb=l2_emb,
                                                  dense_mode=dense_mode, training=True, dropout_p=dropout_p, seed=0,
                                                  opt_kind=opt_kind, _capturing=True)
+                G['sc_pin'].copy_(w['scalars'][0:4], non_blocking=True)
         finally:
             w.c.device_step = 0
             self.timing = timing
