@@ -50,6 +50,7 @@ def parse():
                     help='BASELINE.json config: 2 = full Ali-CCP vocab, B=8192 per GPU (headline); 4 = scaled vocab '
                          '(x 4 per GPU, so the shard per GPU stays constant), B=65536 per GPU, int32 ids')
     ap.add_argument('--no-eager-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of the CUDA-graph replay of the step')
     ap.add_argument('--ids', default='uniform', choices=['uniform', 'zipf'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--overlap', action='store_true', help='run the dense optimiser sweep on a second stream, concurrent with forward/backward (default: on the main stream)')
@@ -71,6 +72,7 @@ def workload_config(args, n_gpus):
                         "Ali-CCP-shaped, full vocab 6,571,961 rows" if args.vocab_scale == 1.0 else
                         "SATrans EN+MetaNet train step, Ali-CCP-shaped, vocab x%g (BASELINE config %d)" % (args.vocab_scale, args.config),
             "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "fields": 19, "ids": args.ids,
+"step_launch": "cuda graph replay" if (n_gpus == 1 and not args.no_graph and not args.overlap) else "eager launches",
             "optimizer": "Adam lr=0.005 + L2(emb)=1e-5, " + ("lazy touched-rows-only" if args.lazy else
                                                                "dense every-row (reference semantics)"),
             "dropout": 0.1, "l2": "inputs>L2 (3 x %.0f MB of table state swept per step per GPU, new batch every step)"
@@ -368,9 +370,18 @@ def run_b200(args):
     hp = model._opt_hparams
     model.train()
 
-    def step(i, overlap=args.overlap):
+    use_graph = world == 1 and not args.no_graph and not args.overlap
+
+    def step(i, overlap=args.overlap, eager=False):
+        """One optimiser step on a device-resident batch: the engine call fit() makes per batch -- the CUDA-graph replay of the
+        whole step (single GPU; the first steps of a shape run eagerly), or the eager launch sequence."""
         k = i % n_batches
-        return eng.train_step(Xd[k * B:(k + 1) * B], yd[k * B:(k + 1) * B], lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
+        xb, yb = Xd[k * B:(k + 1) * B], yd[k * B:(k + 1) * B]
+        if use_graph and not eager and eng.step_count >= 2:
+            w, _ = eng.graph_train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'], l2_emb=1e-5,
+                                        dense_mode=not args.lazy, dropout_p=0.1, seed0=1021)
+            return eng.last_y_pred, w
+        return eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
                               opt_kind=hp['kind'], l2_emb=1e-5, dense_mode=not args.lazy, training=True, dropout_p=0.1, seed=1021 + i,
                               overlap=overlap)
 
@@ -384,8 +395,14 @@ def run_b200(args):
     for i in range(W):
         step(i)
     barrier()
-    # ---- timed region: K steps, device-resident inputs ------------------------------------------------------
+    # ---- phase breakdown (CUDA events around every phase of the EAGER launch sequence; not part of `value`) -----------------
     eng.timing = {}
+    for i in range(min(K, 10)):
+        _, w = step(W + i, eager=True)
+    phases = eng.timing_ms()
+    eng.timing = None
+    barrier()
+    # ---- timed region: K steps, device-resident inputs ------------------------------------------------------
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
@@ -399,8 +416,6 @@ def run_b200(args):
         clocks.mark(tw0, tw1)
     ms = ev0.elapsed_time(ev1) / K
     launches = eng.launches - l0
-    phases = eng.timing_ms()
-    eng.timing = None
     n_unique = float(w['scalars'][2].item())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

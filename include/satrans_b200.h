@@ -124,6 +124,10 @@ typedef struct SatWork {
     int32_t device_step;  /* != 0: the dropout seed and the optimiser's step-dependent constants come from step_state
                              (advanced on the device by sat_step_begin) instead of the by-value arguments, so that a
                              whole training step can be captured ONCE in a CUDA graph and replayed            */
+    int32_t defer_finish; /* != 0: sat_backward* stop after the layer kernels; the caller runs sat_backward_finish (fixed-order
+                             reduction of the per-CTA partials + encoder backward) later, e.g. on a second stream beside the
+                             HBM-bound table sweep                                                                    */
+    int32_t pad2;
     int32_t head_bwd_done; /* set by sat_forward_tc when it also ran the logit head's backward (training, labels given); read by
                              the next sat_backward*, which then skips its own head kernel; cleared by sat_forward      */
     int32_t* perm;        /* [cap_B] sorted position -> sample index (bucketed by scenario) */
@@ -229,6 +233,10 @@ int sat_forward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, c
  *      of satrans.py:197-256. ------------------------------------------------------------------- */
 int sat_backward(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w,
                  float dropout_p, uint64_t seed, void* stream);
+
+/* the tail of sat_backward / sat_backward_tc when w->defer_finish was set: per-CTA partials -> w->dgrad and w->dtheta, then the
+ * scenario-encoder backward.  passes: 0 after sat_backward, the value given to sat_backward_tc otherwise. */
+int sat_backward_finish(const SatModel* m, SatWork* w, int32_t passes, void* stream);
 
 /* ---- touched-row bookkeeping.  sat_rows_clear zeroes this shard's bitmap; sat_rows_mark sets one bit per
  *      row the batch reads IN THE OWNING SHARD's bitmap (remote atomics over NVLink when R > 1);

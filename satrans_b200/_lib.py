@@ -48,7 +48,7 @@ assert len(WORK_BUFFERS) == SAT_WORK_BUFFERS
 
 
 class SatWork(C.Structure):
-    _fields_ = [('B', i32), ('cap_B', i32), ('device_step', i32), ('head_bwd_done', i32)] + [(n, vp) for n in WORK_BUFFERS]
+    _fields_ = [('B', i32), ('cap_B', i32), ('device_step', i32), ('defer_finish', i32), ('pad2', i32), ('head_bwd_done', i32)] + [(n, vp) for n in WORK_BUFFERS]
 
 
 class SatAdam(C.Structure):
@@ -70,6 +70,7 @@ PROTOTYPES = {
     'sat_forward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, vp, C.POINTER(SatWork), vp, i32, f32, C.c_uint64, vp]),
     'sat_backward': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, vp]),
     'sat_backward_tc': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), f32, C.c_uint64, i32, vp]),
+    'sat_backward_finish': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), i32, vp]),
     'sat_rows_clear': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_rows_mark': (C.c_int, [C.POINTER(SatModel), vp, i32, i32, C.POINTER(SatWork), vp]),
     'sat_rows_rank': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),

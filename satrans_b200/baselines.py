@@ -114,6 +114,7 @@ class Star_Trans(_ScoringModel):
         self._init_layout(device)
         self.to(device)
 
+    @torch.no_grad()
     def forward(self, X):
         Xd, x = self._gather_fields(X, self._keep)
         dom = Xd[:, self.feature_index[self.domain_column][0]].to(torch.int32)      # .long() of the reference: truncation
@@ -169,6 +170,7 @@ class AutoInt(_ScoringModel):
         self._init_layout(device)
         self.to(device)
 
+    @torch.no_grad()
     def forward(self, X):
         Xd, x = self._gather_fields(X, list(range(len(self._sparse_feats))))
         flat = x.reshape(x.shape[0], -1)

@@ -493,10 +493,18 @@ class BaseModel(nn.Module):
                 else:
                     xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
                 hp = self._hparams()
-                y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
-                                           l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
-                                           training=True, dropout_p=self.dropout_rate,
-                                           seed=(int(torch.initial_seed()) + eng.step_count) & (2 ** 63 - 1))
+                seed0 = int(torch.initial_seed()) & (2 ** 63 - 1)
+                if eng.use_cuda_graph and eng.dist is None and eng.step_count >= 2 and (s1 - s0) == batch_size:
+                    # full-size batches after the first two steps: the whole step is ONE CUDA-graph launch (engine.graph_train_step)
+                    w, _ = eng.graph_train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
+                                                l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                                dropout_p=self.dropout_rate, seed0=seed0)
+                    y_pred = eng.last_y_pred
+                else:
+                    y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
+                                               l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
+                                               training=True, dropout_p=self.dropout_rate,
+                                               seed=(seed0 + eng.step_count) & (2 ** 63 - 1))
                 losses[step_num].copy_(w['scalars'][0:2])
                 if want_metrics:
                     preds[s0:s1] = y_pred

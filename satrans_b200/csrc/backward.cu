@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(256) k_dense_reduce(const RedArgs a) {
 using namespace sat;
 
 int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
+extern "C" int sat_backward_finish(const SatModel* m, SatWork* w, int32_t passes, void* stream);
 
 // passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
 static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int32_t ld, SatWork* w, float dropout_p,
@@ -419,17 +420,30 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
         }
         if (rc) return rc;
     }
+    if (w->defer_finish) return SAT_OK;            // the caller runs sat_backward_finish (e.g. beside the table sweep)
+    return sat_backward_finish(m, w, passes, stream);
+}
+
+extern "C" int sat_backward_finish(const SatModel* m, SatWork* w, int32_t passes, void* stream) {
+    if (!m || !w || !w->gpart || !w->dgrad || !w->dtheta) return sat_host::fail(SAT_EINVAL, "sat_backward_finish: null argument");
+    if (w->B == 0) return SAT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_keys = (m->flags & SAT_FLAG_POS) ? m->n_dom * m->L * 2 : m->n_dom;
+    // the grids the backward kernels were launched with (same formulas as backward_impl / sat_forward_tc)
+    const int spt = NT / m->F, spt2 = NT2 / m->F;
+    const int max_tiles = (w->B + spt - 1) / spt + m->n_dom, max_tiles2 = (w->B + spt2 - 1) / spt2 + m->n_dom;
+    const int grid2 = max_tiles < 148 * 2 ? max_tiles : 148 * 2, grid1 = max_tiles < 148 ? max_tiles : 148;
+    const int grid_a = max_tiles2 < 148 * 2 ? max_tiles2 : 148 * 2;
+    const bool head_done = w->head_bwd_done != 0;
     RedArgs ra;
     ra.m = *m; ra.gpart = w->gpart; ra.counters = w->counters; ra.dgrad = w->dgrad; ra.dtheta = w->dtheta;
     ra.g_attn = grid_a; ra.g_meta = passes == 0 ? grid1 : grid_a; ra.g_head = head_done ? grid_a : grid2; ra.spt_meta = passes == 0 ? spt : spt2;
-    {
-        const long long total = (long long)m->L * LAYER_FLOATS + m->F * D + m->n_dense + 1 + (long long)n_keys * PSZ;
-        long long blocks = (total + 63) / 64;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k_dense_reduce<<<(int)blocks, 256, 0, s>>>(ra);
-        rc = sat_host::check_launch("k_dense_reduce");
-        if (rc) return rc;
-    }
+    const long long total = (long long)m->L * LAYER_FLOATS + m->F * D + m->n_dense + 1 + (long long)n_keys * PSZ;
+    long long blocks = (total + 63) / 64;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_dense_reduce<<<(int)blocks, 256, 0, s>>>(ra);
+    const int rc = sat_host::check_launch("k_dense_reduce");
+    if (rc) return rc;
     return sat_encoder_bwd(m, w, stream);
 }
 

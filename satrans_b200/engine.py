@@ -279,8 +279,14 @@ class Engine:
             check(l.sat_forward_tc(d, X.data_ptr(), kind, X.shape[1], y_ptr, C.byref(w.c), y_pred.data_ptr(),
                                    int(training), float(p), seed, passes, s), 'sat_forward_tc')
 
-    def _backward_call(self, X, kind, w, p, seed, s):
+    def _backward_passes(self):
+        return {'fp32': 0, 'tf32x3': 3, 'tf32': 1, 'bf16': 2}[self.backward_precision or self.precision]
+
+    def _backward_call(self, X, kind, w, p, seed, s, defer_finish=False):
+        """defer_finish: stop after the layer kernels; the caller runs _backward_finish (partial-row reduction + encoder
+        backward) later, e.g. on the second stream beside the table sweep."""
         l, d = lib(), C.byref(self.desc)
+        w.c.defer_finish = int(bool(defer_finish))
         bp = self.backward_precision or self.precision
         passes = {'fp32': 0, 'tf32x3': 3, 'tf32': 1, 'bf16': 2}[bp]
         if passes and passes != self._passes() and self.precision != 'fp32':
@@ -292,6 +298,9 @@ class Engine:
         else:
             check(l.sat_backward_tc(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), float(p), seed, passes, s),
                   'sat_backward_tc')
+
+    def _backward_finish(self, w, stream):
+        check(lib().sat_backward_finish(C.byref(self.desc), C.byref(w.c), self._backward_passes(), stream), 'sat_backward_finish')
 
     def _barrier(self, w, stream=None):
         """Stream-ordered cross-process barrier through the peer-mapped flags (one tiny kernel, no NCCL call)."""
@@ -484,33 +493,40 @@ class Engine:
         t = self._tic('forward')
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
         self._toc(t)
+        tail_on_side = bool(single and dense_mode and not sweep_on_side and self.side_streams)
         t = self._tic('backward')
-        self._backward_call(X, kind, w, p, sd, s)
+        self._backward_call(X, kind, w, p, sd, s, defer_finish=tail_on_side)
         self._toc(t)
-        if use_side:
-            main.wait_event(self._ev_marked)           # sorted order + touched-row ranks are ready
-        t = self._tic('rows_reduce')
-        self._reduce_rows(w)
-        self._toc(t)
-        if not single:
-            t = self._tic('allreduce')
-            self.dist.all_reduce_sum(w['dgrad'])
-            self._toc(t)
-        tail_on_side = bool(dense_mode and not sweep_on_side and self.side_streams)
         if tail_on_side:
-            # the short touched-row / dense-parameter updates run beside the HBM-bound sweep (disjoint rows)
+            # Everything that only the (short) touched-row and dense-parameter updates need -- the fixed-order reduction of the
+            # per-CTA partial gradients, the encoder backward, the sorted segmented reduce of dE0 -- runs on the second stream
+            # beside the HBM-bound sweep over the untouched rows (disjoint data; the sweep only needs the touched-row bitmap,
+            # which the second stream produced before: same-stream order).
             self._ev_fork.record(main)
             side.wait_event(self._ev_fork)
-            t = self._tic('adam_rows+dense (side stream)', side)
-            check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, side.cuda_stream), 'sat_tables_adam')
-            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_dense_adam')
-            self._toc(t)
+            main.wait_event(self._ev_marked)           # (the sweep reads the bitmap)
+            with torch.cuda.stream(side):
+                t = self._tic('finish+rows+adam (side stream)', side)
+                self._backward_finish(w, side.cuda_stream)
+                self._reduce_rows(w)
+                check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, side.cuda_stream), 'sat_tables_adam')
+                check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_dense_adam')
+                self._toc(t)
             self._ev_swept.record(side)
             t = self._tic('adam_sweep')
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
             self._toc(t)
             main.wait_event(self._ev_swept)
         else:
+            if use_side:
+                main.wait_event(self._ev_marked)       # sorted order + touched-row ranks are ready
+            t = self._tic('rows_reduce')
+            self._reduce_rows(w)
+            self._toc(t)
+            if not single:
+                t = self._tic('allreduce')
+                self.dist.all_reduce_sum(w['dgrad'])
+                self._toc(t)
             t = self._tic('adam_rows')
             # (lazy mode: ADAM_UNTOUCHED only clears the sweep's slice of the sum-of-squares partials)
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a),
@@ -534,7 +550,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def graph_train_step(self, Xh, yh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
-        """One optimiser step on a HOST batch, replayed from a CUDA graph (single-GPU mode).
+        """One optimiser step on a host (or device-resident) batch, replayed from a CUDA graph (single-GPU mode).
 
         The whole step -- H2D copies of the batch and of the four hyper-parameters from pinned staging buffers,
         sat_step_begin (step counter, dropout seed = seed0 + step - 1 and Adam's bias corrections advance ON THE DEVICE) and
@@ -551,12 +567,12 @@ class Engine:
             G = self._capture_step(key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0)
         # H2D copies of the batch: stream-ordered in front of the replay, straight from the caller's buffers when they are pinned
         # (no host-side staging pass), through the pinned staging buffers otherwise
-        if Xh.is_pinned():
+        if Xh.is_cuda or Xh.is_pinned():
             G['Xs'].copy_(Xh, non_blocking=True)
         else:
             G['x_pin'].copy_(Xh)
             G['Xs'].copy_(G['x_pin'], non_blocking=True)
-        if yh.dtype == torch.float32 and yh.is_pinned():
+        if yh.is_cuda or (yh.dtype == torch.float32 and yh.is_pinned()):
             G['ys'].copy_(yh, non_blocking=True)
         else:
             G['y_pin'].copy_(yh)
@@ -571,6 +587,7 @@ class Engine:
         self.step_count += 1
         w.dev_step = self.step_count
         self.launches += G['launches']
+        self.last_y_pred = G['y_pred']             # (B,) predictions of this step: a static buffer, overwritten by the next replay
         return G['w'], G['sc_pin']
 
     def _capture_step(self, key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):

@@ -7,7 +7,7 @@ set -u
 TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-graph"
 # 1. launch list (every launch with its device time; cold-cache, serialised: compare SHARES)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
 # 2. one full capture per dominant kernel
@@ -26,7 +26,7 @@ if len(rows) >= 3:
             'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active', 'launch__grid_size',
             'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
             'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__issue_inst0.avg.pct_of_peak_sustained_active')
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals) if h in keep or 'pipe_tensor' in h}
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals) if h in keep or 'pipe_tensor' in h or 'issue_stalled' in h}
     json.dump(d, open(sys.argv[1], 'w'), indent=1)
 PY
     rm -f $OUT/${TAG}_$K.ncu-rep      # (tens of MB each; the text / json pages are what gets committed)
