@@ -38,7 +38,7 @@ extern "C" {
 #define SAT_P 4096           /* generated weights per key: 32*64 + 64*32    */
 #define SAT_MAXF 32          /* max sparse fields (tokens) per sample       */
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
-#define SAT_REG_PARTS (148 * 8 + 148 * 4) /* doubles in SatWork.reg_part */
+#define SAT_REG_PARTS (148 * 256 + 148 * 4) /* doubles in SatWork.reg_part */
 #define SAT_WORK_BUFFERS 32  /* pointer members of SatWork */
 #define SAT_GRID_MAX (148 * 2) /* most CTAs any token kernel is launched with: rows of the per-CTA partial buffers */
 #define SAT_SORT_RADIX_BITS 9  /* digit width of the touched-row radix sort */

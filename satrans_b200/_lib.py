@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('SAT_LIB') or os.path.join(HERE, 'lib', 'libsatrans_b2
 CSRC = os.path.join(HERE, 'csrc')
 
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
-SAT_REG_PARTS = 148 * 8 + 148 * 4
+SAT_REG_PARTS = 148 * 256 + 148 * 4
 SAT_WORK_BUFFERS = 32
 SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
 SAT_ABI_VERSION = 2

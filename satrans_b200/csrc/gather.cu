@@ -14,7 +14,7 @@ namespace sat {
 
 constexpr int GATHER_THREADS = 256;
 #ifndef SAT_GATHER_DEFAULT
-#define SAT_GATHER_DEFAULT 2
+#define SAT_GATHER_DEFAULT 5
 #endif
 
 template <int KIND, int GATHER_UNROLL, int MIN_BLOCKS>
@@ -230,8 +230,8 @@ extern "C" int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind,
     const long long items = (long long)B * m->F;
     cudaStream_t s = (cudaStream_t)stream;
     // SAT_GATHER_VARIANT (tuning aid; measured in profiles/): 0 = 4 rows in flight per thread, 1 = 8 rows, 2 = 4 rows at full
-    // occupancy (<= 32 registers; the default), 3 = 8 rows at 6 CTAs per SM, 4 = TMA bulk row fetch + bulk store, 5 = 2 rows at
-    // full occupancy
+    // occupancy (<= 32 registers), 3 = 8 rows at 6 CTAs per SM, 4 = TMA bulk row fetch + bulk store, 5 = 2 rows at full occupancy
+    // (the default: measured best), 6 = 1 row at full occupancy
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("SAT_GATHER_VARIANT"); variant = e ? atoi(e) : SAT_GATHER_DEFAULT; }
 #define SAT_GATHER_LAUNCH(KIND)                                                                                              \
@@ -247,15 +247,17 @@ extern "C" int sat_gather_fwd(const SatModel* m, const void* x, int32_t id_kind,
             const int grid = (int)(chunks < 148 * 2 ? chunks : 148 * 2);                                                     \
             k_gather_tma<KIND><<<grid, GB_ROWS, GB_SMEM_BYTES, s>>>(*m, x, ld, B, out, err_flag);                            \
         } else {                                                                                                             \
-            const int unroll = (variant == 1 || variant == 3) ? 8 : (variant == 5 ? 2 : 4);                                                       \
+            const int unroll = (variant == 1 || variant == 3) ? 8 : (variant == 5 ? 2 : (variant == 6 ? 1 : 4));                                                       \
             const long long per_block = (GATHER_THREADS / 8) * unroll;                                                       \
             long long blocks = (items + per_block - 1) / per_block;                                                          \
             if (blocks > 148 * 16) blocks = 148 * 16;                                                                        \
             if (variant == 1) k_gather<KIND, 8, 1><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);      \
             else if (variant == 3) k_gather<KIND, 8, 6><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
             else if (variant == 5) k_gather<KIND, 2, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
+            else if (variant == 6) k_gather<KIND, 1, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
             else if (variant == 0) k_gather<KIND, 4, 1><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
-            else k_gather<KIND, 4, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);                   \
+            else if (variant == 2) k_gather<KIND, 4, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag); \
+            else k_gather<KIND, 2, 8><<<(int)blocks, GATHER_THREADS, 0, s>>>(*m, x, ld, B, out, err_flag);                   \
         }                                                                                                                    \
     } while (0)
     switch (id_kind) {

@@ -14,6 +14,7 @@
 //   m += (g - m) * (1 - b1);  v = v * b2 + (1 - b2) * g * g;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -73,7 +74,21 @@ __device__ __forceinline__ void block_sum_to(double val, double* __restrict__ ds
 
 constexpr int SWEEP_THREADS = 256;
 constexpr int SWEEP_UNROLL = 4;
-constexpr int SWEEP_BLOCKS = 148 * 8;     // SAT_REG_PARTS = SWEEP_BLOCKS + ROWS_BLOCKS
+constexpr int SWEEP_BLOCKS = 148 * 256;   // slots of reg_part reserved for the sweep: SAT_REG_PARTS = SWEEP_BLOCKS + ROWS_BLOCKS
+// CTAs the sweep is launched with.  Many short-lived CTAs instead of one resident wave of grid-stride loops: the short launch
+// chain that updates the touched rows / dense parameters runs beside the sweep on a high-priority stream and gets SM slots as
+// sweep CTAs retire (with 148 x 8 persistent CTAs it had to wait for the whole sweep).  SAT_SWEEP_BPS overrides (tuning aid).
+static int sweep_blocks() {
+    static int n = 0;
+    if (!n) {
+        const char* e = getenv("SAT_SWEEP_BPS");
+        int bps = e ? atoi(e) : 128;
+        if (bps < 1) bps = 1;
+        if (bps > 256) bps = 256;
+        n = 148 * bps;
+    }
+    return n;
+}
 
 // Dense sweep over all table rows NOT touched by the batch.  One float4 per thread per access; p/m/v are
 // read once and written once.  reg_part[blockIdx] receives sum(p_old^2) over the rows this block swept.
@@ -239,7 +254,9 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
             return sat_host::fail(SAT_ECUDA, "sat_tables_adam: memset failed");
     }
     if ((which & SAT_ADAM_UNTOUCHED) && a->dense_mode) {
-        k_adam_sweep<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(
+        if (cudaMemsetAsync(w->reg_part, 0, SWEEP_BLOCKS * sizeof(double), s) != cudaSuccess)       // (slots of CTAs not launched)
+            return sat_host::fail(SAT_ECUDA, "sat_tables_adam: memset failed");
+        k_adam_sweep<<<sweep_blocks(), SWEEP_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
             w->bitmap, n_vec, c, dev_const, w->reg_part);
         int rc = sat_host::check_launch("k_adam_sweep");
@@ -253,7 +270,9 @@ extern "C" int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(w->reg_part + SWEEP_BLOCKS, 0, ROWS_BLOCKS * sizeof(double), s) != cudaSuccess)
         return sat_host::fail(SAT_ECUDA, "sat_tables_sumsq: memset failed");
-    k_sumsq<<<SWEEP_BLOCKS, SWEEP_THREADS, 0, s>>>(reinterpret_cast<const float4*>(m->tables), m->local_rows * 8, w->reg_part);
+    if (cudaMemsetAsync(w->reg_part, 0, SWEEP_BLOCKS * sizeof(double), s) != cudaSuccess)
+        return sat_host::fail(SAT_ECUDA, "sat_tables_sumsq: memset failed");
+    k_sumsq<<<148 * 8, SWEEP_THREADS, 0, s>>>(reinterpret_cast<const float4*>(m->tables), m->local_rows * 8, w->reg_part);
     return sat_host::check_launch("k_sumsq");
 }
 

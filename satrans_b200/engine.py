@@ -452,6 +452,8 @@ class Engine:
         s = main.cuda_stream
         if self._sweep_stream is None:
             self._sweep_stream = torch.cuda.Stream(device=self.device)
+            # the short update chain beside the sweep: high priority, so that its CTAs are placed as soon as sweep CTAs retire
+            self._tail_stream = torch.cuda.Stream(device=self.device, priority=-1)
             self._ev_marked = torch.cuda.Event()
             self._ev_swept = torch.cuda.Event()
             self._ev_fork = torch.cuda.Event()
@@ -502,17 +504,19 @@ class Engine:
             # per-CTA partial gradients, the encoder backward, the sorted segmented reduce of dE0 -- runs on the second stream
             # beside the HBM-bound sweep over the untouched rows (disjoint data; the sweep only needs the touched-row bitmap,
             # which the second stream produced before: same-stream order).
+            tail = self._tail_stream
             self._ev_fork.record(main)
-            side.wait_event(self._ev_fork)
+            tail.wait_event(self._ev_fork)
+            tail.wait_event(self._ev_marked)           # sorted order + touched-row ranks (second stream)
             main.wait_event(self._ev_marked)           # (the sweep reads the bitmap)
-            with torch.cuda.stream(side):
-                t = self._tic('finish+rows+adam (side stream)', side)
-                self._backward_finish(w, side.cuda_stream)
+            with torch.cuda.stream(tail):
+                t = self._tic('finish+rows+adam (side stream)', tail)
+                self._backward_finish(w, tail.cuda_stream)
                 self._reduce_rows(w)
-                check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, side.cuda_stream), 'sat_tables_adam')
-                check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_dense_adam')
+                check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_TOUCHED, tail.cuda_stream), 'sat_tables_adam')
+                check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), tail.cuda_stream), 'sat_dense_adam')
                 self._toc(t)
-            self._ev_swept.record(side)
+            self._ev_swept.record(tail)
             t = self._tic('adam_sweep')
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
             self._toc(t)

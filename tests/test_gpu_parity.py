@@ -241,8 +241,9 @@ def test_two_runs_are_bit_identical(precision):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize('precision', PRECISIONS)
 @pytest.mark.parametrize('opt,loss', [('sgd', 'binary_crossentropy'), ('adagrad', 'mse'), ('rmsprop', 'mae')])
-def test_compile_string_variants_match_reference(opt, loss):
+def test_compile_string_variants_match_reference(opt, loss, precision):
     """compile('<optimizer>', '<loss>') (reference meta_basemodel.py:612-640) through the drop-in API: two train_on_batch steps on
     the q_small golden model == the reference's own two steps (tests/golden/compile_variants.npz)."""
     import os
@@ -252,7 +253,7 @@ def test_compile_string_variants_match_reference(opt, loss):
     v = np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))
     tag = '%s_%s' % (opt, loss)
     lr = float(v[tag + '/lr'])
-    model = model_from_golden(g)                      # package default: tcgen05 3xTF32
+    model = model_from_golden(g, precision=precision)
     model.dropout_rate = 0.0
     model.compile(opt, loss)
     assert abs(model._opt_hparams['lr'] - lr) < 1e-8          # (the fixture stores lr as float32)
@@ -264,8 +265,10 @@ def test_compile_string_variants_match_reference(opt, loss):
     # Adagrad / RMSprop start from a zero accumulator, so their normalised steps lr * g / (sqrt(v) + eps) amplify the fp32 round-off
     # of small gradient elements (RMSprop's first step is +-10 lr whatever |g| is).  The yardstick for "as close to the reference as
     # a correct implementation can be" is the reference's own conditioning: the SAME two steps evaluated by the oracle in fp64 differ
-    # from the reference's fp32 end state by e64 per tensor; the kernels must stay within 3 x that (+ fp32 round-off), and match
-    # at least as large a fraction of the elements to fp32 round-off (- 2 %).
+    # from the reference's fp32 end state by e64 per tensor; the CUDA-core fp32 path must stay within 3 x that (+ fp32 round-off), the
+    # 3xTF32 path within 24 x (its products carry 2^-21 relative error instead of fp32's 2^-24: the lo x lo term is dropped), and
+    # both must match at least as large a fraction of the elements to fp32 round-off (- 2 %).
+    amp = 3.0 if precision == 'fp32' else 24.0
     tr64 = O.Trainer({k: t.double() for k, t in g.state().items()}, g.cfg, lr=lr, optimizer=opt, loss=loss)
     for step in range(2):
         tr64.step(g.X(step).double(), g.y(step).double(), train_mode=False)
@@ -278,5 +281,5 @@ def test_compile_string_variants_match_reference(opt, loss):
             assert err.max().item() <= tight, k
         else:
             e64 = (tr64.params[k].detach().float()[subsample(k)] - ref).abs()
-            assert err.max().item() <= 3 * e64.max().item() + tight, (k, err.max().item(), e64.max().item(), tight)
+            assert err.max().item() <= amp * e64.max().item() + tight, (k, err.max().item(), e64.max().item(), tight)
             assert (err <= tight).float().mean().item() >= (e64 <= tight).float().mean().item() - 0.02, k

@@ -53,7 +53,7 @@ if __name__ == '__main__':
     if os.environ.get('SAT_GATHER_CHILD'):
         child()
     else:
-        for v in (sys.argv[1:] or ["0", "2", "4", "5"]):
+        for v in (sys.argv[1:] or ["2", "5", "6"]):
             env = dict(os.environ, SAT_GATHER_VARIANT=v, SAT_GATHER_CHILD='1')
             r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=300)
             sys.stdout.write(r.stdout)

@@ -14,6 +14,9 @@ for S in $STEPS; do
     benchlong) timeout 600 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err ;;
     gather) timeout 600 python tools/gather_sweep.py > $OUT/${TAG}_gather.jsonl 2>&1 ;;
     profile) timeout 1500 tools/profile_r2.sh $TAG > $OUT/${TAG}_profile.log 2>&1 ;;
+    sweepvar) for BPS in 8 32 128 256; do SAT_SWEEP_BPS=$BPS timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print(json.dumps({'bps': $BPS, 'ms': d['ms_per_step'], 'e2e_ms': d['e2e']['ms_per_step'], 'sweep_frac': d['roofline']['frac'], 'phases': d['phases_ms']}))" >> $OUT/${TAG}_sweepvar.jsonl; done ;;
     configs) timeout 900 python bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err ;;
   esac
 done
@@ -21,3 +24,4 @@ echo "== pytest"; tail -15 $OUT/${TAG}_pytest.log 2>/dev/null
 echo "== smoke"; tail -3 $OUT/${TAG}_smoke.log 2>/dev/null
 echo "== bench"; cut -c1-1500 $OUT/${TAG}_bench.json 2>/dev/null; tail -5 $OUT/${TAG}_bench.err 2>/dev/null
 echo "== gather"; cat $OUT/${TAG}_gather.jsonl 2>/dev/null | cut -c1-200
+echo "== sweepvar"; cat $OUT/${TAG}_sweepvar.jsonl 2>/dev/null | cut -c1-400

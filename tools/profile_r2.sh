@@ -7,17 +7,9 @@ set -u
 TAG=${1:-r2}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-graph"
-# 1. launch list (every launch with its device time; cold-cache, serialised: compare SHARES)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
-# 2. one full capture per dominant kernel
-for K in k_forward_tc k_bwd_meta_tc k_bwd_attn k_adam_sweep k_rows_reduce k_dense_reduce k_radix_scatter k_gather; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o $OUT/${TAG}_$K $BENCH > $OUT/${TAG}_$K.log 2>&1
-  if [ -f $OUT/${TAG}_$K.ncu-rep ]; then
-    ncu -i $OUT/${TAG}_$K.ncu-rep --page details > $OUT/${TAG}_details_$K.txt 2>/dev/null
-    ncu -i $OUT/${TAG}_$K.ncu-rep --page raw --csv 2>/dev/null | python - "$OUT/${TAG}_raw_$K.json" <<'PY'
+cat > /tmp/sat_rawparse.py <<'PY'
 import csv, json, sys
-rows = list(csv.reader(sys.stdin))
+rows = list(csv.reader(open(sys.argv[1])))
 if len(rows) >= 3:
     hdr, units, vals = rows[0], rows[1], rows[2]
     keep = ('Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
@@ -27,8 +19,18 @@ if len(rows) >= 3:
             'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
             'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__issue_inst0.avg.pct_of_peak_sustained_active')
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals) if h in keep or 'pipe_tensor' in h or 'issue_stalled' in h}
-    json.dump(d, open(sys.argv[1], 'w'), indent=1)
+    json.dump(d, open(sys.argv[2], 'w'), indent=1)
 PY
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-graph"
+# 1. launch list (every launch with its device time; cold-cache, serialised: compare SHARES)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
+# 2. one full capture per dominant kernel
+for K in k_forward_tc k_bwd_meta_tc k_bwd_attn k_adam_sweep k_rows_reduce k_dense_reduce k_radix_scatter k_gather; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o $OUT/${TAG}_$K $BENCH > $OUT/${TAG}_$K.log 2>&1
+  if [ -f $OUT/${TAG}_$K.ncu-rep ]; then
+    ncu -i $OUT/${TAG}_$K.ncu-rep --page details > $OUT/${TAG}_details_$K.txt 2>/dev/null
+    ncu -i $OUT/${TAG}_$K.ncu-rep --page raw --csv 2>/dev/null > $OUT/${TAG}_raw_$K.csv
+    python /tmp/sat_rawparse.py $OUT/${TAG}_raw_$K.csv $OUT/${TAG}_raw_$K.json; rm -f $OUT/${TAG}_raw_$K.csv
     rm -f $OUT/${TAG}_$K.ncu-rep      # (tens of MB each; the text / json pages are what gets committed)
   fi
 done
