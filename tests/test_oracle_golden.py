@@ -189,3 +189,25 @@ def test_interacting_layer_restatement_properties():
     a = O.interacting_layer(x, p, 4, True, True)
     b = O.self_attention_layer(x, p2, 4, True)
     assert torch.allclose(torch.nn.functional.layer_norm(a, (32,), eps=1e-6), b, atol=1e-5)
+
+
+@pytest.mark.parametrize('opt,loss', VARIANTS[1:])
+def test_interval_budget_of_normalising_optimisers(opt, loss):
+    """tests/optim_bounds.py (the per-element budget the GPU tests hold Adagrad / RMSprop steps to) exercised on the CPU: the fp32
+    oracle stands in for the kernels and must stay inside the budget of a 3e-7 gradient tolerance around the fp64 oracle, and a
+    deliberately wrong step (lr off by 1 %) must fall outside the budget of the GPU tests' tolerance."""
+    import numpy as np
+    import os
+    import optim_bounds
+    from golden_util import GOLDEN_DIR
+    g = Golden('q_small')
+    lr = float(np.load(os.path.join(GOLDEN_DIR, 'compile_variants.npz'))['%s_%s/lr' % (opt, loss)])
+    for impl_lr, gtol, ok in ((lr, 3e-7, True), (lr * 1.01, 2e-5, False)):
+        tr = O.Trainer(g.state(), g.cfg, lr=impl_lr, optimizer=opt, loss=loss)
+        try:
+            optim_bounds.check_normalising_steps(O, g, opt, loss, lr, lambda X, y: tr.step(X, y, train_mode=False)[0],
+                                                 lambda: {k: t.detach().clone() for k, t in tr.params.items()}, gtol=gtol)
+            passed = True
+        except AssertionError:
+            passed = False
+        assert passed == ok, (impl_lr, gtol)
