@@ -56,6 +56,9 @@ def parse():
     ap.add_argument('--overlap', action='store_true', help='run the dense optimiser sweep on a second stream, concurrent with forward/backward (default: on the main stream)')
     ap.add_argument('--lazy', action='store_true', help='touched-rows-only table updates (NOT reference semantics)')
     ap.add_argument('--cpu-budget-s', type=float, default=25.0)
+    ap.add_argument('--sweep-interval', type=int, default=8,
+                    help='the every-row table update (L2 + Adam over rows no batch read) runs once per this many steps, each row '
+                         'receiving its steps one after the other (bit-identical parameters; single GPU); 1 = after every step')
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'],
                     help="forward GEMMs: fp32 CUDA cores | tcgen05 3xTF32 (fp32-level parity, default) | tcgen05 TF32")
     args = ap.parse_args()
@@ -75,8 +78,10 @@ def workload_config(args, n_gpus):
 "step_launch": "cuda graph replay" if (n_gpus == 1 and not args.no_graph and not args.overlap) else "eager launches",
             "optimizer": "Adam lr=0.005 + L2(emb)=1e-5, " + ("lazy touched-rows-only" if args.lazy else
                                                                "dense every-row (reference semantics)"),
-            "dropout": 0.1, "l2": "inputs>L2 (3 x %.0f MB of table state swept per step per GPU, new batch every step)"
-                                  % (841.2 * args.vocab_scale / n_gpus),
+            "table_sweep_interval": (args.sweep_interval if (n_gpus == 1 and not args.lazy and not args.overlap) else 1),
+            "dropout": 0.1, "l2": "inputs>L2 (3 x %.0f MB of table state swept per sweep per GPU, new batch every step; the "
+                                  "per-step working set -- 20 MB of rows gathered from 841 MB of tables + ~340 MB of saved "
+                                  "activations / gradients -- exceeds the 126 MB L2)" % (841.2 * args.vocab_scale / n_gpus),
             "forward_gemms": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 3xTF32 error-compensated (fp32-level parity)",
                               "tf32": "tcgen05 TF32"}[args.precision],
             "parallelism": "1 GPU" if n_gpus == 1 else "row-sharded tables + dp%d dense" % n_gpus}
@@ -371,6 +376,8 @@ def run_b200(args):
     model.train()
 
     use_graph = world == 1 and not args.no_graph and not args.overlap
+    defer = args.sweep_interval if (world == 1 and not args.lazy and not args.overlap) else 1
+    model.table_sweep_interval = defer
 
     def step(i, overlap=args.overlap, eager=False):
         """One optimiser step on a device-resident batch: the engine call fit() makes per batch -- the CUDA-graph replay of the
@@ -379,11 +386,11 @@ def run_b200(args):
         xb, yb = Xd[k * B:(k + 1) * B], yd[k * B:(k + 1) * B]
         if use_graph and not eager and eng.step_count >= 2:
             w, _ = eng.graph_train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'], l2_emb=1e-5,
-                                        dense_mode=not args.lazy, dropout_p=0.1, seed0=1021)
+                                        dense_mode=not args.lazy, dropout_p=0.1, seed0=1021, defer=defer)
             return eng.last_y_pred, w
         return eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
                               opt_kind=hp['kind'], l2_emb=1e-5, dense_mode=not args.lazy, training=True, dropout_p=0.1, seed=1021 + i,
-                              overlap=overlap)
+                              overlap=overlap, defer=defer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -397,8 +404,9 @@ def run_b200(args):
     barrier()
     # ---- phase breakdown (CUDA events around every phase of the EAGER launch sequence; not part of `value`) -----------------
     eng.timing = {}
-    for i in range(min(K, 10)):
+    for i in range(min(K, 10) if defer <= 1 else 2 * defer):
         _, w = step(W + i, eager=True)
+    eng.sync_tables()
     phases = eng.timing_ms()
     eng.timing = None
     barrier()
@@ -409,6 +417,7 @@ def run_b200(args):
     ev0.record()
     for i in range(K):
         _, w = step(W + i)
+    eng.sync_tables()                      # (the last sweep epoch closes inside the timed region: every row is up to date)
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -425,14 +434,16 @@ def run_b200(args):
 
     # ---- e2e: the public per-batch API with HOST buffers (pinned), H2D + D2H inside the timed region -------
     for i in range(3):
-        model.train_on_batch(X_host[:B], y_host[:B])
+        model.train_on_batch(X_host[:B], y_host[:B], defer_reg=defer > 1)
+    model.sync_tables()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     e0.record()
     for i in range(K):
         k = (i + 3) % n_batches
-        model.train_on_batch(X_host[k * B:(k + 1) * B], y_host[k * B:(k + 1) * B])
+        model.train_on_batch(X_host[k * B:(k + 1) * B], y_host[k * B:(k + 1) * B], defer_reg=defer > 1)
+    model.sync_tables()
     e1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -446,7 +457,9 @@ def run_b200(args):
     e2e_ms = float(t.item())
     e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(B * X_host.shape[1] * 4 + B * 4), "d2h_bytes_per_step": 16,
-           "api": "SATrans.train_on_batch(x_host, y_host) -> (bce, reg)"}
+           "api": "SATrans.train_on_batch(x_host, y_host) -> (bce, reg)" if defer <= 1 else
+                  "SATrans.train_on_batch(x_host, y_host, defer_reg=True) -> (bce, None) per step (synchronous: the bce of the step "
+                  "is read back), + SATrans.sync_tables() at the end, inside the timed region"}
     if rank != 0:
         if world > 1:
             dist.barrier()          # keep this rank's table shard mapped until rank 0 is done with the extras
@@ -463,7 +476,18 @@ def run_b200(args):
         tr = traffic_tab.get(key) if full_cfg2 else None
         return (tr['dram_bytes_read'] + tr['dram_bytes_write']) if tr else None
 
-    if 'adam_sweep' in phases:
+    if 'table_sweep' in phases:
+        sweep_bytes = (rows - n_unique) * 6 * 128 + 2 * rows       # p, m, v read + written once per EPOCH; the per-row step byte
+        ach = sweep_bytes / (phases['table_sweep'] * 1e-3) / 1e9
+        roof = {"kernel": "k_defer_sweep", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic_of('k_defer_sweep'), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": phases['table_sweep'],
+                "launches_per_step": 1.0 / defer,
+                "note": "every-row table update (L2 + Adam of the rows no batch read) once per %d steps: 6 x 128 B per row per "
+                        "LAUNCH (p, m, v read once + written once, each row taken through the epoch's steps in registers) + 2 B "
+                        "per row of step bookkeeping; CUDA events around the launch (sweep + its 1-CTA finalize) on the main "
+                        "stream" % defer}
+    elif 'adam_sweep' in phases:
         ach = sweep_bytes / (phases['adam_sweep'] * 1e-3) / 1e9
         roof = {"kernel": "k_adam_sweep", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic_of('k_adam_sweep'), "peak_source": peak_src,

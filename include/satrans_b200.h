@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SAT_ABI_VERSION 2
+#define SAT_ABI_VERSION 3
 
 #define SAT_OK 0
 #define SAT_EINVAL (-1)      /* bad argument / unsupported shape            */
@@ -187,6 +187,11 @@ typedef struct SatAdam {
     int32_t kind;         /* SAT_OPT_*                                                           */
     float* tab_m; float* tab_v;       /* [local_rows][32] optimiser state of the tables (unused ones may be NULL) */
     float* dense_m; float* dense_v;   /* [n_dense_params]                                       */
+    /* deferred table sweep (sat_defer_*; NULL when unused): */
+    uint8_t* row_upto;    /* [local_rows] steps of the current sweep epoch already applied to the row             */
+    float* defer_state;   /* [SAT_DEFER_STATE_WORDS] [0] i32 steps begun in this epoch, [1] i32 overflow flag,
+                             [8 + 16 j ..] the optimiser constants of the epoch's step j                        */
+    double* defer_reg;    /* [SAT_DEFER_REG_DOUBLES] per-step partial sums of squares, see sat_defer_sweep        */
 } SatAdam;
 
 /* ---- library info ------------------------------------------------------------------------- */
@@ -283,6 +288,32 @@ int sat_step_set(SatWork* w, int32_t step, float lr, float beta1, float beta2, f
 #define SAT_ADAM_TOUCHED 1
 #define SAT_ADAM_UNTOUCHED 2
 int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, int32_t which, void* stream);
+
+/* ---- deferred table sweep: the reference's every-row-every-step update (meta_basemodel.py:577-593 + main.py:343) with the
+ *      rows NOT read by a batch brought up to date in batches of up to SAT_DEFER_MAX steps.  A row the batch does not read gets
+ *      g = 2*l2*w, which depends on nothing but the row itself and the step's constants, so applying its steps later -- one
+ *      after the other, same arithmetic, the constants of every step kept in a ring -- gives bit-identical (p, m, v); the table
+ *      state then crosses HBM once per sweep epoch instead of once per step.  Order inside one training step:
+ *        sat_defer_begin                     ring[n] = this step's constants, n += 1            (before anything else)
+ *        sat_defer_catchup                   after sat_rows_rank, BEFORE the forward: the rows this batch reads (w->uniq_rows)
+ *                                            get the steps of the epoch they have not seen yet
+ *        sat_tables_adam(SAT_ADAM_TOUCHED | SAT_ADAM_DEFERRED)   as before, and marks those rows as up to date
+ *      and after at most SAT_DEFER_MAX steps (or before anything else reads the tables)
+ *        sat_defer_sweep                     every row up to date, epoch closed (n = 0); a->defer_reg[0..n) receives
+ *                                            l2 * sum(table^2) as each step of the epoch saw it (the regulariser term of
+ *                                            its loss), [SAT_DEFER_MAX] their running total, [SAT_DEFER_MAX + 1] the count.
+ *      No floating-point atomics: every partial sum has its own slot and is added in a fixed order. ---------------------- */
+#define SAT_DEFER_MAX 16
+#define SAT_ADAM_DEFERRED 4
+#define SAT_DEFER_STATE_WORDS (8 + 16 * SAT_DEFER_MAX)
+#define SAT_DEFER_ROWS_BLOCKS (148 * 4)
+#define SAT_DEFER_SWEEP_BLOCKS (148 * 64)
+/* doubles: [0..18) results | touch [MAX][ROWS_BLOCKS] | catch-up [MAX launches][ROWS_BLOCKS][MAX] | sweep [SWEEP_BLOCKS][MAX] */
+#define SAT_DEFER_REG_DOUBLES (32 + SAT_DEFER_MAX * SAT_DEFER_ROWS_BLOCKS + SAT_DEFER_MAX * SAT_DEFER_ROWS_BLOCKS * SAT_DEFER_MAX + \
+                               SAT_DEFER_SWEEP_BLOCKS * SAT_DEFER_MAX)
+int sat_defer_begin(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
+int sat_defer_catchup(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
+int sat_defer_sweep(const SatModel* m, const SatAdam* a, void* stream);
 int sat_dense_adam(const SatModel* m, SatWork* w, const SatAdam* a, void* stream);
 /* sum of squares of all table rows into w->reg_part (regulariser without an optimiser step). */
 int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream);

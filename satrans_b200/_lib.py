@@ -15,14 +15,17 @@ SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 256 + 148 * 4
 SAT_WORK_BUFFERS = 32
 SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
-SAT_ABI_VERSION = 2
+SAT_ABI_VERSION = 3
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
 FLAG_LOSS_MSE, FLAG_LOSS_MAE = 32, 64
 OPT_ADAM, OPT_SGD, OPT_ADAGRAD, OPT_RMSPROP = 0, 1, 2, 3
 ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
-ADAM_TOUCHED, ADAM_UNTOUCHED = 1, 2
+ADAM_TOUCHED, ADAM_UNTOUCHED, ADAM_DEFERRED = 1, 2, 4
+SAT_DEFER_MAX = 16
+SAT_DEFER_STATE_WORDS = 8 + 16 * SAT_DEFER_MAX
+SAT_DEFER_REG_DOUBLES = 32 + SAT_DEFER_MAX * 148 * 4 + SAT_DEFER_MAX * 148 * 4 * SAT_DEFER_MAX + 148 * 64 * SAT_DEFER_MAX
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -54,7 +57,8 @@ class SatWork(C.Structure):
 class SatAdam(C.Structure):
     _fields_ = [('lr', f32), ('beta1', f32), ('beta2', f32), ('eps', f32), ('l2_emb', f32),
                 ('step', i32), ('dense_mode', i32), ('kind', i32),
-                ('tab_m', vp), ('tab_v', vp), ('dense_m', vp), ('dense_v', vp)]
+                ('tab_m', vp), ('tab_v', vp), ('dense_m', vp), ('dense_v', vp),
+                ('row_upto', vp), ('defer_state', vp), ('defer_reg', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/satrans_b200.h declares
@@ -85,6 +89,9 @@ PROTOTYPES = {
     'sat_step_begin': (C.c_int, [C.POINTER(SatWork), C.c_uint64, vp]),
     'sat_step_set': (C.c_int, [C.POINTER(SatWork), i32, f32, f32, f32, f32, vp]),
     'sat_tables_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), i32, vp]),
+    'sat_defer_begin': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
+    'sat_defer_catchup': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
+    'sat_defer_sweep': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatAdam), vp]),
     'sat_dense_adam': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), C.POINTER(SatAdam), vp]),
     'sat_tables_sumsq': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), vp]),
     'sat_finalize_loss': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), f32, i32, vp]),

@@ -221,6 +221,7 @@ class BaseModel(nn.Module):
         """l2 * sum(square(w)) over the registered weights as a (1,) tensor (reference
         meta_basemodel.py:577-593).  `fit` never calls this: the fused optimiser sweep produces the same
         number as a by-product; it is kept for API compatibility and evaluated with torch ops."""
+        self.sync_tables()
         total = torch.zeros((1,), device=self._tables.device)
         for weight_list, l1, l2 in self.regularization_weight:
             for w in weight_list:
@@ -246,9 +247,32 @@ class BaseModel(nn.Module):
         return embs, dense_vals
 
     # ---- row-sharded tables (multi-GPU) ---------------------------------------------------------------
+    # ---- deferred table sweep (engine.sync_tables): anything that reads or moves the parameters closes the epoch first --------
+    table_sweep_interval = 8     # fit(): the every-row table update runs once per this many steps (1 = after every step);
+                                 # parameters and optimiser state are bit-identical either way (include/satrans_b200.h, sat_defer_*)
+
+    def sync_tables(self):
+        """Bring every table row up to date (no-op unless a deferred sweep epoch is open)."""
+        eng = getattr(self, '_engine', None)
+        if eng is not None:
+            eng.sync_tables()
+
+    def state_dict(self, *args, **kwargs):
+        self.sync_tables()
+        return super().state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.sync_tables()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.sync_tables()
+        return super().load_state_dict(*args, **kwargs)
+
     def load_full_tables(self, full):
         """Copy this process' rows out of a full [total_rows, d] table (rows g with g % world == rank)."""
         rank, world = self._shard
+        self.sync_tables()
         with torch.no_grad():
             self._tables.copy_(torch.as_tensor(full)[rank::world].to(self._tables.device))
 
@@ -477,10 +501,17 @@ class BaseModel(nn.Module):
             self._shuffle_gen = torch.Generator(device='cpu')
             self._shuffle_gen.manual_seed(torch.initial_seed() & (2 ** 63 - 1))
         gen = self._shuffle_gen
+        # the every-row table update runs once per `table_sweep_interval` steps (bit-identical parameters, engine.train_step);
+        # the regulariser term of a step is then known when its sweep epoch closes: the epoch's loss takes it from there
+        defer = int(self.table_sweep_interval) if (self.dense_table_updates and eng.dist is None) else 1
         for epoch in range(initial_epoch, epochs):
             callbacks.on_epoch_begin(epoch)
             epoch_logs = {}
             start_time = time.time()
+            reg0 = None
+            if defer > 1:
+                eng.sync_tables()
+                reg0 = eng.deferred_reg_total()
             order = torch.randperm(sample_num, generator=gen).to(dev) if shuffle else None
             preds = torch.empty(sample_num, dtype=torch.float32, device=dev) if want_metrics else None
             losses = torch.zeros((steps_per_epoch, 2), dtype=torch.float32, device=dev)
@@ -498,14 +529,14 @@ class BaseModel(nn.Module):
                     # full-size batches after the first two steps: the whole step is ONE CUDA-graph launch (engine.graph_train_step)
                     w, _ = eng.graph_train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                                 l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
-                                                dropout_p=self.dropout_rate, seed0=seed0)
+                                                dropout_p=self.dropout_rate, seed0=seed0, defer=defer)
                     y_pred = eng.last_y_pred
                 else:
                     y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                                l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                                training=True, dropout_p=self.dropout_rate,
-                                               seed=(seed0 + eng.step_count) & (2 ** 63 - 1))
-                losses[step_num].copy_(w['scalars'][0:2])
+                                               seed=(seed0 + eng.step_count) & (2 ** 63 - 1), defer=defer)
+                losses[step_num, 0:(1 if defer > 1 else 2)].copy_(w['scalars'][0:(1 if defer > 1 else 2)])
                 if want_metrics:
                     preds[s0:s1] = y_pred
                 step_num += 1
@@ -516,7 +547,11 @@ class BaseModel(nn.Module):
                         " - %s: %.4f" % (k, v) for k, v in eval_result.items())))
             eng.check_errors(eng.workspace(1, True))
             lh = losses.double().cpu().numpy()
-            epoch_logs["loss"] = float(lh.sum()) / sample_num                 # (bce + reg) summed / N (:353)
+            reg_sum = 0.0
+            if defer > 1:                               # every table row up to date before metrics / validation / callbacks
+                eng.sync_tables()
+                reg_sum = float(eng.deferred_reg_total()) - float(reg0)
+            epoch_logs["loss"] = (float(lh.sum()) + reg_sum) / sample_num     # (bce + reg) summed / N (:353)
             if want_metrics and getattr(self, 'device_metrics', True) and batch_size <= 16384:
                 # per-batch sklearn-equivalent metrics on the device (sat_batch_metrics): one CTA per training batch
                 from . import _lib
@@ -565,10 +600,15 @@ class BaseModel(nn.Module):
         callbacks.on_train_end()
         return self.history
 
-    def train_on_batch(self, x, y):
+    def train_on_batch(self, x, y, defer_reg=False):
         """One optimiser step on one batch given as HOST data (dict / list of columns or an (B, n_cols) array)
         and labels; returns (bce_sum, reg_loss) as Python floats — the per-step body of `fit`
-        (reference meta_basemodel.py:311-328, incl. its `.item()` synchronisation)."""
+        (reference meta_basemodel.py:311-328, incl. its `.item()` synchronisation).
+
+        defer_reg=True: the every-row table update runs once per `table_sweep_interval` steps, like inside `fit` (parameters and
+        optimiser state bit-identical); the step's regulariser term is then not known yet and (bce_sum, None) is returned --
+        `sync_tables()` closes the sweep epoch, `engine.deferred_reg()` has the per-step terms afterwards."""
+        defer = int(self.table_sweep_interval) if (defer_reg and self.dense_table_updates and self.engine.dist is None) else 1
         if torch.is_tensor(x) and x.dtype in (torch.float32, torch.int32, torch.int64):
             X = x                                           # (pinned) host or device tensor in a kernel-ready dtype: no host pass
         else:
@@ -587,22 +627,23 @@ class BaseModel(nn.Module):
             w, sc_pin = eng.graph_train_step(X, np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y,
                                              lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                              l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
-                                             dropout_p=self.dropout_rate, seed0=seed0)
+                                             dropout_p=self.dropout_rate, seed0=seed0, defer=defer)
             torch.cuda.current_stream().synchronize()     # like the reference's .item(): the step is done, the scalars are on the host
             sc = sc_pin.tolist()
             if sc[3] != 0:
                 eng.check_errors(w)
-            return sc[0], sc[1]
+            return sc[0], (sc[1] if defer <= 1 else None)
         else:
             Xd = torch.as_tensor(X).to(dev, non_blocking=True)
             yd = torch.as_tensor(y).to(dev, non_blocking=True).float().reshape(-1)
             _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
                                   opt_kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
-                                  training=True, dropout_p=self.dropout_rate, seed=(seed0 + eng.step_count) & (2 ** 63 - 1))
+                                  training=True, dropout_p=self.dropout_rate, seed=(seed0 + eng.step_count) & (2 ** 63 - 1),
+                                  defer=defer)
         sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()
         if sc[3] != 0:
             eng.check_errors(w)
-        return sc[0], sc[1]
+        return sc[0], (sc[1] if defer <= 1 else None)
 
     # ---- evaluate / predict ------------------------------------------------------------------------------
     def evaluate(self, x, y, batch_size=256):

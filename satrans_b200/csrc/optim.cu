@@ -52,6 +52,46 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, con
     }
 }
 
+// The same update for a row that no batch read (g = 2*l2*w, a smooth function of the row itself), used by BOTH table sweeps
+// (every-step k_adam_sweep and the deferred k_defer_*), so that deferring is bit-neutral.  The multi-step sweep is bound by the
+// SFU (MUFU issues at a quarter of the FMA rate), so the arithmetic is trimmed to 6 MUFU + ~40 FMA-pipe instructions per float4
+// instead of 12 + ~130 for IEEE sqrt and two IEEE divisions per element: approximate square roots (sqrt.approx.ftz, <= 2 ulp),
+// the bias correction as a multiplication by the reciprocal (computed once per step), and ONE reciprocal per PAIR of
+// denominators (1/a = b / (a b); every denominator is >= eps, so the product is far from underflow for eps >= 1e-18).  The deviation from torch's op order is a few ulp of an update that is itself <= lr per step.
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1/a, 1/b, 1/c, 1/d from two reciprocals (of the pair products: >= eps^2, safe from underflow for eps >= 1e-18)
+__device__ __forceinline__ float4 rcp4(float a, float b, float c, float d) {
+    const float rab = rcp_approx(__fmul_rn(a, b)), rcd = rcp_approx(__fmul_rn(c, d));
+    return make_float4(__fmul_rn(rab, b), __fmul_rn(rab, a), __fmul_rn(rcd, d), __fmul_rn(rcd, c));
+}
+__device__ __forceinline__ void adam4_untouched(float4& p, float4& m, float4& v, const AdamConst& c, float inv_bc2_sqrt) {
+    // (__fmul_rn / __fsub_rn: never contracted into an FMA with their consumers -- the compiler decides contraction per call
+    //  site, and the every-step and the deferred sweep must round identically)
+    const float4 g = make_float4(__fmul_rn(c.two_l2, p.x), __fmul_rn(c.two_l2, p.y), __fmul_rn(c.two_l2, p.z), __fmul_rn(c.two_l2, p.w));
+    if (c.kind == SAT_OPT_SGD) {
+        p.x = fmaf(-c.lr, g.x, p.x); p.y = fmaf(-c.lr, g.y, p.y); p.z = fmaf(-c.lr, g.z, p.z); p.w = fmaf(-c.lr, g.w, p.w);
+        return;
+    }
+    float4 num = g;
+    float scale = c.lr, dscale = 1.f;
+    if (c.kind == SAT_OPT_ADAM) {
+        m.x = fmaf(__fsub_rn(g.x, m.x), c.one_minus_b1, m.x); m.y = fmaf(__fsub_rn(g.y, m.y), c.one_minus_b1, m.y);
+        m.z = fmaf(__fsub_rn(g.z, m.z), c.one_minus_b1, m.z); m.w = fmaf(__fsub_rn(g.w, m.w), c.one_minus_b1, m.w);
+        num = m; scale = c.step_size; dscale = inv_bc2_sqrt;
+    }
+    if (c.kind == SAT_OPT_ADAGRAD) {
+        v.x = fmaf(g.x, g.x, v.x); v.y = fmaf(g.y, g.y, v.y); v.z = fmaf(g.z, g.z, v.z); v.w = fmaf(g.w, g.w, v.w);
+    } else {            // Adam, RMSprop (alpha in b2)
+        v.x = fmaf(__fmul_rn(c.one_minus_b2, g.x), g.x, __fmul_rn(v.x, c.b2)); v.y = fmaf(__fmul_rn(c.one_minus_b2, g.y), g.y, __fmul_rn(v.y, c.b2));
+        v.z = fmaf(__fmul_rn(c.one_minus_b2, g.z), g.z, __fmul_rn(v.z, c.b2)); v.w = fmaf(__fmul_rn(c.one_minus_b2, g.w), g.w, __fmul_rn(v.w, c.b2));
+    }
+    const float4 r = rcp4(fmaf(sqrt_approx(v.x), dscale, c.eps), fmaf(sqrt_approx(v.y), dscale, c.eps),
+                          fmaf(sqrt_approx(v.z), dscale, c.eps), fmaf(sqrt_approx(v.w), dscale, c.eps));
+    p.x = fmaf(-scale, __fmul_rn(num.x, r.x), p.x); p.y = fmaf(-scale, __fmul_rn(num.y, r.y), p.y);
+    p.z = fmaf(-scale, __fmul_rn(num.z, r.z), p.z); p.w = fmaf(-scale, __fmul_rn(num.w, r.w), p.w);
+}
+
 __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const float4& g, const AdamConst& c) {
     adam1(p.x, m.x, v.x, g.x, c); adam1(p.y, m.y, v.y, g.y, c);
     adam1(p.z, m.z, v.z, g.z, c); adam1(p.w, m.w, v.w, g.w, c);
@@ -97,6 +137,7 @@ k_adam_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict_
              long long n_vec /* total_rows * 8 */, const AdamConst c_in, const float* __restrict__ dev_const,
              double* __restrict__ reg_part) {
     const AdamConst c = resolve_const(c_in, dev_const);
+    const float inv_bc2_sqrt = 1.f / c.bc2_sqrt;
     float sq = 0.f;
     const long long stride = (long long)gridDim.x * SWEEP_THREADS;
     for (long long i0 = (long long)blockIdx.x * SWEEP_THREADS + threadIdx.x; i0 < n_vec; i0 += stride * SWEEP_UNROLL) {
@@ -122,8 +163,7 @@ k_adam_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict_
                 const long long i = i0 + u * stride;
                 sq = fmaf(p[u].x, p[u].x, sq); sq = fmaf(p[u].y, p[u].y, sq);
                 sq = fmaf(p[u].z, p[u].z, sq); sq = fmaf(p[u].w, p[u].w, sq);
-                const float4 g = make_float4(c.two_l2 * p[u].x, c.two_l2 * p[u].y, c.two_l2 * p[u].z, c.two_l2 * p[u].w);
-                adam4(p[u], m[u], v[u], g, c);
+                adam4_untouched(p[u], m[u], v[u], c, inv_bc2_sqrt);
                 __stcs(P + i, p[u]);
                 if (c.kind == SAT_OPT_ADAM) __stcs(M + i, m[u]);
                 if (c.kind != SAT_OPT_SGD) __stcs(V + i, v[u]);
@@ -137,11 +177,19 @@ constexpr int ROWS_THREADS = 256;
 constexpr int ROWS_BLOCKS = 148 * 4;
 
 // Touched rows: g = accumulated dE + 2*l2*p, Adam, clear the accumulator for the next step.
+// Deferred mode (upto != nullptr): the rows are marked as up to date through this step (index n - 1 of the sweep epoch, n =
+// defer_state[0]) and the sum-of-squares partials go to this step's slots of the deferred buffer.
 __global__ void __launch_bounds__(ROWS_THREADS)
 k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const int32_t* __restrict__ uniq_rows,
             float4* __restrict__ row_grad, const int32_t* __restrict__ counters, const AdamConst c_in,
-            const float* __restrict__ dev_const, double* __restrict__ reg_part) {
+            const float* __restrict__ dev_const, double* __restrict__ reg_part, uint8_t* __restrict__ upto,
+            const float* __restrict__ defer_state) {
     const AdamConst c = resolve_const(c_in, dev_const);
+    int n_begun = 0;
+    if (upto) {
+        n_begun = reinterpret_cast<const int*>(defer_state)[0];
+        reg_part += (long long)(n_begun - 1) * ROWS_BLOCKS;
+    }
     const long long n_vec = (long long)counters[CNT_NUNIQ] * 8;
     float sq = 0.f;
     for (long long i = (long long)blockIdx.x * ROWS_THREADS + threadIdx.x; i < n_vec;
@@ -159,8 +207,171 @@ k_adam_rows(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__
         P[e] = p;
         if (c.kind == SAT_OPT_ADAM) M[e] = m;
         if (c.kind != SAT_OPT_SGD) V[e] = v;
+        if (upto && (i & 7) == 0) upto[e >> 3] = (uint8_t)n_begun;
     }
     block_sum_to((double)sq, reg_part + blockIdx.x);
+}
+
+// ---- deferred table sweep (include/satrans_b200.h: sat_defer_*) -----------------------------------------------------------
+constexpr int DEFER_MAX = SAT_DEFER_MAX;
+constexpr int DEFER_RING = 16;            // words per ring entry of SatAdam.defer_state
+static_assert(SAT_DEFER_STATE_WORDS == 8 + DEFER_RING * DEFER_MAX, "layout of SatAdam.defer_state");
+constexpr int DF_RES = 0, DF_TOUCH = 32, DF_CATCH = DF_TOUCH + DEFER_MAX * SAT_DEFER_ROWS_BLOCKS,
+              DF_SWEEP = DF_CATCH + DEFER_MAX * SAT_DEFER_ROWS_BLOCKS * DEFER_MAX;
+static_assert(SAT_DEFER_ROWS_BLOCKS == ROWS_BLOCKS, "the touched-row kernel writes one partial per CTA");
+static_assert(DF_SWEEP + SAT_DEFER_SWEEP_BLOCKS * DEFER_MAX == SAT_DEFER_REG_DOUBLES, "layout of SatAdam.defer_reg");
+
+__device__ __forceinline__ AdamConst ring_const(const float* __restrict__ st, int j, int kind) {
+    const float* r = st + 8 + DEFER_RING * j;
+    AdamConst c;
+    c.one_minus_b1 = r[0]; c.b2 = r[1]; c.one_minus_b2 = r[2]; c.step_size = r[3]; c.bc2_sqrt = r[4]; c.eps = r[5]; c.lr = r[6];
+    c.two_l2 = r[7]; c.kind = kind;
+    return c;
+}
+
+__global__ void k_defer_begin(float* __restrict__ st, const AdamConst c_in, const float* __restrict__ dev_const) {
+    const AdamConst c = resolve_const(c_in, dev_const);
+    int* sti = reinterpret_cast<int*>(st);
+    const int j = sti[0];
+    if (j >= DEFER_MAX) { sti[1] = 1; return; }            // the caller did not sweep in time: reported by sat_defer_sweep
+    float* r = st + 8 + DEFER_RING * j;
+    r[0] = c.one_minus_b1; r[1] = c.b2; r[2] = c.one_minus_b2; r[3] = c.step_size; r[4] = c.bc2_sqrt; r[5] = c.eps; r[6] = c.lr;
+    r[7] = c.two_l2; r[8] = 1.f / c.bc2_sqrt;           // (the same IEEE quotient k_adam_sweep forms once per launch)
+    sti[0] = j + 1;
+}
+
+// One float4 of a row through the steps [j0, j1) of the epoch as a row that no batch read (g = 2*l2*w): exactly what
+// k_adam_sweep does to it once per step.  The sum of squares each step saw goes to this thread's column of s_sq[step].
+__device__ __forceinline__ void defer_steps(float4& p, float4& m, float4& v, int j0, int j1, const float* __restrict__ st,
+                                            int kind, float (*s_sq)[ROWS_THREADS]) {
+    for (int j = j0; j < j1; ++j) {
+        const AdamConst c = ring_const(st, j, kind);
+        float sq = p.x * p.x;
+        sq = fmaf(p.y, p.y, sq); sq = fmaf(p.z, p.z, sq); sq = fmaf(p.w, p.w, sq);
+        s_sq[j][threadIdx.x] += sq;
+        adam4_untouched(p, m, v, c, st[8 + DEFER_RING * j + 8]);
+    }
+}
+
+// per-step block sums of s_sq -> dst[j], j < DEFER_MAX (every slot is written: no memset between epochs)
+__device__ __forceinline__ void defer_block_sums(float (*s_sq)[ROWS_THREADS], double* __restrict__ dst) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j = wid; j < DEFER_MAX; j += ROWS_THREADS / 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < ROWS_THREADS / 32; ++k) t += (double)s_sq[j][lane + 32 * k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) dst[j] = t;
+    }
+}
+
+// The rows this batch reads (sorted unique list) receive the steps of the epoch they have not seen: after this kernel they
+// hold exactly the values a sweep after every step would have left, and the forward may gather them.
+__global__ void __launch_bounds__(ROWS_THREADS)
+k_defer_catchup(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, uint8_t* __restrict__ upto,
+                const int32_t* __restrict__ uniq_rows, const int32_t* __restrict__ counters, const float* __restrict__ st,
+                int kind, double* __restrict__ reg_catch) {
+    __shared__ float s_sq[DEFER_MAX][ROWS_THREADS];
+#pragma unroll
+    for (int j = 0; j < DEFER_MAX; ++j) s_sq[j][threadIdx.x] = 0.f;
+    const int cur = reinterpret_cast<const int*>(st)[0] - 1;           // index of the step now running
+    const long long n_vec = (long long)counters[CNT_NUNIQ] * 8;
+    if (cur > 0) {
+        // (warp-uniform trip count: n_vec is a multiple of 8, the warps' first elements of 32)
+        const int lane = threadIdx.x & 31;
+        for (long long b0 = (long long)blockIdx.x * ROWS_THREADS + (threadIdx.x & ~31); b0 < n_vec; b0 += (long long)gridDim.x * ROWS_THREADS) {
+            const long long i = b0 + lane;
+            long long row = 0;
+            int j0 = cur;
+            if (i < n_vec) { row = __ldg(uniq_rows + (i >> 3)); j0 = upto[row]; }
+            __syncwarp();                        // the 8 lanes of a row have read upto[row] before one of them rewrites it
+            if (j0 < cur) {
+                const long long e = row * 8 + (i & 7);
+                float4 p = P[e], m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
+                if (kind == SAT_OPT_ADAM) m = M[e];
+                if (kind != SAT_OPT_SGD) v = V[e];
+                defer_steps(p, m, v, j0, cur, st, kind, s_sq);
+                P[e] = p;
+                if (kind == SAT_OPT_ADAM) M[e] = m;
+                if (kind != SAT_OPT_SGD) V[e] = v;
+                if ((i & 7) == 0) upto[row] = (uint8_t)cur;
+            }
+        }
+    }
+    defer_block_sums(s_sq, reg_catch + ((long long)max(cur, 0) * ROWS_BLOCKS + blockIdx.x) * DEFER_MAX);
+}
+
+// End of the epoch: every row receives the steps it has not seen, upto = 0.
+__global__ void __launch_bounds__(ROWS_THREADS)
+k_defer_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, uint8_t* __restrict__ upto,
+              long long n_vec, const float* __restrict__ st, int kind, double* __restrict__ reg_sweep) {
+    __shared__ float s_sq[DEFER_MAX][ROWS_THREADS];
+#pragma unroll
+    for (int j = 0; j < DEFER_MAX; ++j) s_sq[j][threadIdx.x] = 0.f;
+    const int n = min(reinterpret_cast<const int*>(st)[0], DEFER_MAX);
+    constexpr int U = 2;
+    const long long stride = (long long)gridDim.x * ROWS_THREADS;
+    const int lane = threadIdx.x & 31;
+    // (warp-uniform trip count: n_vec is a multiple of 8, the warps' first elements of 32)
+    for (long long b0 = (long long)blockIdx.x * ROWS_THREADS + (threadIdx.x & ~31); b0 < n_vec; b0 += stride * U) {
+        float4 p[U], m[U], v[U];
+        int j0[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = b0 + lane + u * stride;
+            j0[u] = -1;                                                  // past the end
+            if (i < n_vec) j0[u] = upto[i >> 3];
+            if (j0[u] >= 0 && j0[u] < n) {
+                p[u] = __ldcs(P + i);
+                if (kind == SAT_OPT_ADAM) m[u] = __ldcs(M + i);
+                if (kind != SAT_OPT_SGD) v[u] = __ldcs(V + i);
+            }
+        }
+        __syncwarp();                            // the 8 lanes of a row have read upto[row] before one of them clears it
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = b0 + lane + u * stride;
+            if (j0[u] >= 0 && j0[u] < n) {
+                defer_steps(p[u], m[u], v[u], j0[u], n, st, kind, s_sq);
+                __stcs(P + i, p[u]);
+                if (kind == SAT_OPT_ADAM) __stcs(M + i, m[u]);
+                if (kind != SAT_OPT_SGD) __stcs(V + i, v[u]);
+            }
+            if (j0[u] > 0 && (i & 7) == 0) upto[i >> 3] = 0;
+        }
+    }
+    defer_block_sums(s_sq, reg_sweep + (long long)blockIdx.x * DEFER_MAX);
+}
+
+// Per-step regulariser terms of the closed epoch, in a fixed order: touched rows of the step, then the catch-up launches, then
+// the sweep.  res[j] = l2 * sum, res[DEFER_MAX] += their total, res[DEFER_MAX + 1] = n; the epoch counter returns to 0.
+__global__ void __launch_bounds__(256)
+k_defer_finalize(float* __restrict__ st, double* __restrict__ reg, float l2, int sweep_blocks) {
+    __shared__ double s_out;
+    int* sti = reinterpret_cast<int*>(st);
+    const int n = min(sti[0], DEFER_MAX);
+    double total = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double a = 0.0;
+        for (int b = threadIdx.x; b < ROWS_BLOCKS; b += 256) a += reg[DF_TOUCH + (long long)j * ROWS_BLOCKS + b];
+        for (int l = j + 1; l < n; ++l)
+            for (int b = threadIdx.x; b < ROWS_BLOCKS; b += 256) a += reg[DF_CATCH + ((long long)l * ROWS_BLOCKS + b) * DEFER_MAX + j];
+        for (int b = threadIdx.x; b < sweep_blocks; b += 256) a += reg[DF_SWEEP + (long long)b * DEFER_MAX + j];
+        block_sum_to(a, &s_out);
+        __syncthreads();
+        const double r = (double)l2 * s_out;
+        total += r;
+        if (threadIdx.x == 0) reg[DF_RES + j] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        reg[DF_RES + DEFER_MAX] += total;
+        reg[DF_RES + DEFER_MAX + 1] = (double)n;
+        reg[DF_RES + DEFER_MAX + 2] = (double)sti[1];       // != 0: more than SAT_DEFER_MAX steps were begun without a sweep
+        sti[0] = 0;
+    }
 }
 
 // Flat dense-parameter buffer (148 k floats in the EN configuration).
@@ -241,9 +452,13 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
     const long long n_vec = m->local_rows * 8;
     cudaStream_t s = (cudaStream_t)stream;
     if (which & SAT_ADAM_TOUCHED) {
+        const bool deferred = which & SAT_ADAM_DEFERRED;
+        if (deferred && (!a->row_upto || !a->defer_state || !a->defer_reg || !a->dense_mode))
+            return sat_host::fail(SAT_EINVAL, "sat_tables_adam: SAT_ADAM_DEFERRED needs dense_mode and the deferred-sweep buffers");
         k_adam_rows<<<ROWS_BLOCKS, ROWS_THREADS, 0, s>>>(
             reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v),
-            w->uniq_rows, reinterpret_cast<float4*>(w->row_grad), w->counters, c, dev_const, w->reg_part + SWEEP_BLOCKS);
+            w->uniq_rows, reinterpret_cast<float4*>(w->row_grad), w->counters, c, dev_const,
+            deferred ? a->defer_reg + DF_TOUCH : w->reg_part + SWEEP_BLOCKS, deferred ? a->row_upto : nullptr, a->defer_state);
         int rc = sat_host::check_launch("k_adam_rows");
         if (rc) return rc;
     }
@@ -263,6 +478,47 @@ extern "C" int sat_tables_adam(const SatModel* m, SatWork* w, const SatAdam* a, 
         if (rc) return rc;
     }
     return SAT_OK;
+}
+
+static int defer_args_ok(const SatModel* m, const SatAdam* a, const char* who) {
+    if (!m || !a || !a->row_upto || !a->defer_state || !a->defer_reg || (a->kind == SAT_OPT_ADAM && !a->tab_m) ||
+        (a->kind != SAT_OPT_SGD && !a->tab_v) || a->kind < 0 || a->kind > SAT_OPT_RMSPROP)
+        return sat_host::fail(SAT_EINVAL, "%s: null argument / bad optimiser kind", who);
+    if (m->n_shards != 1) return sat_host::fail(SAT_EINVAL, "%s: the deferred sweep is single-process (n_shards == 1)", who);
+    return SAT_OK;
+}
+
+extern "C" int sat_defer_begin(const SatModel* m, SatWork* w, const SatAdam* a, void* stream) {
+    int rc = defer_args_ok(m, a, "sat_defer_begin");
+    if (rc) return rc;
+    if (!w) return sat_host::fail(SAT_EINVAL, "sat_defer_begin: null workspace");
+    if (a->step < 1) return sat_host::fail(SAT_EINVAL, "sat_defer_begin: step must be >= 1");
+    const AdamConst c = make_const(a, true);
+    k_defer_begin<<<1, 1, 0, (cudaStream_t)stream>>>(a->defer_state, c, w->device_step ? w->step_state + SS_CONST : nullptr);
+    return sat_host::check_launch("k_defer_begin");
+}
+
+extern "C" int sat_defer_catchup(const SatModel* m, SatWork* w, const SatAdam* a, void* stream) {
+    int rc = defer_args_ok(m, a, "sat_defer_catchup");
+    if (rc) return rc;
+    if (!w || !w->uniq_rows || !w->counters) return sat_host::fail(SAT_EINVAL, "sat_defer_catchup: null workspace");
+    k_defer_catchup<<<ROWS_BLOCKS, ROWS_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v), a->row_upto,
+        w->uniq_rows, w->counters, a->defer_state, a->kind, a->defer_reg + DF_CATCH);
+    return sat_host::check_launch("k_defer_catchup");
+}
+
+extern "C" int sat_defer_sweep(const SatModel* m, const SatAdam* a, void* stream) {
+    int rc = defer_args_ok(m, a, "sat_defer_sweep");
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_defer_sweep<<<SAT_DEFER_SWEEP_BLOCKS, ROWS_THREADS, 0, s>>>(
+        reinterpret_cast<float4*>(m->tables), reinterpret_cast<float4*>(a->tab_m), reinterpret_cast<float4*>(a->tab_v), a->row_upto,
+        m->local_rows * 8, a->defer_state, a->kind, a->defer_reg + DF_SWEEP);
+    rc = sat_host::check_launch("k_defer_sweep");
+    if (rc) return rc;
+    k_defer_finalize<<<1, 256, 0, s>>>(a->defer_state, a->defer_reg, a->l2_emb, SAT_DEFER_SWEEP_BLOCKS);
+    return sat_host::check_launch("k_defer_finalize");
 }
 
 extern "C" int sat_tables_sumsq(const SatModel* m, SatWork* w, void* stream) {

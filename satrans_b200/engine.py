@@ -94,6 +94,9 @@ class Engine:
         # backward of the MetaNet/QKV block: None = follow `precision`; 'fp32' forces the CUDA-core kernel
         self.backward_precision = None
         self._peer_tables = None
+        # deferred table sweep (sat_defer_*): steps begun since the last sweep, the SatAdam of the last deferred step
+        self.defer_pending = 0
+        self._defer_adam = None
 
     def attach_dist(self, ctx):
         """Row-sharded multi-GPU mode (collective: every rank calls it).  The model must have been built with
@@ -163,6 +166,9 @@ class Engine:
         ptrs = (m._tables.data_ptr(), m._dense.data_ptr())
         if self._bound_ptrs == ptrs:
             return
+        if self.defer_pending:
+            raise _lib.SatError('the parameter buffers moved while deferred table updates were pending: call '
+                                'model.sync_tables() before moving / replacing the parameters')
         if not m._tables.is_cuda:
             raise _lib.SatError('the SATrans B200 path needs the model on a CUDA device (got %s); there is no '
                                 'CPU fallback' % m._tables.device)
@@ -211,7 +217,7 @@ class Engine:
                 (self._adam['tab_v'].device != self.device or self._adam['tab_v'].shape != m._tables.shape):
             # the parameters moved (model.cpu() / .cuda() around a checkpoint, as reference main.py does): the optimiser
             # state follows them, like torch.optim's state tensors follow param.data only if re-created -- here it is kept
-            for k in ('tab_m', 'tab_v', 'dense_m', 'dense_v'):
+            for k in ('tab_m', 'tab_v', 'dense_m', 'dense_v', 'row_upto', 'defer_state', 'defer_reg'):
                 if self._adam[k] is not None:
                     self._adam[k] = self._adam[k].to(self.device)
 
@@ -243,6 +249,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def gather(self, X):
         """(B, F, 32) field embeddings of the batch — input_from_feature_columns + cat."""
+        self.sync_tables()
         self.bind()
         kind = self._check_x(X)
         B = X.shape[0]
@@ -335,6 +342,7 @@ class Engine:
 
     def forward(self, X, y=None, training=False, dropout_p=0.1, seed=0):
         """y_pred (B,) in sample order.  With y: also leaves BCE partials / dLogit in the workspace."""
+        self.sync_tables()
         self.bind()
         kind = self._check_x(X)
         B = X.shape[0]
@@ -368,6 +376,7 @@ class Engine:
         """forward + BCE(sum) + backward.  Afterwards: w['dgrad'] = flat dense-parameter gradient,
         w['row_grad'][:n_unique] / w['uniq_rows'][:n_unique] = dBCE/d(table row) of the touched rows
         (the 2*l2*w regulariser term is added inside the optimiser), w['scalars'][0:2] = (bce, reg)."""
+        self.sync_tables()
         self.bind()
         kind = self._check_x(X)
         B = X.shape[0]
@@ -397,6 +406,7 @@ class Engine:
     def _adam_state(self, kind=0):
         """Optimiser state buffers: Adam m+v, Adagrad / RMSprop v only, SGD none."""
         if self._adam is None or self._adam.get('kind') != kind:
+            self.sync_tables()
             m = self.model
             self._graphs, self._graph_seen = {}, {}
             need_m, need_v = kind == _lib.OPT_ADAM, kind != _lib.OPT_SGD
@@ -406,8 +416,44 @@ class Engine:
                 'tab_v': torch.zeros_like(m._tables) if need_v else None,
                 'dense_m': torch.zeros_like(m._dense) if need_m else None,
                 'dense_v': torch.zeros_like(m._dense) if need_v else None,
+                'row_upto': None, 'defer_state': None, 'defer_reg': None,
             }
         return self._adam
+
+    def _defer_buffers(self, st):
+        if st['row_upto'] is None:
+            st['row_upto'] = torch.zeros(self.model._tables.shape[0], dtype=torch.uint8, device=self.device)
+            st['defer_state'] = torch.zeros(_lib.SAT_DEFER_STATE_WORDS, dtype=torch.float32, device=self.device)
+            st['defer_reg'] = torch.zeros(_lib.SAT_DEFER_REG_DOUBLES, dtype=torch.float64, device=self.device)
+        return st
+
+    def sync_tables(self):
+        """Close the current sweep epoch of the deferred table updates: every table row (and its optimiser state) is brought up to
+        date, exactly as if the every-row sweep had run after each step.  A no-op when nothing is pending.  Every engine entry
+        point that reads the tables calls it first; call it yourself before touching model._tables / the optimiser state
+        directly.  Stream-ordered on the current stream (no host synchronisation)."""
+        if self.defer_pending == 0:
+            return
+        t = self._tic('table_sweep')
+        check(lib().sat_defer_sweep(C.byref(self.desc), C.byref(self._defer_adam), self._stream()), 'sat_defer_sweep')
+        self._toc(t)
+        self.defer_pending = 0
+        self.launches += 2
+
+    def deferred_reg_total(self):
+        """Sum of the regulariser terms of every step of every closed sweep epoch so far (Python float; synchronises)."""
+        if self._adam is None or self._adam.get('defer_reg') is None:
+            return 0.0
+        return float(self._adam['defer_reg'][_lib.SAT_DEFER_MAX].item())
+
+    def deferred_reg(self):
+        """(per-step regulariser terms of the last closed sweep epoch, running total over all closed epochs) as device tensors
+        (float64); valid after sync_tables()."""
+        r = self._adam['defer_reg']
+        n = int(r[_lib.SAT_DEFER_MAX + 1].item())
+        if int(r[_lib.SAT_DEFER_MAX + 2].item()):
+            raise _lib.SatError('deferred table sweep: more than %d steps were begun without a sweep' % _lib.SAT_DEFER_MAX)
+        return r[0:n], r[_lib.SAT_DEFER_MAX]
 
     def _launch_count(self, with_update, dense_mode=True):
         """Kernels of THIS library launched by one loss_and_grads / train_step (memsets and NCCL calls not counted)."""
@@ -428,14 +474,24 @@ class Engine:
         return n
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0, _capturing=False):
+                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0, _capturing=False, defer=1):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
-        finalize kernel (read them with .item() only when needed: that synchronises)."""
+        finalize kernel (read them with .item() only when needed: that synchronises).
+
+        defer = K > 1 (single GPU, dense_mode): the every-row table sweep runs once per K steps instead of after every step
+        (include/satrans_b200.h, sat_defer_*): the rows this batch reads are brought up to date before the forward, all others
+        when the epoch closes (after K steps, or at sync_tables()) -- parameters and optimiser state are bit-identical to
+        defer=1.  scalars[1] of a deferred step is NOT its regulariser term (that needs every row): read deferred_reg() after
+        sync_tables()."""
         self.bind()
         kind = self._check_x(X)
         B = X.shape[0]
         w = self.workspace(B, True)
+        single_gpu = self.dist is None or self.dist.world == 1
+        deferred = bool(int(defer) > 1 and single_gpu and dense_mode and not overlap)
+        if not _capturing and self.defer_pending and (not deferred or self.defer_pending >= min(int(defer), _lib.SAT_DEFER_MAX)):
+            self.sync_tables()
         st = self._adam_state(opt_kind)
         if not _capturing:                       # (a captured step takes its step index from the device-side state)
             self.step_count += 1
@@ -447,6 +503,11 @@ class Engine:
         a.tab_v = st['tab_v'].data_ptr() if st['tab_v'] is not None else None
         a.dense_m = st['dense_m'].data_ptr() if st['dense_m'] is not None else None
         a.dense_v = st['dense_v'].data_ptr() if st['dense_v'] is not None else None
+        if deferred:
+            self._defer_buffers(st)
+            a.row_upto, a.defer_state, a.defer_reg = (st['row_upto'].data_ptr(), st['defer_state'].data_ptr(),
+                                                      st['defer_reg'].data_ptr())
+            self._defer_adam = a
         l, d = lib(), C.byref(self.desc)
         main = torch.cuda.current_stream()
         s = main.cuda_stream
@@ -458,12 +519,15 @@ class Engine:
             self._ev_swept = torch.cuda.Event()
             self._ev_fork = torch.cuda.Event()
             self._ev_bucket = torch.cuda.Event()
+            self._ev_caught = torch.cuda.Event()
         side = self._sweep_stream
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
         single = self.dist is None or self.dist.world == 1
         use_side = bool(single and self.side_streams)
         t = self._tic('prepare')
+        if deferred:                                   # this step's optimiser constants enter the epoch's ring
+            check(l.sat_defer_begin(d, C.byref(w.c), C.byref(a), s), 'sat_defer_begin')
         if use_side:
             # the touched-row bitmap / ranks and the token sort depend on the ids only: they run on the second stream beside
             # bucketing + encoder + weight packing + the forward, and are joined before the row-gradient reduce
@@ -471,15 +535,22 @@ class Engine:
             side.wait_event(self._ev_fork)
             with torch.cuda.stream(side):
                 self._mark_rows(X, w, kind)
+                if deferred:                           # the rows this batch reads catch up with the epoch BEFORE the forward
+                    check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_defer_catchup')
+                    self._ev_caught.record(side)
             self._prepare(X, w, kind)
             self._ev_bucket.record(main)
             side.wait_event(self._ev_bucket)           # the sort reads the scenario permutation
             with torch.cuda.stream(side):
                 self._sort_rows(X, w, kind)
             self._ev_marked.record(side)
+            if deferred:
+                main.wait_event(self._ev_caught)
         else:
             self._prepare(X, w, kind)
             self._mark_rows(X, w, kind)
+            if deferred:
+                check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(a), s), 'sat_defer_catchup')
             self._sort_rows(X, w, kind)
         self._toc(t)
         sweep_on_side = bool(dense_mode and overlap and single)
@@ -495,7 +566,7 @@ class Engine:
         t = self._tic('forward')
         self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
         self._toc(t)
-        tail_on_side = bool(single and dense_mode and not sweep_on_side and self.side_streams)
+        tail_on_side = bool(single and dense_mode and not sweep_on_side and self.side_streams and not deferred)
         t = self._tic('backward')
         self._backward_call(X, kind, w, p, sd, s, defer_finish=tail_on_side)
         self._toc(t)
@@ -534,9 +605,10 @@ class Engine:
             t = self._tic('adam_rows')
             # (lazy mode: ADAM_UNTOUCHED only clears the sweep's slice of the sum-of-squares partials)
             check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a),
-                                    _lib.ADAM_TOUCHED | (0 if dense_mode else _lib.ADAM_UNTOUCHED), s), 'sat_tables_adam')
+                                    _lib.ADAM_TOUCHED | (0 if dense_mode else _lib.ADAM_UNTOUCHED) |
+                                    (_lib.ADAM_DEFERRED if deferred else 0), s), 'sat_tables_adam')
             self._toc(t)
-            if dense_mode and not sweep_on_side:
+            if dense_mode and not sweep_on_side and not deferred:
                 t = self._tic('adam_sweep')
                 check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
                 self._toc(t)
@@ -549,11 +621,13 @@ class Engine:
         if not single:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
         if not _capturing:
-            self.launches += self._launch_count(True, dense_mode) + 1
+            self.launches += self._launch_count(True, dense_mode) + 1 + (1 if deferred else 0)    # (begin + catch-up - sweep)
+            if deferred:
+                self.defer_pending += 1
         return y_pred, w
 
     # ------------------------------------------------------------------------------------------
-    def graph_train_step(self, Xh, yh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
+    def graph_train_step(self, Xh, yh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0, defer=1):
         """One optimiser step on a host (or device-resident) batch, replayed from a CUDA graph (single-GPU mode).
 
         The whole step -- H2D copies of the batch and of the four hyper-parameters from pinned staging buffers,
@@ -565,10 +639,13 @@ class Engine:
         flags) into the pinned tensor; it is valid after a synchronisation of the current stream."""
         Xh = torch.as_tensor(Xh)
         yh = torch.as_tensor(yh).reshape(-1)
-        key = (tuple(Xh.shape), Xh.dtype, float(l2_emb), bool(dense_mode), float(dropout_p), int(opt_kind), self.precision)
+        deferred = bool(int(defer) > 1 and dense_mode)
+        key = (tuple(Xh.shape), Xh.dtype, float(l2_emb), bool(dense_mode), float(dropout_p), int(opt_kind), self.precision, deferred)
+        if self.defer_pending and (not deferred or self.defer_pending >= min(int(defer), _lib.SAT_DEFER_MAX)):
+            self.sync_tables()                     # (outside the graph: the host decides when a sweep epoch closes)
         G = self._graphs.get(key)
         if G is None:
-            G = self._capture_step(key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0)
+            G = self._capture_step(key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0, defer)
         # H2D copies of the batch: stream-ordered in front of the replay, straight from the caller's buffers when they are pinned
         # (no host-side staging pass), through the pinned staging buffers otherwise
         if Xh.is_cuda or Xh.is_pinned():
@@ -589,12 +666,14 @@ class Engine:
                                      self._stream()), 'sat_step_set')
         G['graph'].replay()
         self.step_count += 1
+        if deferred:
+            self.defer_pending += 1
         w.dev_step = self.step_count
         self.launches += G['launches']
         self.last_y_pred = G['y_pred']             # (B,) predictions of this step: a static buffer, overwritten by the next replay
         return G['w'], G['sc_pin']
 
-    def _capture_step(self, key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0):
+    def _capture_step(self, key, Xh, lr, betas, eps, opt_kind, l2_emb, dense_mode, dropout_p, seed0, defer=1):
         self.bind()
         B = Xh.shape[0]
         w = self.workspace(B, True)
@@ -619,21 +698,23 @@ class Engine:
                 check(l.sat_step_begin(C.byref(w.c), (int(seed0) - 1) & (2 ** 64 - 1), self._stream()), 'sat_step_begin')
                 G['y_pred'], _ = self.train_step(G['Xs'], G['ys'], lr=lr, betas=betas, eps=eps, l2_emb=l2_emb,
                                                  dense_mode=dense_mode, training=True, dropout_p=dropout_p, seed=0,
-                                                 opt_kind=opt_kind, _capturing=True)
+                                                 opt_kind=opt_kind, _capturing=True, defer=defer)
                 G['sc_pin'].copy_(w['scalars'][0:4], non_blocking=True)
         finally:
             w.c.device_step = 0
             self.timing = timing
         G['graph'] = graph
-        G['launches'] = self._launch_count(True, dense_mode) + 2
+        G['launches'] = self._launch_count(True, dense_mode) + 2 + (1 if key[-1] else 0)
         self._graphs[key] = G
         return G
 
     def adam_state(self):
+        self.sync_tables()
         return self._adam_state(self._adam['kind'] if self._adam else 0)
 
     def reset_optimizer(self):
         """Fresh optimiser state (moments and step counter), as a new torch.optim instance would have."""
+        self.sync_tables()
         self._adam = None
         self.step_count = 0
         self._graphs, self._graph_seen = {}, {}      # captured steps hold the old state pointers

@@ -296,3 +296,79 @@ def test_compile_string_variants_match_reference(opt, loss, precision):
             # (one near-zero element decided the other way at step 1 -- inside its budget above -- shifts every gradient of step 2
             #  a little, which RMSprop's normalisation turns into ~1e-4 moves: only the bulk can be compared with the golden end state)
             assert (err <= tight).float().mean().item() >= min((e64 <= tight).float().mean().item() - 0.05, 0.5), k
+
+
+def _run_steps(g, precision, n_steps, defer, opt_kind=0):
+    from gpu_util import model_from_golden
+    model = model_from_golden(g, precision=precision)
+    eng = model.engine
+    preds, regs = [], []
+    for step in range(n_steps):
+        k = step % 3
+        yp, w = eng.train_step(_dev(g.X(k)), _dev(g.y(k)), lr=float(g.z['lr']), l2_emb=g.cfg.l2_reg_embedding, dense_mode=True,
+                               training=True, dropout_p=0.1, seed=1234 + step, opt_kind=opt_kind, defer=defer)
+        preds.append(yp.clone())
+        if defer <= 1:
+            regs.append(w['scalars'][1].clone())
+        elif eng.defer_pending == defer or step == n_steps - 1:          # the epoch is full (or the run ends): close it
+            eng.sync_tables()
+            regs += list(eng.deferred_reg()[0].clone())
+    st = eng.adam_state()
+    torch.cuda.synchronize()
+    state = [model._tables.detach().cpu().clone(), model._dense.detach().cpu().clone()]
+    state += [st[k].cpu().clone() for k in ('tab_m', 'tab_v', 'dense_m', 'dense_v') if st[k] is not None]
+    return [p.cpu() for p in preds], torch.stack([r.double().cpu() for r in regs]), state
+
+
+@pytest.mark.parametrize('opt_kind', [0, 3])
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_deferred_table_sweep_is_bit_identical(precision, opt_kind):
+    """The every-row table update (reference meta_basemodel.py:577-593 + main.py:343) batched over sweep epochs of K steps
+    (sat_defer_*): predictions of every step, parameters and optimiser state must be BIT-identical to sweeping after every step
+    (the batches re-read rows touched one, two and three steps earlier and rows never touched before), and every step's
+    regulariser term must come out the same (different summation grouping: 1e-9 relative)."""
+    g = Golden('en_small')
+    n_steps = 11
+    p1, r1, s1 = _run_steps(g, precision, n_steps, 1, opt_kind)
+    for K in (4, 16):
+        pk, rk, sk = _run_steps(g, precision, n_steps, K, opt_kind)
+        for a, b in zip(p1, pk):
+            assert torch.equal(a, b)
+        for a, b in zip(s1, sk):
+            assert torch.equal(a, b)
+        assert rk.shape == r1.shape
+        assert torch.allclose(rk, r1, rtol=1e-6, atol=0), (rk, r1)
+
+
+def test_deferred_sweep_through_the_api():
+    """fit() with table_sweep_interval = 8 (default) against 1: same parameters bit for bit, same epoch losses; train_on_batch(
+    defer_reg=True) + sync_tables() against train_on_batch(): same state_dict; reading the state closes the epoch by itself."""
+    from gpu_util import model_from_golden
+    g = Golden('en_small')
+    X = np.concatenate([g.X(k).numpy() for k in range(3)] * 4)
+    y = np.concatenate([g.y(k).numpy() for k in range(3)] * 4)
+    hist, sds = [], []
+    for K in (1, 8):
+        torch.manual_seed(7)
+        model = model_from_golden(g)
+        model.table_sweep_interval = K
+        model.compile('adam', 'binary_crossentropy')
+        h = model.fit(X, y, batch_size=g.B // 2, epochs=2, verbose=0, shuffle=True)
+        hist.append(h.history['loss'])
+        sds.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    for k in sds[0]:
+        assert torch.equal(sds[0][k], sds[1][k]), k
+    assert np.allclose(hist[0], hist[1], rtol=1e-6, atol=0), hist
+    sds = []
+    for defer in (False, True):
+        torch.manual_seed(7)
+        model = model_from_golden(g)
+        model.table_sweep_interval = 4
+        model.compile('adam', 'binary_crossentropy')
+        for step in range(7):
+            bce, reg = model.train_on_batch(g.X(step % 3).numpy(), g.y(step % 3).numpy(), defer_reg=defer)
+            assert (reg is None) == defer
+        sds.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})      # (state_dict() syncs the tables)
+        assert model.engine.defer_pending == 0
+    for k in sds[0]:
+        assert torch.equal(sds[0][k], sds[1][k]), k
