@@ -283,26 +283,59 @@ __device__ __forceinline__ void layernorm32(float (&v)[D], const float* __restri
     }
 }
 
-// 128-byte row load/store helpers (global, 16 B aligned)
+// 128-byte row load/store helpers (global, rows are 128 B aligned).  A thread owns a whole row, so the lanes of a warp touch 32
+// different lines: with 16-byte accesses every 32-byte sector is visited by two instructions (ncu: "only 16 of the 32 bytes
+// transmitted per sector are utilized", half of the L1/L2 sector traffic of the token kernels is excess).  sm_100 has 256-bit
+// global loads / stores (LDG.E.256 / STG.E.256): one full sector per lane and instruction, half the LSU instructions.
+#ifndef SAT_LDST256
+#define SAT_LDST256 1
+#endif
+__device__ __forceinline__ void ldg256_nc(const float* p, float* v) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_cg(const float* p, float* v) {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[D]) {
+#if SAT_LDST256
+#pragma unroll
+    for (int i = 0; i < D; i += 8) ldg256_nc(p + i, &v[i]);
+#else
 #pragma unroll
     for (int i = 0; i < D; i += 4) {
         const float4 t = *reinterpret_cast<const float4*>(p + i);
         v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
     }
+#endif
 }
-// the same through L2 only (ld.global.cg): for a row this kernel has written earlier.  load_row's `const __restrict__` pointer
-// lets the compiler use the non-coherent path (LDG.CONSTANT), which may return the stale L1 copy of such a row.
+// the same through L2 only (ld.global.cg): for a row this kernel has written earlier.  load_row's non-coherent path
+// (LDG.CONSTANT) may return the stale L1 copy of such a row.
 __device__ __forceinline__ void load_row_cg(const float* p, float (&v)[D]) {
+#if SAT_LDST256
+#pragma unroll
+    for (int i = 0; i < D; i += 8) ldg256_cg(p + i, &v[i]);
+#else
 #pragma unroll
     for (int i = 0; i < D; i += 4) {
         const float4 t = __ldcg(reinterpret_cast<const float4*>(p + i));
         v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
     }
+#endif
 }
 __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[D]) {
+#if SAT_LDST256
+#pragma unroll
+    for (int i = 0; i < D; i += 8) stg256(p + i, &v[i]);
+#else
 #pragma unroll
     for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#endif
 }
 
 // 128-byte row <-> shared memory ([token][36] tiles: conflict-free 16 B accesses)

@@ -304,14 +304,20 @@ k_defer_catchup(float4* __restrict__ P, float4* __restrict__ M, float4* __restri
 }
 
 // End of the epoch: every row receives the steps it has not seen, upto = 0.
-__global__ void __launch_bounds__(ROWS_THREADS)
+#ifndef SAT_DSWEEP_U
+#define SAT_DSWEEP_U 2
+#endif
+#ifndef SAT_DSWEEP_MINB
+#define SAT_DSWEEP_MINB 1
+#endif
+__global__ void __launch_bounds__(ROWS_THREADS, SAT_DSWEEP_MINB)
 k_defer_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, uint8_t* __restrict__ upto,
               long long n_vec, const float* __restrict__ st, int kind, double* __restrict__ reg_sweep) {
     __shared__ float s_sq[DEFER_MAX][ROWS_THREADS];
 #pragma unroll
     for (int j = 0; j < DEFER_MAX; ++j) s_sq[j][threadIdx.x] = 0.f;
     const int n = min(reinterpret_cast<const int*>(st)[0], DEFER_MAX);
-    constexpr int U = 2;
+    constexpr int U = SAT_DSWEEP_U;
     const long long stride = (long long)gridDim.x * ROWS_THREADS;
     const int lane = threadIdx.x & 31;
     // (warp-uniform trip count: n_vec is a multiple of 8, the warps' first elements of 32)
