@@ -127,6 +127,75 @@ def _acc(y_true, y_score):
     return float(np.mean(np.asarray(y_true).ravel() == np.where(np.asarray(y_score).ravel() > 0.5, 1, 0)))
 
 
+class _BatchFeeder(object):
+    """fit()'s host -> device batch pipeline: the training matrix and labels stay in pinned host memory; batch i + 1 is copied
+    (after a host-side gather into pinned staging when shuffling) on a copy stream while step i runs."""
+
+    def __init__(self, X, y, batch_size, dev):
+        self.Xh = torch.from_numpy(np.ascontiguousarray(X))
+        self.yh = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        if not self.Xh.is_pinned():
+            self.Xh = self.Xh.pin_memory()
+        if not self.yh.is_pinned():
+            self.yh = self.yh.pin_memory()
+        self.n, self.B, self.dev = len(self.Xh), int(batch_size), dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.Xs = [torch.empty((self.B, self.Xh.shape[1]), dtype=self.Xh.dtype, device=dev) for _ in range(2)]
+        self.ys = [torch.empty(self.B, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.x_pin = self.y_pin = None
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # batch landed in buffer k
+        self.free = [torch.cuda.Event() for _ in range(2)]       # the step that read buffer k has been enqueued and finished with it
+        self.copied = [torch.cuda.Event() for _ in range(2)]     # pinned staging k may be overwritten by the host
+        self.bytes_h2d = 0
+
+    def start_epoch(self, order_host):
+        self.order = order_host
+        if order_host is not None and self.x_pin is None:
+            self.x_pin = [torch.empty((self.B, self.Xh.shape[1]), dtype=self.Xh.dtype).pin_memory() for _ in range(2)]
+            self.y_pin = [torch.empty(self.B, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.i_next, self.i_cur = 0, 0
+        self._issue()                                            # batch 0
+
+    def _issue(self):
+        """Enqueue the copy of batch i_next (if any) on the copy stream."""
+        i = self.i_next
+        s0 = i * self.B
+        if s0 >= self.n:
+            return
+        s1 = min(s0 + self.B, self.n)
+        k = i & 1
+        if self.order is not None:
+            if i >= 2:
+                self.copied[k].synchronize()                     # (two steps old: long done)
+            idx = self.order[s0:s1]
+            torch.index_select(self.Xh, 0, idx, out=self.x_pin[k][:s1 - s0])
+            torch.index_select(self.yh, 0, idx, out=self.y_pin[k][:s1 - s0])
+            xs, ys_ = self.x_pin[k][:s1 - s0], self.y_pin[k][:s1 - s0]
+        else:
+            xs, ys_ = self.Xh[s0:s1], self.yh[s0:s1]
+        with torch.cuda.stream(self.copy_stream):
+            if i >= 2:
+                self.copy_stream.wait_event(self.free[k])
+            self.Xs[k][:s1 - s0].copy_(xs, non_blocking=True)
+            self.ys[k][:s1 - s0].copy_(ys_, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+            self.copied[k].record(self.copy_stream)
+        self.bytes_h2d += xs.numel() * xs.element_size() + ys_.numel() * 4
+        self.i_next = i + 1
+
+    def next_batch(self):
+        i = self.i_cur
+        k = i & 1
+        n = min(self.B, self.n - i * self.B)
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        self._issue()                                            # batch i + 1 crosses PCIe while step i runs
+        return self.Xs[k][:n], self.ys[k][:n]
+
+    def batch_consumed(self):
+        self.free[self.i_cur & 1].record(torch.cuda.current_stream())
+        self.i_cur += 1
+
+
 class BaseModel(nn.Module):
     def __init__(self, linear_feature_columns, dnn_feature_columns, l2_reg_linear=1e-5, l2_reg_embedding=1e-5,
                  init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None,
@@ -247,6 +316,8 @@ class BaseModel(nn.Module):
         return embs, dense_vals
 
     # ---- row-sharded tables (multi-GPU) ---------------------------------------------------------------
+    stream_host_batches = None   # fit(): None = keep the training matrix in HBM unless it exceeds 256 MB; True / False force it
+
     # ---- deferred table sweep (engine.sync_tables): anything that reads or moves the parameters closes the epoch first --------
     table_sweep_interval = 8     # fit(): the every-row table update runs once per this many steps (1 = after every step);
                                  # parameters and optimiser state are bit-identical either way (include/satrans_b200.h, sat_defer_*)
@@ -490,10 +561,22 @@ class BaseModel(nn.Module):
         callbacks.on_train_begin()
         self.stop_training = False
 
-        # the whole training matrix lives in HBM for the epoch; labels too
-        Xd = torch.as_tensor(np.ascontiguousarray(X)).to(dev)
-        yd = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)).to(dev)
         want_metrics = verbose > 0 and len(self.metrics) > 0
+        # Small training sets live in HBM for the whole fit().  Large ones (or stream_host_batches = True) stay in pinned host
+        # memory, like the reference's DataLoader over CPU tensors with its per-batch .to(device) (meta_basemodel.py:311-313): every
+        # step's batch crosses PCIe on a copy stream ONE STEP AHEAD of the step that consumes it (two device buffers), so the copy
+        # rides under the previous step's kernels and the host never waits for the device inside an epoch.
+        stream_batches = self.stream_host_batches
+        if stream_batches is None:
+            stream_batches = X.nbytes > (256 << 20)
+        feeder = None
+        if stream_batches:
+            feeder = _BatchFeeder(X, y, batch_size, dev)
+            Xd = None
+            yd = feeder.yh.to(dev) if want_metrics else None
+        else:
+            Xd = torch.as_tensor(np.ascontiguousarray(X)).to(dev)
+            yd = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)).to(dev)
         if verbose > 0:
             print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(
                 sample_num, len(val_y), steps_per_epoch))
@@ -512,13 +595,18 @@ class BaseModel(nn.Module):
             if defer > 1:
                 eng.sync_tables()
                 reg0 = eng.deferred_reg_total()
-            order = torch.randperm(sample_num, generator=gen).to(dev) if shuffle else None
+            order_host = torch.randperm(sample_num, generator=gen) if shuffle else None
+            order = order_host.to(dev) if (shuffle and (feeder is None or want_metrics)) else None
             preds = torch.empty(sample_num, dtype=torch.float32, device=dev) if want_metrics else None
             losses = torch.zeros((steps_per_epoch, 2), dtype=torch.float32, device=dev)
             step_num = 0
+            if feeder is not None:
+                feeder.start_epoch(order_host)
             for s0 in range(0, sample_num, batch_size):
                 s1 = min(s0 + batch_size, sample_num)
-                if order is not None:
+                if feeder is not None:
+                    xb, yb = feeder.next_batch()
+                elif order is not None:
                     idx = order[s0:s1]
                     xb, yb = Xd.index_select(0, idx).contiguous(), yd.index_select(0, idx).contiguous()
                 else:
@@ -537,6 +625,8 @@ class BaseModel(nn.Module):
                                                training=True, dropout_p=self.dropout_rate,
                                                seed=(seed0 + eng.step_count) & (2 ** 63 - 1), defer=defer)
                 losses[step_num, 0:(1 if defer > 1 else 2)].copy_(w['scalars'][0:(1 if defer > 1 else 2)])
+                if feeder is not None:
+                    feeder.batch_consumed()
                 if want_metrics:
                     preds[s0:s1] = y_pred
                 step_num += 1

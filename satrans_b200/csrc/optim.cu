@@ -305,10 +305,10 @@ k_defer_catchup(float4* __restrict__ P, float4* __restrict__ M, float4* __restri
 
 // End of the epoch: every row receives the steps it has not seen, upto = 0.
 #ifndef SAT_DSWEEP_U
-#define SAT_DSWEEP_U 2
+#define SAT_DSWEEP_U 1
 #endif
 #ifndef SAT_DSWEEP_MINB
-#define SAT_DSWEEP_MINB 1
+#define SAT_DSWEEP_MINB 6
 #endif
 __global__ void __launch_bounds__(ROWS_THREADS, SAT_DSWEEP_MINB)
 k_defer_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, uint8_t* __restrict__ upto,

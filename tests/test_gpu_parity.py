@@ -372,3 +372,26 @@ def test_deferred_sweep_through_the_api():
         assert model.engine.defer_pending == 0
     for k in sds[0]:
         assert torch.equal(sds[0][k], sds[1][k]), k
+
+
+@pytest.mark.parametrize('shuffle', [False, True])
+def test_fit_streaming_host_batches_equals_resident(shuffle):
+    """fit() with the training matrix left in pinned host memory and each batch copied one step ahead on a copy stream
+    (stream_host_batches, the reference's DataLoader + per-batch .to(device), meta_basemodel.py:311-313) == fit() with the matrix
+    resident in HBM: same parameters bit for bit, same epoch losses (ragged last batch included)."""
+    from gpu_util import model_from_golden
+    g = Golden('en_small')
+    X = np.concatenate([g.X(k).numpy() for k in range(3)] * 3)[:-7]
+    y = np.concatenate([g.y(k).numpy() for k in range(3)] * 3)[:-7]
+    hist, sds = [], []
+    for stream in (False, True):
+        torch.manual_seed(11)
+        model = model_from_golden(g)
+        model.stream_host_batches = stream
+        model.compile('adam', 'binary_crossentropy')
+        h = model.fit(X, y, batch_size=64, epochs=2, verbose=0, shuffle=shuffle)
+        hist.append(h.history['loss'])
+        sds.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    for k in sds[0]:
+        assert torch.equal(sds[0][k], sds[1][k]), k
+    assert hist[0] == hist[1], hist
