@@ -351,6 +351,7 @@ class BaseModel(nn.Module):
         """Full [total_rows, d] table on every rank (all-gather of the shards) — e.g. to write a reference-
         compatible checkpoint from a sharded run."""
         rank, world = self._shard
+        self.sync_tables()
         if world == 1:
             return self._tables.detach().clone()
         import torch.distributed as tdist
@@ -698,7 +699,7 @@ class BaseModel(nn.Module):
         defer_reg=True: the every-row table update runs once per `table_sweep_interval` steps, like inside `fit` (parameters and
         optimiser state bit-identical); the step's regulariser term is then not known yet and (bce_sum, None) is returned --
         `sync_tables()` closes the sweep epoch, `engine.deferred_reg()` has the per-step terms afterwards."""
-        defer = int(self.table_sweep_interval) if (defer_reg and self.dense_table_updates and self.engine.dist is None) else 1
+        defer = int(self.table_sweep_interval) if (defer_reg and self.dense_table_updates) else 1
         if torch.is_tensor(x) and x.dtype in (torch.float32, torch.int32, torch.int64):
             X = x                                           # (pinned) host or device tensor in a kernel-ready dtype: no host pass
         else:

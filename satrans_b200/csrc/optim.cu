@@ -490,7 +490,6 @@ static int defer_args_ok(const SatModel* m, const SatAdam* a, const char* who) {
     if (!m || !a || !a->row_upto || !a->defer_state || !a->defer_reg || (a->kind == SAT_OPT_ADAM && !a->tab_m) ||
         (a->kind != SAT_OPT_SGD && !a->tab_v) || a->kind < 0 || a->kind > SAT_OPT_RMSPROP)
         return sat_host::fail(SAT_EINVAL, "%s: null argument / bad optimiser kind", who);
-    if (m->n_shards != 1) return sat_host::fail(SAT_EINVAL, "%s: the deferred sweep is single-process (n_shards == 1)", who);
     return SAT_OK;
 }
 

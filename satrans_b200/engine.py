@@ -314,17 +314,23 @@ class Engine:
         check(lib().sat_peer_barrier(C.byref(self.desc), C.byref(w.c), self._stream() if stream is None else stream),
               'sat_peer_barrier')
 
-    def _mark_rows(self, X, w, kind):
-        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomicOr) | barrier | rank | barrier."""
+    def _mark_rows(self, X, w, kind, catchup=None):
+        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomicOr) | barrier | rank (| catch-up) | barrier.
+        catchup: the SatAdam of a deferred-sweep step -- this shard's rows that ANY rank's batch reads are brought up to date
+        before the last barrier, i.e. before a peer's forward can gather them."""
         l, s, d = lib(), self._stream(), C.byref(self.desc)
         if self.dist is None or self.dist.world == 1:
             check(l.sat_rows_mark_and_rank(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark_and_rank')
+            if catchup is not None:
+                check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(catchup), s), 'sat_defer_catchup')
             return
         check(l.sat_rows_clear(d, C.byref(w.c), s), 'sat_rows_clear')
         self._barrier(w)
         check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
         self._barrier(w)
         check(l.sat_rows_rank(d, C.byref(w.c), s), 'sat_rows_rank')
+        if catchup is not None:
+            check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(catchup), s), 'sat_defer_catchup')
         self._barrier(w)
 
     def _sort_rows(self, X, w, kind):
@@ -437,6 +443,10 @@ class Engine:
         t = self._tic('table_sweep')
         check(lib().sat_defer_sweep(C.byref(self.desc), C.byref(self._defer_adam), self._stream()), 'sat_defer_sweep')
         self._toc(t)
+        if self.dist is not None and self.dist.world > 1:
+            # row-sharded: every rank closes its shard's epoch at the same point of the (SPMD) call sequence; no peer may gather
+            # a row before its owner's sweep has finished
+            self._barrier(self._work[True])
         self.defer_pending = 0
         self.launches += 2
 
@@ -444,7 +454,10 @@ class Engine:
         """Sum of the regulariser terms of every step of every closed sweep epoch so far (Python float; synchronises)."""
         if self._adam is None or self._adam.get('defer_reg') is None:
             return 0.0
-        return float(self._adam['defer_reg'][_lib.SAT_DEFER_MAX].item())
+        t = self._adam['defer_reg'][_lib.SAT_DEFER_MAX].clone()
+        if self.dist is not None and self.dist.world > 1:      # every shard holds the terms of its own rows (collective)
+            self.dist.all_reduce_sum(t)
+        return float(t.item())
 
     def deferred_reg(self):
         """(per-step regulariser terms of the last closed sweep epoch, running total over all closed epochs) as device tensors
@@ -488,8 +501,7 @@ class Engine:
         kind = self._check_x(X)
         B = X.shape[0]
         w = self.workspace(B, True)
-        single_gpu = self.dist is None or self.dist.world == 1
-        deferred = bool(int(defer) > 1 and single_gpu and dense_mode and not overlap)
+        deferred = bool(int(defer) > 1 and dense_mode and not overlap)
         if not _capturing and self.defer_pending and (not deferred or self.defer_pending >= min(int(defer), _lib.SAT_DEFER_MAX)):
             self.sync_tables()
         st = self._adam_state(opt_kind)
@@ -534,9 +546,8 @@ class Engine:
             self._ev_fork.record(main)
             side.wait_event(self._ev_fork)
             with torch.cuda.stream(side):
-                self._mark_rows(X, w, kind)
-                if deferred:                           # the rows this batch reads catch up with the epoch BEFORE the forward
-                    check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(a), side.cuda_stream), 'sat_defer_catchup')
+                self._mark_rows(X, w, kind, a if deferred else None)   # (the rows this batch reads catch up BEFORE the forward)
+                if deferred:
                     self._ev_caught.record(side)
             self._prepare(X, w, kind)
             self._ev_bucket.record(main)
@@ -548,9 +559,7 @@ class Engine:
                 main.wait_event(self._ev_caught)
         else:
             self._prepare(X, w, kind)
-            self._mark_rows(X, w, kind)
-            if deferred:
-                check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(a), s), 'sat_defer_catchup')
+            self._mark_rows(X, w, kind, a if deferred else None)
             self._sort_rows(X, w, kind)
         self._toc(t)
         sweep_on_side = bool(dense_mode and overlap and single)

@@ -109,6 +109,22 @@ def main():
         except AssertionError as e:
             ok = False
             print('[rank %d] %s: Adam steps FAIL %s' % (rank, name, e), flush=True)
+        # ---- deferred table sweep, row-sharded: 6 train-mode steps with the every-row update batched over epochs of 4 steps
+        #      == the same steps with a sweep after each, bit for bit (tables of every shard, dense parameters) --------------
+        runs = []
+        for defer in (1, 4):
+            model.load_full_tables(table0)
+            model.load_state_dict({k: v for k, v in g.full_state_dict().items() if not k.startswith('embedding_dict.')},
+                                  strict=False)
+            eng.reset_optimizer()
+            for step in range(6):
+                Xs, ys = g.X(step % 3)[lo:hi].cuda().contiguous(), g.y(step % 3)[lo:hi].cuda().contiguous()
+                eng.train_step(Xs, ys, lr=lr, l2_emb=l2, dense_mode=True, training=True, dropout_p=0.1, seed=99 + step,
+                               defer=defer)
+            runs.append((model.gather_tables().cpu(), model._dense.detach().cpu().clone()))     # (gather_tables syncs)
+        same = torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+        ok &= same
+        print('[rank %d] %s: deferred sweep (sharded) bit-identical  %s' % (rank, name, 'OK' if same else 'FAIL'), flush=True)
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
