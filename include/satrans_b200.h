@@ -144,8 +144,11 @@ typedef struct SatWork {
     double* loss_part;    /* [max_tiles] per-tile BCE partial sums                          */
     float* dgrad;         /* flat dense-parameter gradient buffer (n_dense_params)          */
     /* touched-row bookkeeping for the embedding update */
-    uint32_t* bitmap;     /* [ceil(total_rows/32)] one bit per table row                    */
-    int32_t* word_rank;   /* [ceil(total_rows/32)] exclusive prefix popcount                */
+    uint32_t* bitmap;     /* [ceil(local_rows/32)] one bit per table row; row-sharded: (n_shards + 1) regions of
+                             sat_stage_words() words: the shard's final bitmap, then this process' marks per destination shard */
+    int32_t* word_rank;   /* [ceil(local_rows/32)] exclusive prefix popcount; row-sharded: (n_shards + 1) regions like the
+                             bitmap: the own ranks, then mirrors of every shard's ranks (and, in the bitmap's regions, of every
+                             shard's final bitmap) pulled with bulk NVLink loads before the token sort                  */
     int32_t* block_sums;  /* [ceil(words/1024)+1]                                           */
     int32_t* uniq_rows;   /* [cap_B*F] sorted unique touched rows                           */
     float* row_grad;      /* [cap_B*F][32] accumulated dE per unique touched row            */
@@ -170,6 +173,14 @@ typedef struct SatWork {
     float* step_state;    /* [32] words, see sat_step_begin: [0..1] u64 seed, [2] i32 step, [4..7] f32 lr, beta1, beta2, eps (the
                              caller copies them in, e.g. from pinned memory inside the graph), [8..15] derived constants  */
 } SatWork;
+
+/* words per region of the row-sharded SatWork.bitmap: the largest shard's rows / 32, the same number on every process */
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline int64_t sat_stage_words(const SatModel* m) {
+    return ((((m->total_rows + m->n_shards - 1) / m->n_shards + 31) / 32) + 3) & ~(int64_t)3;      /* (multiple of 16 bytes) */
+}
 
 /* optimiser kinds (torch.optim defaults; the strings BaseModel._get_optim accepts, reference meta_basemodel.py:612-625) */
 #define SAT_OPT_ADAM 0      /* m, v */

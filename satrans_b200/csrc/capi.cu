@@ -64,8 +64,9 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = training ? 3 * tok * SAT_D * 4 : 0;          // dqkv
     sz[i++] = max_tiles2 * 8;                              // loss_part (sized for the finer tiling)
     sz[i++] = training ? m->n_dense_params * 4 : 0;        // dgrad
-    sz[i++] = training ? words * 4 : 0;                    // bitmap
-    sz[i++] = training ? words * 4 : 0;                    // word_rank
+    // bitmap; row-sharded: [final bitmap of the own shard | staging region per destination shard], sat_stage_words() words each
+    sz[i++] = training ? (sharded ? (int64_t)(m->n_shards + 1) * sat_stage_words(m) : words) * 4 : 0;
+    sz[i++] = training ? (sharded ? (int64_t)(m->n_shards + 1) * sat_stage_words(m) : words) * 4 : 0;   // word_rank (same regions)
     sz[i++] = training ? ((words + 1023) / 1024 + 1) * 4 : 0;   // block_sums
     sz[i++] = training ? touched_cap * 4 : 0;              // uniq_rows
     sz[i++] = training ? touched_cap * SAT_D * 4 : 0;      // row_grad

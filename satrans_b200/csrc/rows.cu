@@ -40,12 +40,32 @@ k_sort_keys(const SatModel m, const void* __restrict__ x, int ld, int B, const i
         int owner = 0;
         long long lrow = row;
         if (m.n_shards > 1) { owner = (int)(row % m.n_shards); lrow = row / m.n_shards; }
-        // volatile loads: the owner's bitmap / ranks may live in a peer GPU's memory
-        const uint32_t wbits = *reinterpret_cast<const volatile uint32_t*>(m.shard_bitmap[owner] + (lrow >> 5));
-        const int slot = *reinterpret_cast<const volatile int32_t*>(m.shard_word_rank[owner] + (lrow >> 5)) +
-                         __popc(wbits & ((1u << (lrow & 31)) - 1u));
+        // row-sharded: the owner's final bitmap / ranks were mirrored into this process' regions 1 + owner by k_rows_pull
+        const long long off = m.n_shards > 1 ? (1 + owner) * sat_stage_words(&m) : 0;
+        const uint32_t wbits = m.shard_bitmap[m.shard_rank][off + (lrow >> 5)];
+        const int slot = m.shard_word_rank[m.shard_rank][off + (lrow >> 5)] + __popc(wbits & ((1u << (lrow & 31)) - 1u));
         keys[t] = ((uint32_t)owner << slot_bits) | (uint32_t)slot;
         vals[t] = (int32_t)t;
+    }
+}
+
+// Row-sharded: every shard's final touched-row bitmap and word ranks -> this process' mirror regions, with coalesced 16-byte
+// NVLink loads (volatile: peer memory).  One remote 4-byte load pair per TOKEN in k_sort_keys cost 1.5 ms of a 15 ms step at
+// B = 65,536 on two GPUs; the bulk pull moves total_rows / 4 bytes per step.
+__global__ void __launch_bounds__(256) k_rows_pull(const SatModel m) {
+    const long long sw = sat_stage_words(&m), n4 = sw / 4;
+    for (int d = 0; d < m.n_shards; ++d) {
+        const uint4* sb = reinterpret_cast<const uint4*>(m.shard_bitmap[d]);
+        const uint4* sr = reinterpret_cast<const uint4*>(m.shard_word_rank[d]);
+        uint4* db = reinterpret_cast<uint4*>(m.shard_bitmap[m.shard_rank] + (1 + d) * sw);
+        uint4* dr = reinterpret_cast<uint4*>(m.shard_word_rank[m.shard_rank] + (1 + d) * sw);
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+            uint4 a, b;
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(sb + i));
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(sr + i));
+            db[i] = a;
+            dr[i] = b;
+        }
     }
 }
 
@@ -359,6 +379,11 @@ extern "C" int sat_rows_sort(const SatModel* m, const void* x, int32_t id_kind, 
     if (slot_bits + bits_for(m->n_shards) > 32) return sat_host::fail(SAT_EINVAL, "sat_rows_sort: key does not fit 32 bits");
     int blocks = (int)((N + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (m->n_shards > 1) {          // (after the barrier that follows sat_rows_rank on every process)
+        k_rows_pull<<<148 * 4, 256, 0, s>>>(*m);
+        int rc = sat_host::check_launch("k_rows_pull");
+        if (rc) return rc;
+    }
     switch (id_kind) {
         case SAT_IDS_F32: k_sort_keys<SAT_IDS_F32><<<blocks, 256, 0, s>>>(*m, x, ld, w->B, w->perm, slot_bits, w->sort_keys, w->sort_vals); break;
         case SAT_IDS_I32: k_sort_keys<SAT_IDS_I32><<<blocks, 256, 0, s>>>(*m, x, ld, w->B, w->perm, slot_bits, w->sort_keys, w->sort_vals); break;

@@ -315,7 +315,7 @@ class Engine:
               'sat_peer_barrier')
 
     def _mark_rows(self, X, w, kind, catchup=None):
-        """Touched-row bitmap + ranks.  Sharded: clear | barrier | mark (remote atomicOr) | barrier | rank (| catch-up) | barrier.
+        """Touched-row bitmap + ranks.  Sharded: clear | mark (local staging regions) | barrier | merge + rank (| catch-up) | barrier.
         catchup: the SatAdam of a deferred-sweep step -- this shard's rows that ANY rank's batch reads are brought up to date
         before the last barrier, i.e. before a peer's forward can gather them."""
         l, s, d = lib(), self._stream(), C.byref(self.desc)
@@ -324,8 +324,9 @@ class Engine:
             if catchup is not None:
                 check(l.sat_defer_catchup(d, C.byref(w.c), C.byref(catchup), s), 'sat_defer_catchup')
             return
+        # (no barrier between clear and mark: the marks are local; the peers finished reading this process' staging regions
+        #  before the previous step's last barrier)
         check(l.sat_rows_clear(d, C.byref(w.c), s), 'sat_rows_clear')
-        self._barrier(w)
         check(l.sat_rows_mark(d, X.data_ptr(), kind, X.shape[1], C.byref(w.c), s), 'sat_rows_mark')
         self._barrier(w)
         check(l.sat_rows_rank(d, C.byref(w.c), s), 'sat_rows_rank')
@@ -536,7 +537,8 @@ class Engine:
         sd = int(seed) & (2 ** 64 - 1)
         p = float(dropout_p if training else 0.0)
         single = self.dist is None or self.dist.world == 1
-        use_side = bool(single and self.side_streams)
+        use_side = bool(self.side_streams)
+        join_before_forward = deferred or not single     # the forward must not gather rows before the catch-up / the peers' barrier
         t = self._tic('prepare')
         if deferred:                                   # this step's optimiser constants enter the epoch's ring
             check(l.sat_defer_begin(d, C.byref(w.c), C.byref(a), s), 'sat_defer_begin')
@@ -547,7 +549,7 @@ class Engine:
             side.wait_event(self._ev_fork)
             with torch.cuda.stream(side):
                 self._mark_rows(X, w, kind, a if deferred else None)   # (the rows this batch reads catch up BEFORE the forward)
-                if deferred:
+                if join_before_forward:
                     self._ev_caught.record(side)
             self._prepare(X, w, kind)
             self._ev_bucket.record(main)
@@ -555,7 +557,7 @@ class Engine:
             with torch.cuda.stream(side):
                 self._sort_rows(X, w, kind)
             self._ev_marked.record(side)
-            if deferred:
+            if join_before_forward:
                 main.wait_event(self._ev_caught)
         else:
             self._prepare(X, w, kind)
