@@ -11,6 +11,8 @@
 // row of SatWork.gpart and k_dense_reduce adds the rows in CTA order, so the gradients are bit-reproducible.
 // Attention uses the FlashAttention identity  sum_j P_ij dP_ij = dR_i . R_i  so no (F x F) tensor is
 // stored; probabilities are recomputed from Q'/K' for the query-role pass and again for the key-role pass.
+#include <stdlib.h>
+
 #include "bwd_common.cuh"
 
 namespace sat {
@@ -357,6 +359,13 @@ __global__ void __launch_bounds__(256) k_dense_reduce(const RedArgs a) {
 using namespace sat;
 
 int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
+int sat_launch_bwd_meta_tc_wg(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
+// SAT_WGRAD_TC=1: weight gradients on the tensor core too (backward_tc_wg.cu; measured slower, see there)
+static bool wgrad_on_tensor_core() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SAT_WGRAD_TC"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
 extern "C" int sat_backward_finish(const SatModel* m, SatWork* w, int32_t passes, void* stream);
 
 // passes = 0: CUDA-core k_bwd_meta; 1 / 3: tensor-core k_bwd_meta_tc (TF32 / 3xTF32), needs sat_pack_weights first
@@ -416,7 +425,8 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
         } else {
             BwdArgs a2 = a;
             a2.tiles = w->tiles2;
-            rc = sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, grid_a, passes, s);
+            rc = wgrad_on_tensor_core() ? sat_launch_bwd_meta_tc_wg(a2, w->wpack, n_keys, grid_a, passes, s)
+                                        : sat_launch_bwd_meta_tc(a2, w->wpack, n_keys, grid_a, passes, s);
         }
         if (rc) return rc;
     }

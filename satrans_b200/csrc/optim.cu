@@ -56,40 +56,48 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, con
 // (every-step k_adam_sweep and the deferred k_defer_*), so that deferring is bit-neutral.  The multi-step sweep is bound by the
 // SFU (MUFU issues at a quarter of the FMA rate), so the arithmetic is trimmed to 6 MUFU + ~40 FMA-pipe instructions per float4
 // instead of 12 + ~130 for IEEE sqrt and two IEEE divisions per element: approximate square roots (sqrt.approx.ftz, <= 2 ulp),
-// the bias correction as a multiplication by the reciprocal (computed once per step), and ONE reciprocal per PAIR of
-// denominators (1/a = b / (a b); every denominator is >= eps, so the product is far from underflow for eps >= 1e-18).  The deviation from torch's op order is a few ulp of an update that is itself <= lr per step.
+// the bias correction as a multiplication by the reciprocal (computed once per step), ONE reciprocal per PAIR of denominators,
+// and two channels per FMA-pipe instruction (FFMA2 / FMUL2 / FADD2).  The deviation from torch's op order is a few ulp of an update that is itself <= lr per step.
 __device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// 1/a, 1/b, 1/c, 1/d from two reciprocals (of the pair products: >= eps^2, safe from underflow for eps >= 1e-18)
-__device__ __forceinline__ float4 rcp4(float a, float b, float c, float d) {
-    const float rab = rcp_approx(__fmul_rn(a, b)), rcd = rcp_approx(__fmul_rn(c, d));
-    return make_float4(__fmul_rn(rab, b), __fmul_rn(rab, a), __fmul_rn(rcd, d), __fmul_rn(rcd, c));
-}
+// Packed fp32 arithmetic (add2 / mul2 / fma2v of common.cuh: two IEEE operations per instruction, written as PTX so that the
+// compiler can neither contract nor re-associate them -- it decides contraction per call site, and the every-step and the
+// deferred sweep must round identically).  The two reciprocals serve the pair products of the four denominators
+// (1/a = b / (a b); every denominator is >= eps, so the product is far from underflow for eps >= 1e-18).
 __device__ __forceinline__ void adam4_untouched(float4& p, float4& m, float4& v, const AdamConst& c, float inv_bc2_sqrt) {
-    // (__fmul_rn / __fsub_rn: never contracted into an FMA with their consumers -- the compiler decides contraction per call
-    //  site, and the every-step and the deferred sweep must round identically)
-    const float4 g = make_float4(__fmul_rn(c.two_l2, p.x), __fmul_rn(c.two_l2, p.y), __fmul_rn(c.two_l2, p.z), __fmul_rn(c.two_l2, p.w));
+    float4 g;
+    mul2(g.x, g.y, p.x, p.y, c.two_l2, c.two_l2); mul2(g.z, g.w, p.z, p.w, c.two_l2, c.two_l2);
     if (c.kind == SAT_OPT_SGD) {
-        p.x = fmaf(-c.lr, g.x, p.x); p.y = fmaf(-c.lr, g.y, p.y); p.z = fmaf(-c.lr, g.z, p.z); p.w = fmaf(-c.lr, g.w, p.w);
+        fma2v(p.x, p.y, g.x, g.y, -c.lr, -c.lr); fma2v(p.z, p.w, g.z, g.w, -c.lr, -c.lr);
         return;
     }
     float4 num = g;
     float scale = c.lr, dscale = 1.f;
-    if (c.kind == SAT_OPT_ADAM) {
-        m.x = fmaf(__fsub_rn(g.x, m.x), c.one_minus_b1, m.x); m.y = fmaf(__fsub_rn(g.y, m.y), c.one_minus_b1, m.y);
-        m.z = fmaf(__fsub_rn(g.z, m.z), c.one_minus_b1, m.z); m.w = fmaf(__fsub_rn(g.w, m.w), c.one_minus_b1, m.w);
+    if (c.kind == SAT_OPT_ADAM) {            // m += (g - m) * (1 - b1)
+        float4 t;
+        add2(t.x, t.y, g.x, g.y, -m.x, -m.y); add2(t.z, t.w, g.z, g.w, -m.z, -m.w);
+        fma2v(m.x, m.y, t.x, t.y, c.one_minus_b1, c.one_minus_b1); fma2v(m.z, m.w, t.z, t.w, c.one_minus_b1, c.one_minus_b1);
         num = m; scale = c.step_size; dscale = inv_bc2_sqrt;
     }
-    if (c.kind == SAT_OPT_ADAGRAD) {
-        v.x = fmaf(g.x, g.x, v.x); v.y = fmaf(g.y, g.y, v.y); v.z = fmaf(g.z, g.z, v.z); v.w = fmaf(g.w, g.w, v.w);
-    } else {            // Adam, RMSprop (alpha in b2)
-        v.x = fmaf(__fmul_rn(c.one_minus_b2, g.x), g.x, __fmul_rn(v.x, c.b2)); v.y = fmaf(__fmul_rn(c.one_minus_b2, g.y), g.y, __fmul_rn(v.y, c.b2));
-        v.z = fmaf(__fmul_rn(c.one_minus_b2, g.z), g.z, __fmul_rn(v.z, c.b2)); v.w = fmaf(__fmul_rn(c.one_minus_b2, g.w), g.w, __fmul_rn(v.w, c.b2));
+    if (c.kind == SAT_OPT_ADAGRAD) {         // v += g * g
+        fma2v(v.x, v.y, g.x, g.y, g.x, g.y); fma2v(v.z, v.w, g.z, g.w, g.z, g.w);
+    } else {                                 // Adam, RMSprop (alpha in b2): v = v * b2 + ((1 - b2) * g) * g
+        float4 a;
+        mul2(a.x, a.y, g.x, g.y, c.one_minus_b2, c.one_minus_b2); mul2(a.z, a.w, g.z, g.w, c.one_minus_b2, c.one_minus_b2);
+        mul2(v.x, v.y, v.x, v.y, c.b2, c.b2); mul2(v.z, v.w, v.z, v.w, c.b2, c.b2);
+        fma2v(v.x, v.y, a.x, a.y, g.x, g.y); fma2v(v.z, v.w, a.z, a.w, g.z, g.w);
     }
-    const float4 r = rcp4(fmaf(sqrt_approx(v.x), dscale, c.eps), fmaf(sqrt_approx(v.y), dscale, c.eps),
-                          fmaf(sqrt_approx(v.z), dscale, c.eps), fmaf(sqrt_approx(v.w), dscale, c.eps));
-    p.x = fmaf(-scale, __fmul_rn(num.x, r.x), p.x); p.y = fmaf(-scale, __fmul_rn(num.y, r.y), p.y);
-    p.z = fmaf(-scale, __fmul_rn(num.z, r.z), p.z); p.w = fmaf(-scale, __fmul_rn(num.w, r.w), p.w);
+    // denominators sqrt(v) * dscale + eps, their reciprocals from the two pair products
+    float4 d = make_float4(c.eps, c.eps, c.eps, c.eps);
+    fma2v(d.x, d.y, sqrt_approx(v.x), sqrt_approx(v.y), dscale, dscale);
+    fma2v(d.z, d.w, sqrt_approx(v.z), sqrt_approx(v.w), dscale, dscale);
+    float ab, cd;
+    mul2(ab, cd, d.x, d.z, d.y, d.w);
+    const float rab = rcp_approx(ab), rcd = rcp_approx(cd);
+    float4 r;
+    mul2(r.x, r.y, rab, rab, d.y, d.x); mul2(r.z, r.w, rcd, rcd, d.w, d.z);
+    mul2(r.x, r.y, r.x, r.y, num.x, num.y); mul2(r.z, r.w, r.z, r.w, num.z, num.w);
+    fma2v(p.x, p.y, r.x, r.y, -scale, -scale); fma2v(p.z, p.w, r.z, r.w, -scale, -scale);      // p -= scale * (num / denom)
 }
 
 __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const float4& g, const AdamConst& c) {
@@ -221,12 +229,20 @@ constexpr int DF_RES = 0, DF_TOUCH = 32, DF_CATCH = DF_TOUCH + DEFER_MAX * SAT_D
 static_assert(SAT_DEFER_ROWS_BLOCKS == ROWS_BLOCKS, "the touched-row kernel writes one partial per CTA");
 static_assert(DF_SWEEP + SAT_DEFER_SWEEP_BLOCKS * DEFER_MAX == SAT_DEFER_REG_DOUBLES, "layout of SatAdam.defer_reg");
 
-__device__ __forceinline__ AdamConst ring_const(const float* __restrict__ st, int j, int kind) {
-    const float* r = st + 8 + DEFER_RING * j;
+// constants of the epoch's step j (st: the block's shared-memory copy of SatAdam.defer_state); inv = 1 / bc2_sqrt
+__device__ __forceinline__ AdamConst ring_const(const float* __restrict__ st, int j, int kind, float& inv) {
+    const float4* r = reinterpret_cast<const float4*>(st + 8 + DEFER_RING * j);
+    const float4 a = r[0], b = r[1];
     AdamConst c;
-    c.one_minus_b1 = r[0]; c.b2 = r[1]; c.one_minus_b2 = r[2]; c.step_size = r[3]; c.bc2_sqrt = r[4]; c.eps = r[5]; c.lr = r[6];
-    c.two_l2 = r[7]; c.kind = kind;
+    c.one_minus_b1 = a.x; c.b2 = a.y; c.one_minus_b2 = a.z; c.step_size = a.w; c.bc2_sqrt = b.x; c.eps = b.y; c.lr = b.z;
+    c.two_l2 = b.w; c.kind = kind;
+    inv = st[8 + DEFER_RING * j + 8];
     return c;
+}
+// the block's copy of the epoch state
+__device__ __forceinline__ void load_defer_state(float* __restrict__ s_st, const float* __restrict__ st) {
+    for (int i = threadIdx.x; i < SAT_DEFER_STATE_WORDS; i += blockDim.x) s_st[i] = st[i];
+    __syncthreads();
 }
 
 __global__ void k_defer_begin(float* __restrict__ st, const AdamConst c_in, const float* __restrict__ dev_const) {
@@ -245,11 +261,12 @@ __global__ void k_defer_begin(float* __restrict__ st, const AdamConst c_in, cons
 __device__ __forceinline__ void defer_steps(float4& p, float4& m, float4& v, int j0, int j1, const float* __restrict__ st,
                                             int kind, float (*s_sq)[ROWS_THREADS]) {
     for (int j = j0; j < j1; ++j) {
-        const AdamConst c = ring_const(st, j, kind);
+        float inv;
+        const AdamConst c = ring_const(st, j, kind, inv);
         float sq = p.x * p.x;
         sq = fmaf(p.y, p.y, sq); sq = fmaf(p.z, p.z, sq); sq = fmaf(p.w, p.w, sq);
         s_sq[j][threadIdx.x] += sq;
-        adam4_untouched(p, m, v, c, st[8 + DEFER_RING * j + 8]);
+        adam4_untouched(p, m, v, c, inv);
     }
 }
 
@@ -274,8 +291,11 @@ k_defer_catchup(float4* __restrict__ P, float4* __restrict__ M, float4* __restri
                 const int32_t* __restrict__ uniq_rows, const int32_t* __restrict__ counters, const float* __restrict__ st,
                 int kind, double* __restrict__ reg_catch) {
     __shared__ float s_sq[DEFER_MAX][ROWS_THREADS];
+    __shared__ __align__(16) float s_st[SAT_DEFER_STATE_WORDS];
 #pragma unroll
     for (int j = 0; j < DEFER_MAX; ++j) s_sq[j][threadIdx.x] = 0.f;
+    load_defer_state(s_st, st);
+    st = s_st;
     const int cur = reinterpret_cast<const int*>(st)[0] - 1;           // index of the step now running
     const long long n_vec = (long long)counters[CNT_NUNIQ] * 8;
     if (cur > 0) {
@@ -314,8 +334,11 @@ __global__ void __launch_bounds__(ROWS_THREADS, SAT_DSWEEP_MINB)
 k_defer_sweep(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, uint8_t* __restrict__ upto,
               long long n_vec, const float* __restrict__ st, int kind, double* __restrict__ reg_sweep) {
     __shared__ float s_sq[DEFER_MAX][ROWS_THREADS];
+    __shared__ __align__(16) float s_st[SAT_DEFER_STATE_WORDS];
 #pragma unroll
     for (int j = 0; j < DEFER_MAX; ++j) s_sq[j][threadIdx.x] = 0.f;
+    load_defer_state(s_st, st);
+    st = s_st;
     const int n = min(reinterpret_cast<const int*>(st)[0], DEFER_MAX);
     constexpr int U = SAT_DSWEEP_U;
     const long long stride = (long long)gridDim.x * ROWS_THREADS;

@@ -395,3 +395,18 @@ def test_fit_streaming_host_batches_equals_resident(shuffle):
     for k in sds[0]:
         assert torch.equal(sds[0][k], sds[1][k]), k
     assert hist[0] == hist[1], hist
+
+
+def test_tensor_core_weight_gradients():
+    """SAT_WGRAD_TC=1 selects backward_tc_wg.cu: the MetaNet / QKV WEIGHT gradients as tcgen05 3xTF32 GEMMs with both operands
+    MN-major in shared memory (SWIZZLE_128B_BASE32B; the token index is the MMA's K).  Same bar as the default path: the
+    golden-vector gradient tests, the config-2-sized check and run-to-run bit identity, in a fresh process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SAT_WGRAD_TC='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x',
+                        '--no-header', '-p', 'no:cacheprovider', '-k', 'tf32x3 and (gradients or two_runs or dense_adam)'],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and ' passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

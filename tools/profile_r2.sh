@@ -10,23 +10,25 @@ mkdir -p $OUT
 cat > /tmp/sat_rawparse.py <<'PY'
 import csv, json, sys
 rows = list(csv.reader(open(sys.argv[1])))
-if len(rows) >= 3:
-    hdr, units, vals = rows[0], rows[1], rows[2]
+start = next((i for i, r in enumerate(rows) if 'Kernel Name' in r), None)
+if start is not None and len(rows) >= start + 3:
+    hdr, units, vals = rows[start], rows[start + 1], rows[start + 2]
     keep = ('Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
             'sm__inst_executed_pipe_tensor.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
             'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
             'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active', 'launch__grid_size',
             'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
             'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__issue_inst0.avg.pct_of_peak_sustained_active')
-    d = {h: (v, u) for h, u, v in zip(hdr, units, vals) if h in keep or 'pipe_tensor' in h or 'issue_stalled' in h}
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals) if h in keep or 'pipe_tensor' in h or 'issue_stalled' in h or h.startswith('dram__bytes')}
     json.dump(d, open(sys.argv[2], 'w'), indent=1)
 PY
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-graph"
 # 1. launch list (every launch with its device time; cold-cache, serialised: compare SHARES)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
 # 2. one full capture per dominant kernel
-for K in k_forward_tc k_bwd_meta_tc k_bwd_attn k_adam_sweep k_rows_reduce k_dense_reduce k_radix_scatter k_gather; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o $OUT/${TAG}_$K $BENCH > $OUT/${TAG}_$K.log 2>&1
+for K in k_forward_tc k_bwd_meta_tc k_bwd_attn k_defer_sweep k_defer_catchup k_gather; do
+  SKIP=4; case $K in k_defer_*) SKIP=1 ;; esac
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 -f -o $OUT/${TAG}_$K $BENCH > $OUT/${TAG}_$K.log 2>&1
   if [ -f $OUT/${TAG}_$K.ncu-rep ]; then
     ncu -i $OUT/${TAG}_$K.ncu-rep --page details > $OUT/${TAG}_details_$K.txt 2>/dev/null
     ncu -i $OUT/${TAG}_$K.ncu-rep --page raw --csv 2>/dev/null > $OUT/${TAG}_raw_$K.csv
