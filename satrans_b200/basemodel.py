@@ -458,8 +458,11 @@ class BaseModel(nn.Module):
         return hp
 
     def _get_loss_func(self, loss):
-        """'binary_crossentropy' | 'mse' | 'mae' (reference meta_basemodel.py:627-640), fused into the forward
-        kernel's logit head; custom callables are not supported."""
+        """'binary_crossentropy' | 'mse' | 'mae' (reference meta_basemodel.py:627-640) are fused into the forward kernel's
+        logit head.  Any other callable `loss(y_pred, y, reduction='sum')` (the reference passes it through unchanged, :638-639)
+        is evaluated by torch on the (B,) prediction vector between the fused forward and the fused backward
+        (Engine.train_step(loss_fn=...))."""
+        self._loss_fn = None
         if isinstance(loss, str):
             if loss in ("binary_crossentropy", "mse", "mae"):
                 self._loss_kind = loss
@@ -467,7 +470,10 @@ class BaseModel(nn.Module):
                     self._engine._bound_ptrs = None       # loss kind travels in the model descriptor
                 return loss
             raise NotImplementedError
-        raise NotImplementedError("custom loss callables are not supported by the fused path")
+        if callable(loss):
+            self._loss_fn = loss
+            return loss
+        raise NotImplementedError("loss must be one of the reference's strings or a callable loss(y_pred, y, reduction='sum')")
 
     def _get_metrics(self, metrics, set_eps=False):
         metrics_ = {}
@@ -614,7 +620,8 @@ class BaseModel(nn.Module):
                     xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1].contiguous()
                 hp = self._hparams()
                 seed0 = int(torch.initial_seed()) & (2 ** 63 - 1)
-                if eng.use_cuda_graph and eng.dist is None and eng.step_count >= 2 and (s1 - s0) == batch_size:
+                loss_fn = getattr(self, '_loss_fn', None)
+                if eng.use_cuda_graph and eng.dist is None and eng.step_count >= 2 and (s1 - s0) == batch_size and loss_fn is None:
                     # full-size batches after the first two steps: the whole step is ONE CUDA-graph launch (engine.graph_train_step)
                     w, _ = eng.graph_train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                                 l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
@@ -624,7 +631,7 @@ class BaseModel(nn.Module):
                     y_pred, w = eng.train_step(xb, yb, lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
                                                l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                                training=True, dropout_p=self.dropout_rate,
-                                               seed=(seed0 + eng.step_count) & (2 ** 63 - 1), defer=defer)
+                                               seed=(seed0 + eng.step_count) & (2 ** 63 - 1), defer=defer, loss_fn=loss_fn)
                 losses[step_num, 0:(1 if defer > 1 else 2)].copy_(w['scalars'][0:(1 if defer > 1 else 2)])
                 if feeder is not None:
                     feeder.batch_consumed()
@@ -713,7 +720,8 @@ class BaseModel(nn.Module):
         gkey = (tuple(X.shape), str(X.dtype), hp['kind'])
         seen = eng._graph_seen.get(gkey, 0)
         eng._graph_seen[gkey] = seen + 1
-        if host_batch and eng.use_cuda_graph and eng.dist is None and seen >= 2:
+        loss_fn = getattr(self, '_loss_fn', None)
+        if host_batch and eng.use_cuda_graph and eng.dist is None and seen >= 2 and loss_fn is None:
             # third and later batches of this shape: the step (H2D copies included) is ONE CUDA-graph launch
             w, sc_pin = eng.graph_train_step(X, np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y,
                                              lr=hp['lr'], betas=hp['betas'], eps=hp['eps'], opt_kind=hp['kind'],
@@ -730,7 +738,7 @@ class BaseModel(nn.Module):
             _, w = eng.train_step(Xd.contiguous(), yd.contiguous(), lr=hp['lr'], betas=hp['betas'], eps=hp['eps'],
                                   opt_kind=hp['kind'], l2_emb=self.l2_reg_embedding, dense_mode=self.dense_table_updates,
                                   training=True, dropout_p=self.dropout_rate, seed=(seed0 + eng.step_count) & (2 ** 63 - 1),
-                                  defer=defer)
+                                  defer=defer, loss_fn=loss_fn)
         sc = w['scalars'][0:4].tolist()                 # device -> host: synchronises, like the reference's .item()
         if sc[3] != 0:
             eng.check_errors(w)

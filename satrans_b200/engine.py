@@ -488,7 +488,7 @@ class Engine:
         return n
 
     def train_step(self, X, y, lr, betas=(0.9, 0.999), eps=1e-8, l2_emb=1e-5, dense_mode=True, training=True,
-                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0, _capturing=False, defer=1):
+                   dropout_p=0.1, seed=0, overlap=False, opt_kind=0, _capturing=False, defer=1, loss_fn=None):
         """One optimiser step with the reference's semantics (dense_mode=True) or lazy/sparse table updates
         (dense_mode=False).  Returns (y_pred, workspace); scalars[0:2] = (bce sum, reg loss) after the step's
         finalize kernel (read them with .item() only when needed: that synchronises).
@@ -497,7 +497,12 @@ class Engine:
         (include/satrans_b200.h, sat_defer_*): the rows this batch reads are brought up to date before the forward, all others
         when the epoch closes (after K steps, or at sync_tables()) -- parameters and optimiser state are bit-identical to
         defer=1.  scalars[1] of a deferred step is NOT its regulariser term (that needs every row): read deferred_reg() after
-        sync_tables()."""
+        sync_tables().
+
+        loss_fn: a custom loss callable `loss_fn(y_pred, y, reduction='sum')` on torch tensors (reference
+        meta_basemodel.py:627-640 accepts any callable).  The fused kernels then run the forward without labels, torch
+        evaluates the loss and d loss / d y_pred on the (B,) prediction vector, and the backward starts from that
+        (dLoss/dlogit = dLoss/dy_pred * y_pred * (1 - y_pred), written in scenario-sorted order); scalars[0] = the loss value."""
         self.bind()
         kind = self._check_x(X)
         B = X.shape[0]
@@ -575,7 +580,16 @@ class Engine:
             self._ev_swept.record(side)
         y_pred = torch.empty(B, dtype=torch.float32, device=self.device)
         t = self._tic('forward')
-        self._forward_call(X, kind, y.data_ptr(), w, y_pred, 1, p, sd, s)
+        self._forward_call(X, kind, y.data_ptr() if loss_fn is None else None, w, y_pred, 1, p, sd, s)
+        loss_val = None
+        if loss_fn is not None:
+            with torch.enable_grad():
+                yp = y_pred.detach().clone().requires_grad_(True)
+                loss_t = loss_fn(yp, y.reshape(-1).to(yp.dtype), reduction='sum')
+                (g_yp,) = torch.autograd.grad(loss_t, yp)
+            dz = g_yp * y_pred * (1.0 - y_pred)                     # through the sigmoid of the logit head
+            w['dz'][:B] = dz.index_select(0, w['perm'][:B].long())  # sorted position p -> sample perm[p]
+            loss_val = loss_t.detach()
         self._toc(t)
         tail_on_side = bool(single and dense_mode and not sweep_on_side and self.side_streams and not deferred)
         t = self._tic('backward')
@@ -629,6 +643,8 @@ class Engine:
             if sweep_on_side:
                 main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
+        if loss_val is not None:
+            w['scalars'][0] = loss_val.to(torch.float32)
         if not single:
             self.dist.all_reduce_sum(w['scalars'][0:2])     # global BCE sum and L2 term
         if not _capturing:

@@ -410,3 +410,49 @@ def test_tensor_core_weight_gradients():
                         '--no-header', '-p', 'no:cacheprovider', '-k', 'tf32x3 and (gradients or two_runs or dense_adam)'],
                        env=env, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0 and ' passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_custom_loss_callable(precision):
+    """compile(loss=<callable>) (the reference passes any callable through, meta_basemodel.py:627-640, and calls it as
+    loss(y_pred, y, reduction='sum'), :317): torch evaluates the loss and its derivative on the prediction vector between the fused
+    forward and the fused backward.  A callable that IS binary cross-entropy / mse must reproduce the built-in fused losses
+    (two optimiser steps: losses and every parameter to fp32 round-off); a focal-style loss must match torch autograd through the
+    oracle."""
+    import torch.nn.functional as F
+    from gpu_util import model_from_golden
+    g = Golden('en_small')
+    for name, fn in (('binary_crossentropy', F.binary_cross_entropy), ('mse', F.mse_loss)):
+        sds, losses = [], []
+        for loss in (name, fn):
+            model = model_from_golden(g, precision=precision)
+            model.dropout_rate = 0.0
+            model.compile('sgd', loss)
+            losses.append([model.train_on_batch(g.X(k).numpy(), g.y(k).numpy())[0] for k in range(2)])
+            sds.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+        assert np.allclose(losses[0], losses[1], rtol=2e-6, atol=0), (name, losses)
+        for k in sds[0]:
+            scale = max(sds[0][k].abs().max().item(), 1e-3)
+            assert (sds[0][k] - sds[1][k]).abs().max().item() <= 2e-6 * scale, (name, k)
+
+    def focal(yp, y, reduction='sum'):
+        pt = torch.where(y > 0.5, yp, 1.0 - yp)
+        v = -((1.0 - pt) ** 2) * torch.log(pt.clamp_min(1e-12))
+        return v.sum() if reduction == 'sum' else v.mean()
+
+    model = model_from_golden(g, precision=precision)
+    model.dropout_rate = 0.0
+    lr = 0.01
+    model.compile(torch.optim.SGD(model.parameters(), lr=lr), focal)
+    got_loss = model.train_on_batch(g.X().numpy(), g.y().numpy())[0]
+    st = {k: t.clone().requires_grad_(k in O.trainable_keys(g.cfg)) for k, t in g.state().items()}
+    yp = O.forward(st, g.X(), g.cfg).squeeze(-1)
+    ref_loss = focal(yp, g.y())
+    (ref_loss + O.reg_loss(st, g.cfg)).backward()
+    assert abs(got_loss - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in O.trainable_keys(g.cfg):
+        step = (st[k].detach() - sd[k]) / lr                      # = the gradient the fused path applied
+        ref = st[k].grad
+        tol = 1e-3 * ref.abs().max().item() + 4e-7 * st[k].detach().abs().max().item() / lr + 1e-6   # (+ fp32 storage of p -/- lr g)
+        assert (step - ref)[subsample(k)].abs().max().item() <= tol, k

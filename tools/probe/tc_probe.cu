@@ -1,7 +1,8 @@
 // Probes of the tcgen05 shared-memory-operand (SS) MMA path used while designing tensor-core WEIGHT gradients
 // (dW = A^T G with the token index as the MMA's K dimension).  Findings on B200 (tests/wgrad_probe.py):
 //   * kind::tf32 SS MMAs with K-major SWIZZLE_NONE operands and an arbitrary LBO work (sat_debug_ss 0/0, sat_debug_wgrad);
-//   * any MN-major tf32 operand (a_major / b_major = 1, canonical interleaved layout, either LBO/SBO order) returns zeros;
+//   * MN-major tf32 operands (a_major / b_major = 1) return zeros with SWIZZLE_NONE (and with every other layout type) EXCEPT
+//     SWIZZLE_128B_BASE32B, which works: see mn_probe.cu (round 2) and csrc/backward_tc_wg.cu;
 //   * a full k_bwd_meta_tc with these weight-gradient GEMMs (commit "Tensor-core weight gradients in k_bwd_meta_tc") was
 //     parity-green but ~7 % SLOWER than the CUDA-core wgrad32 version (scalar transposing stores, 48 MMAs per 32x32 block,
 //     per-GEMM drain latency), so the shipped kernel keeps weight gradients on the CUDA cores.
