@@ -250,8 +250,10 @@ def test_constructor_error_contract():
         m.compile('adamw')                                     # unknown optimizer string (meta_basemodel.py:623)
     with pytest.raises(NotImplementedError):
         m.compile('adam', loss='hinge')                        # unknown loss string (meta_basemodel.py:637)
+    m.compile('adam', loss=lambda p, y, reduction='sum': (p - y).abs().sum())          # a callable is accepted (meta_basemodel.py:638-639)
+    assert callable(m._loss_fn)
     with pytest.raises(NotImplementedError):
-        m.compile('adam', loss=lambda p, y, reduction='sum': (p - y).abs().sum())      # custom loss callables are not fused
+        m.compile('adam', loss=3.14)                               # neither a known string nor a callable
     import torch
     with pytest.raises(NotImplementedError):
         m.compile(torch.optim.Adam(m.parameters(), lr=0.01, amsgrad=True), 'binary_crossentropy')
