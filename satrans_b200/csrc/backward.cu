@@ -360,6 +360,18 @@ using namespace sat;
 
 int sat_launch_bwd_meta_tc(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
 int sat_launch_bwd_meta_tc_wg(const sat::BwdArgs& a, const float* wpack, int n_keys, int grid, int passes, cudaStream_t s);
+int sat_launch_bwd_attn2_h2(const sat::BwdArgs& a, int grid, cudaStream_t s);
+int sat_launch_bwd_attn2_h4(const sat::BwdArgs& a, int grid, cudaStream_t s);
+int sat_launch_bwd_attn2_h8(const sat::BwdArgs& a, int grid, cudaStream_t s);
+#ifndef SAT_BWD_ATTN_SPLIT_DEFAULT
+#define SAT_BWD_ATTN_SPLIT_DEFAULT 0
+#endif
+// SAT_BWD_ATTN_SPLIT=0 / 1: attention backward with one / two threads per token (backward_attn.cu / backward_attn2.cu)
+static bool attn_token_split() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SAT_BWD_ATTN_SPLIT"); v = e ? (atoi(e) != 0) : SAT_BWD_ATTN_SPLIT_DEFAULT; }
+    return v == 1;
+}
 // SAT_WGRAD_TC=1: weight gradients on the tensor core too (backward_tc_wg.cu; measured slower, see there)
 static bool wgrad_on_tensor_core() {
     static int v = -1;
@@ -411,11 +423,12 @@ static int backward_impl(const SatModel* m, const void* x, int32_t id_kind, int3
     for (int l = m->L - 1; l >= 0; --l) {
         a.layer = l;
         aa.layer = l;
+        const bool split = attn_token_split() && m->H >= 2;      // two threads per token (backward_attn2.cu)
         switch (m->H) {
             case 1: rc = sat_launch_bwd_attn_h1(aa, grid_a, s); break;
-            case 2: rc = sat_launch_bwd_attn_h2(aa, grid_a, s); break;
-            case 4: rc = sat_launch_bwd_attn_h4(aa, grid_a, s); break;
-            case 8: rc = sat_launch_bwd_attn_h8(aa, grid_a, s); break;
+            case 2: rc = split ? sat_launch_bwd_attn2_h2(aa, grid_a, s) : sat_launch_bwd_attn_h2(aa, grid_a, s); break;
+            case 4: rc = split ? sat_launch_bwd_attn2_h4(aa, grid_a, s) : sat_launch_bwd_attn_h4(aa, grid_a, s); break;
+            case 8: rc = split ? sat_launch_bwd_attn2_h8(aa, grid_a, s) : sat_launch_bwd_attn_h8(aa, grid_a, s); break;
             default: return sat_host::fail(SAT_EINVAL, "sat_backward: heads=%d not in {1,2,4,8}", m->H);
         }
         if (rc) return rc;

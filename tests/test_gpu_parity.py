@@ -456,3 +456,18 @@ def test_custom_loss_callable(precision):
         ref = st[k].grad
         tol = 1e-3 * ref.abs().max().item() + 4e-7 * st[k].detach().abs().max().item() / lr + 1e-6   # (+ fp32 storage of p -/- lr g)
         assert (step - ref)[subsample(k)].abs().max().item() <= tol, k
+
+
+def test_attention_backward_with_two_threads_per_token():
+    """SAT_BWD_ATTN_SPLIT=1 selects backward_attn2.cu (every token split over two threads in sibling warps: 256 threads, <= 128
+    registers, 16 warps per SM).  Same bar as the default kernel -- golden-vector gradients (2- and 4-head models), Adam steps,
+    run-to-run bit identity -- in a fresh process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SAT_BWD_ATTN_SPLIT='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_parity.py'), '-m', 'gpu', '-q', '-x',
+                        '--no-header', '-p', 'no:cacheprovider', '-k', 'gradients_match or two_runs or dense_adam'],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and ' passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
