@@ -544,6 +544,11 @@ def run_b200(args):
                                    "(the tiny tables) are served by L1/L2, so DRAM traffic is below the algorithmic bytes"})
         if roof is not None:
             roof["others"] = others
+            try:        # the three token kernels (85 % of the step) are latency-bound: their pipe utilisation from the ncu captures
+                roof["token_kernels"] = dict(json.load(open(os.path.join(ROOT, 'profiles', 'r2_pipe_utilisation.json'))),
+                                             note="static: ncu --set full captures of this build (profiles/r2_details_k_*.txt), not re-measured by this run")
+            except Exception:
+                pass
         extra["gather"] = others[-1]
         model.eval()
         Bi = 32768
