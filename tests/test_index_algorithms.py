@@ -5,6 +5,7 @@ by the bit-identical-runs and gradient-parity tests):
   * the CTA -> tile partition with every CTA inside one scenario,
   * one pass of the stable LSD radix sort (tile histograms, digit-major scan, warp-match ranking)."""
 import numpy as np
+import pytest
 
 RCH = 32
 CI_HEAD, CI_TAIL, CI_SINGLE = 1, 2, 4
@@ -169,3 +170,85 @@ def test_radix_sort_is_stable():
             k, v = radix_pass(k, v, p * RB)
         order = np.argsort(keys, kind='stable')
         assert np.array_equal(k, keys[order]) and np.array_equal(v, order)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# deferred table sweep (csrc/optim.cu: k_defer_begin / k_defer_catchup / k_adam_rows / k_defer_sweep, engine.train_step(defer=K))
+# ---------------------------------------------------------------------------------------------------------------------
+def _adam_row(p, m, v, g, c):
+    """torch.optim.Adam's update of one row in float32 (the arithmetic both the model below and the reference loop use)."""
+    f = np.float32
+    m = (m + (g - m) * f(1 - c['b1'])).astype(f)
+    v = (v * f(c['b2']) + f(1 - c['b2']) * g * g).astype(f)
+    denom = (np.sqrt(v) / f(c['bc2_sqrt']) + f(c['eps'])).astype(f)
+    p = (p - f(c['step_size']) * (m / denom)).astype(f)
+    return p, m, v
+
+
+def _consts(t, lr=0.005, b1=0.9, b2=0.999, eps=1e-8):
+    return {'b1': b1, 'b2': b2, 'eps': eps, 'step_size': lr / (1 - b1 ** t), 'bc2_sqrt': np.sqrt(1 - b2 ** t)}
+
+
+@pytest.mark.parametrize('K', [1, 4, 7, 16])
+def test_deferred_sweep_model_equals_per_step_sweep(K):
+    """CPU model of the deferred table sweep: every row that no batch read is regularised + Adam-updated every step in the
+    reference (meta_basemodel.py:577-593, main.py:343).  The model below defers those updates exactly as the kernels do -- a ring
+    of per-step constants, one byte per row counting the steps of the epoch already applied, catch-up of the rows a batch is
+    about to read, a sweep that closes the epoch after K steps -- and must leave bit-identical rows, must hand the 'forward' rows
+    that are up to date, and must report the same per-step sum of squares."""
+    rng = np.random.default_rng(3)
+    f = np.float32
+    R, d, T, l2 = 60, 4, 23, f(1e-5)
+    p0 = rng.normal(0, 1e-2, (R, d)).astype(f)
+    touched = [np.unique(rng.integers(0, R, rng.integers(1, 12))) for _ in range(T)]
+    grads = [rng.normal(0, 1e-3, (len(u), d)).astype(f) for u in touched]
+    # --- the reference loop: every row every step
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    seen_ref, reg_ref = [], []
+    for t in range(1, T + 1):
+        seen_ref.append(p[touched[t - 1]].copy())                 # what the forward of step t reads
+        reg_ref.append(float(np.sum(p.astype(np.float64) ** 2)))
+        g = f(2) * l2 * p
+        g[touched[t - 1]] += grads[t - 1]
+        for r in range(R):
+            p[r], m[r], v[r] = _adam_row(p[r], m[r], v[r], g[r], _consts(t))
+    # --- the deferred model
+    q, qm, qv = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    upto = np.zeros(R, dtype=np.uint8)
+    ring, n_begun, reg_def = [], 0, {}
+    reg_acc = {}
+
+    def untouched_steps(r, j0, j1, base_step):
+        for j in range(j0, j1):
+            reg_acc[base_step + j] = reg_acc.get(base_step + j, 0.0) + float(np.sum(q[r].astype(np.float64) ** 2))
+            q[r], qm[r], qv[r] = _adam_row(q[r], qm[r], qv[r], f(2) * l2 * q[r], ring[j])
+
+    def sweep(base_step):
+        nonlocal n_begun, ring
+        for r in range(R):
+            untouched_steps(r, int(upto[r]), n_begun, base_step)
+            upto[r] = 0
+        for j in range(n_begun):
+            reg_def[base_step + j] = reg_acc.pop(base_step + j)
+        n_begun, ring = 0, []
+
+    base = 1                                                      # global index of the epoch's first step
+    for t in range(1, T + 1):
+        if n_begun >= K:                                          # the host closes the epoch before step t begins
+            sweep(base)
+            base = t
+        ring.append(_consts(t)); n_begun += 1                     # sat_defer_begin
+        cur = n_begun - 1
+        rows = touched[t - 1]
+        for r in rows:                                            # sat_defer_catchup
+            untouched_steps(r, int(upto[r]), cur, base)
+            upto[r] = cur
+        assert np.array_equal(q[rows], seen_ref[t - 1]), t        # the forward gathers up-to-date rows
+        for i, r in enumerate(rows):                              # k_adam_rows (deferred): this step's update, row marked current
+            reg_acc[t] = reg_acc.get(t, 0.0) + float(np.sum(q[r].astype(np.float64) ** 2))
+            q[r], qm[r], qv[r] = _adam_row(q[r], qm[r], qv[r], grads[t - 1][i] + f(2) * l2 * q[r], _consts(t))
+            upto[r] = n_begun
+        assert n_begun <= 16
+    sweep(base)                                                   # sync_tables()
+    assert np.array_equal(q, p) and np.array_equal(qm, m) and np.array_equal(qv, v)
+    assert np.allclose([reg_def[t] for t in range(1, T + 1)], reg_ref, rtol=1e-12, atol=0)
