@@ -40,6 +40,7 @@ extern "C" {
 #define SAT_LAYER_FLOATS 4288 /* packed per-layer parameter block, see SatModel */
 #define SAT_REG_PARTS (148 * 256 + 148 * 4) /* doubles in SatWork.reg_part */
 #define SAT_WORK_BUFFERS 32  /* pointer members of SatWork */
+#define SAT_ACT_PER_LAYER 6  /* activation rows saved per layer and token by a training forward (SatWork.acts) */
 #define SAT_GRID_MAX (148 * 2) /* most CTAs any token kernel is launched with: rows of the per-CTA partial buffers */
 #define SAT_SORT_RADIX_BITS 9  /* digit width of the touched-row radix sort */
 #define SAT_SORT_TILE 2048     /* sorted entries per CTA and radix pass */
@@ -137,7 +138,7 @@ typedef struct SatWork {
     float* theta;         /* [n_keys][4096] generated MetaNet weights per key               */
     float* dtheta;        /* [n_keys][4096] their gradient                                  */
     float* enc_du;        /* [n_keys][64] gradient w.r.t. the encoder inputs                */
-    float* acts;          /* training only: [L][5][cap_B*F][32] saved x, zq, zk, v, r + [cap_B*F][32] final x */
+    float* acts;          /* training only: [L][6][cap_B*F][32] saved x, zq, zk, v, r, y + [cap_B*F][32] final x + ReLU masks */
     float* dz;            /* [cap_B] dLoss/dlogit per sorted position                       */
     float* dx;            /* [2][cap_B*F][32] ping-pong activation gradients                */
     float* dqkv;          /* [3][cap_B*F][32] dq', dk', dv between the two backward kernels */

@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 SAT_D, SAT_HID, SAT_P, SAT_MAXF, SAT_LAYER_FLOATS = 32, 64, 4096, 32, 4288
 SAT_REG_PARTS = 148 * 256 + 148 * 4
 SAT_WORK_BUFFERS = 32
+SAT_ACT_PER_LAYER = 6      # activation rows saved per layer and token by a training forward
 SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
 SAT_ABI_VERSION = 3
 SAT_MAX_SHARDS = 8

@@ -26,11 +26,14 @@ struct FwdArgs {
     float* gpart;              // ... and the head's parameter-gradient partials (gpart_layout in bwd_common.cuh)
 };
 
-enum { ACT_X = 0, ACT_ZQ = 1, ACT_ZK = 2, ACT_V = 3, ACT_R = 4, ACT_PER_LAYER = 5 };
+// saved per layer and token (training): layer input x, pre-LayerNorm MetaNet outputs z_q / z_k, v, attention output r, and the
+// pre-LayerNorm layer output y = drop(act(r W_out^T)) + x (so that the backward does not recompute the output projection)
+enum { ACT_X = 0, ACT_ZQ = 1, ACT_ZK = 2, ACT_V = 3, ACT_R = 4, ACT_Y = 5, ACT_PER_LAYER = SAT_ACT_PER_LAYER };
+static_assert(ACT_PER_LAYER == 6, "activation slots");
 
 // ReLU decisions of the MetaNet hidden layer (64 bits per token, layer and side), saved by the forward so that the
 // backward differentiates exactly the function the forward evaluated (the forward may run on the tensor cores).
-// They live behind the activations: acts + (L*5+1)*act_stride, as uint32 [L][2 sides][tokens][2].
+// They live behind the activations: acts + (L*ACT_PER_LAYER+1)*act_stride, as uint32 [L][2 sides][tokens][2].
 __device__ __forceinline__ uint32_t* relu_mask_ptr(float* acts, long long act_stride, int L, int layer, int side, long long tok) {
     uint32_t* base = reinterpret_cast<uint32_t*>(acts + ((long long)L * ACT_PER_LAYER + 1) * act_stride);
     return base + (((long long)layer * 2 + side) * (act_stride / 32) + tok) * 2;

@@ -107,7 +107,14 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
             zero(o);
             uint32_t relu_mask = 0xffffffffu;
             float rstd = 0.f;
-            if (valid) {
+            if (valid && !relu_out) {
+                // y (pre-LayerNorm output of the layer) was saved by the forward: nothing of the output projection is recomputed
+                load_row(act_l + ACT_Y * a.act_stride + tokpos, o);
+                load_row(a.dx + tokpos, dy);
+                cp_async_wait_all();                       // own rows of T0 / T2 / T3 have landed
+                rstd = normalize32(o);                     // o := yhat
+            } else if (valid) {
+                // 'relu' flag: the sign pattern of r @ WO^T is needed, so the projection is recomputed
                 float xin[D];
                 load_row(act_l + ACT_X * a.act_stride + tokpos, xin);
                 load_row(a.dx + tokpos, dy);
@@ -121,8 +128,8 @@ __global__ void __launch_bounds__(BA_NT, 2) k_bwd_attn(const BwdArgs a) {
                     drop_pair(dco, i >> 1, fk[0], fk[1]);
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        if (relu_out && o[i + e] <= 0.f) relu_mask &= ~(1u << (i + e));
-                        float v = relu_out ? fmaxf(o[i + e], 0.f) : o[i + e];
+                        if (o[i + e] <= 0.f) relu_mask &= ~(1u << (i + e));
+                        float v = fmaxf(o[i + e], 0.f);
                         v *= fk[e];
                         o[i + e] = use_res ? v + xin[i + e] : v;      // o := y (pre-LN)
                     }

@@ -58,7 +58,7 @@ extern "C" int sat_workspace_sizes(const SatModel* m, int32_t cap_B, int32_t tra
     sz[i++] = n_keys * SAT_P * 4;                          // theta
     sz[i++] = training ? n_keys * SAT_P * 4 : 0;           // dtheta
     sz[i++] = training ? 16 * n_keys * 64 * 4 : 0;         // enc_du: one partial per block of k_encoder_bwd (4096 / 256)
-    sz[i++] = training ? ((int64_t)m->L * 5 + 1) * tok * SAT_D * 4 + (int64_t)m->L * 2 * tok * 2 * 4 : 0;   // acts + ReLU masks
+    sz[i++] = training ? ((int64_t)m->L * SAT_ACT_PER_LAYER + 1) * tok * SAT_D * 4 + (int64_t)m->L * 2 * tok * 2 * 4 : 0;   // acts + ReLU masks
     sz[i++] = cap_B * 4;                                   // dz
     sz[i++] = training ? tok * SAT_D * 4 : 0;              // dx
     sz[i++] = training ? 3 * tok * SAT_D * 4 : 0;          // dqkv

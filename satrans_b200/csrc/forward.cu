@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(NT, 2) k_forward(const FwdArgs a) {
                         x[i + e] = use_res ? v + x[i + e] : v;
                     }
                 }
+                if (TRAIN) store_row(act_l + ACT_Y * a.act_stride + tokpos, x);      // y (pre-LayerNorm): k_bwd_attn starts from it
                 float mean, rstd;
                 layernorm32(x, sLN, sLN + 32, mean, rstd);
             }

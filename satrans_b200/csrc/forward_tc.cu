@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_forward_tc(const FwdArgs a, const 
                     x[i + e] = use_res ? vv + x[i + e] : vv;
                 }
             }
+            if (TRAIN && valid) store_row(act_l + ACT_Y * a.act_stride + tokpos, x);      // y (pre-LayerNorm): k_bwd_attn starts from it
             float mean, rstd;
             layernorm32(x, sLN, sLN + 32, mean, rstd);
         }

@@ -262,13 +262,14 @@ class SATrans(BaseModel):
         lay = self._layout
         B, F, L, H, d = Xd.shape[0], lay['F'], lay['L'], lay['H'], _lib.SAT_D
         cap_tok = w.cap_B * F
-        acts = w['acts'][:(L * 5 + 1) * cap_tok * d].view(L * 5 + 1, cap_tok, d)
+        A = _lib.SAT_ACT_PER_LAYER
+        acts = w['acts'][:(L * A + 1) * cap_tok * d].view(L * A + 1, cap_tok, d)
         perm = w['perm'][:B].long()
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(B, device=perm.device)
         for l, layer in enumerate(self.domain_int_layers):
-            zq = acts[l * 5 + 1, :B * F].view(B, F, d)[inv]              # ACT_ZQ / ACT_ZK, sorted position -> sample order
-            zk = acts[l * 5 + 2, :B * F].view(B, F, d)[inv]
+            zq = acts[l * A + 1, :B * F].view(B, F, d)[inv]              # ACT_ZQ / ACT_ZK, sorted position -> sample order
+            zk = acts[l * A + 2, :B * F].view(B, F, d)[inv]
             qn, kn = layer.Q_meta_mlp.ffn_layer_norm, layer.K_meta_mlp.ffn_layer_norm
             q = Fn.layer_norm(zq, (d,), qn.weight, qn.bias, 1e-6) if 'Q' in self.meta_mode else zq
             k = Fn.layer_norm(zk, (d,), kn.weight, kn.bias, 1e-6) if 'K' in self.meta_mode else zk

@@ -5,7 +5,7 @@ import torch
 
 from golden_util import Golden
 from oracle import satrans_oracle as O
-from satrans_b200 import DenseFeat, SATrans, SparseFeat
+from satrans_b200 import DenseFeat, SATrans, SparseFeat, _lib
 
 
 def model_from_golden(g: Golden, device='cuda:0', precision=None):
@@ -43,7 +43,8 @@ def relu_masks(model, w, B):
     lay = model._layout
     L, F = lay['L'], lay['F']
     cap_tok = w.cap_B * F
-    raw = w['acts'].view(torch.int32)[(L * 5 + 1) * cap_tok * 32:(L * 5 + 1) * cap_tok * 32 + L * 2 * cap_tok * 2]
+    A = _lib.SAT_ACT_PER_LAYER
+    raw = w['acts'].view(torch.int32)[(L * A + 1) * cap_tok * 32:(L * A + 1) * cap_tok * 32 + L * 2 * cap_tok * 2]
     raw = raw.view(L, 2, cap_tok, 2)[:, :, :B * F].reshape(L, 2, B, F, 2).cpu()
     perm = w['perm'][:B].long().cpu()
     bits = torch.arange(32, dtype=torch.int64)

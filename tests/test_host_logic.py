@@ -51,7 +51,7 @@ def test_workspace_sizes_host_only():
     mt = ctypes.c_int32()
     assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 1, sizes, ctypes.byref(mt)) == 0
     s = dict(zip(_lib.WORK_BUFFERS, sizes))
-    assert s['acts'] == (3 * 5 + 1) * 8192 * 19 * 32 * 4 + 3 * 2 * 8192 * 19 * 2 * 4
+    assert s['acts'] == (3 * _lib.SAT_ACT_PER_LAYER + 1) * 8192 * 19 * 32 * 4 + 3 * 2 * 8192 * 19 * 2 * 4
     assert s['bitmap'] == (6571961 + 31) // 32 * 4
     assert mt.value == (8192 + 9) // 10 + 4
     assert l.sat_workspace_sizes(ctypes.byref(d), 8192, 0, sizes, ctypes.byref(mt)) == 0
