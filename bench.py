@@ -5,6 +5,12 @@ domain_col=301) on synthetic Ali-CCP-shaped batches, B=8192, full Ali-CCP vocabu
 
 One "step" = one optimiser step with the REFERENCE's semantics (meta_basemodel.py:311-328): train-mode
 forward (dropout on), BCE(sum), dense L2 over all table rows, backward, dense Adam over every parameter.
+The rows no batch read receive their L2 + Adam updates in sweep epochs of `--sweep-interval` (8) steps, each row taken
+through its steps one after the other: bit-identical to updating them every step (tests/test_gpu_parity.py::
+test_deferred_table_sweep_is_bit_identical); the last epoch is closed INSIDE every timed region.
+`value` = the step replayed from a CUDA graph on device-resident batches; `e2e` = SATrans.fit() -- the reference's public
+training call -- on pinned host data (every batch copied H2D one step ahead on a copy stream, every step's scalars copied
+back D2H, fit() returning after the tables are in sync and the epoch loss is on the host); N > 1: train_on_batch per step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]             # this framework (prints ONE JSON line)
     python bench.py --impl reference [--steps K] [--warmup W]        # the reference itself on the host CPUs
@@ -15,11 +21,13 @@ through its own public API -- SATrans(...).compile(Adam).fit(x, y, batch_size) -
 oracle port of the same step (`kind: "port"`).
 
 Keys beyond the base contract: `infer` (eval-mode scoring samples/s at B=32768), `phases_ms` (CUDA-event breakdown of
-the step), `roofline` (dominant kernel = dense L2+Adam sweep; `roofline.others` = the stand-alone multi-field gather at
-B = 8,192 and 262,144 with its ncu DRAM bytes beside the algorithmic bytes), `cpu_baseline`, `eager_gpu_baseline` (the
+the step), `roofline` (the kernel that moves the most bytes = the every-row L2+Adam sweep, HBM-bound; `roofline.others` = the
+stand-alone multi-field gather at B = 8,192 and 262,144 with its ncu DRAM bytes beside the algorithmic bytes;
+`roofline.token_kernels` = pipe utilisation of the three latency-bound token kernels from the ncu captures), `cpu_baseline`, `eager_gpu_baseline` (the
 reference's eager PyTorch path on the same B200, BASELINE.md section 3.1), `bf16` (the kind::f16 variant, never the headline).
-Timing: CUDA events on the launching streams, W>=3 warm-up steps; every step uses a different batch and
-sweeps 3 x 841 MB of table state (> the 126 MB L2), so no explicit L2 flush is needed ("l2": "inputs>L2").
+Timing: CUDA events on the launching streams, W>=3 warm-up steps; every step uses a different batch whose working set
+(20 MB of gathered rows out of 841 MB of tables + ~400 MB of saved activations / gradients) exceeds the 126 MB L2, and
+every sweep streams 3 x 841 MB of table state, so no explicit L2 flush is needed ("l2": "inputs>L2").
 """
 import argparse
 import json
