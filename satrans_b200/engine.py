@@ -592,8 +592,11 @@ class Engine:
             loss_val = loss_t.detach()
         self._toc(t)
         tail_on_side = bool(single and dense_mode and not sweep_on_side and self.side_streams and not deferred)
+        # deferred sweep, one GPU: the dense-parameter chain (fixed-order reduction of the per-CTA partials, encoder backward, dense
+        # Adam) runs on the second stream beside the table-row chain (sorted segmented reduce, touched-row Adam): disjoint data
+        split_tail = bool(single and deferred and self.side_streams)
         t = self._tic('backward')
-        self._backward_call(X, kind, w, p, sd, s, defer_finish=tail_on_side)
+        self._backward_call(X, kind, w, p, sd, s, defer_finish=tail_on_side or split_tail)
         self._toc(t)
         if tail_on_side:
             # Everything that only the (short) touched-row and dense-parameter updates need -- the fixed-order reduction of the
@@ -618,6 +621,16 @@ class Engine:
             self._toc(t)
             main.wait_event(self._ev_swept)
         else:
+            if split_tail:
+                tail = self._tail_stream
+                self._ev_fork.record(main)
+                tail.wait_event(self._ev_fork)
+                with torch.cuda.stream(tail):
+                    t = self._tic('finish+adam_dense (side stream)', tail)
+                    self._backward_finish(w, tail.cuda_stream)
+                    check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), tail.cuda_stream), 'sat_dense_adam')
+                    self._toc(t)
+                self._ev_swept.record(tail)
             if use_side:
                 main.wait_event(self._ev_marked)       # sorted order + touched-row ranks are ready
             t = self._tic('rows_reduce')
@@ -637,9 +650,12 @@ class Engine:
                 t = self._tic('adam_sweep')
                 check(l.sat_tables_adam(d, C.byref(w.c), C.byref(a), _lib.ADAM_UNTOUCHED, s), 'sat_tables_adam')
                 self._toc(t)
-            t = self._tic('adam_dense')
-            check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
-            self._toc(t)
+            if split_tail:
+                main.wait_event(self._ev_swept)
+            else:
+                t = self._tic('adam_dense')
+                check(l.sat_dense_adam(d, C.byref(w.c), C.byref(a), s), 'sat_dense_adam')
+                self._toc(t)
             if sweep_on_side:
                 main.wait_event(self._ev_swept)
         check(l.sat_finalize_loss(d, C.byref(w.c), float(l2_emb), int(self.precision != 'fp32'), s), 'sat_finalize_loss')
