@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SAT_ABI_VERSION 3
+#define SAT_ABI_VERSION 4
 
 #define SAT_OK 0
 #define SAT_EINVAL (-1)      /* bad argument / unsupported shape            */
@@ -345,7 +345,7 @@ int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind, int32_t l
                     uint64_t seed, int32_t passes, void* stream);
 
 /* ---- "next" row: SelfAttention_Layer.forward (reference submodules.py:178-238) through the same
- *      per-sample field-attention code.  x, out: [B][F][32]; W_*: [32][32] used as x @ W; forward only. ---------- */
+ *      per-sample field-attention code.  x, out: [B][F][32]; W_*: [32][32] used as x @ W; forward.    ---------- */
 int sat_selfatt_fwd(const float* x, float* out, const float* wq, const float* wk, const float* wv, const float* wres,
                     const float* ln_g, const float* ln_b, int32_t B, int32_t F, int32_t H, int32_t use_res,
                     int32_t training, float dropout_p, uint64_t seed, void* stream);
@@ -353,20 +353,25 @@ int sat_selfatt_fwd(const float* x, float* out, const float* wq, const float* wk
 /* ---- the general form: SelfAttention_Layer (n_wq = 1, ln given, scaling = 1), MDR_InteractingLayer (reference
  *      star_trans.py:146-242: wq / ln_g / ln_b hold n_wq <= 8 scenario-specific sets, dom[b] in 1..n_wq selects set dom-1, any
  *      other id leaves a zero output; the 'sum' / 'dot' merge with the shared W_Query is done by the caller) and deepctr-torch's
- *      InteractingLayer (AutoInt: ln_g = ln_b = NULL, scaling = 0, dropout_p = 0).  Forward only. ---------------------------- */
+ *      InteractingLayer (AutoInt: ln_g = ln_b = NULL, scaling = 0, dropout_p = 0).  Forward. --------------------------------- */
 int sat_field_attention_fwd(const float* x, float* out, const float* wq, int32_t n_wq, const float* wk, const float* wv,
                             const float* wres, const float* ln_g, const float* ln_b, const int32_t* dom, int32_t B, int32_t F,
                             int32_t H, int32_t use_res, int32_t scaling, int32_t training, float dropout_p, uint64_t seed,
                             void* stream);
-/* ---- backward of the same layer for n_wq = 1, dom = NULL (SelfAttention_Layer: ln_g given, scaling = 1; InteractingLayer: ln_g =
- *      NULL): replaces torch autograd over reference submodules.py:208-238.  Only x is needed from the forward (it is recomputed
- *      per tile with the same seed, so the dropout masks are the forward's).  dx and the parameter gradients are OVERWRITTEN
- *      (not accumulated); every sum has a fixed order.  scratch: sat_field_attention_bwd_scratch(B, F) bytes. ---------------- */
+/* ---- backward of the same layer with ONE W_Query / LayerNorm set (SelfAttention_Layer: ln_g given, scaling = 1;
+ *      InteractingLayer: ln_g = NULL): replaces torch autograd over reference submodules.py:208-238.  Only x is needed from the
+ *      forward (it is recomputed per tile with the same seed, so the dropout masks are the forward's).  sample_idx = NULL: the
+ *      launch works on samples 0..B-1.  sample_idx = B sample indices (device int32): it works on those samples only -- rows of
+ *      x / dy / dx and the dropout counters are those of sample sample_idx[i], every other row of dx is left untouched.  That is
+ *      one scenario of an MDR_InteractingLayer (reference star_trans.py:218-239 under autograd): the caller launches once per
+ *      scenario with that scenario's W_Query / LayerNorm and adds the shared-parameter gradients in scenario order.  dx rows
+ *      and the parameter gradients are OVERWRITTEN (not accumulated); every sum has a fixed order.
+ *      scratch: sat_field_attention_bwd_scratch(B, F) bytes. ------------------------------------------------------------- */
 int64_t sat_field_attention_bwd_scratch(int32_t B, int32_t F);
 int sat_field_attention_bwd(const float* x, const float* dy, float* dx, const float* wq, const float* wk, const float* wv,
-                            const float* wres, const float* ln_g, int32_t B, int32_t F, int32_t H, int32_t use_res, int32_t scaling,
-                            int32_t training, float dropout_p, uint64_t seed, float* dwq, float* dwk, float* dwv, float* dwres,
-                            float* dln_g, float* dln_b, float* scratch, void* stream);
+                            const float* wres, const float* ln_g, const int32_t* sample_idx, int32_t B, int32_t F, int32_t H,
+                            int32_t use_res, int32_t scaling, int32_t training, float dropout_p, uint64_t seed, float* dwq,
+                            float* dwk, float* dwv, float* dwres, float* dln_g, float* dln_b, float* scratch, void* stream);
 /* ---- logit head of the baselines (reference star_trans.py:762-775, autoint.py:107-121): y[b] = sigmoid(bias + feat[b] . w[0:n]
  *      + dense[b] . w[n:n+n_dense]); feat: [B][n], dense: [B][ld_dense] or NULL, bias may be NULL, apply_sigmoid = 0 -> logit. */
 int sat_head_fwd(const float* feat, int32_t n, const float* dense, int32_t n_dense, int32_t ld_dense, const float* w,

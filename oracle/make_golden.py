@@ -28,6 +28,7 @@ import sys
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -299,6 +300,48 @@ def build_star_trans():
     for k, v in st.items():
         if not k.startswith('linear_model.'):
             out['model/state/' + k] = v.numpy()
+    # training goldens of the same model (reference basemodel.py:309-328: BCE(sum) + L2(embeddings), dense Adam), dropout off
+    # (eval mode with gradients) so that they do not depend on torch's mask stream; drawn AFTER everything above, so the forward
+    # goldens keep their bits
+    yl = (torch.rand(64, generator=g) < 0.3).float()
+    out['model/y'] = yl.numpy()
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def ref_step(first):
+        model.optim.zero_grad()
+        loss = model.loss_func(model(X).squeeze(), yl, reduction='sum')
+        reg = model.get_regularization_loss()
+        (loss + reg).sum().backward()
+        if first:
+            out['model/loss'], out['model/reg'] = loss.detach().numpy(), reg.detach().numpy()
+            for k, p_ in model.named_parameters():
+                if p_.grad is not None and not k.startswith('linear_model.'):
+                    out['model/grad/' + k] = p_.grad.detach().clone().numpy()
+            # the restatement under torch autograd gives the same gradients
+            so = {k: v.detach().clone().requires_grad_(True) for k, v in st.items() if v.dtype.is_floating_point}
+            lo = F.binary_cross_entropy(O.star_trans_forward(so, X, schema.fields, schema.domain_col, schema.num_domains, 4, 2, 1).squeeze(),
+                                        yl, reduction='sum')
+            lo = lo + sum(1e-5 * (v * v).sum() for k, v in so.items() if k.startswith('embedding_dict.'))
+            lo.backward()
+            for k, p_ in model.named_parameters():
+                if p_.grad is not None and not k.startswith('linear_model.'):
+                    gmax = float(p_.grad.abs().max())
+                    assert float((so[k].grad - p_.grad).abs().max()) <= 1e-5 * gmax + 1e-12, k
+        model.optim.step()
+        return float(loss)
+
+    # (a) two plain-SGD steps (the reference's 'sgd' string: lr 0.01): the update is linear in the gradient, so the end state
+    #     can be held to the gradient tolerance element by element
+    model.compile('sgd', 'binary_crossentropy', metrics=[])
+    ref_step(True)
+    ref_step(False)
+    for k, v in model.state_dict().items():
+        if not k.startswith('linear_model.'):
+            out['model/sgd_after2/' + k] = v.detach().clone().numpy()
+    # (b) three Adam steps (main.py:343; lr 0.01) from the same start: the loss trajectory
+    model.load_state_dict(state0)
+    model.compile(torch.optim.Adam(model.parameters(), lr=0.01), 'binary_crossentropy', metrics=[])
+    out['model/adam_losses'] = np.array([ref_step(False) for _ in range(3)], dtype=np.float64)
     return out
 
 

@@ -16,7 +16,7 @@ SAT_REG_PARTS = 148 * 256 + 148 * 4
 SAT_WORK_BUFFERS = 32
 SAT_ACT_PER_LAYER = 6      # activation rows saved per layer and token by a training forward
 SAT_GRID_MAX, SAT_SORT_RADIX_BITS, SAT_SORT_TILE, SAT_ROWS_CHUNK = 148 * 2, 9, 2048, 32
-SAT_ABI_VERSION = 3
+SAT_ABI_VERSION = 4
 SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
@@ -99,7 +99,7 @@ PROTOTYPES = {
     'sat_selfatt_fwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, C.c_uint64, vp]),
     'sat_field_attention_fwd': (C.c_int, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64, vp]),
     'sat_field_attention_bwd_scratch': (C.c_int64, [i32, i32]),
-    'sat_field_attention_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64,
+    'sat_field_attention_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, C.c_uint64,
                                           vp, vp, vp, vp, vp, vp, vp, vp]),
     'sat_head_fwd': (C.c_int, [vp, i32, vp, i32, i32, vp, vp, i32, vp, i32, vp]),
     'sat_pack_weights': (C.c_int, [C.POINTER(SatModel), C.POINTER(SatWork), i32, vp]),

@@ -1,24 +1,187 @@
-"""Scoring (inference) path of the attention baselines of BASELINE config 5 through this framework's kernels: multi-field
-embedding gather -> field-attention layers -> logit head.  Same constructors, state-dict keys and predict() contract as the
-reference classes; TRAINING IS NOT BUILT for them (fit / train_on_batch raise) -- SATrans is the trained model of this package.
+"""The attention baselines of BASELINE config 5 ("next" rows 2 and 3) through this framework's kernels:
+multi-field embedding gather -> field-attention layers -> logit head.  Same constructors, state-dict keys and
+compile / fit / evaluate / predict contract as the reference classes.
+
+Scoring (predict / forward under no_grad) launches only this package's kernels.  Training (fit / train_on_batch, reference
+basemodel.py:201-384: BCE(sum) + L2(embeddings), every parameter stepped by the torch.optim instance) is the reference's loop with
+the hot ops replaced: the gather and the attention layers run their forward AND backward in the CUDA kernels (autograd
+Functions around sat_gather_fwd and sat_field_attention_fwd / _bwd; the embedding backward is a sorted-index segmented sum, no
+float atomics), while the 1-row logit head, AutoInt's plain DNN tower, the loss and the optimiser update are torch library ops.
+SATrans (satrans.py) is the model whose whole step is fused; these two are trained for parity and completeness, not speed.
 
     Star_Trans   reference models/star_trans.py:674-775 (SelfAttention_Layer x att_layer_num, MDR_InteractingLayer x
                  domain_att_layer_num, dnn_linear), pinned by tests/golden/star_trans.npz
     AutoInt      reference models/autoint.py:39-123 on deepctr-torch's InteractingLayer / DNN -- PARITY UNPINNED (the layers live in
                  an un-vendored third-party package); its plain DNN tower runs as torch.nn.Linear (library GEMM)
 """
+import time
+
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as Fnn
 
 from . import _lib
-from .basemodel import BaseModel
+from .basemodel import BaseModel, CallbackList
 from .inputs import DenseFeat, SparseFeat
 from .selfatt import InteractingLayer, MDR_InteractingLayer, SelfAttention_Layer
 
 
+class _EmbeddingRows(torch.autograd.Function):
+    """E (B, F, 32) = the batch's rows of every field's table (sat_gather_fwd).  Backward = the reference's dense embedding
+    gradient (nn.Embedding(sparse=False)): rows sorted by global index, equal rows summed in batch order (torch.segment_reduce:
+    sequential per segment, so two runs agree bit for bit), one dense gradient per table returned as views of one buffer."""
+
+    @staticmethod
+    def forward(ctx, model, Xd, *weights):
+        ctx.model = model
+        ctx.save_for_backward(Xd)
+        return model.engine.gather(Xd)
+
+    @staticmethod
+    def backward(ctx, dE):
+        model = ctx.model
+        (Xd,) = ctx.saved_tensors
+        lay = model._layout
+        dev = dE.device
+        ids = Xd[:, lay['sparse_cols']].long()                                          # the reference's .long(): truncation
+        rows = (ids + torch.as_tensor(lay['row_off'][:-1], device=dev)[None, :]).reshape(-1)
+        srt, order = torch.sort(rows, stable=True)
+        uniq, counts = torch.unique_consecutive(srt, return_counts=True)
+        seg = torch.segment_reduce(dE.reshape(-1, dE.shape[-1]).float().index_select(0, order), 'sum', lengths=counts)
+        g = torch.zeros_like(model._tables)
+        g[uniq] = seg
+        off = lay['row_off']
+        return (None, None) + tuple(g[off[i]:off[i + 1]] for i in range(len(off) - 1))
+
+
 class _ScoringModel(BaseModel):
-    """Shared plumbing: gather through the engine's kernel, scoring-only contract."""
+    """Shared plumbing of the two baselines: gather through the engine's kernel, scoring through the package's kernels only,
+    training as the reference's loop around the differentiable kernels."""
+
+    def _field_embeddings(self, Xd):
+        """(B, all sparse fields, 32); differentiable w.r.t. the tables when autograd is recording."""
+        if torch.is_grad_enabled():
+            return _EmbeddingRows.apply(self, Xd, *[self.embedding_dict[f.embedding_name].weight for f in self._sparse_feats])
+        return self.engine.gather(Xd)
+
+    # ---- compile: real torch.optim instances (reference basemodel.py:540-582) ----------------------------------------------
+    def compile(self, optimizer, loss=None, metrics=None):
+        self.metrics_names = ["loss"]
+        if isinstance(optimizer, str):
+            table = {"sgd": lambda p: torch.optim.SGD(p, lr=0.01), "adam": torch.optim.Adam, "adagrad": torch.optim.Adagrad,
+                     "rmsprop": torch.optim.RMSprop}
+            if optimizer not in table:
+                raise NotImplementedError
+            self.optim = table[optimizer](self.parameters())
+        else:
+            self.optim = optimizer
+        if isinstance(loss, str):
+            table = {"binary_crossentropy": Fnn.binary_cross_entropy, "mse": Fnn.mse_loss, "mae": Fnn.l1_loss}
+            if loss not in table:
+                raise NotImplementedError
+            self.loss_func = table[loss]
+        else:
+            self.loss_func = loss
+        self.metrics = self._get_metrics(metrics)
+
+    def _train_step(self, Xd, yd):
+        """One step of the reference's loop (basemodel.py:309-328) on device tensors -> (y_pred, loss, reg) detached."""
+        self.optim.zero_grad()
+        y_pred = self.forward(Xd).squeeze()
+        loss = self.loss_func(y_pred, yd.squeeze(), reduction='sum')
+        reg = self.get_regularization_loss()
+        (loss + reg + self.aux_loss.to(loss.device)).sum().backward()
+        self.optim.step()
+        return y_pred.detach(), loss.detach(), reg.detach()
+
+    def train_on_batch(self, x, y):
+        """One optimiser step on one batch given as host data -> (loss, reg) floats, like SATrans.train_on_batch."""
+        self.train()
+        Xd = self._as_device_matrix(self._stack_inputs(x))
+        yd = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(Xd.device)
+        with torch.enable_grad():
+            _, loss, reg = self._train_step(Xd, yd)
+        self.engine.check_errors(self.engine.workspace(1, False))
+        return float(loss), float(reg)
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, valid_cnt_per_epoch=1, verbose=1, initial_epoch=0,
+            validation_split=0., validation_data=None, shuffle=True, callbacks=None):
+        """Same signature / History contract as the reference (basemodel.py:201-384)."""
+        do_validation, val_x, val_y = False, [], []
+        if validation_data:
+            do_validation = True
+            if len(validation_data) not in (2, 3):
+                raise ValueError('When passing a `validation_data` argument, it must contain either 2 items '
+                                 '(x_val, y_val), or 3 items (x_val, y_val, val_sample_weights)')
+            val_x, val_y = validation_data[0], validation_data[1]
+        X = self._stack_inputs(x)
+        y = np.asarray(y).reshape(len(X), -1)[:, 0]
+        if not validation_data and validation_split and 0. < validation_split < 1.:
+            do_validation = True
+            split_at = int(len(X) * (1. - validation_split))
+            X, val_x, y, val_y = X[:split_at], X[split_at:], y[:split_at], y[split_at:]
+        batch_size = 256 if batch_size is None else batch_size
+        dev = self._tables.device
+        Xd = torch.as_tensor(np.ascontiguousarray(X)).to(dev)
+        yd = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)).to(dev)
+        n = len(X)
+        steps = (n - 1) // batch_size + 1
+        callbacks = CallbackList((callbacks or []) + [self.history])
+        callbacks.set_model(self)
+        callbacks.on_train_begin()
+        self.stop_training = False
+        if verbose > 0:
+            print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(n, len(val_y), steps))
+        if getattr(self, '_shuffle_gen', None) is None:
+            self._shuffle_gen = torch.Generator(device='cpu')
+            self._shuffle_gen.manual_seed(torch.initial_seed() & (2 ** 63 - 1))
+        for epoch in range(initial_epoch, epochs):
+            callbacks.on_epoch_begin(epoch)
+            t0 = time.time()
+            self.train()
+            order = torch.randperm(n, generator=self._shuffle_gen).to(dev) if shuffle else None
+            total = torch.zeros((), dtype=torch.float64, device=dev)
+            preds = torch.empty(n, dtype=torch.float32, device=dev)
+            for s0 in range(0, n, batch_size):
+                s1 = min(s0 + batch_size, n)
+                if order is not None:
+                    xb, yb = Xd.index_select(0, order[s0:s1]).contiguous(), yd.index_select(0, order[s0:s1])
+                else:
+                    xb, yb = Xd[s0:s1].contiguous(), yd[s0:s1]
+                with torch.enable_grad():
+                    yp, loss, reg = self._train_step(xb, yb)
+                total += loss.double() + reg.double().sum()
+                preds[s0:s1] = yp.reshape(-1)
+            self.engine.check_errors(self.engine.workspace(1, False))
+            epoch_logs = {"loss": float(total) / n}
+            if verbose > 0 and self.metrics:
+                ph = preds.cpu().numpy().astype("float64")
+                yh = (yd.index_select(0, order) if order is not None else yd).cpu().numpy()
+                for name, fn in self.metrics.items():
+                    vals = []
+                    for s0 in range(0, n, batch_size):
+                        try:
+                            vals.append(fn(yh[s0:s0 + batch_size], ph[s0:s0 + batch_size]))
+                        except ValueError:
+                            vals.append(float('nan'))
+                    epoch_logs[name] = np.sum(vals) / steps
+            if do_validation:
+                for name, result in self.evaluate(val_x, val_y, batch_size).items():
+                    epoch_logs["val_" + name] = result
+            if verbose > 0:
+                print('Epoch {0}/{1}'.format(epoch + 1, epochs))
+                msg = "{0}s - loss: {1: .4f}".format(int(time.time() - t0), epoch_logs["loss"])
+                for name in self.metrics:
+                    msg += " - " + name + ": {0: .4f}".format(epoch_logs.get(name, float('nan')))
+                    if do_validation:
+                        msg += " - val_" + name + ": {0: .4f}".format(epoch_logs["val_" + name])
+                print(msg)
+            callbacks.on_epoch_end(epoch, epoch_logs)
+            if self.stop_training:
+                break
+        callbacks.on_train_end()
+        return self.history
 
     def _init_layout(self, device):
         sparse = self._sparse_feats
@@ -47,12 +210,18 @@ class _ScoringModel(BaseModel):
 
     def _gather_fields(self, X, keep):
         Xd = self._as_device_matrix(X)
-        E = self.engine.gather(Xd)                                   # (B, all sparse fields, 32): one launch
+        E = self._field_embeddings(Xd)                               # (B, all sparse fields, 32): one launch
         if len(keep) != E.shape[1]:
             E = E[:, keep, :].contiguous()
         return Xd, E
 
     def _head(self, feat, dense, w, bias, sigmoid=True):
+        if torch.is_grad_enabled():                                  # training: the 1-row head through torch autograd
+            z = feat if dense is None else torch.cat([feat, dense], dim=1)
+            z = Fnn.linear(z, w, None)
+            if bias is not None:
+                z = z + bias
+            return torch.sigmoid(z) if sigmoid else z
         B, n = feat.shape
         y = torch.empty(B, dtype=torch.float32, device=feat.device)
         nd = 0 if dense is None else dense.shape[1]
@@ -61,20 +230,16 @@ class _ScoringModel(BaseModel):
                                            B, y.data_ptr(), int(sigmoid), torch.cuda.current_stream().cuda_stream), 'sat_head_fwd')
         return y.unsqueeze(1)
 
-    def fit(self, *a, **k):
-        raise NotImplementedError("%s is a scoring-only baseline here (BASELINE config 5): training is not built" % type(self).__name__)
-
-    train_on_batch = fit
-
     def predict(self, x, batch_size=256, y=None, domain_ids=None):
         self.eval()
         X = self._stack_inputs(x)
         n = len(X)
         out = torch.empty(n, dtype=torch.float32, device=self._tables.device)
         Xd = torch.as_tensor(np.ascontiguousarray(X)).to(self._tables.device)
-        for s0 in range(0, n, batch_size):
-            s1 = min(s0 + batch_size, n)
-            out[s0:s1] = self.forward(Xd[s0:s1].contiguous())[:, 0]
+        with torch.no_grad():
+            for s0 in range(0, n, batch_size):
+                s1 = min(s0 + batch_size, n)
+                out[s0:s1] = self.forward(Xd[s0:s1].contiguous())[:, 0]
         if n:
             self.engine.check_errors(self.engine.workspace(1, False))
         return out.cpu().numpy().astype("float64").reshape(-1, 1)
@@ -114,7 +279,6 @@ class Star_Trans(_ScoringModel):
         self._init_layout(device)
         self.to(device)
 
-    @torch.no_grad()
     def forward(self, X):
         Xd, x = self._gather_fields(X, self._keep)
         dom = Xd[:, self.feature_index[self.domain_column][0]].to(torch.int32)      # .long() of the reference: truncation
@@ -170,7 +334,6 @@ class AutoInt(_ScoringModel):
         self._init_layout(device)
         self.to(device)
 
-    @torch.no_grad()
     def forward(self, X):
         Xd, x = self._gather_fields(X, list(range(len(self._sparse_feats))))
         flat = x.reshape(x.shape[0], -1)
@@ -182,7 +345,6 @@ class AutoInt(_ScoringModel):
             parts.append(att.reshape(att.shape[0], -1))
         if len(self.dnn_hidden_units) > 0:
             dnn_in = flat if not self._dense_cols else torch.cat([flat, Xd[:, self._dense_cols].float()], dim=1)
-            with torch.no_grad():
-                parts.append(self.dnn(dnn_in))
+            parts.append(self.dnn(dnn_in))
         stack = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1).contiguous()
         return self._head(stack, None, self.dnn_linear.weight, self.out.bias)       # y = sigmoid(dnn_linear(stack) + out.bias)

@@ -8,7 +8,7 @@
 //       outside 1..n keeps a zero output
 //   InteractingLayer     (deepctr-torch 0.2.9, AutoInt; not vendored -> parity unpinned): no 1/sqrt(dh) scaling by default,
 //       no dropout, no LayerNorm:  out = relu(softmax(Q K^T) V + X W_Res)
-// One thread = one field token, a CTA = floor(192/F) whole samples; forward only (inference and train-mode dropout).
+// One thread = one field token, a CTA = floor(192/F) whole samples; the forward (inference and train-mode dropout; backward: selfatt_bwd.cu).
 #include "fwd_common.cuh"
 
 namespace sat {

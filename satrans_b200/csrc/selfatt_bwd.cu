@@ -24,6 +24,8 @@ struct SelfAttBwdArgs {
     float* dx;             // [B][F][32]
     const float* wq; const float* wk; const float* wv; const float* wres;
     const float* ln_g;     // NULL: no LayerNorm (InteractingLayer)
+    const int32_t* idx;    // NULL: samples 0..B-1; else the B sample indices this launch works on (one scenario of an
+                           // MDR_InteractingLayer): rows of x / dy / dx and the dropout counters are those of sample idx[i]
     float* part;           // [gridDim.x][SB_PART]
     int B, F, use_res, training, scaling;
     float p_drop;
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(SB_NT, 1) k_selfatt_bwd(const SelfAttBwdArgs a
     float* sdLNw = sdLN + (tid >> 5) * 64;
 
     for (int t = t0; t < t1; ++t) {
-        const int b = t * spt + s;
         const int cnt = min(spt, a.B - t * spt);
         const bool valid = s < cnt;
+        const int b = !valid ? 0 : a.idx ? a.idx[t * spt + s] : t * spt + s;
         const int ntok = cnt * F;
         const long long tok = ((long long)b * F + f) * D;
         const uint32_t token_gid = (uint32_t)b * (uint32_t)F + (uint32_t)f;
@@ -334,7 +336,8 @@ extern "C" int64_t sat_field_attention_bwd_scratch(int32_t B, int32_t F) {
 }
 
 extern "C" int sat_field_attention_bwd(const float* x, const float* dy, float* dx, const float* wq, const float* wk, const float* wv,
-                                       const float* wres, const float* ln_g, int32_t B, int32_t F, int32_t H, int32_t use_res,
+                                       const float* wres, const float* ln_g, const int32_t* sample_idx, int32_t B, int32_t F,
+                                       int32_t H, int32_t use_res,
                                        int32_t scaling, int32_t training, float dropout_p, uint64_t seed, float* dwq, float* dwk,
                                        float* dwv, float* dwres, float* dln_g, float* dln_b, float* scratch, void* stream) {
     if (!x || !dy || !dx || !wq || !wk || !wv || !dwq || !dwk || !dwv || !scratch || (use_res && (!wres || !dwres)) ||
@@ -344,7 +347,7 @@ extern "C" int sat_field_attention_bwd(const float* x, const float* dy, float* d
     if (dropout_p < 0.f || dropout_p >= 1.f) return sat_host::fail(SAT_EINVAL, "sat_field_attention_bwd: dropout_p=%f", dropout_p);
     if (B <= 0) return SAT_OK;
     SelfAttBwdArgs a;
-    a.x = x; a.dy = dy; a.dx = dx; a.wq = wq; a.wk = wk; a.wv = wv; a.wres = wres; a.ln_g = ln_g; a.part = scratch;
+    a.x = x; a.dy = dy; a.dx = dx; a.wq = wq; a.wk = wk; a.wv = wv; a.wres = wres; a.ln_g = ln_g; a.idx = sample_idx; a.part = scratch;
     a.B = B; a.F = F; a.use_res = use_res; a.training = training; a.scaling = scaling; a.p_drop = dropout_p; a.seed = seed;
     const int grid = sab_grid(B, F);
     const size_t smem = sb_smem_bytes(F);

@@ -1,9 +1,9 @@
 """Field self-attention layers of the baselines that share SATrans' attention front end ("next" rows of SURVEY.md section 8f, the
 AutoInt / STAR-Trans scoring of BASELINE config 5), run through the same per-sample field-attention kernel code as SATrans
 (`sat_field_attention_fwd` / `sat_field_attention_bwd`).  Same constructors and state-dict keys as the reference classes.
-SelfAttention_Layer and InteractingLayer are differentiable (a torch.autograd.Function around the two kernels: gradients w.r.t. the
-input and every parameter, dropout masks of the backward = the forward's through the shared counter-based seed);
-MDR_InteractingLayer is forward only (scoring), using it under autograd raises.
+All three layers are differentiable (a torch.autograd.Function around the two kernels: gradients w.r.t. the input and every
+parameter, dropout masks of the backward = the forward's through the shared counter-based seed); MDR_InteractingLayer's backward
+runs the backward kernel once per scenario on that scenario's sample list.
 
     SelfAttention_Layer    reference submodules.py:178-238 (key `W_Key`) and star_trans.py:335-396 (key `W_key`)
     MDR_InteractingLayer   reference star_trans.py:146-242: one W_Query and one LayerNorm per scenario
@@ -63,10 +63,69 @@ class _FieldAttention(torch.autograd.Function):
         scratch = torch.empty(max(1, l.sat_field_attention_bwd_scratch(B, F) // 4), dtype=torch.float32, device=x.device)
         p = lambda t: None if t is None else t.data_ptr()
         _lib.check(l.sat_field_attention_bwd(
-            x.data_ptr(), dy.data_ptr(), dx.data_ptr(), p(wq), p(wk), p(wv), p(wres), p(g), B, F, heads, int(wres is not None),
-            int(scaling), int(training), float(p_drop), seed, p(dwq), p(dwk), p(dwv), p(dwres), p(dg), p(db), scratch.data_ptr(),
-            torch.cuda.current_stream().cuda_stream), 'sat_field_attention_bwd')
+            x.data_ptr(), dy.data_ptr(), dx.data_ptr(), p(wq), p(wk), p(wv), p(wres), p(g), None, B, F, heads,
+            int(wres is not None), int(scaling), int(training), float(p_drop), seed, p(dwq), p(dwk), p(dwv), p(dwres), p(dg), p(db),
+            scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), 'sat_field_attention_bwd')
         return dx, dwq, dwk, dwv, dwres, dg, db, None, None, None, None, None
+
+
+class _ScenarioAttention(torch.autograd.Function):
+    """y = MDR_InteractingLayer(x, dom) with the effective per-scenario W_Query stack wq (n, 32, 32) and LayerNorm stacks (n, 32).
+    Forward: ONE launch of sat_field_attention_fwd (the kernel picks every sample's set).  Backward: the samples are grouped by
+    scenario (stable sort of the ids) and sat_field_attention_bwd runs once per scenario on that scenario's sample list with its
+    own W_Query / LayerNorm -- the reference's masked per-scenario loop (star_trans.py:218-239) under autograd; gradients of the
+    shared W_key / W_Value / W_Res are added in scenario order (fixed order: bit-reproducible).  Samples whose id is outside 1..n
+    have a zero output and receive a zero input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, dom, wq, wk, wv, wres, ln_g, ln_b, heads, scaling, training, p_drop, seed):
+        x = x.contiguous().float()
+        B, F, _ = x.shape
+        n = wq.shape[0]
+        out = torch.empty_like(x)
+        c = lambda t: None if t is None else t.detach().contiguous().float()
+        wq_, wk_, wv_, wres_, g_, b_ = c(wq), c(wk), c(wv), c(wres), c(ln_g), c(ln_b)
+        p = lambda t: None if t is None else t.data_ptr()
+        _lib.check(_lib.lib().sat_field_attention_fwd(
+            x.data_ptr(), out.data_ptr(), p(wq_), n, p(wk_), p(wv_), p(wres_), p(g_), p(b_), dom.data_ptr(), B, F, heads,
+            int(wres is not None), int(scaling), int(training), float(p_drop), seed, torch.cuda.current_stream().cuda_stream),
+            'sat_field_attention_fwd')
+        ctx.save_for_backward(x, dom, wq_, wk_, wv_, wres_, g_)
+        ctx.cfg = (heads, scaling, training, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, dom, wq, wk, wv, wres, g = ctx.saved_tensors
+        heads, scaling, training, p_drop, seed = ctx.cfg
+        B, F, _ = x.shape
+        n = wq.shape[0]
+        dy = dy.contiguous().float()
+        dx = torch.zeros_like(x)
+        dwq, dg, db = torch.zeros_like(wq), torch.zeros_like(g), torch.zeros_like(g)
+        shared = torch.zeros((n, 3 if wres is not None else 2, 32, 32), dtype=torch.float32, device=x.device)
+        key = torch.where((dom >= 1) & (dom <= n), dom, torch.full_like(dom, n + 1))
+        order = torch.argsort(key, stable=True).to(torch.int32)
+        counts = torch.bincount(key.long(), minlength=n + 2)[1:n + 1].tolist()      # (one host sync per layer and backward)
+        l = _lib.lib()
+        scratch = torch.empty(max(1, l.sat_field_attention_bwd_scratch(max(counts + [1]), F) // 4), dtype=torch.float32,
+                              device=x.device)
+        s = torch.cuda.current_stream().cuda_stream
+        start = 0
+        for d, cnt in enumerate(counts):
+            if cnt:
+                idx = order[start:start + cnt].contiguous()
+                _lib.check(l.sat_field_attention_bwd(
+                    x.data_ptr(), dy.data_ptr(), dx.data_ptr(), wq[d].data_ptr(), wk.data_ptr(), wv.data_ptr(),
+                    wres.data_ptr() if wres is not None else None, g[d].data_ptr(), idx.data_ptr(), cnt, F, heads,
+                    int(wres is not None), int(scaling), int(training), float(p_drop), seed, dwq[d].data_ptr(),
+                    shared[d, 0].data_ptr(), shared[d, 1].data_ptr(), shared[d, 2].data_ptr() if wres is not None else None,
+                    dg[d].data_ptr(), db[d].data_ptr(), scratch.data_ptr(), s), 'sat_field_attention_bwd')
+            start += cnt
+        tot = shared[0].clone()
+        for d in range(1, n):                                                        # scenario order
+            tot += shared[d]
+        return (dx, None, dwq, tot[0], tot[1], tot[2] if wres is not None else None, dg, db, None, None, None, None, None)
 
 
 def _run(layer, inputs, wq, n_wq, wk, ln_g, ln_b, dom, scaling, p_drop):
@@ -74,9 +133,6 @@ def _run(layer, inputs, wq, n_wq, wk, ln_g, ln_b, dom, scaling, p_drop):
         raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
     if not inputs.is_cuda:
         raise _lib.SatError('%s needs CUDA tensors; there is no CPU fallback' % type(layer).__name__)
-    if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in layer.parameters())) and dom is not None:
-        if inputs.requires_grad:
-            raise NotImplementedError("the backward of %s is not built (forward / scoring only)" % type(layer).__name__)
     x = inputs.detach().contiguous().float()
     B, F, _ = x.shape
     out = torch.empty_like(x)
@@ -184,6 +240,8 @@ class MDR_InteractingLayer(nn.Module):
         self.to(device)
 
     def forward(self, inputs, domain_ids):
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.W_key.requires_grad):
+            return self._forward_differentiable(inputs, domain_ids)
         with torch.no_grad():
             wq = torch.stack([w.detach() for w in self.domain_W_Queries])              # (n, 32, 32)
             if self.merge == 'sum':                                                     # reference star_trans.py:209-217
@@ -198,3 +256,23 @@ class MDR_InteractingLayer(nn.Module):
             raise ValueError('domain_ids must hold one id per sample')
         return _run(self, inputs, wq.data_ptr(), self.num_domains, _ptr(self.W_key), ln_g.data_ptr(), ln_b.data_ptr(),
                     dom.data_ptr(), self.scaling, self.dropout_rate)
+
+    def _forward_differentiable(self, inputs, domain_ids):
+        if len(inputs.shape) != 3:
+            raise ValueError("Unexpected inputs dimensions %d, expect to be 3 dimensions" % (len(inputs.shape)))
+        if not inputs.is_cuda:
+            raise _lib.SatError('MDR_InteractingLayer needs CUDA tensors; there is no CPU fallback')
+        dom = domain_ids.detach().to(device=inputs.device, dtype=torch.int32).contiguous()
+        if dom.numel() != inputs.shape[0]:
+            raise ValueError('domain_ids must hold one id per sample')
+        wq = torch.stack(list(self.domain_W_Queries))              # torch autograd carries the merge and the stacking
+        if self.merge == 'sum':                                    # reference star_trans.py:209-217
+            wq = wq + self.W_Query
+        elif self.merge == 'dot':
+            wq = wq * self.W_Query
+        ln_g = torch.stack([ln.weight for ln in self.domain_layer_norms])
+        ln_b = torch.stack([ln.bias for ln in self.domain_layer_norms])
+        self._calls += 1
+        seed = (int(torch.initial_seed()) + self._calls) & (2 ** 64 - 1)
+        return _ScenarioAttention.apply(inputs, dom, wq, self.W_key, self.W_Value, self.W_Res if self.use_res else None, ln_g, ln_b,
+                                        self.head_num, bool(self.scaling), bool(self.training), float(self.dropout_rate), seed)

@@ -106,3 +106,46 @@ def table_grads(model, w, l2):
     for f, a, b in zip(model._sparse_feats, model._row_off[:-1], model._row_off[1:]):
         out['embedding_dict.%s.weight' % f.embedding_name] = dense[int(a):int(b)]
     return out, rows
+
+
+def field_attention_dropout_masks(B, seed, p_drop=0.1, F=8, H=4):
+    """The keep-masks the field-attention kernels draw for (seed, B, F, H) in train mode, read out of the FORWARD kernel alone
+    with inputs that make every output element a product of mask bits (the masks are counter-based: they depend on the seed,
+    the token index, the dropout site and the element index, never on the data):
+        pass 0: x = ones, W_Q = W_K = 0, W_V = I, no residual / LayerNorm -> out[b,i,c] = keep_out[b,i,c] * (mean of keep_att) / .81
+        pass s: x[b,j] = one-hot at channel (j + s) % dh of every head       -> out[b,i,h*dh+c] = keep_att[h,b,i,j] * keep_out / (F * .81)
+    A few shifts s resolve every attention bit (an element hidden by a dropped output channel shows up under another shift).
+    Returns {'att': (H, B, F, F) , 'out': (B, F, 32)} float 0/1 masks in the layout of oracle._drop."""
+    dh = 32 // H
+    assert F <= dh
+    lib = _lib.lib()
+    dev = 'cuda:0'
+    eye = torch.eye(32, device=dev).contiguous()
+    zero = torch.zeros((32, 32), device=dev)
+
+    def run(x):
+        out = torch.empty_like(x)
+        _lib.check(lib.sat_field_attention_fwd(x.data_ptr(), out.data_ptr(), zero.data_ptr(), 1, zero.data_ptr(), eye.data_ptr(), None,
+                                               None, None, None, B, F, H, 0, 1, 1, float(p_drop), int(seed),
+                                               torch.cuda.current_stream().cuda_stream), 'sat_field_attention_fwd')
+        return out.cpu()
+    keep_out = (run(torch.ones((B, F, 32), device=dev)) != 0).float()
+    att = torch.full((H, B, F, F), -1.0)
+    for shift in range(dh):
+        x = torch.zeros((B, F, 32), device=dev)
+        for j in range(F):
+            for h in range(H):
+                x[:, j, h * dh + (j + shift) % dh] = 1.0
+        o = run(x)
+        for j in range(F):
+            for h in range(H):
+                c = h * dh + (j + shift) % dh
+                seen = keep_out[:, :, c] > 0                                   # (B, F): query tokens whose channel c survived
+                bit = (o[:, :, c] != 0).float()
+                att[h][:, :, j] = torch.where(seen & (att[h][:, :, j] < 0), bit, att[h][:, :, j])
+        if (att >= 0).all():
+            break
+    assert (att >= 0).all()
+    frac = 1.0 - att.mean().item()
+    assert abs(frac - p_drop) < 0.03 and abs(1.0 - keep_out.mean().item() - p_drop) < 0.03, (frac, keep_out.mean().item())
+    return {'att': att, 'out': keep_out}

@@ -33,7 +33,7 @@ def test_header_symbols_exported_and_bound():
     l = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(l, name), name
-    assert l.sat_abi_version() == _lib.SAT_ABI_VERSION == 3
+    assert l.sat_abi_version() == _lib.SAT_ABI_VERSION == 4
     # struct mirrors: sizes implied by the header layout
     assert ctypes.sizeof(_lib.SatModel) == 10 * 4 + 10 * 8 + 5 * 8 + 8 + 8 + 7 * 8 * 8
     assert ctypes.sizeof(_lib.SatWork) == 24 + _lib.SAT_WORK_BUFFERS * 8
