@@ -62,16 +62,28 @@ extern "C" {
 #define SAT_FLAG_RES 16      /* att_res: residual connection                                              */
 #define SAT_FLAG_LOSS_MSE 32 /* loss = F.mse_loss(y_pred, y, 'sum') instead of binary cross-entropy (meta_basemodel.py:627-640) */
 #define SAT_FLAG_LOSS_MAE 64 /* loss = F.l1_loss(y_pred, y, 'sum')                                         */
+/* The reference's ablation variants of the scenario-specific projection (satrans.py:59-81,158-176).  GATE_* and BILINEAR run
+ * in the CUDA-core token kernels only (sat_forward / sat_backward; sat_forward_tc / sat_backward_tc refuse them); they replace
+ * the MetaNet of that side (SAT_FLAG_META_Q / _K are then clear), so Q' / K' carry no MetaNet LayerNorm and no dropout. */
+#define SAT_FLAG_GATE_Q 128  /* 'gate' in flag and 'Q' in meta_mode: Q' = (x W_Q) * theta_Q[0:32] * 2     (satrans.py:61-62) */
+#define SAT_FLAG_GATE_K 256  /* 'gate' in flag and 'K' in meta_mode: K' = (x W_K) * theta_K[0:32] * 2     (satrans.py:68-69) */
+#define SAT_FLAG_BILINEAR 512 /* 'bilinear' in flag: per head h, Q'_h = (x W_Q)_h @ B_h with B_h[i][j] = theta_Q[(h*dh + i)*dh + j],
+                                dh = 32 / H; K' = x W_K                                                  (satrans.py:63-64,79-81) */
+#define SAT_FLAG_ONLYEMB 1024 /* 'onlyemb' in flag: no scenario encoder; domain_embeddings.weight is [n_dom][4096] and
+                                theta[key] = relu(domain_embeddings[g(key)])                             (satrans.py:173-176) */
+/* generated weights per key that are live: 32 (gate), 1024 / H (bilinear), 4096 (MetaNet); rows of theta keep the stride SAT_P */
+#define SAT_META_PSZ(flags, H) (((flags) & (SAT_FLAG_GATE_Q | SAT_FLAG_GATE_K)) ? 32 : ((flags) & SAT_FLAG_BILINEAR) ? 1024 / (H) : SAT_P)
 
 /*
  * Model description.  All dense (non-table) parameters live in ONE flat fp32 buffer `dense`
  * (gradients / Adam moments use the same layout), at these float offsets:
  *
  *   off_dom   : domain_embeddings.weight            [n_dom][32]          reference satrans.py:145
+ *                                                   [n_dom][4096] with SAT_FLAG_ONLYEMB (then off_encw / off_encb are unused)
  *   off_lid   : layerid_embeddings.weight           [L][32]   (POS only) reference satrans.py:169
  *   off_qkv   : qkvid_embeddings.weight             [3][32]   (POS only) reference satrans.py:170
- *   off_encw  : domain_map_dnn_Q.linears.0.weight   [4096][enc_in]       reference satrans.py:178, submodules.py:31
- *   off_encb  : domain_map_dnn_Q.linears.0.bias     [4096]
+ *   off_encw  : domain_map_dnn_Q.linears.0.weight   [P][enc_in]          reference satrans.py:178, submodules.py:31
+ *   off_encb  : domain_map_dnn_Q.linears.0.bias     [P]                  P = SAT_META_PSZ(flags, H): 4096 unless gate / bilinear
  *   off_layers: L blocks of SAT_LAYER_FLOATS floats:                     reference satrans.py:31-47
  *                 +0    W_Query [32][32]  (x @ W)
  *                 +1024 W_Key   [32][32]

@@ -53,8 +53,21 @@ CASES = {
     # output, satrans.py:91-97, when dropout is the identity), so this case pins the forward only.
     'relu_small_fwd': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK',
                                                 flag='sota-relu')),
+    # the ablation variants of the scenario-specific projection (satrans.py:59-81,158-176): a generated gate / per-head bilinear
+    # map instead of the MetaNet, a wide scenario embedding instead of the scenario encoder; with and without 'pos'
+    'gate_small': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK', flag='sota-gate')),
+    'gatepos_small': ('alimama', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=2, meta_mode='K', flag='sota-gate-pos')),
+    'bilinear_small': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK', flag='sota-bilinear')),
+    'bilinearpos_small': ('aliccp', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=2, meta_mode='Q',
+                                                   flag='sota-bilinear-pos')),
+    # (B = 48: at B = 40 one element of the shared Q/K MetaNet LayerNorm bias has |g| = 2e-8 ~ Adam's eps, 5e-5 of the tensor's
+    #  max-norm -- its step direction is decided by round-off in any fp32 implementation, a useless fixture for Adam parity)
+    'onlyemb_small': ('aliccp', 5e-5, 48, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK', flag='sota-onlyemb')),
+    'onlyembpos_small': ('alimama', 5e-5, 40, dict(domain_att_layer_num=2, att_head_num=4, meta_mode='QK',
+                                                   flag='sota-onlyemb-pos')),
 }
 FORWARD_ONLY = {'relu_small_fwd'}
+VARIANT_CASES = ('gate_small', 'gatepos_small', 'bilinear_small', 'bilinearpos_small', 'onlyemb_small', 'onlyembpos_small')
 
 
 def subsample(key):
@@ -424,6 +437,12 @@ def main():
         path = os.path.join(ROOT, 'tests', 'golden', 'star_trans.npz')
         np.savez_compressed(path, **build_star_trans())
         print('star_trans ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+        return
+    if os.environ.get('SAT_GOLDEN_ONLY_CASES'):        # comma-separated case names
+        for name in os.environ['SAT_GOLDEN_ONLY_CASES'].split(','):
+            path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+            np.savez_compressed(path, **build_case(name))
+            print(name, '->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
         return
     path = os.path.join(ROOT, 'tests', 'golden', 'selfatt_layer.npz')
     np.savez_compressed(path, **build_selfatt())

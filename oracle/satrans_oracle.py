@@ -58,9 +58,21 @@ class OracleConfig:
         return [self.embedding_dim] + [int(u) for u in self.meta_dnn_hidden_units]
 
     @property
-    def meta_param_size(self) -> int:       # satrans.py:156
+    def meta_param_size(self) -> int:       # satrans.py:156-162
+        if 'bilinear' in self.flag:
+            return self.embedding_dim ** 2 // self.heads
+        if 'gate' in self.flag:
+            return self.embedding_dim
         u = self.units
         return sum(u[i] * u[i + 1] for i in range(len(u) - 1))
+
+    @property
+    def metanet(self) -> bool:              # the MetaNet itself (satrans.py:65,72) and not its 'gate' / 'bilinear' ablations
+        return 'gate' not in self.flag and 'bilinear' not in self.flag
+
+    @property
+    def onlyemb(self) -> bool:              # satrans.py:173-176: wide scenario embedding, no encoder
+        return 'onlyemb' in self.flag
 
     @property
     def pos(self) -> bool:
@@ -93,12 +105,13 @@ def trainable_keys(cfg: OracleConfig) -> List[str]:
         p = 'domain_int_layers.%d.' % i
         keys += [p + 'W_Query', p + 'W_Key', p + 'W_Value', p + 'Out_linear.weight',
                  p + 'layer_norm.weight', p + 'layer_norm.bias']
-        if 'Q' in cfg.meta_mode or ('K' in cfg.meta_mode and not cfg.pos):
+        if cfg.metanet and ('Q' in cfg.meta_mode or ('K' in cfg.meta_mode and not cfg.pos)):
             keys += [p + 'Q_meta_mlp.ffn_layer_norm.weight', p + 'Q_meta_mlp.ffn_layer_norm.bias']
-        if cfg.pos and 'K' in cfg.meta_mode:
+        if cfg.metanet and cfg.pos and 'K' in cfg.meta_mode:
             keys += [p + 'K_meta_mlp.ffn_layer_norm.weight', p + 'K_meta_mlp.ffn_layer_norm.bias']
-    keys += ['domain_map_dnn_Q.linears.0.weight', 'domain_map_dnn_Q.linears.0.bias']
-    if cfg.pos:
+    if not cfg.onlyemb:
+        keys += ['domain_map_dnn_Q.linears.0.weight', 'domain_map_dnn_Q.linears.0.bias']
+    if cfg.pos and not cfg.onlyemb:         # ('onlyemb' slices the position part of the concatenation away: zero gradient)
         keys += ['layerid_embeddings.weight', 'qkvid_embeddings.weight']
     keys += ['dnn_linear.weight', 'dnn_linear.bias']
     return keys
@@ -122,7 +135,7 @@ def init_state(cfg: OracleConfig, seed: int = 1021, dtype=torch.float32) -> "Ord
 
     for n, v in zip(cfg.sparse_names, cfg.vocab_sizes):
         st['embedding_dict.%s.weight' % n] = normal((v, d), cfg.init_std)
-    st['domain_embeddings.weight'] = normal((cfg.num_domains + 1, d), 1.0)
+    st['domain_embeddings.weight'] = normal((cfg.num_domains + 1, cfg.meta_param_size if cfg.onlyemb else d), 1.0)
     for i in range(cfg.layers):
         p = 'domain_int_layers.%d.' % i
         for w in ('W_Query', 'W_Key', 'W_Value', 'Out_linear.weight'):
@@ -133,8 +146,9 @@ def init_state(cfg: OracleConfig, seed: int = 1021, dtype=torch.float32) -> "Ord
             st[p + m + '.ffn_layer_norm.weight'] = torch.ones(d, dtype=dtype)
             st[p + m + '.ffn_layer_norm.bias'] = torch.zeros(d, dtype=dtype)
     enc_in = 2 * d if cfg.pos else d
-    st['domain_map_dnn_Q.linears.0.weight'] = normal((cfg.meta_param_size, enc_in), 1e-4)
-    st['domain_map_dnn_Q.linears.0.bias'] = uniform((cfg.meta_param_size,), 1.0 / math.sqrt(enc_in))
+    if not cfg.onlyemb:
+        st['domain_map_dnn_Q.linears.0.weight'] = normal((cfg.meta_param_size, enc_in), 1e-4)
+        st['domain_map_dnn_Q.linears.0.bias'] = uniform((cfg.meta_param_size,), 1.0 / math.sqrt(enc_in))
     if cfg.pos:
         st['layerid_embeddings.weight'] = normal((cfg.layers, d), 1.0)
         st['qkvid_embeddings.weight'] = normal((3, d), 1.0)
@@ -207,9 +221,13 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
     ids, x = gather_fields(st, X, cfg)                                     # [K1]
     dom = X[:, cfg.col_of(cfg.domain_col)].long()                          # satrans.py:203
     e = F.relu(st['domain_embeddings.weight'][dom])                        # satrans.py:204,213
-    We, be = st['domain_map_dnn_Q.linears.0.weight'], st['domain_map_dnn_Q.linears.0.bias']
+    if cfg.onlyemb:                                                        # satrans.py:173-176: identity "encoder"
+        encode = lambda u: u
+    else:
+        We, be = st['domain_map_dnn_Q.linears.0.weight'], st['domain_map_dnn_Q.linears.0.bias']
+        encode = lambda u: u @ We.t() + be
     if not cfg.pos:
-        theta = e @ We.t() + be                                            # satrans.py:218  [K2]
+        theta = encode(e)                                                  # satrans.py:218  [K2]
         thetas = [(theta, theta)] * L
     else:
         thetas = []
@@ -218,7 +236,7 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
             for q in range(2):                                             # q=2 (V) is generated but unused
                 pos_emb = st['layerid_embeddings.weight'][l] + st['qkvid_embeddings.weight'][q]
                 u = F.relu(torch.cat([e, pos_emb.expand(e.shape[0], -1)], dim=1))
-                per.append(u @ We.t() + be)
+                per.append(encode(u))
             thetas.append(tuple(per))
     aux['ids'], aux['E0'], aux['layer_in'], aux['att'] = ids, x, [], []
     for l in range(L):
@@ -230,16 +248,22 @@ def forward(st: Dict[str, torch.Tensor], X: torch.Tensor, cfg: OracleConfig,
         v = inp @ st[p + 'W_Value']
         qn = p + 'Q_meta_mlp.ffn_layer_norm.'
         kn = p + ('K_meta_mlp' if cfg.pos else 'Q_meta_mlp') + '.ffn_layer_norm.'
-        if 'Q' in cfg.meta_mode:                                           # satrans.py:60-66 [K4]
+        if 'Q' in cfg.meta_mode and 'gate' in cfg.flag:                    # satrans.py:61-62
+            q = q * thetas[l][0].unsqueeze(1).expand(q.shape) * 2
+        elif 'Q' in cfg.meta_mode and cfg.metanet:                         # satrans.py:60-66 [K4]
             q = meta_net(q, thetas[l][0][:, :P], cfg.units, st[qn + 'weight'], st[qn + 'bias'], masks, 'l%d.q' % l,
                          relu_mask=None if relu_masks is None else relu_masks['l%d.q' % l])
-        if 'K' in cfg.meta_mode:                                           # satrans.py:67-73 [K4]
+        if 'K' in cfg.meta_mode and 'gate' in cfg.flag:                    # satrans.py:68-69
+            k = k * thetas[l][1].unsqueeze(1).expand(k.shape) * 2
+        elif 'K' in cfg.meta_mode and cfg.metanet:                         # satrans.py:67-73 [K4]
             k = meta_net(k, thetas[l][1][:, :P], cfg.units, st[kn + 'weight'], st[kn + 'bias'], masks, 'l%d.k' % l,
                          relu_mask=None if relu_masks is None else relu_masks['l%d.k' % l])
         B_, F_ = q.shape[0], q.shape[1]
         qh = q.reshape(B_, F_, H, dh).permute(2, 0, 1, 3)                  # satrans.py:75-77 [K5]
         kh = k.reshape(B_, F_, H, dh).permute(2, 0, 1, 3)
         vh = v.reshape(B_, F_, H, dh).permute(2, 0, 1, 3)
+        if 'bilinear' in cfg.flag:                                         # satrans.py:79-81 (bilinear_params = the Q side's theta)
+            qh = qh @ thetas[l][0].reshape(-1, H, dh, dh).permute(1, 0, 2, 3)
         s = torch.matmul(qh, kh.transpose(-1, -2)) / (dh ** 0.5)           # satrans.py:84-86 [K6]
         a = F.softmax(s, dim=-1)
         a = _drop(a, 0.1, masks, 'l%d.att' % l)                            # satrans.py:87

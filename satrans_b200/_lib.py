@@ -21,6 +21,7 @@ SAT_MAX_SHARDS = 8
 IDS_F32, IDS_I32, IDS_I64 = 0, 1, 2
 FLAG_POS, FLAG_META_Q, FLAG_META_K, FLAG_RELU, FLAG_RES = 1, 2, 4, 8, 16
 FLAG_LOSS_MSE, FLAG_LOSS_MAE = 32, 64
+FLAG_GATE_Q, FLAG_GATE_K, FLAG_BILINEAR, FLAG_ONLYEMB = 128, 256, 512, 1024
 OPT_ADAM, OPT_SGD, OPT_ADAGRAD, OPT_RMSPROP = 0, 1, 2, 3
 ERR_BAD_ID, ERR_BAD_DOMAIN = 1, 2
 ADAM_TOUCHED, ADAM_UNTOUCHED, ADAM_DEFERRED = 1, 2, 4

@@ -385,6 +385,9 @@ class BaseModel(nn.Module):
     def precision(self, value):
         if value not in ('fp32', 'tf32x3', 'tf32', 'bf16'):
             raise ValueError("precision must be 'fp32', 'tf32x3', 'tf32' or 'bf16', got %r" % (value,))
+        from . import _lib
+        if value != 'fp32' and self._layout.get('flags', 0) & (_lib.FLAG_GATE_Q | _lib.FLAG_GATE_K | _lib.FLAG_BILINEAR):
+            raise NotImplementedError("the 'gate' / 'bilinear' flag variants run in the CUDA-core kernels only (precision='fp32')")
         self.engine.precision = value
 
     def _as_device_matrix(self, X):

@@ -175,6 +175,69 @@ __device__ __forceinline__ void metanet_side_bwd(const BwdArgs& a, bool has_meta
     __syncthreads();
 }
 
+// Backward of the ablation variants of one side (reference satrans.py:61-64,68-69,79-81 under autograd; forward.cu):
+//   bilinear (Q side, heads = H > 0):  Q'_h = qp_h @ B_h  ->  dB_h += qp_h^T dQ'_h  (the full 32x32 product qp^T dQ' is accumulated
+//                                      at sdTh[1024 + i*32 + j]; k_bwd_meta keeps its diagonal blocks),  dqp_h = dQ'_h @ B_h^T
+//   gate:                              Q' = qp * g * 2       ->  dg += sum_tokens 2 qp dQ' (tokens added in order), dqp = dQ' * 2 g
+// with qp = x @ W recomputed.  On entry dqp = dLoss/dQ', on exit dLoss/d(x @ W).  All threads of the CTA must call this.
+template <int H>
+__device__ __forceinline__ void bilinear_dq(const float* __restrict__ sTh, float (&dqp)[D]) {
+    constexpr int DH = D / H;
+    float out[D];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int i = 0; i < DH; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) acc = fmaf(dqp[h * DH + j], sTh[(h * DH + i) * DH + j], acc);
+            out[h * DH + i] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i) dqp[i] = out[i];
+}
+__device__ __forceinline__ void variant_side_bwd(bool gate, int heads, bool valid, int ntok, int tid,
+                                                 const float* __restrict__ sWp, const float* __restrict__ sTh,
+                                                 float* __restrict__ sdTh, float* __restrict__ sA, float* __restrict__ sG,
+                                                 const float* __restrict__ act_x, long long tokpos, float (&dqp)[D]) {
+    float qp[D];
+    zero(qp);
+    if (valid) {
+        float xin[D];
+        load_row(act_x + tokpos, xin);
+        vm_outer<D, D, D>(sWp, xin, qp);
+    }
+    if (heads > 0) {
+        if (valid) { sts_row(sA + tid * KV_LD, qp); sts_row(sG + tid * KV_LD, dqp); }
+        __syncthreads();
+        wgrad32(sA, sG, ntok, sdTh + 1024, D, tid);
+        __syncthreads();
+        if (valid) {
+            switch (heads) {
+                case 1: bilinear_dq<1>(sTh, dqp); break;
+                case 2: bilinear_dq<2>(sTh, dqp); break;
+                case 4: bilinear_dq<4>(sTh, dqp); break;
+                default: bilinear_dq<8>(sTh, dqp); break;
+            }
+        }
+    }
+    if (gate) {
+        if (valid) {
+            float pr[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) { pr[i] = 2.f * qp[i] * dqp[i]; dqp[i] = dqp[i] * (2.f * sTh[i]); }
+            sts_row(sA + tid * KV_LD, pr);
+        }
+        __syncthreads();
+        if (tid < D) {
+            float acc = 0.f;
+            for (int t = 0; t < ntok; ++t) acc += sA[t * KV_LD + tid];
+            sdTh[tid] += acc;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* sW = smem;                    // WQ WK WV
@@ -193,6 +256,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, F = m.F, L = m.L, l = a.layer;
     const bool pos = m.flags & SAT_FLAG_POS;
     const bool meta_q = m.flags & SAT_FLAG_META_Q, meta_k = m.flags & SAT_FLAG_META_K;
+    const bool gate_q = m.flags & SAT_FLAG_GATE_Q, gate_k = m.flags & SAT_FLAG_GATE_K;
+    const int bil_heads = (m.flags & SAT_FLAG_BILINEAR) ? m.H : 0;
     const int s = tid / F, f = tid - s * F;
     // every CTA stays inside ONE scenario (one set of generated-weight gradients per CTA, see scenario_partition)
     int t0, t1, g_cta, c0_, c1_;
@@ -232,6 +297,9 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
         {   // ---- Q side ---------------------------------------------------------------------------------
             float dqp[D];
             if (valid) load_row(a.dqkv + 0 * a.act_stride + tokpos, dqp); else zero(dqp);
+            if (gate_q || bil_heads)
+                variant_side_bwd(gate_q, bil_heads, valid, ntok, tid, sW + OFF_WQ, sThQ, sdThQ, sA, sG, act_l + ACT_X * a.act_stride,
+                                 tokpos, dqp);
             metanet_side_bwd(a, meta_q, valid, ntok, tid, lane, sW + OFF_WQ, sThQ, sdThQ, sLN + 64, sdLNq, sdW + OFF_WQ, sA,
                              sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZQ * a.act_stride,
                              relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 0, tokpos / D), tokpos,
@@ -241,6 +309,8 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
         {   // ---- K side ---------------------------------------------------------------------------------
             float dkp[D];
             if (valid) load_row(a.dqkv + 1 * a.act_stride + tokpos, dkp); else zero(dkp);
+            if (gate_k)
+                variant_side_bwd(true, 0, valid, ntok, tid, sW + OFF_WK, thK, sdThKuse, sA, sG, act_l + ACT_X * a.act_stride, tokpos, dkp);
             metanet_side_bwd(a, meta_k, valid, ntok, tid, lane, sW + OFF_WK, thK, sdThKuse, klng, sdLNk, sdW + OFF_WK, sA,
                              sG, act_l + ACT_X * a.act_stride, act_l + ACT_ZK * a.act_stride,
                              relu_mask_ptr(const_cast<float*>(a.acts), a.act_stride, L, l, 1, tokpos / D), tokpos,
@@ -265,6 +335,14 @@ __global__ void __launch_bounds__(NT, 1) k_bwd_meta(const BwdArgs a) {
         if (valid) store_row(a.dx + tokpos, dxa);
     }
     __syncthreads();
+    if (bil_heads) {        // d B_h = the h-th diagonal dh x dh block of qp^T dQ' (accumulated at sdThQ[1024 + i*32 + j])
+        const int dh = D / bil_heads;
+        for (int e = tid; e < D * dh; e += NT) {
+            const int row = e / dh, j = e - row * dh;                     // row = h*dh + i
+            sdThQ[e] = sdThQ[1024 + row * D + (row / dh) * dh + j];
+        }
+        __syncthreads();
+    }
     const GPart gp = gpart_layout(m);
     float* part = a.gpart + gp.meta + ((long long)l * SAT_GRID_MAX + blockIdx.x) * GP_META;
     store_partial(part, sdW, 3072, tid);
@@ -479,5 +557,7 @@ extern "C" int sat_backward_tc(const SatModel* m, const void* x, int32_t id_kind
                                uint64_t seed, int32_t passes, void* stream) {
     if (passes < 1 || passes > 3) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: passes must be 1, 2 or 3, got %d", passes);
     if (!w || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_backward_tc: workspace has no packed weights");
+    if (m && (m->flags & (SAT_FLAG_GATE_Q | SAT_FLAG_GATE_K | SAT_FLAG_BILINEAR)))
+        return sat_host::fail(SAT_EINVAL, "sat_backward_tc: the gate / bilinear variants run in sat_backward (CUDA-core kernels) only");
     return backward_impl(m, x, id_kind, ld, w, dropout_p, seed, passes, stream);
 }

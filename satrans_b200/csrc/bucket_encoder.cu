@@ -132,10 +132,11 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encoder_fwd(SatModel m, int n_k
     __shared__ float s_u[ENC_MAX_KEYS][2 * D];
     const int o = blockIdx.x * ENC_THREADS + threadIdx.x;
     const int ein = m.enc_in;
+    const bool live = o < SAT_META_PSZ(m.flags, m.H);       // gate / bilinear variants generate fewer weights: the rest of theta is 0
     float w[2 * D];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) w[i] = (i < ein) ? m.dense[m.off_encw + (long long)o * ein + i] : 0.f;
-    const float bias = m.dense[m.off_encb + o];
+    for (int i = 0; i < 2 * D; ++i) w[i] = (live && i < ein) ? m.dense[m.off_encw + (long long)o * ein + i] : 0.f;
+    const float bias = live ? m.dense[m.off_encb + o] : 0.f;
     for (int k0 = 0; k0 < n_keys; k0 += ENC_MAX_KEYS) {
         const int nk = min(ENC_MAX_KEYS, n_keys - k0);
         __syncthreads();
@@ -163,10 +164,11 @@ k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* _
     __shared__ float s_red[ENC_THREADS / 32][2 * D];
     const int o = blockIdx.x * ENC_THREADS + threadIdx.x;
     const int ein = m.enc_in;
+    const bool live = o < SAT_META_PSZ(m.flags, m.H);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float w[2 * D], dw[2 * D];
 #pragma unroll
-    for (int i = 0; i < 2 * D; ++i) { w[i] = (i < ein) ? m.dense[m.off_encw + (long long)o * ein + i] : 0.f; dw[i] = 0.f; }
+    for (int i = 0; i < 2 * D; ++i) { w[i] = (live && i < ein) ? m.dense[m.off_encw + (long long)o * ein + i] : 0.f; dw[i] = 0.f; }
     float db = 0.f;
     for (int k0 = 0; k0 < n_keys; k0 += ENC_MAX_KEYS) {
         const int nk = min(ENC_MAX_KEYS, n_keys - k0);
@@ -177,7 +179,7 @@ k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* _
         }
         __syncthreads();
         for (int k = 0; k < nk; ++k) {
-            const float g = dtheta[(long long)(k0 + k) * PSZ + o];
+            const float g = live ? dtheta[(long long)(k0 + k) * PSZ + o] : 0.f;
             db += g;
             // du[k][i]: reduce g*w[i] over the 256 outputs of this block
 #pragma unroll
@@ -198,6 +200,7 @@ k_encoder_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta, float* _
             __syncthreads();
         }
     }
+    if (!live) return;
 #pragma unroll
     for (int i = 0; i < 2 * D; ++i)
         if (i < ein) dgrad[m.off_encw + (long long)o * ein + i] = dw[i];
@@ -224,6 +227,30 @@ __global__ void k_encoder_bwd_emb(SatModel m, int n_keys, const float* __restric
             dgrad[m.off_lid + (long long)l * D + (i - D)] += d;
             dgrad[m.off_qkv + (long long)q * D + (i - D)] += d;
         }
+    }
+}
+
+// 'onlyemb' (reference satrans.py:173-176): no encoder, theta[key] = relu(domain_embeddings[g(key)]) with a [n_dom][4096] table
+// (with 'pos' the layer / qkv id embeddings sit behind the first 4096 entries of the concatenation and are sliced away, :63,70).
+__global__ void __launch_bounds__(ENC_THREADS) k_onlyemb_fwd(SatModel m, int n_keys, float* __restrict__ theta) {
+    const int o = blockIdx.x * ENC_THREADS + threadIdx.x;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    for (int key = 0; key < n_keys; ++key) {
+        int g, l, q;
+        key_decode(key, m.L, pos, g, l, q);
+        theta[(long long)key * PSZ + o] = fmaxf(m.dense[m.off_dom + (long long)g * PSZ + o], 0.f);
+    }
+}
+// ... and its backward: thread o owns column o of every row; the keys of one scenario are added in key order
+__global__ void __launch_bounds__(ENC_THREADS) k_onlyemb_bwd(SatModel m, int n_keys, const float* __restrict__ dtheta,
+                                                             float* __restrict__ dgrad) {
+    const int o = blockIdx.x * ENC_THREADS + threadIdx.x;
+    const bool pos = m.flags & SAT_FLAG_POS;
+    for (int key = 0; key < n_keys; ++key) {
+        int g, l, q;
+        key_decode(key, m.L, pos, g, l, q);
+        const long long e = m.off_dom + (long long)g * PSZ + o;
+        if (m.dense[e] > 0.f) dgrad[e] += dtheta[(long long)key * PSZ + o];
     }
 }
 
@@ -259,6 +286,10 @@ extern "C" int sat_bucket_by_domain(const SatModel* m, const void* x, int32_t id
 
 extern "C" int sat_encoder_fwd(const SatModel* m, SatWork* w, void* stream) {
     if (!m || !w || !w->theta) return sat_host::fail(SAT_EINVAL, "sat_encoder_fwd: null argument");
+    if (m->flags & SAT_FLAG_ONLYEMB) {
+        k_onlyemb_fwd<<<PSZ / ENC_THREADS, ENC_THREADS, 0, (cudaStream_t)stream>>>(*m, n_keys_of(m), w->theta);
+        return sat_host::check_launch("k_onlyemb_fwd");
+    }
     k_encoder_fwd<<<PSZ / ENC_THREADS, ENC_THREADS, 0, (cudaStream_t)stream>>>(*m, n_keys_of(m), w->theta);
     return sat_host::check_launch("k_encoder_fwd");
 }
@@ -267,6 +298,10 @@ extern "C" int sat_encoder_bwd(const SatModel* m, SatWork* w, void* stream) {
     if (!m || !w || !w->dtheta || !w->dgrad || !w->enc_du) return sat_host::fail(SAT_EINVAL, "sat_encoder_bwd: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     const int nk = n_keys_of(m);
+    if (m->flags & SAT_FLAG_ONLYEMB) {
+        k_onlyemb_bwd<<<PSZ / ENC_THREADS, ENC_THREADS, 0, s>>>(*m, nk, w->dtheta, w->dgrad);
+        return sat_host::check_launch("k_onlyemb_bwd");
+    }
     k_encoder_bwd<<<PSZ / ENC_THREADS, ENC_THREADS, 0, s>>>(*m, nk, w->dtheta, w->dgrad, w->enc_du);
     k_encoder_bwd_emb<<<1, 64, 0, s>>>(*m, nk, w->enc_du, PSZ / ENC_THREADS, w->dgrad);
     return sat_host::check_launch("k_encoder_bwd");

@@ -153,6 +153,8 @@ extern "C" int sat_forward_tc(const SatModel* m, const void* x, int32_t id_kind,
                               float* y_pred, int32_t training, float dropout_p, uint64_t seed, int32_t passes, void* stream) {
     using namespace sat;
     if (!m || !x || !w || !y_pred || !w->wpack || !w->tiles2) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: null argument");
+    if (m->flags & (SAT_FLAG_GATE_Q | SAT_FLAG_GATE_K | SAT_FLAG_BILINEAR))
+        return sat_host::fail(SAT_EINVAL, "sat_forward_tc: the gate / bilinear variants run in sat_forward (CUDA-core kernels) only");
     if (m->F <= 0 || m->F > SAT_MAXF) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: F=%d not in 1..%d", m->F, SAT_MAXF);
     if (m->n_dense > 64) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: n_dense=%d > 64", m->n_dense);
     if (training && !w->acts) return sat_host::fail(SAT_EINVAL, "sat_forward_tc: training needs w->acts");

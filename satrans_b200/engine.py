@@ -91,6 +91,8 @@ class Engine:
         # parity: y_pred within 1e-7 of the CUDA-core path); 'fp32' = CUDA-core FFMA kernels (bit-tight parity tests use it);
         # 'tf32' = tcgen05 plain TF32 (fast mode)
         self.precision = 'tf32x3'
+        if model._layout.get('flags', 0) & (_lib.FLAG_GATE_Q | _lib.FLAG_GATE_K | _lib.FLAG_BILINEAR):
+            self.precision = 'fp32'       # the gate / bilinear ablation variants exist in the CUDA-core token kernels only
         # backward of the MetaNet/QKV block: None = follow `precision`; 'fp32' forces the CUDA-core kernel
         self.backward_precision = None
         self._peer_tables = None

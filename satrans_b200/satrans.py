@@ -88,10 +88,16 @@ class SATrans(BaseModel):
                          device=device, gpus=gpus, table_shard=table_shard)
         if not isinstance(flag, str):
             raise TypeError("flag must be a str (the reference substring-tests it: satrans.py:46,158-173)")
-        for unsupported in ('gate', 'bilinear', 'onlyemb'):
-            if unsupported in flag:
-                raise NotImplementedError("flag variant '%s' (reference satrans.py:61-64,158-176) is not built; the "
-                                          "README configurations use none of them" % unsupported)
+        # ablation variants of the scenario-specific projection (reference satrans.py:59-81,158-176): 'gate' / 'bilinear' replace
+        # the MetaNet by a generated gate / per-head bilinear map, 'onlyemb' replaces the scenario encoder by a wide embedding
+        gate, bilinear, onlyemb = 'gate' in flag, 'bilinear' in flag, 'onlyemb' in flag
+        if gate and bilinear:
+            raise ValueError("'gate' and 'bilinear' cannot be combined (the reference's own forward fails on the shapes: "
+                             "meta_param_size is the bilinear one, satrans.py:158-162, and the gate needs embedding_size)")
+        if gate and not ('Q' in meta_mode or 'K' in meta_mode):
+            raise ValueError("'gate' needs 'Q' and / or 'K' in meta_mode")
+        if onlyemb and (gate or bilinear):
+            raise NotImplementedError("'onlyemb' combined with 'gate' / 'bilinear' is not built")
         if len(domain_column_list) != 1:
             raise NotImplementedError("multi-column scenarios (reference satrans.py:186-188,205-207) are not built")
         d = self.embedding_size
@@ -137,13 +143,21 @@ class SATrans(BaseModel):
             [Meta_Transformer_Layer(d, units, flag, meta_mode, att_head_num, att_res, device='cpu')
              for _ in range(domain_att_layer_num)])
         meta_param_size = sum(units[i] * units[i + 1] for i in range(len(units) - 1))
+        if bilinear:                                   # reference satrans.py:158-162
+            meta_param_size = (d ** 2) // att_head_num
+        elif gate:
+            meta_param_size = d
         if 'pos' in flag:
             self.domain_embedding_dim *= 2
             self.layerid_embeddings = nn.Embedding(domain_att_layer_num, d)
             self.qkvid_embeddings = nn.Embedding(3, d)
-        self.domain_map_dnn_Q = DNN_v2(self.domain_embedding_dim, [meta_param_size])
-        self.domain_map_dnn_K = self.domain_map_dnn_Q
-        self.domain_map_dnn_V = self.domain_map_dnn_Q
+        if onlyemb:                                    # reference satrans.py:173-176: a wide embedding, identity "encoder"
+            self.domain_embeddings = nn.Embedding(num_domains_list[0] + 1, meta_param_size)
+            self.domain_map_dnn_Q = lambda x: x
+        else:
+            self.domain_map_dnn_Q = DNN_v2(self.domain_embedding_dim, [meta_param_size])
+            self.domain_map_dnn_K = self.domain_map_dnn_Q
+            self.domain_map_dnn_V = self.domain_map_dnn_Q
         self.dnn_linear = nn.Linear(field_num * d + n_dense, 1)
 
         # ---- flat dense-parameter buffer ------------------------------------------------------------------
@@ -151,15 +165,18 @@ class SATrans(BaseModel):
         n_dom = num_domains_list[0] + 1
         lay = dict(F=field_num, L=L, H=att_head_num, n_dom=n_dom, n_dense=n_dense, n_cols=self._n_cols(),
                    enc_in=self.domain_embedding_dim)
-        lay['flags'] = ((_lib.FLAG_POS if pos else 0) | (_lib.FLAG_META_Q if 'Q' in meta_mode else 0) |
-                        (_lib.FLAG_META_K if 'K' in meta_mode else 0) | (_lib.FLAG_RELU if 'relu' in flag else 0) |
-                        (_lib.FLAG_RES if att_res else 0))
+        meta = not (gate or bilinear)                  # the MetaNet itself (with its LayerNorm and dropout) on that side
+        lay['flags'] = ((_lib.FLAG_POS if pos else 0) | (_lib.FLAG_META_Q if meta and 'Q' in meta_mode else 0) |
+                        (_lib.FLAG_META_K if meta and 'K' in meta_mode else 0) | (_lib.FLAG_RELU if 'relu' in flag else 0) |
+                        (_lib.FLAG_RES if att_res else 0) | (_lib.FLAG_GATE_Q if gate and 'Q' in meta_mode else 0) |
+                        (_lib.FLAG_GATE_K if gate and 'K' in meta_mode else 0) | (_lib.FLAG_BILINEAR if bilinear else 0) |
+                        (_lib.FLAG_ONLYEMB if onlyemb else 0))
         off = 0
-        lay['off_dom'] = off; off += n_dom * d
+        lay['off_dom'] = off; off += n_dom * (meta_param_size if onlyemb else d)
         lay['off_lid'] = off; off += (L * d if pos else 0)
         lay['off_qkv'] = off; off += (3 * d if pos else 0)
-        lay['off_encw'] = off; off += meta_param_size * lay['enc_in']
-        lay['off_encb'] = off; off += meta_param_size
+        lay['off_encw'] = off; off += (0 if onlyemb else meta_param_size * lay['enc_in'])
+        lay['off_encb'] = off; off += (0 if onlyemb else meta_param_size)
         lay['off_layers'] = off; off += L * _lib.SAT_LAYER_FLOATS
         lay['off_headw'] = off; off += field_num * d + n_dense
         lay['off_headb'] = off; off += 1
@@ -185,8 +202,9 @@ class SATrans(BaseModel):
         slots = [(self.domain_embeddings.weight, lay['off_dom'])]
         if 'pos' in self.flag:
             slots += [(self.layerid_embeddings.weight, lay['off_lid']), (self.qkvid_embeddings.weight, lay['off_qkv'])]
-        enc = self.domain_map_dnn_Q.linears[0]
-        slots += [(enc.weight, lay['off_encw']), (enc.bias, lay['off_encb'])]
+        if 'onlyemb' not in self.flag:
+            enc = self.domain_map_dnn_Q.linears[0]
+            slots += [(enc.weight, lay['off_encw']), (enc.bias, lay['off_encb'])]
         for i, layer in enumerate(self.domain_int_layers):
             o = lay['off_layers'] + i * _lib.SAT_LAYER_FLOATS
             slots += [(layer.W_Query, o), (layer.W_Key, o + 1024), (layer.W_Value, o + 2048),

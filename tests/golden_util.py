@@ -10,6 +10,8 @@ from oracle import satrans_oracle as O
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = ['en_small', 'enp_small', 'q_small']
 FORWARD_ONLY_CASES = ['relu_small_fwd']
+# the 'gate' / 'bilinear' / 'onlyemb' ablation flags of the reference (satrans.py:59-81,158-176), with and without 'pos'
+VARIANT_CASES = ['gate_small', 'gatepos_small', 'bilinear_small', 'bilinearpos_small', 'onlyemb_small', 'onlyembpos_small']
 ENC_W = 'domain_map_dnn_Q.linears.0.weight'
 
 
@@ -41,7 +43,8 @@ class Golden:
         full = dict(st)
         for a in ('K', 'V'):
             for s in ('weight', 'bias'):
-                full['domain_map_dnn_%s.linears.0.%s' % (a, s)] = st['domain_map_dnn_Q.linears.0.%s' % s]
+                if 'domain_map_dnn_Q.linears.0.%s' % s in st:         # ('onlyemb' has no encoder)
+                    full['domain_map_dnn_%s.linears.0.%s' % (a, s)] = st['domain_map_dnn_Q.linears.0.%s' % s]
         for i in range(L):
             for a in ('K', 'V'):
                 for s in ('weight', 'bias'):

@@ -235,9 +235,20 @@ def test_constructor_error_contract():
         make(meta_dnn_hidden_units=(32, 32))
     with pytest.raises(NotImplementedError, match='att_head_num'):
         make(att_head_num=16)
-    for flag in ('sota-gate', 'sota-bilinear', 'sota-onlyemb'):
-        with pytest.raises(NotImplementedError, match="flag variant"):
-            make(flag=flag)
+    # the ablation flags build (state-dict shapes of reference satrans.py:158-176); their invalid combinations raise
+    sd = make(flag='sota-gate', meta_mode='QK').state_dict()
+    assert sd['domain_map_dnn_Q.linears.0.weight'].shape == (32, 32)
+    sd = make(flag='sota-bilinear-pos', att_head_num=4).state_dict()
+    assert sd['domain_map_dnn_Q.linears.0.weight'].shape == (256, 64)
+    sd = make(flag='sota-onlyemb').state_dict()
+    assert sd['domain_embeddings.weight'].shape[1] == 4096 and not any(k.startswith('domain_map_dnn') for k in sd)
+    with pytest.raises(ValueError, match="cannot be combined"):
+        make(flag='sota-gate-bilinear')
+    with pytest.raises(NotImplementedError, match="onlyemb"):
+        make(flag='sota-gate-onlyemb')
+    m = make(flag='sota-gate', meta_mode='Q')
+    with pytest.raises(NotImplementedError, match="CUDA-core"):
+        m.precision = 'tf32x3'
     with pytest.raises(NotImplementedError, match='multi-column'):
         c = cols()
         SATrans(c, c, ['dom', 'f0'], [3, 7], att_layer_num=0, domain_att_layer_num=2, att_head_num=4, device='cpu', flag='sota')

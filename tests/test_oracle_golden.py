@@ -3,10 +3,10 @@ import pytest
 import torch
 
 from oracle import satrans_oracle as O
-from golden_util import CASES, FORWARD_ONLY_CASES, Golden, subsample
+from golden_util import CASES, FORWARD_ONLY_CASES, VARIANT_CASES, Golden, subsample
 
 
-@pytest.mark.parametrize('name', CASES + FORWARD_ONLY_CASES)
+@pytest.mark.parametrize('name', CASES + FORWARD_ONLY_CASES + VARIANT_CASES)
 def test_gather_bit_exact_and_forward(name):
     g = Golden(name)
     st = g.state()
@@ -19,7 +19,7 @@ def test_gather_bit_exact_and_forward(name):
     assert torch.allclose(yp, g.arr('y_pred'), atol=1e-6, rtol=0)
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + VARIANT_CASES)
 def test_loss_and_grads(name):
     g = Golden(name)
     yp, bce, reg, grads = O.loss_and_grads(g.state(), g.X(), g.y(), g.cfg)
@@ -41,16 +41,23 @@ def test_fp64_oracle_agrees(name):
     assert torch.allclose(yp.float(), g.arr('y_pred'), atol=1e-6, rtol=0)
 
 
-def assert_adam_close(got, ref, lr, step, key):
+def assert_adam_close(got, ref, lr, step, key, grad1=None):
     """Post-Adam parameters: Adam's normalised step lr*m/(sqrt(v)+eps) amplifies gradient round-off for
     elements whose |g| is near eps=1e-8 (and for the analytically-zero K-LN-bias gradient), so the bar is:
-    99.5 % of elements within fp32 round-off, every element within 5 % of the maximum possible movement."""
+    99.5 % of elements within fp32 round-off, every element within 5 % of the maximum possible movement.
+    grad1 (optional): the reference's first-step gradient of this tensor.  Elements whose |g| is below the stated gradient
+    tolerance (1e-4 x the tensor's max-norm) are decided by round-off in ANY fp32 implementation (|g| ~ eps: the step is
+    anywhere between 0 and lr); they are exempt from the tight criterion -- which on a 32-element tensor otherwise demands
+    100 % -- and stay under the 5 % rule like every element."""
     err = (got - ref).abs().flatten()
     if key.endswith('K_meta_mlp.ffn_layer_norm.bias'):
         assert err.max().item() <= 3 * lr * step, key
         return
     tight = 2e-5 * max(ref.abs().max().item(), 1e-3) + 1e-7
-    frac_ok = (err <= tight).float().mean().item()
+    ok = err <= tight
+    if grad1 is not None:
+        ok = ok | (grad1.abs().flatten() < 1e-4 * grad1.abs().max().item())
+    frac_ok = ok.float().mean().item()
     assert frac_ok >= 0.995, (key, step, frac_ok)
     assert err.max().item() <= 0.05 * lr * step, (key, step, err.max().item())
 
