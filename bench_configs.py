@@ -2,7 +2,7 @@
 """Secondary measurements for the BASELINE.json configurations that bench.py's single headline line does not cover
 (SURVEY.md §8d).  One JSON line per measurement on stdout; run on one B200:
 
-    python bench_configs.py [--only infer_sweep,selfatt,alimama,zipf,lazy,config4,fit]
+    python bench_configs.py [--only infer_sweep,selfatt,baselines,alimama,zipf,lazy,config4,fit]
 
   infer_sweep : config 5 — eval-mode scoring, batch 1 Ki .. 1 Mi, meta_mode QK and QKV (identical math in the
                 reference: satrans.py has no 'V' branch), fp32 CUDA-core vs tcgen05 3xTF32 vs tcgen05 TF32
@@ -12,6 +12,10 @@
   selfatt     : config 5's "SelfAttention_Layer x 3" (reference submodules.py:178-238) on (B, 19, 32) inputs, eval mode
   config4     : config 4 on one GPU — vocab x16 (105 M rows, 13.5 GB of tables + 27 GB of Adam state), B=65,536, int32 ids
   fit         : config 1(b) — fit() / predict() end to end from host numpy columns (verbose=0 and verbose=1 with sklearn metrics)
+  baselines   : config 5's "AutoInt / STAR-Trans baselines through the field-attention kernel": satrans_b200.AutoInt / Star_Trans
+                on the Ali-CCP-shaped full vocabulary -- scoring sweep (forward under no_grad: gather + attention layers + head,
+                this package's kernels only) and one training step (B = 8192; gather / attention forward + backward in the kernels,
+                head / DNN tower / torch.optim.Adam in torch)
 
 All timings: CUDA events, >=3 warm-up iterations, inputs resident in HBM.
 """
@@ -118,9 +122,10 @@ def selfatt_sweep():
         x = torch.randn(B, 19, 32, device='cuda:0') * 0.05
 
         def run():
-            h = x
-            for lay in layers:
-                h = lay(h)
+            with torch.no_grad():
+                h = x
+                for lay in layers:
+                    h = lay(h)
             return h
         ms = timeit(run, 10 if B <= 65536 else 4)
         print(json.dumps({"bench": "selfatt_x3", "metric": "infer_samples_per_sec", "value": B / (ms * 1e-3), "unit": "samples/s",
@@ -128,6 +133,45 @@ def selfatt_sweep():
                           "hbm_gbs_algorithmic": 3 * 2 * B * 19 * 128 / (ms * 1e-3) / 1e9}), flush=True)
         del x
     torch.cuda.empty_cache()
+
+
+def baselines_bench():
+    import torch
+    from satrans_b200 import AutoInt, Star_Trans, synth
+    schema = synth.aliccp_schema()
+    cols = schema.feature_columns(32)
+    for name in ('AutoInt', 'Star_Trans'):
+        if name == 'AutoInt':
+            model = AutoInt(cols, cols, att_layer_num=3, att_head_num=2, device='cuda:0', seed=1021)
+        else:
+            model = Star_Trans(cols, cols, schema.domain_col, schema.num_domains, att_layer_num=2, domain_att_layer_num=1,
+                               att_head_num=4, use_linear=False, device='cuda:0', seed=1021)
+        model.eval()
+        for B in (16384, 262144):
+            xs, _ = synth.make_inputs(schema, B, seed=7)
+            X = torch.from_numpy(np.stack([xs[f].astype(np.int32) for f in schema.fields], axis=1)).cuda()
+
+            def score():
+                with torch.no_grad():
+                    return model(X)
+            ms = timeit(score, 10 if B <= 65536 else 4)
+            print(json.dumps({"bench": "baseline_scoring", "model": name, "metric": "infer_samples_per_sec", "value": B / (ms * 1e-3),
+                              "unit": "samples/s", "ms": ms, "batch": B}), flush=True)
+            del X
+        B = 8192
+        xs, ys = synth.make_inputs(schema, B, seed=9, ctr=0.04)
+        X = torch.from_numpy(np.stack([xs[f].astype(np.int32) for f in schema.fields], axis=1)).cuda()
+        y = torch.from_numpy(ys.astype(np.float32)).cuda()
+        model.train()
+        model.compile(torch.optim.Adam(model.parameters(), lr=0.005), 'binary_crossentropy')
+        ms = timeit(lambda: model._train_step(X, y), 5)
+        print(json.dumps({"bench": "baseline_train_step", "model": name, "metric": "train_samples_per_sec", "value": B / (ms * 1e-3),
+                          "unit": "samples/s", "ms": ms, "batch": B,
+                          "note": "reference semantics (dense L2 + torch.optim.Adam on all 6.57 M rows every step); gather and "
+                                  "attention layers forward + backward in this package's kernels, head / tower / optimiser in torch"}),
+              flush=True)
+        del model, X
+        torch.cuda.empty_cache()
 
 
 def fit_bench():
@@ -164,7 +208,7 @@ def fit_bench():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--only', default='infer_sweep,selfatt,alimama,zipf,lazy,config4,fit')
+    ap.add_argument('--only', default='infer_sweep,selfatt,baselines,alimama,zipf,lazy,config4,fit')
     args = ap.parse_args()
     from satrans_b200 import synth
     only = set(args.only.split(','))
@@ -182,6 +226,8 @@ def main():
         fit_bench()
     if 'selfatt' in only:
         selfatt_sweep()
+    if 'baselines' in only:
+        baselines_bench()
     if 'infer_sweep' in only:
         infer_sweep(('fp32', 'tf32x3', 'tf32'))
 

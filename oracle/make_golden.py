@@ -355,6 +355,93 @@ def build_star_trans():
     model.load_state_dict(state0)
     model.compile(torch.optim.Adam(model.parameters(), lr=0.01), 'binary_crossentropy', metrics=[])
     out['model/adam_losses'] = np.array([ref_step(False) for _ in range(3)], dtype=np.float64)
+    # a second configuration with the optional logit terms: the linear model (use_linear, over EVERY column), one head per
+    # scenario (use_domain_dnn_linear), the scenario column kept as a field, merge='dot': forward, loss and every gradient
+    torch.manual_seed(2031)
+    model2 = Star_Trans(cols, cols, schema.domain_col, schema.num_domains, domain_id_as_feature=True, att_layer_num=1,
+                        domain_att_layer_num=2, att_head_num=2, merge='dot', use_linear=True, use_domain_dnn_linear=True,
+                        seed=1021, device='cpu').eval()
+    with torch.no_grad():
+        for k, v in model2.state_dict().items():
+            if k.startswith('embedding_dict.'):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.3)
+            if k.startswith('linear_model.'):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+            if 'layer_norm' in k and k.endswith('weight'):
+                v.add_(1.0)
+    st2 = {k: v.detach().clone() for k, v in model2.state_dict().items()}
+    model2.zero_grad()
+    yp2 = model2(X)
+    loss2 = F.binary_cross_entropy(yp2.squeeze(), yl, reduction='sum')
+    (loss2 + model2.get_regularization_loss()).sum().backward()
+    out['model2/y_pred'], out['model2/loss'] = yp2.detach().numpy(), np.float32(loss2.item())
+    for k, v in st2.items():
+        out['model2/state/' + k] = v.numpy()
+    so = {k: v.detach().clone().requires_grad_(True) for k, v in st2.items()}
+    o2 = O.star_trans_forward(so, X, schema.fields, schema.domain_col, schema.num_domains, 2, 1, 2, merge='dot', use_linear=True,
+                              use_domain_dnn_linear=True, domain_id_as_feature=True)
+    assert torch.allclose(o2.detach(), yp2.detach(), atol=1e-6, rtol=0), (o2 - yp2).abs().max()
+    lo = F.binary_cross_entropy(o2.squeeze(), yl, reduction='sum') + sum(1e-5 * (v * v).sum() for k, v in so.items()
+                                                                          if k.startswith('embedding_dict.'))
+    lo.backward()
+    for k, p_ in model2.named_parameters():
+        if p_.grad is not None:
+            out['model2/grad/' + k] = p_.grad.detach().clone().numpy()
+            gmax = float(p_.grad.abs().max())
+            assert float((so[k].grad - p_.grad).abs().max()) <= 1e-5 * gmax + 1e-12, k
+    return out
+
+
+def build_meta_module():
+    """BaseModel.meta_transformation (models/basemodel.py:191-199) + MetaNet with units (32, 64, 32) of the unmodified reference --
+    the scenario-specific pre-transformation of the single-task baselines ('usemetatrans' in flag, e.g. autoint.py:86-89), the
+    part of that path that IS vendored: output and gradients of sum(out * cot) for 'metanorm' on / off, eval mode."""
+    sys.path.insert(0, ROOT)
+    from oracle import satrans_oracle as O
+    import_reference()
+    from models.basemodel import BaseModel
+    from deepctr_torch.inputs import SparseFeat
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    cols = [SparseFeat('a', 10, embedding_dim=32), SparseFeat('301', 5, embedding_dim=32)]
+    B, Fn = 24, 8
+    shared = None
+    for flag in ('usemetatrans', 'usemetatrans-metanorm'):
+        torch.manual_seed(77)
+        m = BaseModel(cols, cols, flag=flag, domain_column='301', num_domains=3).eval()
+        with torch.no_grad():
+            if shared is None:                                # (both variants share the scenario embedding + encoder: stored once)
+                m.domain_map_dnn.linears[0].weight.copy_(torch.randn(m.domain_map_dnn.linears[0].weight.shape, generator=g) * 0.05)
+                shared = {k: v.detach().clone() for k, v in m.state_dict().items() if k.startswith(('domain_embeddings.', 'domain_map_dnn.'))}
+            else:
+                m.load_state_dict(shared, strict=False)
+            if 'metanorm' in flag:
+                m.meta_net.ffn_layer_norm.weight.add_(torch.randn(32, generator=g) * 0.1)
+                m.meta_net.ffn_layer_norm.bias.add_(torch.randn(32, generator=g) * 0.1)
+        X = torch.stack([torch.randint(0, 10, (B,), generator=g), torch.randint(0, 4, (B,), generator=g)], dim=1).float()
+        x = torch.randn((B, Fn, 32), generator=g) * 0.5
+        cot = torch.randn((B, Fn, 32), generator=g)
+        xg = x.clone().requires_grad_(True)
+        m.zero_grad()
+        y = m.meta_transformation(X, xg)
+        (y * cot).sum().backward()
+        tag = 'metanorm' if 'metanorm' in flag else 'plain'
+        out[tag + '/X'], out[tag + '/x'], out[tag + '/cot'], out[tag + '/y'] = X.numpy(), x.numpy(), cot.numpy(), y.detach().numpy()
+        out[tag + '/grad/x'] = xg.grad.numpy()
+        keys = [k for k in m.state_dict() if k.startswith(('domain_embeddings.', 'domain_map_dnn.', 'meta_net.'))]
+        named = dict(m.named_parameters())
+        for k in keys:
+            out[('shared' if k in shared else tag) + '/state/' + k] = m.state_dict()[k].detach().clone().numpy()
+            out[tag + '/grad/' + k] = named[k].grad.detach().clone().numpy()[subsample('domain_map_dnn_Q.' + k.split('.', 1)[1])
+                                                                             if k.startswith('domain_map_dnn.') else slice(None)]
+        # the oracle's restatement (autoint_forward's 'usemetatrans' branch uses exactly these calls)
+        st = {k: torch.from_numpy(out[('shared' if k in shared else tag) + '/state/' + k]) for k in keys}
+        e = F.relu(st['domain_embeddings.weight'][X[:, 1].long()])
+        theta = e @ st['domain_map_dnn.linears.0.weight'].t() + st['domain_map_dnn.linears.0.bias']
+        norm = 'metanorm' in flag
+        o = O.meta_net(x, theta, [32, 64, 32], st['meta_net.ffn_layer_norm.weight'] if norm else None,
+                       st['meta_net.ffn_layer_norm.bias'] if norm else None)
+        assert torch.allclose(o, y.detach(), atol=1e-6, rtol=0), (o - y).abs().max()
     return out
 
 
@@ -433,6 +520,11 @@ def main():
         np.savez_compressed(path, **build_compile_variants())
         print('compile_variants ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
         return
+    if os.environ.get('SAT_GOLDEN_ONLY_META'):
+        path = os.path.join(ROOT, 'tests', 'golden', 'meta_module.npz')
+        np.savez_compressed(path, **build_meta_module())
+        print('meta_module ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+        return
     if os.environ.get('SAT_GOLDEN_ONLY_STAR'):
         path = os.path.join(ROOT, 'tests', 'golden', 'star_trans.npz')
         np.savez_compressed(path, **build_star_trans())
@@ -452,6 +544,9 @@ def main():
     path = os.path.join(ROOT, 'tests', 'golden', 'star_trans.npz')
     np.savez_compressed(path, **build_star_trans())
     print('star_trans ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+    path = os.path.join(ROOT, 'tests', 'golden', 'meta_module.npz')
+    np.savez_compressed(path, **build_meta_module())
+    print('meta_module ->', path, '%.1f KB' % (os.path.getsize(path) / 1024))
     for name in CASES:
         out = build_case(name)
         path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')

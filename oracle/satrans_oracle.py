@@ -194,6 +194,8 @@ def meta_net(x, mlp_params, units, ln_w, ln_b, masks=None, mname=None, p_drop=0.
             x = F.relu(x) if relu_mask is None else x * relu_mask.to(x.dtype)
     x = _drop(x, p_drop, masks, mname)      # submodules.py:99
     x = x + res                             # submodules.py:100
+    if ln_w is None:                        # use_norm=False (the baselines' meta module without 'metanorm', basemodel.py:146-147)
+        return x
     return _layer_norm(x, ln_w, ln_b)       # submodules.py:101-102
 
 
@@ -361,12 +363,13 @@ def mdr_interacting_layer(x, domain_ids, p, heads: int, num_domains: int, merge:
 
 
 def star_trans_forward(st, X, sparse_names, domain_col, num_domains, heads, att_layer_num, domain_att_layer_num, merge='no',
-                       use_res=True, dense_names=()):
-    """Star_Trans.forward (star_trans.py:744-775) with use_linear=False, domain_id_as_feature=False, att_layer_type='deepctr',
-    use_domain_dnn_linear=False (main.py's call): gather of every field except the scenario column, SelfAttention_Layer x
-    att_layer_num, MDR_InteractingLayer x domain_att_layer_num, flatten (+ dense), dnn_linear, sigmoid."""
+                       use_res=True, dense_names=(), use_linear=False, use_domain_dnn_linear=False, domain_id_as_feature=False):
+    """Star_Trans.forward (star_trans.py:744-775), att_layer_type='deepctr': gather of every field (without the scenario column
+    unless domain_id_as_feature, :698-704), SelfAttention_Layer x att_layer_num, MDR_InteractingLayer x domain_att_layer_num,
+    flatten (+ dense), dnn_linear -- or one head per scenario with use_domain_dnn_linear (:762-767; samples of no scenario keep
+    a zero logit) -- plus the linear model's logit with use_linear (:749-750, basemodel.py:63-92; it sees EVERY column), sigmoid."""
     names = list(sparse_names) + list(dense_names)
-    fields = [n for n in sparse_names if n != domain_col]                            # filter_feature_columns, :702-704
+    fields = [n for n in sparse_names if domain_id_as_feature or n != domain_col]    # filter_feature_columns, :702-704
     x = torch.stack([st['embedding_dict.%s.weight' % n][X[:, names.index(n)].long()] for n in fields], dim=1)
     dom = X[:, names.index(domain_col)].long()
     for i in range(att_layer_num):
@@ -381,15 +384,36 @@ def star_trans_forward(st, X, sparse_names, domain_col, num_domains, heads, att_
     out = torch.flatten(x, start_dim=1)
     if dense_names:
         out = torch.cat([out, torch.stack([X[:, names.index(n)] for n in dense_names], dim=1).to(out.dtype)], dim=1)
-    return torch.sigmoid(out @ st['dnn_linear.weight'].t() + st['dnn_linear.bias'])
+    logit = torch.zeros((X.shape[0], 1), dtype=out.dtype)
+    if use_linear:
+        for n in sparse_names:
+            logit = logit + st['linear_model.embedding_dict.%s.weight' % n][X[:, names.index(n)].long()]
+        if dense_names:
+            logit = logit + torch.stack([X[:, names.index(n)] for n in dense_names], dim=1).to(out.dtype) @ st['linear_model.weight']
+    if use_domain_dnn_linear:
+        att = torch.zeros((X.shape[0], 1), dtype=out.dtype)
+        for i in range(num_domains):
+            m = dom == (i + 1)
+            att = torch.where(m[:, None], out @ st['domain_dnn_linears.%d.weight' % i].t() + st['domain_dnn_linears.%d.bias' % i], att)
+        logit = logit + att
+    else:
+        logit = logit + out @ st['dnn_linear.weight'].t() + st['dnn_linear.bias']
+    return torch.sigmoid(logit)
 
 
-def autoint_forward(st, X, sparse_names, heads, att_layer_num, use_res=True, dense_names=()):
+def autoint_forward(st, X, sparse_names, heads, att_layer_num, use_res=True, dense_names=(), domain_col=None, flag='',
+                    meta_units=(32, 64, 32)):
     """AutoInt.forward (autoint.py:82-123, flag without 'usemetatrans'): gather, InteractingLayer x att_layer_num, the deepctr DNN
     tower on the flattened embeddings (+ dense), dnn_linear (no bias) on [att_out | deep_out], PredictionLayer (bias + sigmoid).
     PARITY UNPINNED (InteractingLayer / DNN / PredictionLayer are deepctr-torch 0.2.9 code, not vendored)."""
     names = list(sparse_names) + list(dense_names)
     x = torch.stack([st['embedding_dict.%s.weight' % n][X[:, names.index(n)].long()] for n in sparse_names], dim=1)
+    if 'usemetatrans' in flag:                                                  # autoint.py:86-89, basemodel.py:191-199
+        e = F.relu(st['domain_embeddings.weight'][X[:, names.index(domain_col)].long()])
+        theta = e @ st['domain_map_dnn.linears.0.weight'].t() + st['domain_map_dnn.linears.0.bias']
+        norm = 'metanorm' in flag
+        x = meta_net(x, theta, list(meta_units), st['meta_net.ffn_layer_norm.weight'] if norm else None,
+                     st['meta_net.ffn_layer_norm.bias'] if norm else None)
     flat = torch.flatten(x, start_dim=1)
     if dense_names:
         flat = torch.cat([flat, torch.stack([X[:, names.index(n)] for n in dense_names], dim=1).to(flat.dtype)], dim=1)

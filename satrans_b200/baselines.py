@@ -192,7 +192,7 @@ class _ScoringModel(BaseModel):
         self._dense = torch.zeros(4, dtype=torch.float32, device=device)
 
     def _ensure_flat(self):
-        dev = self.dnn_linear.weight.device
+        dev = self.out.bias.device
         if self._tables.device != dev:
             tables = self._tables.to(dev)
             for f, a, b in zip(self._sparse_feats, self._row_off[:-1], self._row_off[1:]):
@@ -205,7 +205,7 @@ class _ScoringModel(BaseModel):
         out = super()._apply(fn, recurse)
         if hasattr(self, '_layout'):
             self._ensure_flat()
-            self.device = str(self.dnn_linear.weight.device)
+            self.device = str(self.out.bias.device)
         return out
 
     def _gather_fields(self, X, keep):
@@ -255,10 +255,6 @@ class Star_Trans(_ScoringModel):
                          init_std=init_std, seed=seed, task=task, device=device, gpus=gpus)
         if att_layer_type != 'deepctr':
             raise NotImplementedError("att_layer_type='%s' (Transformer_Layer, reference star_trans.py:449-509) is not built" % att_layer_type)
-        if use_linear:
-            raise NotImplementedError("use_linear=True (the dim-1 linear tables) is not built; main.py's Star_Trans call passes False")
-        if use_domain_dnn_linear:
-            raise NotImplementedError("use_domain_dnn_linear=True is not built")
         self.use_linear, self.use_dnn, self.num_domains = use_linear, use_dnn, num_domains
         self.use_domain_dnn_linear, self.domain_column = use_domain_dnn_linear, domain_column
         d = self.embedding_size
@@ -275,7 +271,10 @@ class Star_Trans(_ScoringModel):
                                          for _ in range(att_layer_num)])
         self.domain_int_layers = nn.ModuleList([MDR_InteractingLayer(d, num_domains, att_head_num, merge, att_res, device='cpu')
                                                 for _ in range(domain_att_layer_num)])
-        self.dnn_linear = nn.Linear(field_num * d + len(self._dense_cols), 1)
+        if use_domain_dnn_linear:                                        # reference star_trans.py:728-731: one head per scenario
+            self.domain_dnn_linears = nn.ModuleList([nn.Linear(field_num * d + len(self._dense_cols), 1) for _ in range(num_domains)])
+        else:
+            self.dnn_linear = nn.Linear(field_num * d + len(self._dense_cols), 1)
         self._init_layout(device)
         self.to(device)
 
@@ -287,7 +286,24 @@ class Star_Trans(_ScoringModel):
         for layer in self.domain_int_layers:
             x = layer(x, dom)
         dense = Xd[:, self._dense_cols].float().contiguous() if self._dense_cols else None
-        return self._head(x.reshape(x.shape[0], -1), dense, self.dnn_linear.weight, self.dnn_linear.bias)
+        feat = x.reshape(x.shape[0], -1)
+        if not self.use_linear and not self.use_domain_dnn_linear:       # main.py's configuration: one fused head launch
+            return self._head(feat, dense, self.dnn_linear.weight, self.dnn_linear.bias)
+        # the optional logit terms are small torch ops (a dim-1 lookup per field / a per-scenario weight row)
+        if self.use_domain_dnn_linear:                                   # reference star_trans.py:762-767
+            stack = feat if dense is None else torch.cat([feat, dense], dim=1)
+            W = torch.cat([lin.weight for lin in self.domain_dnn_linears], dim=0)          # (n, in)
+            bvec = torch.cat([lin.bias for lin in self.domain_dnn_linears], dim=0)         # (n,)
+            d64 = dom.long()
+            inside = (d64 >= 1) & (d64 <= self.num_domains)
+            sel = (d64 - 1).clamp(0, self.num_domains - 1)
+            logit = ((stack * W.index_select(0, sel)).sum(dim=1) + bvec.index_select(0, sel)) * inside.to(stack.dtype)
+            logit = logit.unsqueeze(1)
+        else:
+            logit = self._head(feat, dense, self.dnn_linear.weight, self.dnn_linear.bias, sigmoid=False)
+        if self.use_linear:                                              # reference star_trans.py:749-750
+            logit = logit + self.linear_model(Xd)
+        return torch.sigmoid(logit)
 
 
 class _DNN(nn.Module):
@@ -312,10 +328,21 @@ class AutoInt(_ScoringModel):
                  dnn_hidden_units=(256, 128), dnn_activation='relu', l2_reg_dnn=0, l2_reg_embedding=1e-5, dnn_use_bn=False,
                  dnn_dropout=0, init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None, flag=None,
                  domain_column=None, num_domains=None, meta_dnn_hidden_units=(32, 64, 32)):
-        if flag and 'usemetatrans' in flag:
-            raise NotImplementedError("'usemetatrans' (BaseModel.meta_transformation, reference basemodel.py:191-199) is not built")
         super().__init__(linear_feature_columns, dnn_feature_columns, l2_reg_linear=0, l2_reg_embedding=l2_reg_embedding,
                          init_std=init_std, seed=seed, task=task, device=device, gpus=gpus, flag=flag)
+        self.flag = flag if flag is not None else ''
+        self.domain_column = domain_column
+        if domain_column:
+            # the "meta module" every reference baseline carries when main.py hands it a scenario column (basemodel.py:132-148):
+            # part of the checkpoint; evaluated only with 'usemetatrans' in flag (meta_transformation below)
+            from .satrans import DNN_v2, MetaNet
+            units = [int(u) for u in meta_dnn_hidden_units]
+            self.domain_embeddings = nn.Embedding(num_domains + 1, self.embedding_size)
+            self.meta_dnn_hidden_units = units
+            self.domain_map_dnn = DNN_v2(self.embedding_size, [sum(units[i] * units[i + 1] for i in range(len(units) - 1))])
+            self.meta_net = MetaNet(self.embedding_size, 0.1, 'metanorm' in self.flag, units)
+        elif 'usemetatrans' in self.flag:
+            raise ValueError("'usemetatrans' needs domain_column / num_domains")
         if len(dnn_hidden_units) <= 0 and att_layer_num <= 0:
             raise ValueError("Either hidden_layer or att_layer_num must > 0")
         if dnn_activation != 'relu' or dnn_use_bn:
@@ -334,8 +361,30 @@ class AutoInt(_ScoringModel):
         self._init_layout(device)
         self.to(device)
 
+    def meta_transformation(self, Xd, x):
+        """BaseModel.meta_transformation (reference basemodel.py:191-199) + MetaNet.forward (submodules.py:77-103) on the gathered
+        embeddings: x <- [LN](dropout(MLP_theta(x)) + x) with the MLP weights theta generated from the sample's scenario embedding.
+        The scenario encoder runs once per scenario, not per sample; the per-sample products are torch.bmm (library GEMMs:
+        this is an optional pre-transformation of a baseline, not the SATrans hot path)."""
+        dom = Xd[:, self.feature_index[self.domain_column][0]].long()
+        theta = self.domain_map_dnn.linears[0](torch.relu(self.domain_embeddings.weight))       # (num_domains + 1, P)
+        units, off, h = self.meta_dnn_hidden_units, 0, x
+        for i in range(len(units) - 1):
+            W = theta[:, off:off + units[i] * units[i + 1]].reshape(-1, units[i], units[i + 1])
+            off += units[i] * units[i + 1]
+            h = torch.bmm(h, W.index_select(0, dom))
+            if i < len(units) - 2:
+                h = torch.relu(h)
+        h = Fnn.dropout(h, 0.1, self.training) + x
+        if self.meta_net.use_norm:
+            ln = self.meta_net.ffn_layer_norm
+            h = Fnn.layer_norm(h, (h.shape[-1],), ln.weight, ln.bias, 1e-6)
+        return h
+
     def forward(self, X):
         Xd, x = self._gather_fields(X, list(range(len(self._sparse_feats))))
+        if 'usemetatrans' in self.flag:                               # reference autoint.py:86-89
+            x = self.meta_transformation(Xd, x).contiguous()
         flat = x.reshape(x.shape[0], -1)
         att = x
         for layer in self.int_layers:

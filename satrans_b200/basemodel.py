@@ -93,13 +93,15 @@ class PredictionLayer(nn.Module):
 
 class Linear(nn.Module):
     """The per-feature dim-1 tables of the linear part (reference meta_basemodel.py:34-92).  SATrans.forward
-    never evaluates it (use_linear is ignored, l2_reg_linear=0), it only carries state-dict entries."""
+    never evaluates it (use_linear is ignored, l2_reg_linear=0), there it only carries state-dict entries; the attention
+    baselines with use_linear=True call forward() (plain torch lookups: F one-float rows per sample, not a hot op)."""
 
     def __init__(self, feature_columns, feature_index, init_std=0.0001, device='cpu'):
         super().__init__()
         self.feature_index = feature_index
         sparse = [f for f in feature_columns if isinstance(f, SparseFeat)]
         dense = [f for f in feature_columns if isinstance(f, DenseFeat)]
+        self._sparse, self._dense_feats = sparse, dense
         self.embedding_dict = nn.ModuleDict({f.embedding_name: nn.Embedding(f.vocabulary_size, 1) for f in sparse})
         for t in self.embedding_dict.values():
             nn.init.normal_(t.weight, mean=0, std=init_std)
@@ -107,6 +109,17 @@ class Linear(nn.Module):
             self.weight = nn.Parameter(torch.empty(sum(f.dimension for f in dense), 1))
             nn.init.normal_(self.weight, mean=0, std=init_std)
         self.to(device)
+
+    def forward(self, X):
+        """linear_logit (B, 1) = sum_f w_f[id_f] + dense @ weight (reference basemodel.py:63-92)."""
+        logit = torch.zeros((X.shape[0], 1), dtype=torch.float32, device=X.device)
+        if self._sparse:
+            logit = logit + torch.cat([self.embedding_dict[f.embedding_name](X[:, self.feature_index[f.name][0]].long())
+                                       for f in self._sparse], dim=-1).sum(dim=-1, keepdim=True)
+        if self._dense_feats:
+            cols = [c for f in self._dense_feats for c in range(*self.feature_index[f.name])]
+            logit = logit + X[:, cols].float().matmul(self.weight)
+        return logit
 
 
 def _auc(y_true, y_score):

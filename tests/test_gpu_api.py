@@ -562,8 +562,8 @@ def test_star_trans_training_matches_reference():
     model = build()
     model.compile('sgd', 'binary_crossentropy', metrics=[])
     _, loss, reg = model._train_step(X, y)
-    assert abs(loss.item() - float(z['model/loss'])) <= 1e-5 * float(z['model/loss'])
-    assert abs(reg.item() - float(z['model/reg'])) <= 1e-5 * float(z['model/reg'])
+    assert abs(loss.item() - float(z['model/loss'].item())) <= 1e-5 * float(z['model/loss'].item())
+    assert abs(reg.item() - float(z['model/reg'].item())) <= 1e-5 * float(z['model/reg'].item())
     grads = {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}
     names = [f[len('model/grad/'):] for f in z.files if f.startswith('model/grad/')]
     assert len(names) > 30 and set(names) <= set(grads)
@@ -593,6 +593,94 @@ def test_star_trans_training_matches_reference():
     assert set(ev) == {'binary_crossentropy', 'auc'} and np.isfinite(ev['binary_crossentropy'])
     l, r = model.train_on_batch(xs, z['model/y'])
     assert np.isfinite(l) and r > 0
+
+
+def test_star_trans_optional_logit_terms_match_reference():
+    """Star_Trans with the linear model's logit (use_linear, reference basemodel.py:63-92), one head per scenario
+    (use_domain_dnn_linear, star_trans.py:762-767), the scenario column kept as a field and merge='dot': y_pred, loss and every
+    gradient against the unmodified reference (tests/golden/star_trans.npz, model2/*)."""
+    import json
+    import os
+    from satrans_b200 import SparseFeat, Star_Trans
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'star_trans.npz'))
+    meta = json.loads(bytes(z['model/fields']).decode())
+    cols = [SparseFeat(f, v, 32) for f, v in zip(meta['fields'], meta['vocab'])]
+    model = Star_Trans(cols, cols, meta['domain_col'], meta['num_domains'], domain_id_as_feature=True, att_layer_num=1,
+                       domain_att_layer_num=2, att_head_num=2, merge='dot', use_linear=True, use_domain_dnn_linear=True,
+                       seed=1021, device='cuda:0').eval()
+    sd = {k[len('model2/state/'):]: torch.from_numpy(z[k]) for k in z.files if k.startswith('model2/state/')}
+    assert set(sd) == set(model.state_dict())                          # same checkpoint keys as the reference
+    model.load_state_dict(sd)
+    X = torch.from_numpy(z['model/X']).cuda()
+    y = torch.from_numpy(z['model/y']).cuda()
+    with torch.no_grad():
+        assert torch.allclose(model(X).cpu(), torch.from_numpy(z['model2/y_pred']), atol=2e-6, rtol=0)
+    model.compile('sgd', 'binary_crossentropy', metrics=[])
+    _, loss, _ = model._train_step(X, y)
+    assert abs(loss.item() - float(z['model2/loss'])) <= 1e-5 * float(z['model2/loss'])
+    grads = {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}
+    names = [f[len('model2/grad/'):] for f in z.files if f.startswith('model2/grad/')]
+    assert any(k.startswith('linear_model.') for k in names) and any(k.startswith('domain_dnn_linears.') for k in names)
+    assert set(names) <= set(grads)
+    for k in names:
+        _close(grads[k], torch.from_numpy(z['model2/grad/' + k]), 1e-4, k)
+
+
+def test_autoint_usemetatrans_matches_reference_meta_module_and_oracle():
+    """AutoInt with main.py's call (domain_column / num_domains / flag): the meta module's checkpoint keys exist, and with
+    'usemetatrans' in flag the scenario-specific pre-transformation (reference basemodel.py:191-199, submodules.py:77-103) equals
+    the unmodified reference's output and gradients (tests/golden/meta_module.npz); the whole model then equals the oracle
+    (InteractingLayer / DNN tower: parity unpinned) in y_pred and every gradient."""
+    import os
+    import torch.nn.functional as Fnn
+    from satrans_b200 import AutoInt, SparseFeat
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'meta_module.npz'))
+    cols = [SparseFeat('a', 10, embedding_dim=32), SparseFeat('301', 5, embedding_dim=32)]
+    for tag, flag in (('plain', 'usemetatrans'), ('metanorm', 'usemetatrans-metanorm')):
+        model = AutoInt(cols, cols, device='cuda:0', flag=flag, domain_column='301', num_domains=3).eval()
+        sd = {}
+        for k in z.files:
+            for pre in ('shared/state/', tag + '/state/'):
+                if k.startswith(pre):
+                    sd[k[len(pre):]] = torch.from_numpy(z[k])
+        assert set(sd) <= set(model.state_dict())                      # domain_embeddings / domain_map_dnn / meta_net keys
+        model.load_state_dict(sd, strict=False)
+        x = torch.from_numpy(z[tag + '/x']).cuda().requires_grad_(True)
+        model.zero_grad()
+        y = model.meta_transformation(torch.from_numpy(z[tag + '/X']).cuda(), x)
+        assert torch.allclose(y.detach().cpu(), torch.from_numpy(z[tag + '/y']), atol=2e-6, rtol=0)
+        (y * torch.from_numpy(z[tag + '/cot']).cuda()).sum().backward()
+        got = {'x': x.grad.cpu()}
+        got.update({k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None})
+        for k in [f[len(tag) + 6:] for f in z.files if f.startswith(tag + '/grad/')]:
+            g_ = got[k][::8] if k == 'domain_map_dnn.linears.0.weight' else got[k]
+            _close(g_, torch.from_numpy(z[tag + '/grad/' + k]), 1e-4, (tag, k))
+    # the whole model with the transformation in front of the interacting layers
+    schema, cfg, st = _small()
+    cols = schema.feature_columns(32)
+    torch.manual_seed(5)
+    model = AutoInt(cols, cols, att_layer_num=2, att_head_num=2, device='cuda:0', seed=7, flag='usemetatrans-metanorm',
+                    domain_column=schema.domain_col, num_domains=schema.num_domains).eval()
+    with torch.no_grad():
+        model._tables.normal_(0.0, 0.3)
+        model.domain_map_dnn.linears[0].weight.normal_(0.0, 0.05)
+        for lin in model.dnn.linears:
+            lin.weight.normal_(0.0, 0.05)
+        model.dnn_linear.weight.normal_(0.0, 0.05)
+    xs, ys = synth.make_inputs(schema, 120, seed=11)
+    Xh = torch.from_numpy(synth.stack_columns(xs, schema.fields))
+    yh = torch.from_numpy(np.asarray(ys, dtype=np.float32))
+    so = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items() if not k.startswith('linear_model.')}
+    ref = O.autoint_forward(so, Xh, schema.fields, 2, 2, domain_col=schema.domain_col, flag='usemetatrans-metanorm')
+    Fnn.binary_cross_entropy(ref.squeeze(), yh, reduction='sum').backward()
+    model.compile('sgd', 'binary_crossentropy', metrics=[])
+    model.l2_reg_embedding = 0.0
+    model.regularization_weight = []
+    yp, _, _ = model._train_step(Xh.cuda(), yh.cuda())
+    assert torch.allclose(yp.cpu(), ref.detach().squeeze(), atol=3e-6, rtol=0)
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            _close(p.grad.cpu(), so[k].grad, 1e-4, k)
 
 
 def test_autoint_training_matches_the_oracle():

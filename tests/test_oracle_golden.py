@@ -218,3 +218,32 @@ def test_interval_budget_of_normalising_optimisers(opt, loss):
         except AssertionError:
             passed = False
         assert passed == ok, (impl_lr, gtol)
+
+
+def test_meta_module_matches_reference():
+    """BaseModel.meta_transformation + MetaNet (units 32-64-32, with / without 'metanorm') of the unmodified reference
+    (tests/golden/meta_module.npz) vs the oracle calls that autoint_forward's 'usemetatrans' branch makes: output and gradients."""
+    import os
+    import numpy as np
+    import torch.nn.functional as F
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'meta_module.npz'))
+    for tag in ('plain', 'metanorm'):
+        st = {}
+        for k in z.files:
+            for pre in ('shared/state/', tag + '/state/'):
+                if k.startswith(pre):
+                    st[k[len(pre):]] = torch.from_numpy(z[k]).clone().requires_grad_(True)
+        X, x = torch.from_numpy(z[tag + '/X']), torch.from_numpy(z[tag + '/x']).clone().requires_grad_(True)
+        e = F.relu(st['domain_embeddings.weight'][X[:, 1].long()])
+        theta = e @ st['domain_map_dnn.linears.0.weight'].t() + st['domain_map_dnn.linears.0.bias']
+        norm = tag == 'metanorm'
+        y = O.meta_net(x, theta, [32, 64, 32], st['meta_net.ffn_layer_norm.weight'] if norm else None,
+                       st['meta_net.ffn_layer_norm.bias'] if norm else None)
+        assert torch.allclose(y.detach(), torch.from_numpy(z[tag + '/y']), atol=1e-6, rtol=0)
+        (y * torch.from_numpy(z[tag + '/cot'])).sum().backward()
+        got = {'x': x.grad}
+        got.update({k: v.grad for k, v in st.items()})
+        for k in [f[len(tag) + 6:] for f in z.files if f.startswith(tag + '/grad/')]:
+            ref = torch.from_numpy(z[tag + '/grad/' + k])
+            g_ = got[k][::8] if k == 'domain_map_dnn.linears.0.weight' else got[k]
+            assert (g_ - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-9, (tag, k)
