@@ -236,6 +236,9 @@ class BaseModel(nn.Module):
 
         # ---- embedding tables: ONE [total_rows, d] buffer, every nn.Embedding.weight is a view of it -----
         sparse = [f for f in dnn_feature_columns if isinstance(f, SparseFeat)]
+        if len(set(f.embedding_name for f in sparse)) != len(sparse):
+            raise NotImplementedError("two SparseFeat columns sharing one embedding_name (one table looked up by two columns, "
+                                      "deepctr's shared-embedding form) are not built: every field owns its slice of the table buffer")
         d = self.embedding_size
         self._sparse_feats = sparse
         self._row_off = np.concatenate([[0], np.cumsum([f.vocabulary_size for f in sparse])]).astype(np.int64)

@@ -249,6 +249,10 @@ def test_constructor_error_contract():
     m = make(flag='sota-gate', meta_mode='Q')
     with pytest.raises(NotImplementedError, match="CUDA-core"):
         m.precision = 'tf32x3'
+    with pytest.raises(NotImplementedError, match='embedding_name'):
+        c = cols()
+        c[0] = SparseFeat('f0', 8, 32, embedding_name='f1')      # shares f1's table
+        make(c)
     with pytest.raises(NotImplementedError, match='multi-column'):
         c = cols()
         SATrans(c, c, ['dom', 'f0'], [3, 7], att_layer_num=0, domain_att_layer_num=2, att_head_num=4, device='cpu', flag='sota')
