@@ -295,3 +295,17 @@ def test_no_floating_point_atomics_in_the_library():
     assert not bad, bad
     for op in ('UTCHMMA', 'UTMALDG', 'UBLKCP', 'LDTM', 'STTM'):
         assert op in sass, op
+
+
+def test_header_is_plain_c_and_matches_the_library(tmp_path):
+    """include/satrans_b200.h compiles as C99 (gcc -pedantic -Werror) and a C program that dlopens the library sees the same
+    ABI version and struct sizes: what a cgo / JNI / plain-C binding of the reference's maintainers would be built on."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'abi_check')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(root, 'include'),
+                    os.path.join(root, 'tests', 'abi_check.c'), '-o', exe, '-ldl'], check=True)
+    r = subprocess.run([exe, os.path.join(root, 'satrans_b200', 'lib', 'libsatrans_b200.so')], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert 'abi 4 header 4' in r.stdout
