@@ -2,12 +2,13 @@
 """Secondary measurements for the BASELINE.json configurations that bench.py's single headline line does not cover
 (SURVEY.md §8d).  One JSON line per measurement on stdout; run on one B200:
 
-    python bench_configs.py [--only infer_sweep,selfatt,baselines,alimama,zipf,lazy,config4,fit]
+    python bench_configs.py [--only infer_sweep,selfatt,baselines,variants,alimama,zipf,lazy,config4,fit]
 
   infer_sweep : config 5 — eval-mode scoring, batch 1 Ki .. 1 Mi, meta_mode QK and QKV (identical math in the
                 reference: satrans.py has no 'V' branch), fp32 CUDA-core vs tcgen05 3xTF32 vs tcgen05 TF32
   alimama     : config 3 — ENP+MetaNet (flag 'sota-pos', scenario column shopping_level, dense price), train step B=8192
   zipf        : config 2 with Zipf(1.05) ids instead of uniform (realistic skew: hot rows)
+  variants    : config 2 with the reference's ablation flags: 'gate' / 'bilinear' (CUDA-core token kernels) and 'onlyemb' (tcgen05 path)
   lazy        : config 2 with touched-rows-only table updates (NOT the reference's semantics; reported separately)
   selfatt     : config 5's "SelfAttention_Layer x 3" (reference submodules.py:178-238) on (B, 19, 32) inputs, eval mode
   config4     : config 4 on one GPU — vocab x16 (105 M rows, 13.5 GB of tables + 27 GB of Adam state), B=65,536, int32 ids
@@ -208,7 +209,7 @@ def fit_bench():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--only', default='infer_sweep,selfatt,baselines,alimama,zipf,lazy,config4,fit')
+    ap.add_argument('--only', default='infer_sweep,selfatt,baselines,variants,alimama,zipf,lazy,config4,fit')
     args = ap.parse_args()
     from satrans_b200 import synth
     only = set(args.only.split(','))
@@ -222,6 +223,10 @@ def main():
     if 'config4' in only:
         train_bench('aliccp_x16_config4_train', synth.aliccp_schema(16.0), 'sota', 0.005, 'uniform', False, 'tf32x3', B=65536,
                     steps=8, int_ids=True, nb=2)
+    if 'variants' in only:      # the reference's ablation flags (satrans.py:59-81,158-176) on the config-2 step
+        train_bench('aliccp_en_train_gate', synth.aliccp_schema(), 'sota-gate', 0.005, 'uniform', False, 'fp32', steps=16)
+        train_bench('aliccp_en_train_bilinear', synth.aliccp_schema(), 'sota-bilinear', 0.005, 'uniform', False, 'fp32', steps=16)
+        train_bench('aliccp_en_train_onlyemb', synth.aliccp_schema(), 'sota-onlyemb', 0.005, 'uniform', False, 'tf32x3', steps=16)
     if 'fit' in only:
         fit_bench()
     if 'selfatt' in only:
