@@ -309,3 +309,37 @@ def test_header_is_plain_c_and_matches_the_library(tmp_path):
     r = subprocess.run([exe, os.path.join(root, 'satrans_b200', 'lib', 'libsatrans_b200.so')], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert 'abi 4 header 4' in r.stdout
+
+
+def test_column_store_to_input_matrix(tmp_path):
+    """SURVEY 8f rank 4 (host logic): a column store with the reference's wire content (one array per column and group,
+    utils.py:266-278) -> the model's (N, n_cols) input matrix; the scenario column is shifted to start from 1 (main.py:108-110);
+    the HDF5 container itself needs h5py (absent here: a clear ImportError, never a silent fallback)."""
+    import pytest
+    from satrans_b200 import SATrans, data, synth
+    schema = synth.aliccp_schema(1e-4)
+    xs, ys = synth.make_inputs(schema, 500, seed=5)
+    stored = {k: v.astype(np.int32) for k, v in xs.items()}
+    stored['301'] = stored['301'] - 1                              # ids stored from 0, as in the reference's file
+    stored['click'] = ys.astype(np.int64)
+    store = data.NpyDirColumnStore(str(tmp_path))
+    store.write('ctr_train', stored)
+    x, y = data.load_aliccp(store, 'ctr_train')
+    assert list(x) == data.ALICCP_SPARSE == schema.fields and np.array_equal(y, ys)
+    assert x['301'].min() == 1 and np.array_equal(x['301'], xs['301'])
+    cols = schema.feature_columns(32)
+    model = SATrans(cols, cols, [schema.domain_col], [schema.num_domains], att_layer_num=0, domain_att_layer_num=1, att_head_num=4,
+                    meta_mode='QK', seed=3, device='cpu', flag='sota')
+    X = data.to_input_matrix(model, x, pin=False)
+    assert X.dtype == torch.int32 and X.shape == (500, 19)
+    assert np.array_equal(X.numpy(), np.stack([xs[f] for f in schema.fields], axis=1))
+    with pytest.raises(KeyError):
+        store.read('ctr_test', ['101'])
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match='h5py'):
+            data.H5ColumnStore(str(tmp_path / 'alicpp.h5'))
+    row = data.append_result_row(str(tmp_path / 'alicpp_results.csv'), 'SATrans_32_0.005_3_4_QK_1021_301_sota', [0.61, 0.62], 0.1623)
+    assert row.endswith('SATrans_32_0.005_3_4_QK_1021_301_sota,0.610000,0.620000,0.162300')
+    assert open(str(tmp_path / 'alicpp_results.csv')).read().strip() == row
