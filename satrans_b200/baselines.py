@@ -55,7 +55,7 @@ class _EmbeddingRows(torch.autograd.Function):
         return (None, None) + tuple(g[off[i]:off[i + 1]] for i in range(len(off) - 1))
 
 
-class _ScoringModel(BaseModel):
+class _AttentionBaseline(BaseModel):
     """Shared plumbing of the two baselines: gather through the engine's kernel, scoring through the package's kernels only,
     training as the reference's loop around the differentiable kernels."""
 
@@ -245,7 +245,7 @@ class _ScoringModel(BaseModel):
         return out.cpu().numpy().astype("float64").reshape(-1, 1)
 
 
-class Star_Trans(_ScoringModel):
+class Star_Trans(_AttentionBaseline):
     def __init__(self, linear_feature_columns, dnn_feature_columns, domain_column, num_domains, domain_id_as_feature=False,
                  att_layer_num=2, domain_att_layer_num=1, att_head_num=2, merge='no', att_layer_type='deepctr',
                  use_domain_dnn_linear=False, att_res=True, use_linear=True, use_dnn=False, dnn_hidden_units=(256, 128),
@@ -323,7 +323,7 @@ class _DNN(nn.Module):
         return x
 
 
-class AutoInt(_ScoringModel):
+class AutoInt(_AttentionBaseline):
     def __init__(self, linear_feature_columns, dnn_feature_columns, att_layer_num=3, att_head_num=2, att_res=True,
                  dnn_hidden_units=(256, 128), dnn_activation='relu', l2_reg_dnn=0, l2_reg_embedding=1e-5, dnn_use_bn=False,
                  dnn_dropout=0, init_std=0.0001, seed=1024, task='binary', device='cpu', gpus=None, flag=None,

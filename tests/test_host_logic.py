@@ -343,3 +343,48 @@ def test_column_store_to_input_matrix(tmp_path):
     row = data.append_result_row(str(tmp_path / 'alicpp_results.csv'), 'SATrans_32_0.005_3_4_QK_1021_301_sota', [0.61, 0.62], 0.1623)
     assert row.endswith('SATrans_32_0.005_3_4_QK_1021_301_sota,0.610000,0.620000,0.162300')
     assert open(str(tmp_path / 'alicpp_results.csv')).read().strip() == row
+
+
+def test_attention_baselines_host_contract():
+    """Star_Trans / AutoInt on the host (parameter containers only): checkpoint keys equal the unmodified reference's
+    (tests/golden/star_trans.npz holds its state dicts), compile() builds real torch.optim instances from the reference's
+    string table (basemodel.py:554-568), unsupported options raise, and nothing computes without CUDA (no CPU fallback)."""
+    import json
+    import os
+    import pytest
+    from satrans_b200 import AutoInt, SparseFeat, Star_Trans
+    from satrans_b200._lib import SatError
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'star_trans.npz'))
+    meta = json.loads(bytes(z['model/fields']).decode())
+    cols = [SparseFeat(f, v, 32) for f, v in zip(meta['fields'], meta['vocab'])]
+    m1 = Star_Trans(cols, cols, meta['domain_col'], meta['num_domains'], att_layer_num=2, domain_att_layer_num=1, att_head_num=4,
+                    merge='no', use_linear=False, seed=1021, device='cpu')
+    ref_keys = {k[len('model/state/'):] for k in z.files if k.startswith('model/state/')}
+    assert ref_keys == {k for k in m1.state_dict() if not k.startswith('linear_model.')}
+    m2 = Star_Trans(cols, cols, meta['domain_col'], meta['num_domains'], domain_id_as_feature=True, att_layer_num=1,
+                    domain_att_layer_num=2, att_head_num=2, merge='dot', use_linear=True, use_domain_dnn_linear=True, device='cpu')
+    assert {k[len('model2/state/'):] for k in z.files if k.startswith('model2/state/')} == set(m2.state_dict())
+    with pytest.raises(NotImplementedError, match='att_layer_type'):
+        Star_Trans(cols, cols, meta['domain_col'], meta['num_domains'], att_layer_type='trans', use_linear=False, device='cpu')
+    a = AutoInt(cols, cols, device='cpu', flag='usemetatrans-metanorm', domain_column=meta['domain_col'], num_domains=meta['num_domains'])
+    keys = set(a.state_dict())
+    assert {'domain_embeddings.weight', 'domain_map_dnn.linears.0.weight', 'domain_map_dnn.linears.0.bias',
+            'meta_net.ffn_layer_norm.weight', 'meta_net.ffn_layer_norm.bias', 'dnn_linear.weight', 'out.bias',
+            'int_layers.2.W_key', 'dnn.linears.1.bias'} <= keys
+    assert 'meta_net.ffn_layer_norm.weight' not in AutoInt(cols, cols, device='cpu', flag='usemetatrans',
+                                                           domain_column=meta['domain_col'], num_domains=3).state_dict()
+    with pytest.raises(ValueError, match='domain_column'):
+        AutoInt(cols, cols, device='cpu', flag='usemetatrans')
+    for name, cls in (('sgd', torch.optim.SGD), ('adam', torch.optim.Adam), ('adagrad', torch.optim.Adagrad), ('rmsprop', torch.optim.RMSprop)):
+        m1.compile(name, 'binary_crossentropy', metrics=['auc'])
+        assert isinstance(m1.optim, cls) and m1.metrics_names == ['loss', 'auc']
+    assert m1.optim.param_groups[0]['lr'] == 0.01
+    with pytest.raises(NotImplementedError):
+        m1.compile('adamw', 'binary_crossentropy')
+    with pytest.raises(NotImplementedError):
+        m1.compile('adam', 'hinge')
+    X = np.zeros((4, len(cols)), dtype=np.int64)
+    with pytest.raises(SatError):
+        m1.predict({f: X[:, i] for i, f in enumerate(meta['fields'])})
+    with pytest.raises(SatError):
+        m1.train_on_batch({f: X[:, i] for i, f in enumerate(meta['fields'])}, np.zeros(4))
