@@ -252,3 +252,67 @@ def test_deferred_sweep_model_equals_per_step_sweep(K):
     sweep(base)                                                   # sync_tables()
     assert np.array_equal(q, p) and np.array_equal(qm, m) and np.array_equal(qv, v)
     assert np.allclose([reg_def[t] for t in range(1, T + 1)], reg_ref, rtol=1e-12, atol=0)
+
+
+# ---- index math of the ablation-flag kernels and of the per-scenario backward launches (round 2) ---------------------------------
+def test_bilinear_gradient_is_the_diagonal_blocks_of_the_outer_product():
+    """k_bwd_meta with SAT_FLAG_BILINEAR (backward.cu): the full 32x32 product M = qp^T dQ' is accumulated at sdTh[1024 + i*32 + j]
+    by the shared 4x4-block routine; the gradient of theta (B_h[i][j] at theta[(h*dh + i)*dh + j], forward.cu) is then read out as
+    sdTh[e] = sdTh[1024 + row*32 + (row/dh)*dh + j] with row = e / dh, j = e % dh.  Restated and checked against autograd-free
+    algebra: d B_h = qp_h^T dQ'_h, and dqp_h = dQ'_h B_h^T."""
+    rng = np.random.default_rng(0)
+    D = 32
+    for H in (1, 2, 4, 8):
+        dh = D // H
+        ntok = 57
+        qp, dq = rng.standard_normal((ntok, D)), rng.standard_normal((ntok, D))
+        theta = rng.standard_normal(D * dh)
+        sd = np.zeros(4096)
+        sd[1024:2048] = (qp.T @ dq).reshape(-1)                       # wgrad32(sA = qp, sG = dQ', acc = sdTh + 1024, ld = 32)
+        for e in range(D * dh):                                       # the remap loop at the end of k_bwd_meta
+            row, j = e // dh, e % dh
+            sd[e] = sd[1024 + row * D + (row // dh) * dh + j]
+        B = theta.reshape(H, dh, dh)
+        for h in range(H):
+            ref = qp[:, h * dh:(h + 1) * dh].T @ dq[:, h * dh:(h + 1) * dh]
+            assert np.allclose(sd[h * dh * dh:(h + 1) * dh * dh].reshape(dh, dh), ref)
+        # forward: q'_h[j] = sum_i qp_h[i] * theta[(h*dh + i)*dh + j];  backward (bilinear_dq): dqp_h[i] = sum_j dq'_h[j] * theta[(h*dh + i)*dh + j]
+        fwd = np.stack([sum(qp[:, h * dh + i, None] * theta[(h * dh + i) * dh:(h * dh + i) * dh + dh][None, :] for i in range(dh))
+                        for h in range(H)], axis=1).reshape(ntok, D)
+        assert np.allclose(fwd, np.concatenate([qp[:, h * dh:(h + 1) * dh] @ B[h] for h in range(H)], axis=1))
+        back = np.zeros((ntok, D))
+        for h in range(H):
+            for i in range(dh):
+                back[:, h * dh + i] = dq[:, h * dh:(h + 1) * dh] @ theta[(h * dh + i) * dh:(h * dh + i) * dh + dh]
+        assert np.allclose(back, np.concatenate([dq[:, h * dh:(h + 1) * dh] @ B[h].T for h in range(H)], axis=1))
+
+
+def test_live_generated_weights_per_key():
+    """SAT_META_PSZ (include/satrans_b200.h): 32 live generated weights per key with a gate, 1024 / H with the per-head bilinear map,
+    4096 with the MetaNet -- the sizes of the reference's scenario-encoder output (satrans.py:156-162)."""
+    GQ, GK, BIL, P = 128, 256, 512, 4096
+    psz = lambda flags, H: 32 if flags & (GQ | GK) else (1024 // H if flags & BIL else P)
+    for H in (1, 2, 4, 8):
+        assert psz(GQ, H) == 32 and psz(GK | 1, H) == 32
+        assert psz(BIL, H) == 32 * 32 // H
+        assert psz(2 | 4 | 16, H) == 32 * 64 + 64 * 32
+
+
+def test_per_scenario_sample_lists_cover_each_sample_once():
+    """_ScenarioAttention.backward (selfatt.py): a stable sort of the clamped scenario ids gives contiguous, batch-ordered sample
+    lists per scenario; samples outside 1..n are on no list (zero gradient)."""
+    import torch
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 3, 8):
+        dom = torch.randint(-1, n + 3, (257,), generator=g, dtype=torch.int32)
+        key = torch.where((dom >= 1) & (dom <= n), dom, torch.full_like(dom, n + 1))
+        order = torch.argsort(key, stable=True).to(torch.int32)
+        counts = torch.bincount(key.long(), minlength=n + 2)[1:n + 1].tolist()
+        seen, start = [], 0
+        for d, cnt in enumerate(counts):
+            idx = order[start:start + cnt]
+            assert bool((dom[idx.long()] == d + 1).all()) and bool((idx[1:] > idx[:-1]).all())      # one scenario, batch order
+            seen += idx.tolist()
+            start += cnt
+        inside = ((dom >= 1) & (dom <= n)).nonzero().flatten().tolist()
+        assert sorted(seen) == inside and len(seen) == len(set(seen))
