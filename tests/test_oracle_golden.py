@@ -32,7 +32,7 @@ def test_loss_and_grads(name):
         assert (got - ref).abs().max().item() <= tol, k
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + VARIANT_CASES)
 def test_fp64_oracle_agrees(name):
     """fp64 restatement vs the reference's fp32 output: the reference's own noise floor."""
     g = Golden(name)
@@ -62,7 +62,7 @@ def assert_adam_close(got, ref, lr, step, key, grad1=None):
     assert err.max().item() <= 0.05 * lr * step, (key, step, err.max().item())
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES + VARIANT_CASES)
 def test_dense_adam_steps(name):
     g = Golden(name)
     st = g.state()
